@@ -1,0 +1,62 @@
+"""Pins oracle/pfp_oracle.c against the reference's own outputs.
+
+The golden fixtures were produced by the unmodified newscanNT.x (tools/make_golden.py); when
+oracle/_ref is present (build container, GPU box) the reference is also run live."""
+import numpy as np
+import pytest
+
+from conftest import assert_same_files, golden, golden_names
+from oracle import pfp_oracle as orc
+
+
+def _text_of(case):
+    if case["fasta"]:
+        text, _ = orc.fasta_extract(case["input"])
+        return text
+    return case["input"]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_golden(name):
+    c = golden().case(name)
+    got = orc.parse(_text_of(c), c["w"], c["p"])
+    assert_same_files(got, c, name)
+    assert got.n_phrases == c["n_phrases"] and got.n_distinct == c["n_distinct"]
+
+
+def test_kr_hash_kat():
+    # first-window example of SURVEY appendix B2: window hash 48505500 for w=10
+    assert orc.window_hash(b"ACGACGCGCT") == 48505500
+    # phrase hash definition (newscan.cpp:229-239): base-256 integer mod the 55-bit prime
+    s = b"\x02ACGACGCGCT"
+    assert orc.kr_hash(s) == int.from_bytes(s, "big") % 27162335252586509
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,w,p", [(101, 10, 100), (102, 4, 10), (103, 12, 37), (104, 31, 64),
+                                       (105, 8, 1000)])
+def test_oracle_matches_live_reference(pkg, seed, w, p):
+    text = pkg.synth.pangenome_text(5000, 8, seed).numpy().tobytes()
+    ref = orc.run_reference(text, w, p)
+    assert_same_files(orc.parse(text, w, p), ref, f"seed{seed}")
+
+
+@pytest.mark.skipif(not orc.have_ref("pscan.x"), reason="oracle/_ref not built")
+def test_threaded_rule_matches_pscan():
+    # helper-thread scanners skip a trigger at the very first window
+    rng = np.random.default_rng(7)
+    text = b"ACGACGCGCT" + rng.choice(np.frombuffer(b"ACGT", np.uint8), 20000).tobytes()
+    ref = orc.run_reference(text, 10, 100, exe="pscan.x", threads=2)
+    got = orc.parse(text, 10, 100, flags=orc.THREADED_RULE)
+    assert_same_files(got, ref, "pscan -t 2")
+    seq = orc.parse(text, 10, 100)
+    assert seq.n_phrases == got.n_phrases + 1
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+def test_fasta_extract_matches_live_reference(pkg):
+    recs = [r.numpy() for r in pkg.synth.pangenome_records(2000, 5, 9)]
+    fa = pkg.synth.to_fasta(recs, width=70)
+    text, trunc = orc.fasta_extract(fa)
+    assert not trunc and text == b"".join(r.tobytes() for r in recs)
+    assert_same_files(orc.parse(text), orc.run_reference(fa, fasta=True), "fasta live")
