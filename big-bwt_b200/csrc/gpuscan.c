@@ -1,0 +1,83 @@
+/* gpuscan.c -- newscan.x-compatible command line over libpfpb200 (reference main():
+ * newscan.cpp:569-650, options :489-556).  Install it (or symlinks to it) as newscan.x and
+ * newscanNT.x next to the unchanged `bigbwt` script, which picks its scanner by path
+ * (bigbwt:22-24,71-78) and only looks at the exit status (bigbwt:231-240). */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+#include "../../include/pfpb200.h"
+
+static void usage(const char *exe, const pfpb200_opts *o) {
+    printf("Usage: %s <input filename> [options]\n", exe);
+    printf("  Options: \n");
+    printf("\t-w W\tsliding window size, def. %u\n", o->w);
+    printf("\t-p M\tmodulo for defining phrases, def. %u\n", o->p);
+    printf("\t-t M\tnumber of .last/.sai segments to write (helper threads of the reference), def. none \n");
+    printf("\t-g G\tCUDA device index, def. 0\n");
+    printf("\t-h  \tshow help and exit\n");
+    printf("\t-s  \tcompute suffix array info\n");
+    printf("\t-f  \tread a FASTA/FASTQ file\n");
+    printf("\t-P  \taccepted for compatibility (collisions are always detected)\n");
+    printf("\t-c  \tcompress the output dictionary\n");
+    exit(1);
+}
+
+int main(int argc, char **argv) {
+    pfpb200_opts o = {10, 100, 0, 0};
+    int device = 0, verbose = 0, c;
+    puts("==== Command line:");
+    for (int i = 0; i < argc; i++) printf(" %s", argv[i]);
+    puts("");
+    while ((c = getopt(argc, argv, "p:w:fsPcht:vg:")) != -1) {
+        switch (c) {
+            case 's': o.flags |= PFPB200_F_SAI; break;
+            case 'P': break;
+            case 'c': o.flags |= PFPB200_F_COMPRESS; break;
+            case 'w': o.w = (uint32_t)atoi(optarg); break;
+            case 'p': o.p = (uint32_t)atoi(optarg); break;
+            case 'f': o.flags |= PFPB200_F_FASTA; break;
+            case 't': o.nseg = atoi(optarg); break;
+            case 'g': device = atoi(optarg); break;
+            case 'v': verbose++; o.flags |= PFPB200_F_VERBOSE; break;
+            case 'h': usage(argv[0], &o); break;
+            default: puts("Unknown option. Use -h for help."); exit(1);
+        }
+    }
+    if (argc != optind + 1) { puts("Invalid number of arguments"); usage(argv[0], &o); }
+    const char *path = argv[optind];
+    if (o.w < 4) { puts("Windows size must be at least 4"); exit(1); }
+    if (o.p < 10) { puts("Modulus must be at least 10"); exit(1); }
+    if (o.nseg < 0) { puts("Number of threads cannot be negative"); exit(1); }
+    printf("Windows size: %u\n", o.w);
+    printf("Stop word modulus: %u\n", o.p);
+    time_t start = time(NULL);
+    pfpb200_ctx *ctx = NULL;
+    int rc = pfpb200_create(device, &ctx);
+    if (rc != PFPB200_OK) {
+        fprintf(stderr, "gpuscan: cannot use CUDA device %d: %s\n", device, pfpb200_strerror(rc));
+        return 1;
+    }
+    pfpb200_stats st;
+    rc = pfpb200_parse_file(ctx, path, &o, &st);
+    if (rc != PFPB200_OK) {
+        fprintf(stderr, "gpuscan: %s: %s\n", pfpb200_strerror(rc), pfpb200_last_error(ctx));
+        pfpb200_destroy(ctx);
+        return 1;
+    }
+    printf("Total input symbols: %llu\n", (unsigned long long)st.n_text);
+    printf("Found %llu distinct words\n", (unsigned long long)st.n_distinct);
+    printf("Sum of lenghts of dictionary words: %llu\n", (unsigned long long)st.sum_word_len);
+    printf("Total number of words: %llu\n", (unsigned long long)st.n_phrases);
+    printf("GPU parse: %.3f ms (scan %.3f, emit %.3f, hash %.3f, dict %.3f, rank %.3f [%u rounds], "
+           "write-dict %.3f, remap %.3f), h2d %.3f ms, d2h %.3f ms, %u kernel launches\n",
+           st.ms_total, st.ms_scan, st.ms_emit, st.ms_hash, st.ms_dedup, st.ms_rank, st.rank_rounds,
+           st.ms_dict, st.ms_remap, st.ms_h2d, st.ms_d2h, st.launches);
+    printf("File read: %.3f s, file write: %.3f s\n", st.sec_read, st.sec_write);
+    printf("==== Elapsed time: %.0f wall clock seconds\n", difftime(time(NULL), start));
+    pfpb200_destroy(ctx);
+    (void)verbose;
+    return 0;
+}

@@ -1,0 +1,380 @@
+// pfp_api.cu -- the C ABI of libpfpb200.so (include/pfpb200.h): context management and the
+// orchestration of the stages K1..K5 for one GPU.
+#include "pfp_common.cuh"
+#include "pfp_stages.cuh"
+#include <stdlib.h>
+#include <time.h>
+
+extern "C" {
+int pfp_io_read_file(const char *path, uint8_t **buf, uint64_t *n, char *err, size_t errlen);
+int pfp_io_write_outputs(const char *path, const pfpb200_opts *opts, const pfpb200_outputs *o,
+                         char *err, size_t errlen);
+}
+
+static double wall_sec() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+__global__ void set_u64_k(u64 *p, u64 v) { *p = v; }
+
+extern "C" int pfpb200_abi_version(void) { return PFPB200_ABI_VERSION; }
+
+extern "C" const char *pfpb200_strerror(int code) {
+    switch (code) {
+        case PFPB200_OK: return "ok";
+        case PFPB200_E_ARG: return "invalid argument";
+        case PFPB200_E_IO: return "file I/O error";
+        case PFPB200_E_CUDA: return "CUDA error (no usable GPU or kernel failure)";
+        case PFPB200_E_NOMEM: return "out of memory";
+        case PFPB200_E_LIMIT: return "algorithm limit exceeded";
+        case PFPB200_E_COLLISION: return "fingerprint collision";
+        case PFPB200_E_INTERNAL: return "internal error";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char *pfpb200_last_error(const pfpb200_ctx *ctx) { return ctx ? ctx->err : ""; }
+
+static u64 splitmix64(u64 &s) {
+    u64 z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
+    if (!out) return PFPB200_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return PFPB200_E_CUDA;   // no CPU fallback: without a GPU there is no product
+    }
+    pfpb200_ctx *ctx = new (std::nothrow) pfpb200_ctx();
+    if (!ctx) return PFPB200_E_NOMEM;
+    ctx->device = device;
+    auto bail = [&](int code) { pfpb200_destroy(ctx); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(PFPB200_E_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(PFPB200_E_CUDA);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(PFPB200_E_CUDA);
+    ctx->stream = ctx->own_stream;
+    // keep freed scratch in the stream-ordered pool: after the first call no allocation
+    // reaches the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if (cudaMalloc(&ctx->d_flags, PFP_FLAG_SLOTS * sizeof(u64)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_flags, PFP_FLAG_SLOTS * sizeof(u64)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_keys, NH_KEY_WORDS * sizeof(u32)) != cudaSuccess)
+        return bail(PFPB200_E_NOMEM);
+    u32 hk[NH_KEY_WORDS];
+    u64 seed = 0x5bd1e9955bd1e995ULL;
+    for (u32 i = 0; i < NH_KEY_WORDS; i++) hk[i] = (u32)(splitmix64(seed) >> 32);
+    if (cudaMemcpy(ctx->d_keys, hk, sizeof(hk), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(ctx->d_flags, 0, PFP_FLAG_SLOTS * sizeof(u64)) != cudaSuccess)
+        return bail(PFPB200_E_CUDA);
+    // fail here, loudly, if the library carries no kernel image for this GPU
+    set_u64_k<<<1, 1, 0, ctx->stream>>>(&ctx->d_flags[15], 1);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return bail(PFPB200_E_CUDA);
+    *out = ctx;
+    return PFPB200_OK;
+}
+
+extern "C" void pfpb200_destroy(pfpb200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pfp_release_scratch(ctx);
+    pfp_release_held(ctx);
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->d_keys) cudaFree(ctx->d_keys);
+    delete ctx;
+}
+
+extern "C" int pfpb200_set_stream(pfpb200_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return PFPB200_E_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    pfp_release_scratch(ctx);
+    pfp_release_held(ctx);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return PFPB200_OK;
+}
+
+static int check_opts(pfpb200_ctx *ctx, const pfpb200_opts *o) {
+    if (!ctx) return PFPB200_E_ARG;
+    if (!o) return pfp_fail(ctx, PFPB200_E_ARG, "null options");
+    if (o->w < 4) return pfp_fail(ctx, PFPB200_E_ARG, "Windows size must be at least 4");   // newscan.cpp:537
+    if (o->p < 10) return pfp_fail(ctx, PFPB200_E_ARG, "Modulus must be at least 10");      // newscan.cpp:541
+    if (o->w > 65536) return pfp_fail(ctx, PFPB200_E_ARG, "window size too large");
+    if (o->nseg < 0) return pfp_fail(ctx, PFPB200_E_ARG, "Number of threads cannot be negative");
+    return PFPB200_OK;
+}
+
+static int begin_call(pfpb200_ctx *ctx) {
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    pfp_release_scratch(ctx);
+    pfp_release_held(ctx);
+    ctx->launches = 0;
+    ctx->err[0] = 0;
+    PFP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, PFP_FLAG_SLOTS * sizeof(u64), ctx->stream));
+    return PFPB200_OK;
+}
+
+struct StageTimer {
+    cudaEvent_t ev[10];
+    int n = 0;
+    int init() {
+        for (int i = 0; i < 10; i++)
+            if (cudaEventCreate(&ev[i]) != cudaSuccess) return -1;
+        return 0;
+    }
+    void mark(cudaStream_t s) { cudaEventRecord(ev[n++], s); }
+    float ms(int a, int b) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b]); return t; }
+    void destroy() { for (int i = 0; i < 10; i++) cudaEventDestroy(ev[i]); }
+};
+
+// text resident on the device -> all outputs on the device
+static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pfpb200_opts *o,
+                             pfpb200_outputs *out, pfpb200_stats *st) {
+    const u32 w = o->w, p = o->p;
+    StageTimer tm;
+    if (tm.init()) return pfp_fail(ctx, PFPB200_E_CUDA, "cudaEventCreate failed");
+    int rc = PFPB200_OK;
+    auto run = [&]() -> int {
+        tm.mark(ctx->stream);                                           // 0
+        // K1
+        u64 *ends = nullptr, k = 0;
+        float ms_scan = 0, ms_emit = 0;
+        PFP_TRY(pfp_scan_stage(ctx, d_text, n, 0, 0, n, w, p, 1, false, &ends, &k, &ms_scan, &ms_emit));
+        const u64 P = k + 1;
+        if (P >= 0xFFFFFFFFull)
+            return pfp_fail(ctx, PFPB200_E_LIMIT, "the parse contains %llu words, more than 2^32-2",
+                            (unsigned long long)P);                     // bigbwt:110-114
+        set_u64_k<<<1, 1, 0, ctx->stream>>>(ends + k, n + w - 1);       // final word (:376-377)
+        PFP_LAUNCHED(ctx);
+        tm.mark(ctx->stream);                                           // 1
+        // K2
+        PhraseArrays ph{};
+        ph.ends = ends;
+        PFP_TRY(pfp_alloc_t(ctx, &ph.fpa, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.fpb, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.key, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.len, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
+        if (o->flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
+        TextView tv{d_text, n, 0, (i64)n};
+        PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, -1, w));
+        tm.mark(ctx->stream);                                           // 2
+        // K3
+        DictArrays D;
+        PFP_TRY(pfp_dedup_stage(ctx, ph, P, &D));
+        PFP_TRY(pfp_free_now(ctx, ph.fpa));
+        PFP_TRY(pfp_free_now(ctx, ph.fpb));
+        PFP_TRY(pfp_free_now(ctx, ph.key));
+        PFP_TRY(pfp_pool_stage(ctx, tv, ends, -1, w, &D));
+        tm.mark(ctx->stream);                                           // 3
+        // K4
+        u32 *order = nullptr, rounds = 0;
+        PFP_TRY(pfp_rank_stage(ctx, D, &order, &rounds));
+        tm.mark(ctx->stream);                                           // 4
+        u8 *dict = nullptr;
+        u32 *occ = nullptr, *rank_of_uid = nullptr;
+        u64 dict_bytes = 0;
+        PFP_TRY(pfp_dict_stage(ctx, D, order, (o->flags & PFPB200_F_COMPRESS) ? w : 0, &dict,
+                               &dict_bytes, &occ, &rank_of_uid));
+        tm.mark(ctx->stream);                                           // 5
+        // K5
+        u32 *parse = nullptr;
+        PFP_TRY(pfp_alloc_t(ctx, &parse, P, true));
+        PFP_TRY(pfp_remap_stage(ctx, D.uid, rank_of_uid, P, parse));
+        tm.mark(ctx->stream);                                           // 6
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PFP_CUDA(ctx, cudaGetLastError());
+        out->dict = dict; out->dict_bytes = dict_bytes;
+        out->occ = occ; out->n_distinct = D.d;
+        out->parse = parse; out->n_phrases = P;
+        out->last = ph.last;
+        out->sai = ph.sai;
+        if (st) {
+            st->n_text = n; st->n_phrases = P; st->n_distinct = D.d;
+            st->sum_word_len = D.sum_len; st->dict_bytes = dict_bytes;
+            st->alg_bytes = n + 4 * P + P + ((o->flags & PFPB200_F_SAI) ? 5 * P : 0) + dict_bytes + 4 * D.d;
+            st->rank_rounds = rounds;
+            st->launches = ctx->launches;
+            st->ms_total = tm.ms(0, 6);
+            st->ms_scan = ms_scan; st->ms_emit = ms_emit;
+            st->ms_hash = tm.ms(1, 2); st->ms_dedup = tm.ms(2, 3); st->ms_rank = tm.ms(3, 4);
+            st->ms_dict = tm.ms(4, 5); st->ms_remap = tm.ms(5, 6);
+        }
+        return PFPB200_OK;
+    };
+    rc = run();
+    if (rc != PFPB200_OK) cudaStreamSynchronize(ctx->stream);
+    pfp_release_scratch(ctx);
+    tm.destroy();
+    return rc;
+}
+
+extern "C" int pfpb200_parse_device(pfpb200_ctx *ctx, const uint8_t *d_text, uint64_t n_text,
+                                    const pfpb200_opts *opts, pfpb200_outputs *dev_out,
+                                    pfpb200_stats *stats) {
+    PFP_TRY(check_opts(ctx, opts));
+    if (!dev_out || (n_text && !d_text)) return pfp_fail(ctx, PFPB200_E_ARG, "null buffer");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    memset(dev_out, 0, sizeof(*dev_out));
+    PFP_TRY(begin_call(ctx));
+    return parse_device_impl(ctx, d_text, n_text, opts, dev_out, stats);
+}
+
+extern "C" int pfpb200_memcpy_d2h(pfpb200_ctx *ctx, void *dst_host, const void *src_device,
+                                  uint64_t bytes) {
+    if (!ctx || (bytes && (!dst_host || !src_device))) return PFPB200_E_ARG;
+    if (bytes == 0) return PFPB200_OK;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFP_CUDA(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFPB200_OK;
+}
+
+// number of leading valid text bytes (newscan.cpp:364: stop at the first byte <= Dollar)
+static u64 valid_prefix(const u8 *t, u64 n) {
+    u64 i = 0;
+    // 8 bytes at a time: a byte b <= 2 iff (b - 3) borrows
+    while (i + 8 <= n) {
+        u64 v;
+        memcpy(&v, t + i, 8);
+        if (((v - 0x0303030303030303ULL) & ~v & 0x8080808080808080ULL) != 0) break;
+        i += 8;
+    }
+    while (i < n && t[i] > PFP_DOLLAR) i++;
+    return i;
+}
+
+extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_t n_text,
+                                  const pfpb200_opts *opts, pfpb200_outputs *host_out,
+                                  pfpb200_stats *stats) {
+    PFP_TRY(check_opts(ctx, opts));
+    if (!host_out || (n_text && !text)) return pfp_fail(ctx, PFPB200_E_ARG, "null buffer");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    memset(host_out, 0, sizeof(*host_out));
+    PFP_TRY(begin_call(ctx));
+    u64 n = valid_prefix(text, n_text);
+    if (n < n_text && (opts->flags & PFPB200_F_VERBOSE))
+        fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    u8 *d_text = nullptr;
+    PFP_TRY(pfp_alloc(ctx, (void **)&d_text, n, true));
+    cudaEventRecord(e0, ctx->stream);
+    if (n) PFP_CUDA(ctx, cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEventRecord(e1, ctx->stream);
+    pfpb200_outputs dv;
+    memset(&dv, 0, sizeof(dv));
+    int rc = parse_device_impl(ctx, d_text, n, opts, &dv, stats);
+    if (rc != PFPB200_OK) return rc;
+    // device -> pinned host
+    const u64 P = dv.n_phrases, d = dv.n_distinct;
+    void *h_dict = nullptr, *h_occ = nullptr, *h_parse = nullptr, *h_last = nullptr, *h_sai = nullptr;
+    auto pin = [&](void **h, size_t bytes) -> int {
+        if (cudaMallocHost(h, bytes ? bytes : 1) != cudaSuccess) {
+            cudaGetLastError();
+            return pfp_fail(ctx, PFPB200_E_NOMEM, "pinned host allocation of %zu bytes failed", bytes);
+        }
+        ctx->pinned.push_back(*h);
+        return PFPB200_OK;
+    };
+    PFP_TRY(pin(&h_dict, dv.dict_bytes));
+    PFP_TRY(pin(&h_occ, d * 4));
+    PFP_TRY(pin(&h_parse, P * 4));
+    PFP_TRY(pin(&h_last, P));
+    if (dv.sai) PFP_TRY(pin(&h_sai, P * PFP_IBYTES));
+    cudaEventRecord(e2, ctx->stream);
+    PFP_CUDA(ctx, cudaMemcpyAsync(h_dict, dv.dict, dv.dict_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaMemcpyAsync(h_occ, dv.occ, d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaMemcpyAsync(h_parse, dv.parse, P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaMemcpyAsync(h_last, dv.last, P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dv.sai)
+        PFP_CUDA(ctx, cudaMemcpyAsync(h_sai, dv.sai, P * PFP_IBYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(e3, ctx->stream);
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        cudaEventElapsedTime(&stats->ms_h2d, e0, e1);
+        cudaEventElapsedTime(&stats->ms_d2h, e2, e3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    host_out->dict = (const u8 *)h_dict; host_out->dict_bytes = dv.dict_bytes;
+    host_out->occ = (const u32 *)h_occ; host_out->n_distinct = d;
+    host_out->parse = (const u32 *)h_parse; host_out->n_phrases = P;
+    host_out->last = (const u8 *)h_last;
+    host_out->sai = (const u8 *)h_sai;
+    // the device copies are no longer needed
+    for (void *q : ctx->held) cudaFreeAsync(q, ctx->stream);
+    ctx->held.clear();
+    return PFPB200_OK;
+}
+
+extern "C" int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts,
+                                  pfpb200_stats *stats) {
+    PFP_TRY(check_opts(ctx, opts));
+    if (!path) return pfp_fail(ctx, PFPB200_E_ARG, "null path");
+    double t0 = wall_sec();
+    uint8_t *file = nullptr;
+    uint64_t fn = 0;
+    if (pfp_io_read_file(path, &file, &fn, ctx->err, sizeof(ctx->err)) != 0) return PFPB200_E_IO;
+    const uint8_t *text = file;
+    uint64_t n = fn;
+    uint8_t *seq = nullptr;
+    if (opts->flags & PFPB200_F_FASTA) {
+        seq = (uint8_t *)malloc(fn ? fn : 1);
+        if (!seq) { free(file); return pfp_fail(ctx, PFPB200_E_NOMEM, "out of memory"); }
+        int trunc = 0;
+        n = pfpb200_fasta_extract(file, fn, seq, &trunc);
+        if (trunc) fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
+        free(file);
+        file = nullptr;
+        text = seq;
+    }
+    double t1 = wall_sec();
+    pfpb200_outputs ho;
+    int rc = pfpb200_parse_host(ctx, text, n, opts, &ho, stats);
+    free(file);
+    free(seq);
+    if (rc != PFPB200_OK) return rc;
+    double t2 = wall_sec();
+    if (pfp_io_write_outputs(path, opts, &ho, ctx->err, sizeof(ctx->err)) != 0) return PFPB200_E_IO;
+    if (stats) {
+        stats->sec_read = (float)(t1 - t0);
+        stats->sec_write = (float)(wall_sec() - t2);
+    }
+    return PFPB200_OK;
+}
+
+extern "C" int pfpb200_scan_triggers(pfpb200_ctx *ctx, const uint8_t *d_buf, uint64_t n_buf,
+                                     uint64_t buf_pos0, uint64_t own_lo, uint64_t own_hi, uint32_t w,
+                                     uint32_t p, const uint64_t **d_triggers, uint64_t *n_triggers,
+                                     float *ms) {
+    pfpb200_opts o = {w, p, 0, 0};
+    PFP_TRY(check_opts(ctx, &o));
+    if (!d_triggers || !n_triggers) return pfp_fail(ctx, PFPB200_E_ARG, "null output");
+    PFP_TRY(begin_call(ctx));
+    u64 *out = nullptr, k = 0;
+    float a = 0, b = 0;
+    int rc = pfp_scan_stage(ctx, d_buf, n_buf, buf_pos0, own_lo, own_hi, w, p, 0, true, &out, &k, &a, &b);
+    cudaStreamSynchronize(ctx->stream);
+    pfp_release_scratch(ctx);
+    if (rc != PFPB200_OK) return rc;
+    *d_triggers = out;
+    *n_triggers = k;
+    if (ms) *ms = a;
+    return PFPB200_OK;
+}

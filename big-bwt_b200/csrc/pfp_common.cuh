@@ -1,0 +1,122 @@
+// pfp_common.cuh -- context, error handling and device primitives shared by all stages.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "pfp_arith.h"
+#include "../../include/pfpb200.h"
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+typedef int64_t i64;
+
+struct pfpb200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    u32 launches = 0;
+    char err[512] = {0};
+    std::vector<void *> scratch;   // freed at the end of every call
+    std::vector<void *> held;      // outputs: freed at the start of the next call / destroy
+    std::vector<void *> pinned;    // host outputs of parse_host
+    // persistent small device state
+    u32 *d_keys = nullptr;         // NH key table (phrase fingerprints)
+    u64 *d_flags = nullptr;        // [0] error bits, [1..] counters read back by the host
+    u64 *h_flags = nullptr;        // pinned mirror
+    // scan-stage result kept for pfpb200_scan_triggers callers
+    u64 *trig_hold = nullptr;
+};
+
+#define PFP_FLAG_SLOTS 16
+#define PFP_ERRBIT_COLLISION 1ull
+#define PFP_ERRBIT_LIMIT 2ull
+#define PFP_ERRBIT_INTERNAL 4ull
+
+int pfp_fail(pfpb200_ctx *ctx, int code, const char *fmt, ...);
+
+#define PFP_CUDA(ctx, call)                                                                 \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return pfp_fail((ctx), e_ == cudaErrorMemoryAllocation ? PFPB200_E_NOMEM        \
+                                                                   : PFPB200_E_CUDA,        \
+                            "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define PFP_TRY(expr)                 \
+    do {                              \
+        int rc_ = (expr);             \
+        if (rc_ != PFPB200_OK) return rc_; \
+    } while (0)
+
+// counts a launch and checks it
+#define PFP_LAUNCHED(ctx)                                                                   \
+    do {                                                                                    \
+        (ctx)->launches++;                                                                  \
+        cudaError_t e_ = cudaGetLastError();                                                \
+        if (e_ != cudaSuccess)                                                              \
+            return pfp_fail((ctx), PFPB200_E_CUDA, "%s:%d launch: %s", __FILE__, __LINE__,  \
+                            cudaGetErrorString(e_));                                        \
+    } while (0)
+
+// ---- scratch memory (stream-ordered pool) ----------------------------------------------
+int pfp_alloc(pfpb200_ctx *ctx, void **p, size_t bytes, bool held = false);
+int pfp_free_now(pfpb200_ctx *ctx, void *p);   // early release of one scratch buffer
+void pfp_release_scratch(pfpb200_ctx *ctx);
+void pfp_release_held(pfpb200_ctx *ctx);
+
+template <typename T>
+static inline int pfp_alloc_t(pfpb200_ctx *ctx, T **p, size_t count, bool held = false) {
+    return pfp_alloc(ctx, (void **)p, (count ? count : 1) * sizeof(T), held);
+}
+
+static inline u32 pfp_blocks(u64 n, u32 per_block) { return (u32)((n + per_block - 1) / per_block); }
+
+// ---- primitives (pfp_prims.cu) -----------------------------------------------------------
+// out[i] = sum_{j<i} in[j]; if d_total != null, *d_total = sum of all (device pointer).
+int pfp_exclusive_scan_u32(pfpb200_ctx *ctx, const u32 *in, u32 *out, u64 n, u32 *d_total);
+int pfp_exclusive_scan_u32_u64(pfpb200_ctx *ctx, const u32 *in, u64 *out, u64 n, u64 *d_total);
+int pfp_exclusive_scan_u8_u32(pfpb200_ctx *ctx, const u8 *in, u32 *out, u64 n, u32 *d_total);
+
+// Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [begin_bit, end_bit).
+// Ping-pongs between (k0,v0) and (k1,v1); *res_k/*res_v point at the sorted pair on return.
+int pfp_radix_sort_pairs(pfpb200_ctx *ctx, u64 *k0, u32 *v0, u64 *k1, u32 *v1, u64 n,
+                         int begin_bit, int end_bit, u64 **res_k, u32 **res_v);
+
+// ---- small device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() {
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ u32 warp_incl_scan(u32 v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (u32)o) v += t;
+    }
+    return v;
+}
+// exclusive scan over a 256-thread block; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32 *total, u32 *sm /*>=9 u32*/) {
+    u32 inc = warp_incl_scan(v);
+    u32 w = threadIdx.x >> 5;
+    __syncthreads();   // protect sm from a previous use
+    if (lane_id() == 31) sm[w] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        u32 x = threadIdx.x < 8 ? sm[threadIdx.x] : 0;
+        u32 xi = warp_incl_scan(x);
+        if (threadIdx.x < 8) sm[threadIdx.x] = xi - x;
+        if (threadIdx.x == 7) sm[8] = xi;
+    }
+    __syncthreads();
+    *total = sm[8];
+    return inc - v + sm[w];
+}

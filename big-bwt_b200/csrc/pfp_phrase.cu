@@ -1,0 +1,404 @@
+// pfp_phrase.cu -- K2 phrase records + fingerprints, K3 dictionary build, phrase pool.
+//
+// K2 replaces save_update_word() (newscan.cpp:245-304): from consecutive trigger positions it
+// derives every phrase (start, length), its `.last` byte (:296) and `.sai` value (:299-301), and
+// a 128-bit fingerprint standing in for kr_hash() (:229-239).  The reference's 64-bit hash only
+// ever reaches the private .parse_old file, so its VALUE is not part of the contract; what
+// matters is that equal phrases get equal ids and different phrases different ones.  We use two
+// NH sums (UMAC's universal family: sum of (x_2i + k_2i)(x_2i+1 + k_2i+1) mod 2^64 over 32-bit
+// words, Toeplitz-shifted keys) folded over 8 KB segments, plus the length; any disagreement
+// inside a run of equal sort keys is reported as a collision, as the reference does (:282-286).
+//
+// K3 replaces the std::map<uint64_t,word_stats> updates (:256-288): radix sort of
+// (key, phrase index), run heads = distinct words, run lengths = occurrences, first index of
+// the run = representative occurrence.
+#include "pfp_common.cuh"
+#include "pfp_stages.cuh"
+
+__device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ u64 fmix64(u64 k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+// 16 bytes of a phrase at phrase offset o (multiple of 16), zero beyond the phrase end.
+// fast path: aligned 32-bit loads + funnel shift by the byte misalignment of the phrase start
+__device__ __forceinline__ void load_chunk(const TextView &tv, i64 s0, u64 len, u64 o, bool special,
+                                           u32 x[4]) {
+    u32 nbv = (u32)((len - o) < 16 ? (len - o) : 16);
+    if (!special) {
+        const u8 *p = tv.T + (s0 + (i64)o - tv.pos0);
+        u32 bs = (u32)((uintptr_t)p & 3);
+        const u32 *p4 = reinterpret_cast<const u32 *>(p - bs);
+        u32 need = bs + nbv;   // bytes needed counted from p4
+        u32 W[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) W[j] = (4u * j < need) ? __ldg(p4 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) x[j] = __funnelshift_r(W[j], W[j + 1], 8 * bs);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            u32 v = 0;
+            for (int b = 0; b < 4; b++) {
+                u32 k = 4 * j + b;
+                if (k < nbv) v |= (u32)tv_byte(tv, s0 + (i64)o + k) << (8 * b);
+            }
+            x[j] = v;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        u32 lo = 4u * j;
+        u32 nb = nbv > lo ? nbv - lo : 0;
+        if (nb < 4) x[j] &= (nb == 0) ? 0u : ((1u << (8 * nb)) - 1u);
+    }
+}
+
+__device__ __forceinline__ void nh_chunk(const u32 *__restrict__ sk, u32 c, const u32 x[4], u64 &pa,
+                                         u64 &pb) {
+    const uint4 k0 = *reinterpret_cast<const uint4 *>(sk + 4 * c);
+    const uint4 k1 = *reinterpret_cast<const uint4 *>(sk + 4 * c + 4);
+    pa += (u64)(x[0] + k0.x) * (u64)(x[1] + k0.y) + (u64)(x[2] + k0.z) * (u64)(x[3] + k0.w);
+    pb += (u64)(x[0] + k1.x) * (u64)(x[1] + k1.y) + (u64)(x[2] + k1.z) * (u64)(x[3] + k1.w);
+}
+
+__device__ __forceinline__ u64 sort_key_of(u64 fa, u64 fb, u32 len) {
+    return fmix64(fa ^ rotl64(fb, 32) ^ ((u64)len * 0x9E3779B97F4A7C15ULL));
+}
+
+__device__ __forceinline__ void write_records(const PhraseArrays &ph, const TextView &tv, u64 j,
+                                              i64 e, u32 w) {
+    ph.last[j] = tv_byte(tv, e - (i64)w);                       // newscan.cpp:296
+    if (ph.sai) {                                               // newscan.cpp:299-301
+        u64 pos = (u64)(e + 1);
+        u8 *d = ph.sai + j * PFP_IBYTES;
+#pragma unroll
+        for (int b = 0; b < PFP_IBYTES; b++) d[b] = (u8)(pos >> (8 * b));
+    }
+}
+
+constexpr int PH_T = 256;
+constexpr int PH_GROUP = 8;                          // lanes per phrase
+constexpr int PH_PER_BLOCK = PH_T / PH_GROUP;        // 32 phrases per CTA iteration
+
+__global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays ph, u64 P,
+                                                      i64 first_start, u32 w,
+                                                      const u32 *__restrict__ keytab,
+                                                      u32 *__restrict__ long_list,
+                                                      u32 *__restrict__ long_count,
+                                                      u64 *__restrict__ flags) {
+    __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
+    for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31, li = lane & 7, grp = lane >> 3;
+    const u32 gmask = 0xFFu << (8 * grp);
+    const u32 warp = threadIdx.x >> 5;
+    for (u64 jw = ((u64)blockIdx.x * (PH_T / 32) + warp) * 4; jw < P;
+         jw += (u64)gridDim.x * PH_PER_BLOCK) {
+        u64 j = jw + grp;
+        if (j >= P) continue;                                  // whole group leaves together
+        i64 e = (i64)ph.ends[j];
+        i64 s0 = (j == 0) ? first_start : (i64)ph.ends[j - 1] - (i64)w + 1;
+        u64 len = (u64)(e - s0 + 1);
+        if (len > 0xFFFFFFFFull) {
+            if (li == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
+            continue;
+        }
+        if (li == 0) write_records(ph, tv, j, e, w);
+        if (len > PHRASE_LONG) {
+            if (li == 0) {
+                u32 slot = atomicAdd(long_count, 1u);
+                long_list[slot] = (u32)j;
+                ph.len[j] = (u32)len;
+            }
+            continue;
+        }
+        bool special = (s0 < 0) || (e >= tv.n_global);
+        u64 fa = 0, fb = 0;
+        u32 nseg = (u32)((len + NH_SEG_BYTES - 1) / NH_SEG_BYTES);
+        for (u32 s = 0; s < nseg; s++) {
+            u64 so = (u64)s * NH_SEG_BYTES;
+            u32 segb = (u32)((len - so) < NH_SEG_BYTES ? (len - so) : NH_SEG_BYTES);
+            u32 nch = (segb + 15) >> 4;
+            u64 pa = 0, pb = 0;
+            for (u32 c = li; c < nch; c += PH_GROUP) {
+                u32 x[4];
+                load_chunk(tv, s0, len, so + 16ull * c, special, x);
+                nh_chunk(sk, c, x, pa, pb);
+            }
+            fa = fa * NH_FOLD_A + pa;
+            fb = fb * NH_FOLD_B + pb;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            fa += __shfl_xor_sync(gmask, fa, o);
+            fb += __shfl_xor_sync(gmask, fb, o);
+        }
+        if (li == 0) {
+            ph.fpa[j] = fa;
+            ph.fpb[j] = fb;
+            ph.len[j] = (u32)len;
+            ph.key[j] = sort_key_of(fa, fb, (u32)len);
+        }
+    }
+}
+
+// phrases longer than PHRASE_LONG: one CTA per phrase, 32 groups stride over the segments
+__global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseArrays ph,
+                                                           i64 first_start, u32 w,
+                                                           const u32 *__restrict__ keytab,
+                                                           const u32 *__restrict__ long_list,
+                                                           const u32 *__restrict__ long_count,
+                                                           u64 fold_a32, u64 fold_b32) {
+    __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
+    __shared__ u64 red[2][PH_T / 32];
+    for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
+    __syncthreads();
+    const u32 li = threadIdx.x & 7, g = threadIdx.x >> 3;   // 32 groups
+    const u32 nlong = *long_count;
+    for (u32 q = blockIdx.x; q < nlong; q += gridDim.x) {
+        u64 j = long_list[q];
+        i64 e = (i64)ph.ends[j];
+        i64 s0 = (j == 0) ? first_start : (i64)ph.ends[j - 1] - (i64)w + 1;
+        u64 len = (u64)(e - s0 + 1);
+        bool special = (s0 < 0) || (e >= tv.n_global);
+        u64 nseg = (len + NH_SEG_BYTES - 1) / NH_SEG_BYTES;
+        u64 fa = 0, fb = 0;
+        i64 s_last = -1;
+        for (u64 s = g; s < nseg; s += PH_PER_BLOCK) {
+            u64 so = s * NH_SEG_BYTES;
+            u32 segb = (u32)((len - so) < NH_SEG_BYTES ? (len - so) : NH_SEG_BYTES);
+            u32 nch = (segb + 15) >> 4;
+            u64 pa = 0, pb = 0;
+            for (u32 c = li; c < nch; c += PH_GROUP) {
+                u32 x[4];
+                load_chunk(tv, s0, len, so + 16ull * c, special, x);
+                nh_chunk(sk, c, x, pa, pb);
+            }
+            fa = fa * fold_a32 + pa;     // Horner with stride 32 segments
+            fb = fb * fold_b32 + pb;
+            s_last = (i64)s;
+        }
+        if (s_last >= 0) {               // bring to the common power FOLD^(nseg-1-s)
+            for (u64 k = (u64)s_last; k + 1 < nseg; k++) { fa *= NH_FOLD_A; fb *= NH_FOLD_B; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fa += __shfl_xor_sync(0xffffffffu, fa, o);
+            fb += __shfl_xor_sync(0xffffffffu, fb, o);
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = fa; red[1][threadIdx.x >> 5] = fb; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 a = 0, b = 0;
+            for (int i = 0; i < PH_T / 32; i++) { a += red[0][i]; b += red[1][i]; }
+            ph.fpa[j] = a;
+            ph.fpb[j] = b;
+            ph.key[j] = sort_key_of(a, b, (u32)len);
+        }
+    }
+}
+
+__global__ void iota_u32_k(u32 *v, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (u32)i;
+}
+
+// run heads of the sorted keys + fingerprint agreement inside runs
+__global__ void mark_heads_k(const u64 *__restrict__ skey, const u32 *__restrict__ sidx, u64 P,
+                             PhraseArrays ph, u8 *__restrict__ head, u64 *__restrict__ flags) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    bool h = (i == 0) || (skey[i] != skey[i - 1]);
+    if (!h) {
+        u32 a = sidx[i], b = sidx[i - 1];
+        if (ph.fpa[a] != ph.fpa[b] || ph.fpb[a] != ph.fpb[b] || ph.len[a] != ph.len[b])
+            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+    }
+    head[i] = h ? 1 : 0;
+}
+
+__global__ void assign_uid_k(const u32 *__restrict__ sidx, const u8 *__restrict__ head,
+                             const u32 *__restrict__ hscan, u64 P, u32 *__restrict__ uid,
+                             u32 *__restrict__ rep, u32 *__restrict__ headpos) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    u32 u = hscan[i] + head[i] - 1;     // inclusive scan - 1
+    u32 j = sidx[i];
+    uid[j] = u;
+    if (head[i]) { rep[u] = j; headpos[u] = (u32)i; }
+}
+
+__global__ void word_stats_k(const u32 *__restrict__ headpos, const u32 *__restrict__ rep,
+                             const u32 *__restrict__ plen, u64 d, u64 P, u32 *__restrict__ count,
+                             u32 *__restrict__ ulen, u32 *__restrict__ uwords,
+                             u64 *__restrict__ flags /* [2]=max len, [3]=sum len */) {
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 L = 0;
+    if (u < d) {
+        u32 nxt = (u + 1 < d) ? headpos[u + 1] : (u32)P;
+        count[u] = nxt - headpos[u];
+        L = plen[rep[u]];
+        ulen[u] = L;
+        uwords[u] = (L + 7) >> 3;
+    }
+    u32 mx = L;
+    u64 sum = L;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && sum) {
+        atomicMax((unsigned long long *)&flags[2], (unsigned long long)mx);
+        atomicAdd((unsigned long long *)&flags[3], (unsigned long long)sum);
+    }
+}
+
+// phrase pool: every distinct word once, zero padded to 8 bytes, 8-byte aligned
+__global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__restrict__ ends,
+                                                    i64 first_start, u32 w,
+                                                    const u32 *__restrict__ rep,
+                                                    const u32 *__restrict__ ulen,
+                                                    const u64 *__restrict__ uoff, u64 d,
+                                                    u64 *__restrict__ pool) {
+    const u32 li = threadIdx.x & 7;
+    for (u64 u = (u64)blockIdx.x * PH_PER_BLOCK + (threadIdx.x >> 3); u < d;
+         u += (u64)gridDim.x * PH_PER_BLOCK) {
+        u64 j = rep[u];
+        i64 e = (i64)ends[j];
+        i64 s0 = (j == 0) ? first_start : (i64)ends[j - 1] - (i64)w + 1;
+        u64 len = ulen[u];
+        bool special = (s0 < 0) || (e >= tv.n_global);
+        u64 nw = (len + 7) >> 3;
+        u64 *dst = pool + uoff[u];
+        for (u64 k = li; k < nw; k += PH_GROUP) {
+            u64 o = 8 * k;
+            u32 nbv = (u32)((len - o) < 8 ? (len - o) : 8);
+            u64 v = 0;
+            if (!special) {
+                const u8 *p = tv.T + (s0 + (i64)o - tv.pos0);
+                u32 bs = (u32)((uintptr_t)p & 7);
+                const u64 *p8 = reinterpret_cast<const u64 *>(p - bs);
+                u64 lo = __ldg(p8);
+                if (bs) {
+                    u64 hi = (bs + nbv > 8) ? __ldg(p8 + 1) : 0ull;
+                    v = (lo >> (8 * bs)) | (hi << (64 - 8 * bs));
+                } else v = lo;
+            } else {
+                for (u32 b = 0; b < nbv; b++) v |= (u64)tv_byte(tv, s0 + (i64)o + b) << (8 * b);
+            }
+            if (nbv < 8) v &= (1ull << (8 * nbv)) - 1ull;
+            dst[k] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 P,
+                   i64 first_start, u32 w) {
+    u32 *long_list = nullptr, *long_count = nullptr;
+    u64 cap = tv.n_buf / PHRASE_LONG + 4;    // at most this many phrases exceed PHRASE_LONG
+    PFP_TRY(pfp_alloc_t(ctx, &long_list, (size_t)cap));
+    PFP_TRY(pfp_alloc_t(ctx, &long_count, 1));
+    PFP_CUDA(ctx, cudaMemsetAsync(long_count, 0, sizeof(u32), ctx->stream));
+    u64 want = (P + PH_PER_BLOCK - 1) / PH_PER_BLOCK;
+    u64 maxb = (u64)ctx->sm_count * 32;
+    u32 nb = (u32)(want < maxb ? want : maxb);
+    if (nb == 0) nb = 1;
+    phrase_hash_k<<<nb, PH_T, 0, ctx->stream>>>(tv, ph, P, first_start, w, ctx->d_keys, long_list,
+                                                long_count, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    u64 fa32 = 1, fb32 = 1;
+    for (int i = 0; i < PH_PER_BLOCK; i++) { fa32 *= NH_FOLD_A; fb32 *= NH_FOLD_B; }
+    u32 nlb = (u32)(cap < (u64)ctx->sm_count ? cap : (u64)ctx->sm_count);
+    phrase_hash_long_k<<<nlb, PH_T, 0, ctx->stream>>>(tv, ph, first_start, w, ctx->d_keys, long_list,
+                                                      long_count, fa32, fb32);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_free_now(ctx, long_list));
+    PFP_TRY(pfp_free_now(ctx, long_count));
+    return PFPB200_OK;
+}
+
+// Sorts phrases by fingerprint key and derives the dictionary.  Reads d (and length stats)
+// back to the host: one synchronisation.
+int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D) {
+    const int TB = 256;
+    u64 *k1 = nullptr, *sk = nullptr;
+    u32 *v0 = nullptr, *v1 = nullptr, *sv = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &k1, P));
+    PFP_TRY(pfp_alloc_t(ctx, &v0, P));
+    PFP_TRY(pfp_alloc_t(ctx, &v1, P));
+    iota_u32_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(v0, P);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_radix_sort_pairs(ctx, ph.key, v0, k1, v1, P, 0, 64, &sk, &sv));
+    u8 *head = nullptr;
+    u32 *hscan = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &head, P));
+    PFP_TRY(pfp_alloc_t(ctx, &hscan, P));
+    mark_heads_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(sk, sv, P, ph, head, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
+    u32 *d_total = reinterpret_cast<u32 *>(&ctx->d_flags[1]);
+    PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, head, hscan, P, d_total));
+    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(u64), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
+        return pfp_fail(ctx, PFPB200_E_LIMIT, "a phrase is longer than 2^32-1 bytes");
+    if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
+        return pfp_fail(ctx, PFPB200_E_COLLISION, "fingerprint collision between different phrases");
+    u64 d = (u32)ctx->h_flags[1];
+    if (d > 0x7FFFFFFEull)
+        return pfp_fail(ctx, PFPB200_E_LIMIT, "%llu distinct words exceed the limit 2^31-2",
+                        (unsigned long long)d);
+    D->d = d;
+    u32 *headpos = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &D->uid, P));
+    PFP_TRY(pfp_alloc_t(ctx, &D->rep, d));
+    PFP_TRY(pfp_alloc_t(ctx, &headpos, d));
+    PFP_TRY(pfp_alloc_t(ctx, &D->count, d));
+    PFP_TRY(pfp_alloc_t(ctx, &D->ulen, d));
+    PFP_TRY(pfp_alloc_t(ctx, &D->uwords, d));
+    assign_uid_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(sv, head, hscan, P, D->uid, D->rep, headpos);
+    PFP_LAUNCHED(ctx);
+    word_stats_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(headpos, D->rep, ph.len, d, P, D->count,
+                                                            D->ulen, D->uwords, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_free_now(ctx, k1));
+    PFP_TRY(pfp_free_now(ctx, v0));
+    PFP_TRY(pfp_free_now(ctx, v1));
+    PFP_TRY(pfp_free_now(ctx, head));
+    PFP_TRY(pfp_free_now(ctx, hscan));
+    PFP_TRY(pfp_free_now(ctx, headpos));
+    return PFPB200_OK;
+}
+
+// Builds the pool of distinct words.  One synchronisation (pool size, max / total word length).
+int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w,
+                   DictArrays *D) {
+    u64 d = D->d;
+    PFP_TRY(pfp_alloc_t(ctx, &D->uoff, d));
+    PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, D->uwords, D->uoff, d, &ctx->d_flags[1]));
+    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(u64), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    D->pool_words = ctx->h_flags[1];
+    D->max_len = (u32)ctx->h_flags[2];
+    D->sum_len = ctx->h_flags[3];
+    PFP_TRY(pfp_alloc_t(ctx, &D->pool, (size_t)D->pool_words));
+    u64 want = (d + PH_PER_BLOCK - 1) / PH_PER_BLOCK;
+    u64 maxb = (u64)ctx->sm_count * 32;
+    u32 nb = (u32)(want < maxb ? want : maxb);
+    if (nb == 0) nb = 1;
+    pool_copy_k<<<nb, PH_T, 0, ctx->stream>>>(tv, ends, first_start, w, D->rep, D->ulen, D->uoff, d,
+                                              D->pool);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}

@@ -1,0 +1,310 @@
+// pfp_prims.cu -- device-wide primitives written for this pipeline: exclusive scan and a
+// stable LSD radix sort of (u64 key, u32 value) pairs.  HBM-bound integer work: coalesced
+// striped loads, warp-level multisplit (match.any) for ranking, shared-memory staging so the
+// scatter leaves the SM as contiguous per-bucket runs.
+#include "pfp_common.cuh"
+#include <stdarg.h>
+
+// ------------------------------------------------------------------------------------------
+// context helpers
+// ------------------------------------------------------------------------------------------
+int pfp_fail(pfpb200_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int pfp_alloc(pfpb200_ctx *ctx, void **p, size_t bytes, bool held) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    bytes = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return pfp_fail(ctx, PFPB200_E_NOMEM, "device allocation of %zu bytes failed: %s", bytes,
+                        cudaGetErrorString(e));
+    }
+    (held ? ctx->held : ctx->scratch).push_back(*p);
+    return PFPB200_OK;
+}
+
+int pfp_free_now(pfpb200_ctx *ctx, void *p) {
+    if (!p) return PFPB200_OK;
+    for (size_t i = 0; i < ctx->scratch.size(); i++)
+        if (ctx->scratch[i] == p) {
+            ctx->scratch[i] = ctx->scratch.back();
+            ctx->scratch.pop_back();
+            cudaFreeAsync(p, ctx->stream);
+            return PFPB200_OK;
+        }
+    return PFPB200_OK;
+}
+
+void pfp_release_scratch(pfpb200_ctx *ctx) {
+    for (void *p : ctx->scratch) cudaFreeAsync(p, ctx->stream);
+    ctx->scratch.clear();
+}
+
+void pfp_release_held(pfpb200_ctx *ctx) {
+    for (void *p : ctx->held) cudaFreeAsync(p, ctx->stream);
+    ctx->held.clear();
+    for (void *p : ctx->pinned) cudaFreeHost(p);
+    ctx->pinned.clear();
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan: reduce tiles -> scan the tile sums (recursively) -> scan tiles with offsets
+// ------------------------------------------------------------------------------------------
+constexpr int SC_T = 256;
+constexpr int SC_I = 8;
+constexpr int SC_TILE = SC_T * SC_I;
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan_t(T v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (u32)o) v += t;
+    }
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T block_excl_scan_t(T v, T *total, T *sm /* 9 */) {
+    T inc = warp_incl_scan_t<T>(v);
+    u32 w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane_id() == 31) sm[w] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T x = threadIdx.x < 8 ? sm[threadIdx.x] : (T)0;
+        T xi = warp_incl_scan_t<T>(x);
+        if (threadIdx.x < 8) sm[threadIdx.x] = xi - x;
+        if (threadIdx.x == 7) sm[8] = xi;
+    }
+    __syncthreads();
+    *total = sm[8];
+    return inc - v + sm[w];
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SC_T) scan_reduce_k(const TIn *__restrict__ in, u64 n,
+                                                      TOut *__restrict__ partial) {
+    __shared__ TOut sm[9];
+    u64 base = (u64)blockIdx.x * SC_TILE;
+    TOut s = 0;
+#pragma unroll
+    for (int k = 0; k < SC_I; k++) {
+        u64 i = base + (u64)k * SC_T + threadIdx.x;
+        if (i < n) s += (TOut)in[i];
+    }
+    TOut total;
+    block_excl_scan_t<TOut>(s, &total, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SC_T) scan_apply_k(const TIn *in,   // may alias out
+                                                     TOut *out, u64 n,
+                                                     const TOut *__restrict__ tile_prefix,
+                                                     TOut *__restrict__ d_total) {
+    __shared__ TOut sm[9];
+    u64 base = (u64)blockIdx.x * SC_TILE + (u64)threadIdx.x * SC_I;
+    TOut v[SC_I];
+    TOut s = 0;
+#pragma unroll
+    for (int k = 0; k < SC_I; k++) {
+        u64 i = base + k;
+        v[k] = (i < n) ? (TOut)in[i] : (TOut)0;
+        s += v[k];
+    }
+    TOut total;
+    TOut ex = block_excl_scan_t<TOut>(s, &total, sm);
+    if (tile_prefix) ex += tile_prefix[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SC_I; k++) {
+        u64 i = base + k;
+        if (i < n) {
+            out[i] = ex;
+            if (d_total && i == n - 1) *d_total = ex + v[k];
+        }
+        ex += v[k];
+    }
+}
+
+template <typename TIn, typename TOut>
+static int exclusive_scan_impl(pfpb200_ctx *ctx, const TIn *in, TOut *out, u64 n, TOut *d_total) {
+    if (n == 0) {
+        if (d_total) PFP_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(TOut), ctx->stream));
+        return PFPB200_OK;
+    }
+    u32 nb = pfp_blocks(n, SC_TILE);
+    if (nb == 1) {
+        scan_apply_k<TIn, TOut><<<1, SC_T, 0, ctx->stream>>>(in, out, n, nullptr, d_total);
+        PFP_LAUNCHED(ctx);
+        return PFPB200_OK;
+    }
+    TOut *partial = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &partial, nb));
+    scan_reduce_k<TIn, TOut><<<nb, SC_T, 0, ctx->stream>>>(in, n, partial);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY((exclusive_scan_impl<TOut, TOut>(ctx, partial, partial, nb, nullptr)));
+    scan_apply_k<TIn, TOut><<<nb, SC_T, 0, ctx->stream>>>(in, out, n, partial, d_total);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_free_now(ctx, partial));
+    return PFPB200_OK;
+}
+
+int pfp_exclusive_scan_u32(pfpb200_ctx *ctx, const u32 *in, u32 *out, u64 n, u32 *d_total) {
+    return exclusive_scan_impl<u32, u32>(ctx, in, out, n, d_total);
+}
+int pfp_exclusive_scan_u32_u64(pfpb200_ctx *ctx, const u32 *in, u64 *out, u64 n, u64 *d_total) {
+    return exclusive_scan_impl<u32, u64>(ctx, in, out, n, d_total);
+}
+int pfp_exclusive_scan_u8_u32(pfpb200_ctx *ctx, const u8 *in, u32 *out, u64 n, u32 *d_total) {
+    return exclusive_scan_impl<u8, u32>(ctx, in, out, n, d_total);
+}
+
+// ------------------------------------------------------------------------------------------
+// radix sort: per pass  histogram -> scan -> ranked scatter   (8-bit digits)
+// ------------------------------------------------------------------------------------------
+constexpr int RS_T = 256;
+constexpr int RS_I = 16;
+constexpr int RS_TILE = RS_T * RS_I;   // 4096 pairs per CTA
+constexpr int RS_WARPS = RS_T / 32;
+constexpr int RS_SUB = RS_TILE / RS_WARPS;   // 512 consecutive items per warp
+
+__global__ void __launch_bounds__(RS_T) rs_hist_k(const u64 *__restrict__ keys, u64 n, int shift,
+                                                  u32 *__restrict__ hist, u32 nblocks) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    u64 base = (u64)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int k = 0; k < RS_I; k++) {
+        u64 i = base + (u64)k * RS_T + threadIdx.x;
+        bool valid = i < n;
+        u32 d = valid ? (u32)((keys[i] >> shift) & 255) : 256u;
+        u32 peers = __match_any_sync(0xffffffffu, d);
+        if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&h[d], __popc(peers));
+    }
+    __syncthreads();
+    hist[(u64)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+struct RsSmem {
+    u64 key[RS_TILE];
+    u32 val[RS_TILE];
+    u32 wcnt[RS_WARPS][256];
+    u32 tile_start[256];
+    u32 gbase[256];
+    u32 scan_sm[9];
+};
+
+__global__ void __launch_bounds__(RS_T) rs_scatter_k(const u64 *__restrict__ kin,
+                                                     const u32 *__restrict__ vin,
+                                                     u64 *__restrict__ kout, u32 *__restrict__ vout,
+                                                     u64 n, int shift,
+                                                     const u32 *__restrict__ offs, u32 nblocks) {
+    extern __shared__ __align__(16) unsigned char rs_raw[];
+    RsSmem &S = *reinterpret_cast<RsSmem *>(rs_raw);
+    const u32 t = threadIdx.x, wi = t >> 5, ln = t & 31;
+    const u64 base = (u64)blockIdx.x * RS_TILE;
+    const u32 count = (u32)((n - base) < (u64)RS_TILE ? (n - base) : (u64)RS_TILE);
+
+    for (int i = t; i < RS_WARPS * 256; i += RS_T) (&S.wcnt[0][0])[i] = 0;
+    __syncthreads();
+
+    u64 k[RS_I];
+    u32 v[RS_I];
+    u32 pos[RS_I];
+#pragma unroll
+    for (int r = 0; r < RS_I; r++) {
+        u32 idx = wi * RS_SUB + r * 32 + ln;
+        bool valid = idx < count;
+        k[r] = valid ? kin[base + idx] : 0;
+        v[r] = valid ? vin[base + idx] : 0;
+    }
+    // warp-level multisplit: rank of each item among equal digits, in (round, lane) order
+#pragma unroll
+    for (int r = 0; r < RS_I; r++) {
+        u32 idx = wi * RS_SUB + r * 32 + ln;
+        bool valid = idx < count;
+        u32 d = valid ? (u32)((k[r] >> shift) & 255) : 256u;
+        u32 peers = __match_any_sync(0xffffffffu, d);
+        u32 rank = __popc(peers & lanemask_lt());
+        u32 prev = valid ? S.wcnt[wi][d] : 0;
+        pos[r] = prev + rank;
+        __syncwarp();
+        if (valid && rank == 0) S.wcnt[wi][d] = prev + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread t owns digit t: exclusive scan over the warps, then over the digits
+    u32 run = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < RS_WARPS; w2++) {
+        u32 c = S.wcnt[w2][t];
+        S.wcnt[w2][t] = run;
+        run += c;
+    }
+    u32 tot;
+    u32 ts = block_excl_scan_256(run, &tot, S.scan_sm);
+    S.tile_start[t] = ts;
+    S.gbase[t] = offs[(u64)t * nblocks + blockIdx.x] - ts;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_I; r++) {
+        u32 idx = wi * RS_SUB + r * 32 + ln;
+        if (idx < count) {
+            u32 d = (u32)((k[r] >> shift) & 255);
+            u32 lp = S.tile_start[d] + S.wcnt[wi][d] + pos[r];
+            S.key[lp] = k[r];
+            S.val[lp] = v[r];
+        }
+    }
+    __syncthreads();
+    for (u32 i = t; i < count; i += RS_T) {
+        u64 key = S.key[i];
+        u32 d = (u32)((key >> shift) & 255);
+        u32 g = S.gbase[d] + i;
+        kout[g] = key;
+        vout[g] = S.val[i];
+    }
+}
+
+int pfp_radix_sort_pairs(pfpb200_ctx *ctx, u64 *k0, u32 *v0, u64 *k1, u32 *v1, u64 n,
+                         int begin_bit, int end_bit, u64 **res_k, u32 **res_v) {
+    *res_k = k0;
+    *res_v = v0;
+    if (n <= 1 || end_bit <= begin_bit) return PFPB200_OK;
+    if (n >= 0xFFFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "radix sort: too many items");
+    static bool attr_set = false;
+    if (!attr_set) {
+        PFP_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(RsSmem)));
+        attr_set = true;
+    }
+    u32 nb = pfp_blocks(n, RS_TILE);
+    u32 *hist = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &hist, (size_t)256 * nb));
+    u64 *ka = k0, *kb = k1;
+    u32 *va = v0, *vb = v1;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        rs_hist_k<<<nb, RS_T, 0, ctx->stream>>>(ka, n, shift, hist, nb);
+        PFP_LAUNCHED(ctx);
+        PFP_TRY(pfp_exclusive_scan_u32(ctx, hist, hist, (u64)256 * nb, nullptr));
+        rs_scatter_k<<<nb, RS_T, sizeof(RsSmem), ctx->stream>>>(ka, va, kb, vb, n, shift, hist, nb);
+        PFP_LAUNCHED(ctx);
+        u64 *tk = ka; ka = kb; kb = tk;
+        u32 *tv = va; va = vb; vb = tv;
+    }
+    PFP_TRY(pfp_free_now(ctx, hist));
+    *res_k = ka;
+    *res_v = va;
+    return PFPB200_OK;
+}

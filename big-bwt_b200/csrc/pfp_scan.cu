@@ -1,0 +1,273 @@
+// pfp_scan.cu -- K1: Karp-Rabin rolling-window trigger scan + compaction of trigger positions.
+//
+// Replaces KR_window::addchar + `hash % p == 0` of the reference (newscan.cpp:194-202,344,367;
+// pscan.cpp:239-247) for a whole shard at once.  The window hash depends only on the last w
+// bytes, so every thread owns a run of K1_RUN consecutive positions, rebuilds the hash of the
+// w-1 bytes in front of its run and then rolls.  A CTA stages a 32 KB tile (+32 B left halo)
+// in shared memory with coalesced 16-byte loads; threads read their run back with
+// conflict-free LDS.128 (slots padded to 144 B).  Output of K1a is one bit per text position;
+// K1c turns bits into ascending 64-bit positions using per-tile offsets from a device scan.
+#include "pfp_common.cuh"
+
+constexpr int K1_T = 256;                    // threads per CTA
+constexpr int K1_RUN = 128;                  // positions per thread
+constexpr int K1_TILE = K1_T * K1_RUN;       // 32768 positions per CTA
+constexpr int K1_SLOT = K1_RUN + 16;         // padded slot: LDS.128 of 8 lanes hits 32 banks
+constexpr int K1_SMEM = (K1_T + 1) * K1_SLOT;
+constexpr int K1_CHUNKS = K1_TILE / 16;
+constexpr int K1_MAXW_FAST = 32;             // halo of two 16-byte chunks
+
+// byte j (-32 <= j < 16) of the 48-byte register window {prev2, prev1, cur}
+#define WIN_BYTE(win, j) (__byte_perm((win)[((j) + 32) >> 2], 0u, 0x4440u | (((j) + 32) & 3)))
+
+__device__ __forceinline__ u32 range_mask32(u64 q0, u64 lo, u64 hi) {
+    // bits i with lo <= q0+i < hi
+    u32 m = 0xFFFFFFFFu;
+    if (lo > q0) m = (lo - q0 >= 32) ? 0u : (0xFFFFFFFFu << (u32)(lo - q0));
+    if (hi <= q0) return 0u;
+    if (hi - q0 < 32) m &= (1u << (u32)(hi - q0)) - 1u;
+    return m;
+}
+
+// stage tile `tile` (+ halo) of the 16-byte-aligned stream A into padded shared memory
+__device__ __forceinline__ void k1_stage_tile(const uint4 *__restrict__ A, u64 q_end, u64 tile,
+                                              unsigned char *sm) {
+    const i64 q0 = (i64)(tile * (u64)K1_TILE);
+#pragma unroll
+    for (int it = 0; it < (K1_CHUNKS + 2 + K1_T - 1) / K1_T; it++) {
+        int c = (int)threadIdx.x + it * K1_T - 2;     // chunk index, -2 and -1 are the halo
+        if (c < K1_CHUNKS) {
+            i64 qc = q0 + (i64)c * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (qc >= 0 && (u64)qc + 16 <= q_end) {
+                v = __ldg(A + (qc >> 4));
+            } else if (qc >= 0 && (u64)qc < q_end) {
+                const unsigned char *b = reinterpret_cast<const unsigned char *>(A) + qc;
+                u32 wds[4] = {0, 0, 0, 0};
+                int nb = (int)(q_end - (u64)qc);
+                for (int i = 0; i < nb; i++) wds[i >> 2] |= (u32)b[i] << ((i & 3) * 8);
+                v = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            }
+            int cc = c + 8;
+            *reinterpret_cast<uint4 *>(sm + (cc >> 3) * K1_SLOT + (cc & 7) * 16) = v;
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(K1_T) kr_scan_k(const uint4 *__restrict__ A, u64 q_end, u64 q_lo,
+                                                  u64 q_hi, pfp_scan_consts C,
+                                                  uint4 *__restrict__ mask,
+                                                  u32 *__restrict__ tile_cnt) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    __shared__ u32 s_cnt;
+    const u32 t = threadIdx.x;
+    const u64 tile = blockIdx.x;
+    if (t == 0) s_cnt = 0;
+    k1_stage_tile(A, q_end, tile, sm);
+    __syncthreads();
+
+    const u32 negw = C.negw, pinv = C.pinv, pshift = C.pshift, plimit = C.plimit;
+    u32 win[12];
+    {   // the two chunks in front of this thread's run: tail of the previous slot
+        uint4 p2 = *reinterpret_cast<const uint4 *>(sm + t * K1_SLOT + 96);
+        uint4 p1 = *reinterpret_cast<const uint4 *>(sm + t * K1_SLOT + 112);
+        win[0] = p2.x; win[1] = p2.y; win[2] = p2.z; win[3] = p2.w;
+        win[4] = p1.x; win[5] = p1.y; win[6] = p1.z; win[7] = p1.w;
+    }
+    // hash of the w-1 bytes in front of the run
+    u32 h = 0;
+#pragma unroll
+    for (int j = -(W - 1); j < 0; j++) h = pfp_push(h, WIN_BYTE(win, j));
+
+    unsigned char *slot = sm + (t + 1) * K1_SLOT;
+    const u64 qrun = tile * (u64)K1_TILE + (u64)t * K1_RUN;
+    u32 cnt = 0;
+#pragma unroll 1
+    for (int kk = 0; kk < K1_RUN / 32; kk++) {
+        u32 m = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            uint4 cur = *reinterpret_cast<const uint4 *>(slot + kk * 32 + half * 16);
+            win[8] = cur.x; win[9] = cur.y; win[10] = cur.z; win[11] = cur.w;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                u32 c_in = WIN_BYTE(win, i);
+                u32 c_out = WIN_BYTE(win, i - W);
+                h = pfp_roll(h, c_in, c_out, negw);
+                if (pfp_is_trigger(h, pinv, pshift, plimit)) m |= 1u << (half * 16 + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { win[i] = win[4 + i]; win[4 + i] = win[8 + i]; }
+        }
+        m &= range_mask32(qrun + (u64)kk * 32, q_lo, q_hi);
+        cnt += __popc(m);
+        *reinterpret_cast<u32 *>(slot + K1_RUN + kk * 4) = m;   // own slot padding
+    }
+    mask[tile * (u64)K1_T + t] = *reinterpret_cast<const uint4 *>(slot + K1_RUN);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((t & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (t == 0) tile_cnt[tile] = s_cnt;
+}
+
+// Any window size: bytes straight from global memory (L1-cached byte loads).  Slow path.
+__global__ void __launch_bounds__(K1_T) kr_scan_generic_k(const unsigned char *__restrict__ A8,
+                                                          u64 q_end, u64 q_lo, u64 q_hi,
+                                                          pfp_scan_consts C,
+                                                          uint4 *__restrict__ mask,
+                                                          u32 *__restrict__ tile_cnt) {
+    __shared__ u32 s_cnt;
+    const u32 t = threadIdx.x;
+    const u64 tile = blockIdx.x;
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+    const i64 w = C.w;
+    const i64 qrun = (i64)(tile * (u64)K1_TILE + (u64)t * K1_RUN);
+    u32 h = 0;
+    for (i64 q = qrun - (w - 1); q < qrun; q++) {
+        u32 c = (q >= 0 && (u64)q < q_end) ? A8[q] : 0u;
+        h = pfp_push(h, c);
+    }
+    u32 mw[4];
+    u32 cnt = 0;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        u32 m = 0;
+        for (int i = 0; i < 32; i++) {
+            i64 q = qrun + kk * 32 + i;
+            u32 c_in = ((u64)q < q_end) ? A8[q] : 0u;
+            i64 qo = q - w;
+            u32 c_out = (qo >= 0 && (u64)qo < q_end) ? A8[qo] : 0u;
+            h = pfp_roll(h, c_in, c_out, C.negw);
+            if (pfp_is_trigger(h, C.pinv, C.pshift, C.plimit)) m |= 1u << i;
+        }
+        m &= range_mask32((u64)qrun + (u64)kk * 32, q_lo, q_hi);
+        cnt += __popc(m);
+        mw[kk] = m;
+    }
+    mask[tile * (u64)K1_T + t] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((t & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (t == 0) tile_cnt[tile] = s_cnt;
+}
+
+// K1c: bits -> ascending global positions
+__global__ void __launch_bounds__(K1_T) kr_emit_k(const uint4 *__restrict__ mask,
+                                                  const u64 *__restrict__ tile_off,
+                                                  u64 pos_bias /* buf_pos0 - delta */,
+                                                  u64 *__restrict__ out) {
+    __shared__ u32 sm[9];
+    const u32 t = threadIdx.x;
+    const u64 tile = blockIdx.x;
+    uint4 mv = mask[tile * (u64)K1_T + t];
+    u32 m[4] = {mv.x, mv.y, mv.z, mv.w};
+    u32 c = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+    u32 tot;
+    u32 ex = block_excl_scan_256(c, &tot, sm);
+    if (tot == 0) return;
+    u64 o = tile_off[tile] + ex;
+    u64 q = tile * (u64)K1_TILE + (u64)t * K1_RUN + pos_bias;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        u32 x = m[kk];
+        while (x) {
+            int b = __ffs(x) - 1;
+            x &= x - 1;
+            out[o++] = q + (u64)(kk * 32 + b);
+        }
+    }
+}
+
+template <int W>
+static void launch_scan(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
+                        const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kr_scan_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
+        attr = true;
+    }
+    kr_scan_k<W><<<ntiles, K1_T, K1_SMEM, ctx->stream>>>(A, q_end, q_lo, q_hi, C, mask, tile_cnt);
+}
+
+#define K1_CASE(W) case W: launch_scan<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
+
+// Runs K1a+scan+K1c.  On return *d_out (scratch, or held when `held`) holds *n_out positions;
+// `extra_slots` more u64 are allocated behind them for the caller (final virtual trigger).
+int pfp_scan_stage(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u64 own_lo,
+                   u64 own_hi, u32 w, u32 p, u64 extra_slots, bool held, u64 **d_out, u64 *n_out,
+                   float *ms_scan, float *ms_emit) {
+    *d_out = nullptr;
+    *n_out = 0;
+    pfp_scan_consts C = pfp_make_scan_consts(w, p);
+    uintptr_t addr = (uintptr_t)d_buf;
+    u64 delta = addr & 15;
+    const uint4 *A = reinterpret_cast<const uint4 *>(addr - delta);
+    u64 q_end = delta + n_buf;
+    // first position whose whole window lies in the text and in the buffer
+    u64 lo = own_lo;
+    if (lo < (u64)w - 1) lo = (u64)w - 1;
+    if (lo < buf_pos0 + w - 1) lo = buf_pos0 + w - 1;
+    u64 hi = own_hi;
+    if (hi > buf_pos0 + n_buf) hi = buf_pos0 + n_buf;
+    cudaEvent_t e0, e1, e2;
+    PFP_CUDA(ctx, cudaEventCreate(&e0));
+    PFP_CUDA(ctx, cudaEventCreate(&e1));
+    PFP_CUDA(ctx, cudaEventCreate(&e2));
+    u64 total = 0;
+    u64 *out = nullptr;
+    if (lo < hi && n_buf > 0) {
+        u64 q_lo = lo - buf_pos0 + delta, q_hi = hi - buf_pos0 + delta;
+        u64 nt64 = (q_end + K1_TILE - 1) / K1_TILE;
+        if (nt64 > 0x7FFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "shard too large");
+        u32 ntiles = (u32)nt64;
+        uint4 *mask = nullptr;
+        u32 *tile_cnt = nullptr;
+        u64 *tile_off = nullptr;
+        PFP_TRY(pfp_alloc_t(ctx, &mask, (size_t)ntiles * K1_T));
+        PFP_TRY(pfp_alloc_t(ctx, &tile_cnt, ntiles));
+        PFP_TRY(pfp_alloc_t(ctx, &tile_off, ntiles));
+        PFP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        switch (w <= K1_MAXW_FAST ? (int)w : 0) {
+            K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7) K1_CASE(8) K1_CASE(9) K1_CASE(10)
+            K1_CASE(11) K1_CASE(12) K1_CASE(13) K1_CASE(14) K1_CASE(15) K1_CASE(16)
+            K1_CASE(20) K1_CASE(24) K1_CASE(28) K1_CASE(31) K1_CASE(32)
+            default:
+                kr_scan_generic_k<<<ntiles, K1_T, 0, ctx->stream>>>(
+                    reinterpret_cast<const unsigned char *>(A), q_end, q_lo, q_hi, C, mask, tile_cnt);
+        }
+        PFP_LAUNCHED(ctx);
+        PFP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, tile_cnt, tile_off, ntiles, &ctx->d_flags[1]));
+        PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[1], &ctx->d_flags[1], sizeof(u64),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        total = ctx->h_flags[1];
+        PFP_TRY(pfp_alloc_t(ctx, &out, (size_t)(total + extra_slots), held));
+        kr_emit_k<<<ntiles, K1_T, 0, ctx->stream>>>(mask, tile_off, buf_pos0 - delta, out);
+        PFP_LAUNCHED(ctx);
+        PFP_CUDA(ctx, cudaEventRecord(e2, ctx->stream));
+        PFP_TRY(pfp_free_now(ctx, mask));
+        PFP_TRY(pfp_free_now(ctx, tile_cnt));
+        PFP_TRY(pfp_free_now(ctx, tile_off));
+        PFP_CUDA(ctx, cudaEventSynchronize(e2));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        if (ms_scan) *ms_scan = a;
+        if (ms_emit) *ms_emit = b;
+    } else {
+        PFP_TRY(pfp_alloc_t(ctx, &out, (size_t)extra_slots, held));
+        if (ms_scan) *ms_scan = 0;
+        if (ms_emit) *ms_emit = 0;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    *d_out = out;
+    *n_out = total;
+    return PFPB200_OK;
+}

@@ -1,0 +1,67 @@
+// pfp_stages.cuh -- data layout in HBM shared by the stages, and the stage entry points.
+#pragma once
+#include "pfp_common.cuh"
+
+// ---- text view ---------------------------------------------------------------------------------
+// A shard buffer T[0..n_buf) whose first byte is global text position pos0.  Global positions
+// -1 and >= n_global are the reference's virtual 0x02 borders (newscan.cpp:329,376).
+struct TextView {
+    const u8 *T;
+    u64 n_buf;
+    i64 pos0;
+    i64 n_global;
+};
+
+__device__ __forceinline__ u8 tv_byte(const TextView &tv, i64 g) {
+    if (g < 0 || g >= tv.n_global) return (u8)PFP_DOLLAR;
+    return tv.T[g - tv.pos0];
+}
+
+// ---- per-phrase arrays (P entries, text order) ----------------------------------------------------
+struct PhraseArrays {
+    u64 *ends;   // inclusive global END position of the phrase (trigger position; n+w-1 for the last)
+    u64 *fpa;    // fingerprint half A
+    u64 *fpb;    // fingerprint half B
+    u64 *key;    // sort key derived from (fpa, fpb, len)
+    u32 *len;    // phrase length in bytes, including the w-byte overlap and virtual borders
+    u8 *last;    // .last stream
+    u8 *sai;     // .sai stream (5 bytes per phrase) or null
+};
+
+// ---- dictionary arrays (d entries, in fingerprint-key order = "uid" order) ---------------------------
+struct DictArrays {
+    u64 d = 0;
+    u32 *uid = nullptr;     // [P] phrase -> uid
+    u32 *rep = nullptr;     // [d] first phrase index of the word
+    u32 *count = nullptr;   // [d] occurrences
+    u32 *ulen = nullptr;    // [d] length in bytes
+    u32 *uwords = nullptr;  // [d] length in 8-byte pool words
+    u64 *uoff = nullptr;    // [d] offset into the pool (8-byte words)
+    u64 *pool = nullptr;    // the words, zero padded to 8 bytes
+    u64 pool_words = 0;
+    u32 max_len = 0;
+    u64 sum_len = 0;
+};
+
+// ---- fingerprint parameters ---------------------------------------------------------------------------
+constexpr u32 NH_SEG_BYTES = 8192;                 // NH key table covers one segment
+constexpr u32 NH_KEY_WORDS = NH_SEG_BYTES / 4 + 8; // + Toeplitz shift for the second sum
+constexpr u64 PHRASE_LONG = 65536;                 // longer phrases get a CTA of their own
+constexpr u64 NH_FOLD_A = 0x9E3779B97F4A7C15ULL;   // odd multipliers folding segment sums
+constexpr u64 NH_FOLD_B = 0xD6E8FEB86659FD93ULL;
+
+// ---- stages -----------------------------------------------------------------------------------------------
+int pfp_scan_stage(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u64 own_lo,
+                   u64 own_hi, u32 w, u32 p, u64 extra_slots, bool held, u64 **d_out, u64 *n_out,
+                   float *ms_scan, float *ms_emit);
+int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 P,
+                   i64 first_start, u32 w);
+int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D);
+int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w,
+                   DictArrays *D);
+// Lexicographic order of the d pool words: order[i] = uid of the word of rank i+1.
+int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *rounds);
+// .dict / .occ bytes and rank-per-uid from the order; outputs are `held` device buffers.
+int pfp_dict_stage(pfpb200_ctx *ctx, const DictArrays &D, const u32 *order, u32 strip_w,
+                   u8 **dict, u64 *dict_bytes, u32 **occ, u32 **rank_of_uid);
+int pfp_remap_stage(pfpb200_ctx *ctx, const u32 *uid, const u32 *rank_of_uid, u64 P, u32 *parse);

@@ -1,0 +1,232 @@
+"""ctypes binding of libpfpb200.so -- the host-side mirror of the reference scanner.
+
+The reference's interface for this stage is the `newscan.x` command line and its five output
+files (bigbwt:71-86).  `Scanner` exposes the same knobs (w, p, -s, -f, -c, -t) over the C ABI
+declared in include/pfpb200.h.  There is no CPU path here: if the CUDA library is missing or no
+GPU is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libpfpb200.so")
+CLI_PATH = os.path.join(PKG_DIR, "gpuscan.x")
+
+F_SAI, F_FASTA, F_COMPRESS, F_VERBOSE = 1, 2, 4, 8
+
+ERRORS = {0: "OK", -1: "E_ARG", -2: "E_IO", -3: "E_CUDA", -4: "E_NOMEM", -5: "E_LIMIT",
+          -6: "E_COLLISION", -7: "E_INTERNAL"}
+
+
+class PfpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pfpb200 {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Opts(C.Structure):
+    _fields_ = [("w", C.c_uint32), ("p", C.c_uint32), ("flags", C.c_uint32), ("nseg", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_text", C.c_uint64), ("n_phrases", C.c_uint64), ("n_distinct", C.c_uint64),
+                ("sum_word_len", C.c_uint64), ("dict_bytes", C.c_uint64), ("alg_bytes", C.c_uint64),
+                ("rank_rounds", C.c_uint32), ("launches", C.c_uint32),
+                ("ms_total", C.c_float), ("ms_scan", C.c_float), ("ms_emit", C.c_float),
+                ("ms_hash", C.c_float), ("ms_dedup", C.c_float), ("ms_rank", C.c_float),
+                ("ms_dict", C.c_float), ("ms_remap", C.c_float), ("ms_h2d", C.c_float),
+                ("ms_d2h", C.c_float), ("sec_read", C.c_float), ("sec_write", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Outputs(C.Structure):
+    _fields_ = [("dict", C.c_void_p), ("dict_bytes", C.c_uint64),
+                ("occ", C.c_void_p), ("n_distinct", C.c_uint64),
+                ("parse", C.c_void_p), ("n_phrases", C.c_uint64),
+                ("last", C.c_void_p), ("sai", C.c_void_p)]
+
+
+@dataclass
+class PfpFiles:
+    """The five output streams as bytes (host copies)."""
+    dict: bytes
+    occ: bytes
+    parse: bytes
+    last: bytes
+    sai: bytes
+    stats: dict = field(default_factory=dict)
+
+    @property
+    def n_phrases(self):
+        return len(self.parse) // 4
+
+    @property
+    def n_distinct(self):
+        return len(self.occ) // 4
+
+
+_lib = None
+
+SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_parse_device",
+           "pfpb200_parse_host", "pfpb200_parse_file", "pfpb200_fasta_extract",
+           "pfpb200_scan_triggers", "pfpb200_memcpy_d2h", "pfpb200_strerror", "pfpb200_last_error", "pfpb200_abi_version"]
+
+
+def load_library():
+    """dlopen libpfpb200.so and declare prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+    L.pfpb200_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.pfpb200_create.restype = C.c_int
+    L.pfpb200_destroy.argtypes = [vp]
+    L.pfpb200_destroy.restype = None
+    L.pfpb200_set_stream.argtypes = [vp, vp]
+    L.pfpb200_set_stream.restype = C.c_int
+    L.pfpb200_parse_device.argtypes = [vp, vp, u64, C.POINTER(Opts), C.POINTER(Outputs), C.POINTER(Stats)]
+    L.pfpb200_parse_device.restype = C.c_int
+    L.pfpb200_parse_host.argtypes = [vp, vp, u64, C.POINTER(Opts), C.POINTER(Outputs), C.POINTER(Stats)]
+    L.pfpb200_parse_host.restype = C.c_int
+    L.pfpb200_parse_file.argtypes = [vp, C.c_char_p, C.POINTER(Opts), C.POINTER(Stats)]
+    L.pfpb200_parse_file.restype = C.c_int
+    L.pfpb200_fasta_extract.argtypes = [vp, u64, vp, C.POINTER(C.c_int)]
+    L.pfpb200_fasta_extract.restype = u64
+    L.pfpb200_scan_triggers.argtypes = [vp, vp, u64, u64, u64, u64, u32, u32, C.POINTER(vp),
+                                        C.POINTER(u64), C.POINTER(C.c_float)]
+    L.pfpb200_scan_triggers.restype = C.c_int
+    L.pfpb200_memcpy_d2h.argtypes = [vp, vp, vp, u64]
+    L.pfpb200_memcpy_d2h.restype = C.c_int
+    L.pfpb200_strerror.argtypes = [C.c_int]
+    L.pfpb200_strerror.restype = C.c_char_p
+    L.pfpb200_last_error.argtypes = [vp]
+    L.pfpb200_last_error.restype = C.c_char_p
+    L.pfpb200_abi_version.restype = C.c_int
+    _lib = L
+    return L
+
+
+def fasta_extract(file_bytes) -> tuple[bytes, bool]:
+    """Host-side FASTA/FASTQ -> text (kseq semantics); needs the library but no GPU."""
+    L = load_library()
+    a = np.frombuffer(bytes(file_bytes), dtype=np.uint8)
+    out = np.empty(a.size + 1, dtype=np.uint8)
+    tr = C.c_int(0)
+    n = L.pfpb200_fasta_extract(a.ctypes.data if a.size else None, a.size, out.ctypes.data, C.byref(tr))
+    return out[:n].tobytes(), bool(tr.value)
+
+
+def _flags(sai, fasta, compress, verbose=False):
+    return (F_SAI if sai else 0) | (F_FASTA if fasta else 0) | (F_COMPRESS if compress else 0) | \
+        (F_VERBOSE if verbose else 0)
+
+
+class Scanner:
+    """One GPU's prefix-free parser: the drop-in for newscan.x / newscanNT.x / pscan.x."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.pfpb200_create(device, C.byref(h))
+        if rc != 0:
+            raise PfpError(rc, f"cannot create a context on CUDA device {device}: "
+                               f"{self.L.pfpb200_strerror(rc).decode()}")
+        self.h = h
+        self.device = device
+        self.stats = Stats()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pfpb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PfpError(rc, self.L.pfpb200_last_error(self.h).decode(errors="replace"))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self.L.pfpb200_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    # -- text already in HBM (torch uint8 CUDA tensor); returns device pointers + sizes ---------
+    def parse_device(self, text, w=10, p=100, sai=True, compress=False) -> Outputs:
+        assert text.is_cuda and text.dtype.itemsize == 1 and text.is_contiguous()
+        o = Opts(w, p, _flags(sai, False, compress), 0)
+        out = Outputs()
+        self._check(self.L.pfpb200_parse_device(self.h, C.c_void_p(text.data_ptr()), text.numel(),
+                                                C.byref(o), C.byref(out), C.byref(self.stats)))
+        return out
+
+    def to_host(self, dev_ptr, nbytes) -> bytes:
+        if not dev_ptr or nbytes == 0:
+            return b""
+        buf = np.empty(nbytes, dtype=np.uint8)
+        self._check(self.L.pfpb200_memcpy_d2h(self.h, C.c_void_p(buf.ctypes.data), C.c_void_p(dev_ptr),
+                                              nbytes))
+        return buf.tobytes()
+
+    def fetch(self, out: Outputs) -> PfpFiles:
+        """Copy the device outputs of parse_device to host bytes."""
+        P, d = out.n_phrases, out.n_distinct
+        g = self.to_host
+        return PfpFiles(dict=g(out.dict, out.dict_bytes), occ=g(out.occ, 4 * d),
+                        parse=g(out.parse, 4 * P), last=g(out.last, P),
+                        sai=g(out.sai, 5 * P), stats=self.stats.as_dict())
+
+    # -- text in host memory -----------------------------------------------------------------------
+    def parse_host(self, text, w=10, p=100, sai=True, compress=False, copy=True) -> PfpFiles:
+        a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) \
+            else np.ascontiguousarray(text, dtype=np.uint8)
+        o = Opts(w, p, _flags(sai, False, compress), 0)
+        out = Outputs()
+        self._check(self.L.pfpb200_parse_host(self.h, C.c_void_p(a.ctypes.data if a.size else 0), a.size,
+                                              C.byref(o), C.byref(out), C.byref(self.stats)))
+        if not copy:
+            return out
+        P, d = out.n_phrases, out.n_distinct
+        s = C.string_at
+        return PfpFiles(dict=s(out.dict, out.dict_bytes), occ=s(out.occ, 4 * d), parse=s(out.parse, 4 * P),
+                        last=s(out.last, P), sai=s(out.sai, 5 * P) if out.sai else b"",
+                        stats=self.stats.as_dict())
+
+    def parse_host_ptr(self, ptr: int, n: int, w=10, p=100, sai=True) -> Outputs:
+        """Host pointer (e.g. pinned torch tensor) in, pinned host pointers out; no Python copies."""
+        o = Opts(w, p, _flags(sai, False, False), 0)
+        out = Outputs()
+        self._check(self.L.pfpb200_parse_host(self.h, C.c_void_p(ptr), n, C.byref(o), C.byref(out),
+                                              C.byref(self.stats)))
+        return out
+
+    # -- file in, files out: what `bigbwt` runs -------------------------------------------------------
+    def parse_file(self, path, w=10, p=100, sai=False, fasta=False, compress=False, nseg=0) -> dict:
+        o = Opts(w, p, _flags(sai, fasta, compress), nseg)
+        self._check(self.L.pfpb200_parse_file(self.h, os.fsencode(path), C.byref(o), C.byref(self.stats)))
+        return self.stats.as_dict()
+
+    # -- K1 alone ---------------------------------------------------------------------------------------
+    def scan_triggers(self, buf, w=10, p=100, buf_pos0=0, own_lo=0, own_hi=None):
+        """Trigger end positions (global, ascending, numpy u64) of a shard in a CUDA uint8 tensor."""
+        n = buf.numel()
+        if own_hi is None:
+            own_hi = buf_pos0 + n
+        ptr, cnt, ms = C.c_void_p(), C.c_uint64(), C.c_float()
+        self._check(self.L.pfpb200_scan_triggers(self.h, C.c_void_p(buf.data_ptr()), n, buf_pos0, own_lo,
+                                                 own_hi, w, p, C.byref(ptr), C.byref(cnt), C.byref(ms)))
+        k = cnt.value
+        pos = np.frombuffer(self.to_host(ptr.value, 8 * k), dtype=np.uint64)
+        return pos, ms.value

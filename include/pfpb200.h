@@ -1,0 +1,140 @@
+/* pfpb200.h -- C ABI of libpfpb200.so: B200-native prefix-free parsing (PFP).
+ *
+ * This library replaces ONE stage of alshai/Big-BWT: the scanner that `bigbwt` runs first
+ * (reference newscan.cpp / newscan.hpp / pscan.cpp).  The reference has no library API for
+ * that stage -- its interface is the newscan.x command line plus five output files
+ * (bigbwt:71-86, utils.h:14-26) -- so the entry points below are what a C / ctypes / cgo
+ * binding of that stage binds: one call per reference function group, plain pointers and
+ * sizes only.  The bundled `gpuscan.x` is a newscan.x-compatible main() over
+ * pfpb200_parse_file(); INTEGRATION.md shows the ctypes stub for `bigbwt`.
+ *
+ * All work runs in hand-written CUDA kernels for sm_100a.  There is NO CPU fallback:
+ * every entry point returns PFPB200_E_CUDA when no device / kernel image is usable.
+ */
+#ifndef PFPB200_H
+#define PFPB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFPB200_ABI_VERSION 1
+
+/* ---- error codes (reference behaviour: message + exit(1), utils.c:12-16) ------------------ */
+#define PFPB200_OK            0
+#define PFPB200_E_ARG        -1  /* w < 4, p < 10 (newscan.cpp:537-544), null pointers, ...      */
+#define PFPB200_E_IO         -2  /* cannot open / read / write a file (utils.c:33-41)            */
+#define PFPB200_E_CUDA       -3  /* no usable GPU, kernel launch or runtime failure              */
+#define PFPB200_E_NOMEM      -4  /* host or device allocation failed (newscan.cpp:603-606)       */
+#define PFPB200_E_LIMIT      -5  /* > 2^31-2 distinct words, > 2^32-1 occurrences or phrases
+                                    (newscan.cpp:114-117,613-617; bigbwt:110-114)                */
+#define PFPB200_E_COLLISION  -6  /* fingerprint collision detected (newscan.cpp:282-286)         */
+#define PFPB200_E_INTERNAL   -7  /* an invariant of the pipeline was violated                    */
+
+/* ---- options: the newscan.x command line (newscan.cpp:500-555) ---------------------------- */
+#define PFPB200_F_SAI       1u   /* -s : also produce .sai (newscan.cpp:320-321)                 */
+#define PFPB200_F_FASTA     2u   /* -f : input is FASTA/FASTQ, kseq semantics (newscan.cpp:332)  */
+#define PFPB200_F_COMPRESS  4u   /* -c : write .dicz instead of .dict (newscan.cpp:410-413)      */
+#define PFPB200_F_VERBOSE   8u   /* -v                                                           */
+
+typedef struct pfpb200_opts {
+    uint32_t w;       /* -w window size, >= 4, default 10 (newscan.cpp:155)                     */
+    uint32_t p;       /* -p modulus,     >= 10, default 100 (newscan.cpp:156)                   */
+    uint32_t flags;   /* PFPB200_F_*                                                             */
+    int32_t  nseg;    /* -t : 0 = single .last/.sai files, T>0 = T segment files
+                         <file>.<i>.last|sai as bwtparse -t T expects (newscan.hpp:274-276)     */
+} pfpb200_opts;
+
+/* ---- counters the reference prints (newscan.cpp:609-611,633-634) + device timings --------- */
+typedef struct pfpb200_stats {
+    uint64_t n_text;        /* "Total input symbols"                                            */
+    uint64_t n_phrases;     /* "Total number of words"                                          */
+    uint64_t n_distinct;    /* "Found .. distinct words"                                        */
+    uint64_t sum_word_len;  /* "Sum of lenghts of dictionary words"                             */
+    uint64_t dict_bytes;    /* size of .dict = sum_word_len + n_distinct + 1                    */
+    uint64_t alg_bytes;     /* algorithmic bytes: text read once + every output written once    */
+    uint32_t rank_rounds;   /* refinement rounds of the lexicographic ranking                   */
+    uint32_t launches;      /* kernels launched by the last call                                */
+    float ms_total;         /* CUDA-event time, text resident in HBM -> all outputs in HBM      */
+    float ms_scan;          /* K1 trigger scan (KR_window::addchar + hash%p, newscan.cpp:194,344)*/
+    float ms_emit;          /* K1 compaction of trigger positions                               */
+    float ms_hash;          /* K2 phrase records + fingerprints (save_update_word :245-304)     */
+    float ms_dedup;         /* K3 dictionary build (std::map update :256-288)                   */
+    float ms_rank;          /* K4 lexicographic ranking (std::sort :636)                        */
+    float ms_dict;          /* K4 epilogue: .dict/.occ bytes (writeDictOcc :394-441)            */
+    float ms_remap;         /* K5 parse remap (remapParse :443-466)                             */
+    float ms_h2d, ms_d2h;   /* host<->device copies (host entry points only)                    */
+    float sec_read, sec_write; /* file I/O wall time (file entry point only)                    */
+} pfpb200_stats;
+
+/* The five output streams (utils.h:14-26).  Pointers are owned by the context and stay valid
+ * until the next parse call on it or pfpb200_destroy().  `sai` is NULL without PFPB200_F_SAI. */
+typedef struct pfpb200_outputs {
+    const uint8_t  *dict;   uint64_t dict_bytes;   /* words + 0x01 each, final 0x00             */
+    const uint32_t *occ;    uint64_t n_distinct;   /* u32 LE occurrences in rank order          */
+    const uint32_t *parse;  uint64_t n_phrases;    /* u32 LE 1-based ranks in text order        */
+    const uint8_t  *last;                          /* n_phrases bytes                           */
+    const uint8_t  *sai;                           /* 5 * n_phrases bytes (IBYTES, utils.h:10)  */
+} pfpb200_outputs;
+
+typedef struct pfpb200_ctx pfpb200_ctx;
+
+/* Create / destroy a context bound to one CUDA device.  The context owns a stream, the
+ * device scratch and the output buffers.  Not thread-safe; one context per host thread. */
+int  pfpb200_create(int device, pfpb200_ctx **ctx);
+void pfpb200_destroy(pfpb200_ctx *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. a torch stream); NULL restores the own stream. */
+int  pfpb200_set_stream(pfpb200_ctx *ctx, void *cuda_stream);
+
+/* Replaces process_file() + sort + writeDictOcc() + remapParse() (newscan.cpp:310-466,
+ * 581-646) for text already resident in HBM.  d_text: device pointer to n_text bytes, every
+ * byte > 0x02.  Outputs are device pointers. */
+int pfpb200_parse_device(pfpb200_ctx *ctx, const uint8_t *d_text, uint64_t n_text,
+                         const pfpb200_opts *opts, pfpb200_outputs *dev_out,
+                         pfpb200_stats *stats);
+
+/* Copy `bytes` of a device-resident output to host memory (synchronous on the context's
+ * stream); for callers of pfpb200_parse_device / pfpb200_scan_triggers without a CUDA runtime
+ * of their own. */
+int pfpb200_memcpy_d2h(pfpb200_ctx *ctx, void *dst_host, const void *src_device, uint64_t bytes);
+
+/* Same for text in host memory (pageable or pinned): input is cut at the first byte <= 0x02
+ * (newscan.cpp:364), copied to the device, parsed; outputs are host pointers (pinned memory
+ * owned by the context). */
+int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_t n_text,
+                       const pfpb200_opts *opts, pfpb200_outputs *host_out,
+                       pfpb200_stats *stats);
+
+/* newscan.x main() (newscan.cpp:569-650): reads `path` (plain or FASTA per opts->flags),
+ * parses on the GPU and writes <path>.dict|.dicz .occ .parse .last [.sai] (segmented
+ * .last/.sai when opts->nseg > 0). */
+int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts,
+                       pfpb200_stats *stats);
+
+/* kseq-equivalent FASTA/FASTQ extraction + toupper + validity cut (kseq.h:177-218,
+ * newscan.cpp:338-349), host side.  `out` must hold n bytes; returns text length and sets
+ * *truncated when an invalid byte ended the input. */
+uint64_t pfpb200_fasta_extract(const uint8_t *file, uint64_t n, uint8_t *out, int *truncated);
+
+/* ---- stage-level entry points (device pointers) ------------------------------------------ *
+ * The scan stage alone: KR_window::addchar + `hash % p == 0` over a shard of the text
+ * (newscan.cpp:194-202,344,367; sharding as pscan.hpp:44-108).  d_buf holds n_buf text bytes
+ * whose first byte is global position buf_pos0; trigger END positions e (global) with
+ * own_lo <= e < own_hi and e >= w-1 are written ascending to a context-owned device array.
+ * The caller must have w-1 bytes of left halo in the buffer (buf_pos0 <= own_lo-(w-1)) unless
+ * own_lo == 0. */
+int pfpb200_scan_triggers(pfpb200_ctx *ctx, const uint8_t *d_buf, uint64_t n_buf,
+                          uint64_t buf_pos0, uint64_t own_lo, uint64_t own_hi,
+                          uint32_t w, uint32_t p, const uint64_t **d_triggers,
+                          uint64_t *n_triggers, float *ms);
+
+const char *pfpb200_strerror(int code);
+/* Message of the last failure on this context (CUDA error string, file name, ...). */
+const char *pfpb200_last_error(const pfpb200_ctx *ctx);
+int pfpb200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFPB200_H */

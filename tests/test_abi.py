@@ -1,0 +1,67 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol the
+public header declares, and refuses to work without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, golden, golden_names
+from oracle import pfp_oracle as orc
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "pfpb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pfpb200_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.pfp.load_library()
+    names = header_functions()
+    assert len(names) >= 11
+    for n in names:
+        assert hasattr(L, n), f"libpfpb200.so does not export {n}"
+    assert set(names) == set(pkg.pfp.SYMBOLS)
+    assert L.pfpb200_abi_version() == 1
+
+
+def test_struct_layouts_match_header(pkg):
+    # sizes the C compiler gives the public structs (natural alignment, no packing)
+    assert C.sizeof(pkg.pfp.Opts) == 16
+    assert C.sizeof(pkg.pfp.Outputs) == 64
+    assert C.sizeof(pkg.pfp.Stats) == 6 * 8 + 2 * 4 + 12 * 4
+
+
+def test_strerror(pkg):
+    L = pkg.pfp.load_library()
+    assert L.pfpb200_strerror(0) == b"ok"
+    assert b"CUDA" in L.pfpb200_strerror(-3)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(pkg.pfp.PfpError) as e:
+        pkg.pfp.Scanner(0)
+    assert e.value.code == -3
+
+
+def test_cli_rejects_bad_arguments(pkg):
+    import subprocess
+    r = subprocess.run([pkg.pfp.CLI_PATH, "/nonexistent", "-w", "3"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Windows size must be at least 4" in r.stdout
+    r = subprocess.run([pkg.pfp.CLI_PATH, "/nonexistent", "-p", "5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Modulus must be at least 10" in r.stdout
+    r = subprocess.run([pkg.pfp.CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 1 and "Invalid number of arguments" in r.stdout
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith(("fasta", "fastq", "pangenome_fasta"))])
+def test_host_fasta_reader_matches_oracle(pkg, name):
+    """The product's own kseq-equivalent reader (pfp_io.c) against the oracle's restatement,
+    which tests/test_oracle_golden.py pins to the reference."""
+    c = golden().case(name)
+    want, want_tr = orc.fasta_extract(c["input"])
+    got, got_tr = pkg.pfp.fasta_extract(c["input"])
+    assert got == want and got_tr == want_tr

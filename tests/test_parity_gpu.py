@@ -1,0 +1,203 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle / the reference's golden outputs.
+Bit-exact: every byte of .dict .occ .parse .last .sai."""
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_same_files, golden, golden_names
+from oracle import pfp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sc(pkg):
+    s = pkg.pfp.Scanner(0)
+    yield s
+    s.close()
+
+
+def unparse(dict_bytes: bytes, parse_bytes: bytes, w: int) -> bytes:
+    """Rebuild the text from .dict + .parse (what the reference's unparse.c does)."""
+    words = dict_bytes[:-1].split(b"\x01")[:-1]
+    ranks = np.frombuffer(parse_bytes, dtype=np.uint32)
+    parts = []
+    for j, r in enumerate(ranks):
+        wd = words[r - 1]
+        parts.append(wd if j == 0 else wd[w:])
+    full = b"".join(parts)
+    return full[1:len(full) - w]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(pkg, sc, name):
+    c = golden().case(name)
+    text = pkg.pfp.fasta_extract(c["input"])[0] if c["fasta"] else c["input"]
+    got = sc.parse_host(text, c["w"], c["p"], sai=True)
+    assert_same_files(got, c, name)
+
+
+@pytest.mark.parametrize("w,p", [(10, 100), (4, 10), (6, 50), (16, 500), (32, 1000), (13, 37),
+                                 (19, 64), (27, 100), (40, 100), (100, 50)])
+def test_trigger_scan_vs_oracle(pkg, sc, w, p):
+    n = 300_000
+    text = pkg.synth.random_dna(n, 21).numpy()
+    for off in (0, 1, 7, 15):          # misaligned shard starts
+        buf = torch.from_numpy(np.concatenate([np.zeros(off, np.uint8), text])).cuda()
+        got, _ = sc.scan_triggers(buf[off:], w, p)
+        want = orc.triggers(text.tobytes(), w, p)
+        assert np.array_equal(got, want), f"w={w} p={p} off={off}: {len(got)} vs {len(want)}"
+
+
+def test_trigger_scan_shard_with_halo(pkg, sc):
+    """A shard [lo,hi) scanned from a buffer with a left halo gives exactly the global triggers
+    in [lo,hi) (pscan.hpp:44-108 semantics, sequential first-window rule)."""
+    w, p, n = 10, 100, 500_000
+    text = pkg.synth.random_dna(n, 22).numpy()
+    want = orc.triggers(text.tobytes(), w, p)
+    whole = torch.from_numpy(text).cuda()
+    cuts = [0, 100_003, 250_000, 250_001, 499_990, n]
+    got_all = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        b0 = max(0, lo - (w - 1))
+        got, _ = sc.scan_triggers(whole[b0:hi], w, p, buf_pos0=b0, own_lo=lo, own_hi=hi)
+        got_all.append(got)
+    assert np.array_equal(np.concatenate(got_all), want)
+
+
+@pytest.mark.parametrize("seed,n,w,p", [(31, 1000, 10, 100), (32, 40_000, 10, 100), (33, 1_000_000, 10, 100),
+                                         (34, 300_000, 4, 10), (35, 300_000, 6, 50), (36, 500_000, 16, 500),
+                                         (37, 500_000, 32, 1000), (38, 200_000, 19, 77), (39, 65_537, 10, 100)])
+def test_random_dna_vs_oracle(pkg, sc, seed, n, w, p):
+    text = pkg.synth.random_dna(n, seed).numpy().tobytes()
+    assert_same_files(sc.parse_host(text, w, p), orc.parse(text, w, p), f"seed{seed}")
+
+
+@pytest.mark.parametrize("w,p", [(10, 100), (6, 50), (16, 500), (32, 1000)])
+def test_pangenome_vs_oracle(pkg, sc, w, p):
+    text = pkg.synth.pangenome_text(100_000, 20, 41).numpy().tobytes()
+    got = sc.parse_host(text, w, p)
+    want = orc.parse(text, w, p)
+    assert_same_files(got, want, f"pangenome w{w} p{p}")
+    assert got.stats["n_distinct"] == want.n_distinct and got.stats["sum_word_len"] == want.sum_word_len
+
+
+def test_all_byte_values_vs_oracle(sc):
+    rng = np.random.default_rng(51)
+    text = rng.integers(3, 256, 400_000, dtype=np.uint8).tobytes()
+    assert_same_files(sc.parse_host(text, 10, 100), orc.parse(text, 10, 100), "bytes")
+    assert_same_files(sc.parse_host(text, 5, 17), orc.parse(text, 5, 17), "bytes w5")
+
+
+def test_long_phrases_vs_oracle(pkg, sc):
+    """Phrases beyond 64 KB take the one-CTA-per-phrase fingerprint path; long shared prefixes
+    stress the ranking rounds."""
+    a = pkg.synth.random_dna(50_000, 61).numpy().tobytes()
+    b = pkg.synth.random_dna(50_000, 62).numpy().tobytes()
+    text = a + b"N" * 200_000 + b + b"N" * 70_000 + a[:1000] + b"N" * 200_000 + b[:3000]
+    assert_same_files(sc.parse_host(text, 10, 100), orc.parse(text, 10, 100), "long")
+    text2 = b"A" * 150_000
+    assert_same_files(sc.parse_host(text2, 10, 100), orc.parse(text2, 10, 100), "allA")
+
+
+def test_low_complexity_vs_oracle(sc):
+    rng = np.random.default_rng(71)
+    unit = b"ACACACACGT"
+    text = unit * 3000 + bytes(rng.choice(np.frombuffer(b"AC", np.uint8), 50_000)) + unit * 2000
+    for (w, p) in [(10, 100), (4, 10), (8, 16)]:
+        assert_same_files(sc.parse_host(text, w, p), orc.parse(text, w, p), f"lowcx w{w}")
+
+
+def test_invalid_byte_truncates(sc):
+    text = b"ACGT" * 5000 + b"\x01" + b"ACGT" * 100
+    got = sc.parse_host(text, 10, 100)
+    assert_same_files(got, orc.parse(text, 10, 100), "invalid")
+    assert got.stats["n_text"] == 20000
+
+
+def test_device_entry_matches_host_entry(pkg, sc):
+    t = pkg.synth.pangenome_text(50_000, 10, 81)
+    want = sc.parse_host(t.numpy().tobytes(), 10, 100)
+    out = sc.parse_device(t.cuda(), 10, 100, sai=True)
+    got = sc.fetch(out)
+    assert_same_files(got, want, "device entry")
+    out = sc.parse_device(t.cuda(), 10, 100, sai=False)
+    assert not out.sai
+
+
+def test_compress_mode_dicz(pkg, sc):
+    """-c: words lose their last w bytes and the leading 0x02 (newscan.cpp:410-413)."""
+    text = pkg.synth.pangenome_text(30_000, 5, 82).numpy().tobytes()
+    w = 10
+    plain = sc.parse_host(text, w, 100)
+    comp = sc.parse_host(text, w, 100, compress=True)
+    words = plain.dict[:-1].split(b"\x01")[:-1]
+    want = b"".join((wd[:-w][1:] if wd[:1] == b"\x02" else wd[:-w]) + b"\x01" for wd in words) + b"\x00"
+    assert comp.dict == want and comp.parse == plain.parse and comp.occ == plain.occ
+
+
+def test_bad_arguments(pkg, sc):
+    with pytest.raises(pkg.pfp.PfpError) as e:
+        sc.parse_host(b"ACGT" * 100, w=3, p=100)
+    assert e.value.code == -1
+    with pytest.raises(pkg.pfp.PfpError):
+        sc.parse_host(b"ACGT" * 100, w=10, p=9)
+
+
+def test_round_trip_properties_32mb(pkg, sc):
+    """Size-independent properties at a size the oracle is too slow for in a unit test."""
+    w, p = 10, 100
+    t = pkg.synth.pangenome_text(2_000_000, 16, 91)
+    text = t.numpy().tobytes()
+    got = sc.parse_host(text, w, p)
+    words = got.dict[:-1].split(b"\x01")[:-1]
+    assert got.dict[-1:] == b"\x00" and len(words) == got.n_distinct
+    assert all(words[i] < words[i + 1] for i in range(len(words) - 1)), "dictionary not sorted/unique"
+    occ = np.frombuffer(got.occ, np.uint32)
+    ranks = np.frombuffer(got.parse, np.uint32)
+    assert occ.sum() == got.n_phrases
+    assert np.array_equal(np.bincount(ranks, minlength=len(words) + 1)[1:], occ)
+    assert unparse(got.dict, got.parse, w) == text
+    sai = np.frombuffer(got.sai, np.uint8).reshape(-1, 5).astype(np.uint64)
+    pos = sum(sai[:, i] << np.uint64(8 * i) for i in range(5))
+    assert pos[-1] == len(text) + w and np.all(np.diff(pos.astype(np.int64)) > 0)
+    tb = np.frombuffer(text, np.uint8)
+    last = np.frombuffer(got.last, np.uint8)
+    assert np.array_equal(last[:-1], tb[pos[:-1].astype(np.int64) - 1 - w]) and last[-1] == tb[-1]
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+def test_cli_files_and_bwt_match_reference(pkg):
+    """gpuscan.x as the drop-in for newscan.x: byte-identical files, and the UNCHANGED bwtparse +
+    pfbwtNT.x turn them into the same .bwt/.sa as the all-reference pipeline (bigbwt -f -S)."""
+    recs = [r.numpy() for r in pkg.synth.pangenome_records(40_000, 6, 95)]
+    fa = pkg.synth.to_fasta(recs)
+    tmp = tempfile.mkdtemp(prefix="pfpcli_")
+    try:
+        ours, ref = os.path.join(tmp, "ours.fa"), os.path.join(tmp, "ref.fa")
+        for pth in (ours, ref):
+            with open(pth, "wb") as f:
+                f.write(fa)
+        subprocess.run([pkg.pfp.CLI_PATH, ours, "-w", "10", "-p", "100", "-s", "-f"], check=True,
+                       stdout=subprocess.PIPE)
+        subprocess.run([orc.ref_exe("newscanNT.x"), ref, "-w", "10", "-p", "100", "-s", "-f"], check=True,
+                       stdout=subprocess.PIPE)
+        assert_same_files(orc.collect_files(ours), orc.collect_files(ref), "cli")
+        for base in (ours, ref):
+            subprocess.run([orc.ref_exe("bwtparse"), base, "-s"], check=True, stdout=subprocess.PIPE)
+            subprocess.run([orc.ref_exe("pfbwtNT.x"), "-w", "10", base, "-S"], check=True, stdout=subprocess.PIPE)
+        for ext in ("bwt", "sa"):
+            assert open(ours + "." + ext, "rb").read() == open(ref + "." + ext, "rb").read(), ext
+        # segmented .last/.sai (-t 3) concatenate to the same streams
+        seg = os.path.join(tmp, "seg.fa")
+        shutil.copy(ref, seg)
+        subprocess.run([pkg.pfp.CLI_PATH, seg, "-w", "10", "-p", "100", "-s", "-f", "-t", "3"], check=True,
+                       stdout=subprocess.PIPE)
+        assert_same_files(orc.collect_files(seg, nseg=3), orc.collect_files(ref), "cli -t 3")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
