@@ -3,7 +3,7 @@
 // Replaces KR_window::addchar + `hash % p == 0` of the reference (newscan.cpp:194-202,344,367;
 // pscan.cpp:239-247) for a whole shard at once.  The window hash depends only on the last w
 // bytes, so every thread owns a run of K1_RUN consecutive positions, rebuilds the hash of the
-// w-1 bytes in front of its run and then rolls.  A CTA stages a 32 KB tile (+32 B left halo)
+// w bytes in front of its run and then rolls.  A CTA stages a 32 KB tile (+32 B left halo)
 // in shared memory with coalesced 16-byte loads; threads read their run back with
 // conflict-free LDS.128 (slots padded to 144 B).  Output of K1a is one bit per text position;
 // K1c turns bits into ascending 64-bit positions using per-tile offsets from a device scan.
@@ -75,10 +75,11 @@ __global__ void __launch_bounds__(K1_T) kr_scan_k(const uint4 *__restrict__ A, u
         win[0] = p2.x; win[1] = p2.y; win[2] = p2.z; win[3] = p2.w;
         win[4] = p1.x; win[5] = p1.y; win[6] = p1.z; win[7] = p1.w;
     }
-    // hash of the w-1 bytes in front of the run
+    // hash of the w bytes in front of the run (the window ending just before it); its first
+    // byte is the one the first roll removes
     u32 h = 0;
 #pragma unroll
-    for (int j = -(W - 1); j < 0; j++) h = pfp_push(h, WIN_BYTE(win, j));
+    for (int j = -W; j < 0; j++) h = pfp_push(h, WIN_BYTE(win, j));
 
     unsigned char *slot = sm + (t + 1) * K1_SLOT;
     const u64 qrun = tile * (u64)K1_TILE + (u64)t * K1_RUN;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(K1_T) kr_scan_generic_k(const unsigned char *_
     const i64 w = C.w;
     const i64 qrun = (i64)(tile * (u64)K1_TILE + (u64)t * K1_RUN);
     u32 h = 0;
-    for (i64 q = qrun - (w - 1); q < qrun; q++) {
+    for (i64 q = qrun - w; q < qrun; q++) {
         u32 c = (q >= 0 && (u64)q < q_end) ? A8[q] : 0u;
         h = pfp_push(h, c);
     }
