@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""bench.py -- PFP parse GB/s (text in -> .dict/.occ/.parse/.last/.sai out), BASELINE.json's metric.
+
+One "step" = one complete prefix-free parse of the workload text:
+  value : device-resident (text already in HBM -> all five outputs in HBM), CUDA events
+  e2e   : through the C-ABI host entry pfpb200_parse_host with pinned HOST buffers, the H2D copy
+          of the text and the D2H copy of all outputs inside the timed region
+Workload at N=1 = BASELINE.json configs[1]: 100 haplotypes of a 40 Mbp chromosome, 0.1 %
+SNP/indel variation, w=10 p=100 (4 GB of text; synthetic, seeded, generated on the GPU).
+`--impl reference` times the reference's own CPU scanner (oracle/_ref, unmodified) on a
+bounded prefix of the same workload with all host threads.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, P = 10, 100
+SEED = 2
+METRIC = "pfp_parse_throughput"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--base-len", type=int, default=40_000_000, help="chromosome length (bp)")
+    ap.add_argument("--haplotypes", type=int, default=100, help="haplotypes per GPU")
+    ap.add_argument("--workload", default="pangenome", choices=["pangenome", "random"])
+    ap.add_argument("--cpu-haplotypes", type=int, default=4, help="prefix timed on the CPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    if a.workload == "random":
+        return f"uniform random ACGT, {a.base_len * a.haplotypes / 1e9:.2f} GB, w={W} p={P}"
+    return (f"{a.haplotypes} haplotypes x {a.base_len / 1e6:g} Mbp, 0.1% SNP/indel "
+            f"({a.base_len * a.haplotypes / 1e9:.2f} GB text), w={W} p={P}, -s")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi while the timed region runs
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU scanner on a bounded prefix of the workload
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_text(a, synth):
+    """First --cpu-haplotypes haplotypes of the workload (same seeds => same bytes), on the CPU."""
+    import torch
+    if a.workload == "random":
+        n = min(a.base_len * a.cpu_haplotypes, a.base_len * a.haplotypes)
+        return synth.random_dna(n, SEED).numpy(), f"first {n / 1e6:.0f} MB of the text"
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    h = min(a.cpu_haplotypes, a.haplotypes)
+    t = synth.pangenome_text(a.base_len, h, SEED, device=dev).cpu().numpy()
+    return t, f"first {h} haplotypes ({t.size / 1e6:.0f} MB of text) of the same workload"
+
+
+def run_reference_scanner(text_np, threads, tmpdir, reps):
+    """Time oracle/_ref pscan (the reference's scaling multi-thread scanner, plain text) or, if it
+    is missing, the oracle port.  Returns (best-effort list of seconds, kind, description)."""
+    from oracle import pfp_oracle as orc
+    path = os.path.join(tmpdir, "sample.txt")
+    text_np.tofile(path)
+    exe = None
+    for cand in ("pscan_fast.x", "pscan.x"):
+        if orc.have_ref(cand):
+            exe = orc.ref_exe(cand)
+            break
+    secs = []
+    if exe:
+        cmd = [exe, path, "-w", str(W), "-p", str(P), "-s", "-t", str(threads)]
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            secs.append(time.perf_counter() - t0)
+        return secs, "reference", f"{os.path.basename(exe)} -t {threads} (unmodified reference, oracle/_ref)", threads
+    data = text_np.tobytes()
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.parse(data, W, P)
+        secs.append(time.perf_counter() - t0)
+    return secs, "port", "oracle/pfp_oracle.c (single thread)", 1
+
+
+def reference_arm(a, synth):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    text, sample = cpu_sample_text(a, synth)
+    tmp = tempfile.mkdtemp(prefix="pfpbench_")
+    try:
+        secs, kind, how, cores = run_reference_scanner(text, threads, tmp, a.warmup + a.steps)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    timed = secs[a.warmup:]
+    total = sum(timed)
+    val = text.size * len(timed) / total / 1e9
+    line = {
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": workload_name(a), "sample": sample, "timing": "wall clock of the scanner process"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{how}; {sample}"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(n_text):
+    """dram bytes per launch of the scan kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        per_byte = t["kr_scan_k"]["dram_bytes_per_text_byte"]
+        return per_byte * n_text
+    except Exception:
+        return None
+
+
+def main():
+    a = parse_args()
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    synth = pkg.synth
+    if a.impl == "reference":
+        return reference_arm(a, synth)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bigbwt_b200 import shards
+    job = shards.ShardedParser(local, world, rank)
+
+    # ---- workload: this rank's shard of the text, generated in HBM ------------------------------
+    if a.workload == "random":
+        n_local = a.base_len * a.haplotypes
+        text = synth.random_dna(n_local, SEED + 1000 * rank, device=dev)
+    else:
+        text = synth.pangenome_text(a.base_len, a.haplotypes, SEED, device=dev,
+                                    first_hap=rank * a.haplotypes)
+    torch.cuda.synchronize()
+    n_local = text.numel()
+    job.set_text(text)
+    n_total = job.n_global
+
+    stream = torch.cuda.Stream(device=dev)
+    job.scanner.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        with torch.cuda.stream(stream):
+            return job.parse_device(W, P, sai=True)
+
+    for _ in range(a.warmup):
+        one_step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    scan_ms, stage_ms = [], {}
+    barrier()
+    ev0.record(stream)
+    for _ in range(a.steps):
+        st = one_step()
+        launches += st["launches"]
+        scan_ms.append(st["ms_scan"])
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage_ms[k] = stage_ms.get(k, 0.0) + v / a.steps
+    ev1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_total * a.steps / (ms * 1e-3) / 1e9
+    last_stats = st
+
+    # ---- e2e: host buffers in, host buffers out ------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        host = torch.empty(n_local, dtype=torch.uint8, pin_memory=True)
+        host.copy_(text)
+        torch.cuda.synchronize()
+        job.release_text()
+        del text
+        torch.cuda.empty_cache()
+        h2d = d2h = 0
+        es = max(1, min(a.steps, 3))
+        for _ in range(1):
+            job.parse_host(host, W, P, sai=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(es):
+            st2 = job.parse_host(host, W, P, sai=True)
+            h2d, d2h = st2["h2d_bytes"], st2["d2h_bytes"]
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n_total * es / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": es, "ms_per_step": 1e3 * dt / es,
+               "how": "pfpb200_parse_host: pinned host text -> H2D -> parse -> D2H of all five outputs"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K1 scan): 1 byte read + 1 bit written per position ---
+    peak, peak_src = load_peaks()
+    scan_ms_avg = sum(scan_ms) / len(scan_ms)
+    scan_bytes = n_local * (1.0 + 1.0 / 8.0)
+    achieved = scan_bytes / (scan_ms_avg * 1e-3) / 1e9
+    traffic = load_traffic(n_local)
+    roofline = {"kernel": "kr_scan_k<10>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms_avg,
+                "share_of_step": scan_ms_avg / (ms / a.steps),
+                "whole_path": {"alg_bytes_per_step": last_stats["alg_bytes"],
+                               "achieved": last_stats["alg_bytes"] * a.steps / (ms * 1e-3) / 1e9,
+                               "frac": last_stats["alg_bytes"] * a.steps / (ms * 1e-3) / 1e9 / (peak * world)}}
+
+    # ---- CPU baseline: the reference's scanner on a bounded prefix, host cores of this box ------
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        text_np, sample = cpu_sample_text(a, synth)
+        tmp = tempfile.mkdtemp(prefix="pfpbench_")
+        try:
+            secs, kind, how, cores = run_reference_scanner(text_np, threads, tmp, 1)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        cpu = {"value": text_np.size / secs[0] / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{how}; {sample}; wall clock {secs[0]:.2f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/u32/u64 integer", "data": "synthetic",
+        "config": {"workload": workload_name(a), "text_bytes_total": n_total, "text_bytes_per_gpu": n_local,
+                   "phrases": last_stats["n_phrases"], "distinct": last_stats["n_distinct"],
+                   "dict_bytes": last_stats["dict_bytes"], "rank_rounds": last_stats["rank_rounds"],
+                   "l2": "inputs larger than L2 (no flush needed)" if n_local > 256e6 else "input smaller than L2",
+                   "parallelism": f"{world} shard(s), one process per GPU"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        "stages_ms": stage_ms,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

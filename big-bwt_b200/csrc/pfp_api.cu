@@ -63,13 +63,6 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(PFPB200_E_CUDA);
     ctx->stream = ctx->own_stream;
-    // keep freed scratch in the stream-ordered pool: after the first call no allocation
-    // reaches the driver
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     if (cudaMalloc(&ctx->d_flags, PFP_FLAG_SLOTS * sizeof(u64)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_flags, PFP_FLAG_SLOTS * sizeof(u64)) != cudaSuccess ||
         cudaMalloc(&ctx->d_keys, NH_KEY_WORDS * sizeof(u32)) != cudaSuccess)
@@ -94,10 +87,13 @@ extern "C" void pfpb200_destroy(pfpb200_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pfp_release_scratch(ctx);
     pfp_release_held(ctx);
+    pfp_arena_destroy(ctx);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->d_keys) cudaFree(ctx->d_keys);
+    for (int i = 0; i < 5; i++)
+        if (ctx->pin_buf[i]) cudaFreeHost(ctx->pin_buf[i]);
     delete ctx;
 }
 
@@ -124,6 +120,7 @@ static int begin_call(pfpb200_ctx *ctx) {
     PFP_CUDA(ctx, cudaSetDevice(ctx->device));
     pfp_release_scratch(ctx);
     pfp_release_held(ctx);
+    PFP_TRY(pfp_arena_consolidate(ctx));
     ctx->launches = 0;
     ctx->err[0] = 0;
     PFP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, PFP_FLAG_SLOTS * sizeof(u64), ctx->stream));
@@ -285,19 +282,26 @@ extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_
     // device -> pinned host
     const u64 P = dv.n_phrases, d = dv.n_distinct;
     void *h_dict = nullptr, *h_occ = nullptr, *h_parse = nullptr, *h_last = nullptr, *h_sai = nullptr;
-    auto pin = [&](void **h, size_t bytes) -> int {
-        if (cudaMallocHost(h, bytes ? bytes : 1) != cudaSuccess) {
-            cudaGetLastError();
-            return pfp_fail(ctx, PFPB200_E_NOMEM, "pinned host allocation of %zu bytes failed", bytes);
+    auto pin = [&](int slot, void **h, size_t bytes) -> int {
+        if (bytes > ctx->pin_cap[slot]) {
+            if (ctx->pin_buf[slot]) cudaFreeHost(ctx->pin_buf[slot]);
+            ctx->pin_buf[slot] = nullptr;
+            ctx->pin_cap[slot] = 0;
+            size_t cap = bytes + bytes / 8 + 4096;
+            if (cudaMallocHost(&ctx->pin_buf[slot], cap) != cudaSuccess) {
+                cudaGetLastError();
+                return pfp_fail(ctx, PFPB200_E_NOMEM, "pinned host allocation of %zu bytes failed", cap);
+            }
+            ctx->pin_cap[slot] = cap;
         }
-        ctx->pinned.push_back(*h);
+        *h = ctx->pin_buf[slot];
         return PFPB200_OK;
     };
-    PFP_TRY(pin(&h_dict, dv.dict_bytes));
-    PFP_TRY(pin(&h_occ, d * 4));
-    PFP_TRY(pin(&h_parse, P * 4));
-    PFP_TRY(pin(&h_last, P));
-    if (dv.sai) PFP_TRY(pin(&h_sai, P * PFP_IBYTES));
+    PFP_TRY(pin(0, &h_dict, dv.dict_bytes));
+    PFP_TRY(pin(1, &h_occ, d * 4));
+    PFP_TRY(pin(2, &h_parse, P * 4));
+    PFP_TRY(pin(3, &h_last, P));
+    if (dv.sai) PFP_TRY(pin(4, &h_sai, P * PFP_IBYTES));
     cudaEventRecord(e2, ctx->stream);
     PFP_CUDA(ctx, cudaMemcpyAsync(h_dict, dv.dict, dv.dict_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PFP_CUDA(ctx, cudaMemcpyAsync(h_occ, dv.occ, d * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -318,8 +322,7 @@ extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_
     host_out->last = (const u8 *)h_last;
     host_out->sai = (const u8 *)h_sai;
     // the device copies are no longer needed
-    for (void *q : ctx->held) cudaFreeAsync(q, ctx->stream);
-    ctx->held.clear();
+    pfp_release_held(ctx);
     return PFPB200_OK;
 }
 

@@ -14,8 +14,20 @@ typedef uint16_t u16;
 typedef uint8_t u8;
 typedef int64_t i64;
 
+// Device scratch arena: a few big cudaMalloc'd slabs carved by a first-fit free list on the
+// host.  All work of a context is ordered on one stream, so a block freed on the host may be
+// handed out again at once.  After the first call on a workload no allocation reaches the driver.
+struct PfpBlock { char *p; size_t n; };
+struct PfpArena {
+    std::vector<PfpBlock> slabs;
+    std::vector<PfpBlock> free_list;   // sorted by address, coalesced
+    std::vector<PfpBlock> used;
+    size_t in_use = 0, peak = 0, total = 0;
+};
+
 struct pfpb200_ctx {
     int device = 0;
+    PfpArena arena;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -23,7 +35,8 @@ struct pfpb200_ctx {
     char err[512] = {0};
     std::vector<void *> scratch;   // freed at the end of every call
     std::vector<void *> held;      // outputs: freed at the start of the next call / destroy
-    std::vector<void *> pinned;    // host outputs of parse_host
+    void *pin_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // host outputs of parse_host,
+    size_t pin_cap[5] = {0, 0, 0, 0, 0};                                 // kept and grown across calls
     // persistent small device state
     u32 *d_keys = nullptr;         // NH key table (phrase fingerprints)
     u64 *d_flags = nullptr;        // [0] error bits, [1..] counters read back by the host
@@ -69,6 +82,8 @@ int pfp_alloc(pfpb200_ctx *ctx, void **p, size_t bytes, bool held = false);
 int pfp_free_now(pfpb200_ctx *ctx, void *p);   // early release of one scratch buffer
 void pfp_release_scratch(pfpb200_ctx *ctx);
 void pfp_release_held(pfpb200_ctx *ctx);
+void pfp_arena_destroy(pfpb200_ctx *ctx);
+int pfp_arena_consolidate(pfpb200_ctx *ctx);
 
 template <typename T>
 static inline int pfp_alloc_t(pfpb200_ctx *ctx, T **p, size_t count, bool held = false) {

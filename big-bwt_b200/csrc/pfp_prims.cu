@@ -18,17 +18,109 @@ int pfp_fail(pfpb200_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
+// ---- arena ---------------------------------------------------------------------------------------
+static void arena_insert_free(PfpArena &A, PfpBlock b) {
+    size_t i = 0;
+    while (i < A.free_list.size() && A.free_list[i].p < b.p) i++;
+    A.free_list.insert(A.free_list.begin() + i, b);
+    // coalesce with the right then the left neighbour (never across slabs: slabs are not adjacent
+    // in general, and if they are, merging is still a valid contiguous device range only within
+    // one allocation -- so check slab membership)
+    auto same_slab = [&](char *x, char *y) {
+        for (auto &s : A.slabs)
+            if (x >= s.p && x < s.p + s.n) return y >= s.p && y < s.p + s.n;
+        return false;
+    };
+    if (i + 1 < A.free_list.size() && A.free_list[i].p + A.free_list[i].n == A.free_list[i + 1].p &&
+        same_slab(A.free_list[i].p, A.free_list[i + 1].p)) {
+        A.free_list[i].n += A.free_list[i + 1].n;
+        A.free_list.erase(A.free_list.begin() + i + 1);
+    }
+    if (i > 0 && A.free_list[i - 1].p + A.free_list[i - 1].n == A.free_list[i].p &&
+        same_slab(A.free_list[i - 1].p, A.free_list[i].p)) {
+        A.free_list[i - 1].n += A.free_list[i].n;
+        A.free_list.erase(A.free_list.begin() + i);
+    }
+}
+
+static void *arena_take(PfpArena &A, size_t bytes) {
+    for (size_t i = 0; i < A.free_list.size(); i++) {
+        if (A.free_list[i].n >= bytes) {
+            char *p = A.free_list[i].p;
+            if (A.free_list[i].n == bytes) A.free_list.erase(A.free_list.begin() + i);
+            else { A.free_list[i].p += bytes; A.free_list[i].n -= bytes; }
+            A.used.push_back({p, bytes});
+            A.in_use += bytes;
+            if (A.in_use > A.peak) A.peak = A.in_use;
+            return p;
+        }
+    }
+    return nullptr;
+}
+
+static void arena_give(PfpArena &A, void *p) {
+    for (size_t i = 0; i < A.used.size(); i++)
+        if (A.used[i].p == (char *)p) {
+            PfpBlock b = A.used[i];
+            A.used[i] = A.used.back();
+            A.used.pop_back();
+            A.in_use -= b.n;
+            arena_insert_free(A, b);
+            return;
+        }
+}
+
+void pfp_arena_destroy(pfpb200_ctx *ctx) {
+    for (auto &s : ctx->arena.slabs) cudaFree(s.p);
+    ctx->arena = PfpArena();
+}
+
+// Called between calls, when nothing is in use: fold several slabs into one so that the next
+// call sees a single contiguous range at least as large as the last peak.
+int pfp_arena_consolidate(pfpb200_ctx *ctx) {
+    PfpArena &A = ctx->arena;
+    if (A.slabs.size() <= 1 || A.in_use != 0) return PFPB200_OK;
+    size_t want = A.total;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &s : A.slabs) cudaFree(s.p);
+    A.slabs.clear();
+    A.free_list.clear();
+    A.total = 0;
+    void *p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return PFPB200_OK; }  // grow lazily again
+    A.slabs.push_back({(char *)p, want});
+    A.free_list.push_back({(char *)p, want});
+    A.total = want;
+    return PFPB200_OK;
+}
+
 int pfp_alloc(pfpb200_ctx *ctx, void **p, size_t bytes, bool held) {
     *p = nullptr;
     if (bytes == 0) bytes = 16;
-    bytes = (bytes + 255) & ~(size_t)255;
-    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return pfp_fail(ctx, PFPB200_E_NOMEM, "device allocation of %zu bytes failed: %s", bytes,
-                        cudaGetErrorString(e));
+    bytes = (bytes + 511) & ~(size_t)511;
+    PfpArena &A = ctx->arena;
+    void *q = arena_take(A, bytes);
+    if (!q) {
+        // grow: a new slab of at least the request, at least 256 MB, at least half of what we have
+        size_t slab = bytes;
+        if (slab < ((size_t)256 << 20)) slab = (size_t)256 << 20;
+        if (slab < A.total / 2) slab = A.total / 2;
+        void *base = nullptr;
+        cudaError_t e = cudaMalloc(&base, slab);
+        if (e != cudaSuccess && slab > bytes) { cudaGetLastError(); slab = bytes; e = cudaMalloc(&base, slab); }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return pfp_fail(ctx, PFPB200_E_NOMEM, "device allocation of %zu bytes failed: %s", bytes,
+                            cudaGetErrorString(e));
+        }
+        A.slabs.push_back({(char *)base, slab});
+        A.total += slab;
+        arena_insert_free(A, {(char *)base, slab});
+        q = arena_take(A, bytes);
+        if (!q) return pfp_fail(ctx, PFPB200_E_INTERNAL, "arena inconsistency");
     }
-    (held ? ctx->held : ctx->scratch).push_back(*p);
+    *p = q;
+    (held ? ctx->held : ctx->scratch).push_back(q);
     return PFPB200_OK;
 }
 
@@ -38,22 +130,20 @@ int pfp_free_now(pfpb200_ctx *ctx, void *p) {
         if (ctx->scratch[i] == p) {
             ctx->scratch[i] = ctx->scratch.back();
             ctx->scratch.pop_back();
-            cudaFreeAsync(p, ctx->stream);
+            arena_give(ctx->arena, p);
             return PFPB200_OK;
         }
     return PFPB200_OK;
 }
 
 void pfp_release_scratch(pfpb200_ctx *ctx) {
-    for (void *p : ctx->scratch) cudaFreeAsync(p, ctx->stream);
+    for (void *p : ctx->scratch) arena_give(ctx->arena, p);
     ctx->scratch.clear();
 }
 
 void pfp_release_held(pfpb200_ctx *ctx) {
-    for (void *p : ctx->held) cudaFreeAsync(p, ctx->stream);
+    for (void *p : ctx->held) arena_give(ctx->arena, p);
     ctx->held.clear();
-    for (void *p : ctx->pinned) cudaFreeHost(p);
-    ctx->pinned.clear();
 }
 
 // ------------------------------------------------------------------------------------------

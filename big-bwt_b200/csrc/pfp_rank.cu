@@ -21,41 +21,140 @@ __device__ __forceinline__ u64 word_key(const u64 *__restrict__ pool, const u64 
     return (r < uwords[u]) ? bswap64(__ldg(pool + uoff[u] + r)) : 0ull;
 }
 
-__global__ void rank_keys0_k(const u64 *pool, const u64 *uoff, const u32 *uwords, u64 d, u64 *keys,
-                             u32 *vals) {
+// ---- alphabet compaction for the first key ------------------------------------------------------------
+// If the words use few distinct byte values in their first 24 bytes (DNA: A C G T N 0x02), an
+// order-preserving code of `bits` bits per symbol packs 64/bits symbols into the first 64-bit
+// key (21 for DNA) instead of 8, so the one global sort already separates almost everything.
+struct AlphaMap {
+    u32 bits;     // bits per symbol in the packed first key (8 = raw bytes)
+    u32 chars;    // symbols covered by the first key
+    u32 depth0;   // whole 8-byte chunks covered by the first key: refinement resumes there
+    u32 pad;
+    u8 lut[256];  // symbol -> code (1..sigma), order preserving; 0 = past the end of the word
+};
+
+constexpr u32 ALPHA_PROBE_WORDS = 3;   // first 24 bytes of every word are inspected
+
+__global__ void alpha_presence_k(const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
+                                 const u32 *__restrict__ ulen, u64 d, u32 *__restrict__ gmask) {
+    __shared__ u32 sm[8];
+    if (threadIdx.x < 8) sm[threadIdx.x] = 0;
+    __syncthreads();
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < d) {
+        u32 len = ulen[u];
+        u32 nb = len < 8 * ALPHA_PROBE_WORDS ? len : 8 * ALPHA_PROBE_WORDS;
+        u32 m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (u32 k = 0; k * 8 < nb; k++) {
+            u64 v = __ldg(pool + uoff[u] + k);
+            for (u32 b = 0; b < 8 && k * 8 + b < nb; b++) {
+                u32 c = (u32)(v >> (8 * b)) & 255u;
+#pragma unroll
+                for (int q = 0; q < 8; q++) m[q] |= ((c >> 5) == (u32)q) ? (1u << (c & 31)) : 0u;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            u32 x = __reduce_or_sync(__activemask(), m[q]);
+            if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1) && x) atomicOr(&sm[q], x);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && sm[threadIdx.x]) atomicOr(&gmask[threadIdx.x], sm[threadIdx.x]);
+}
+
+__global__ void alpha_build_k(const u32 *__restrict__ gmask, AlphaMap *am) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u32 sigma = 0;
+    for (int q = 0; q < 8; q++) sigma += __popc(gmask[q]);
+    u32 bits = 3;            // >= 3 so that the key never reaches past the probed 24 bytes
+    while ((1u << bits) < sigma + 1) bits++;
+    if (bits > 4) {          // large alphabet: plain big-endian bytes
+        am->bits = 8; am->chars = 8; am->depth0 = 1;
+        for (int c = 0; c < 256; c++) am->lut[c] = (u8)c;
+    } else {
+        am->bits = bits; am->chars = 64 / bits; am->depth0 = (64 / bits) / 8;
+        u32 code = 0;
+        for (int c = 0; c < 256; c++) {
+            bool present = (gmask[c >> 5] >> (c & 31)) & 1u;
+            if (present) code++;
+            am->lut[c] = (u8)(present ? code : 0);
+        }
+    }
+    am->pad = 0;
+}
+
+__global__ void rank_keys0_k(const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
+                             const u32 *__restrict__ ulen, u64 d, const AlphaMap *__restrict__ am,
+                             u64 *__restrict__ keys, u32 *__restrict__ vals) {
+    __shared__ u8 lut[256];
+    __shared__ u32 s_bits, s_chars;
+    lut[threadIdx.x & 255] = am->lut[threadIdx.x & 255];
+    if (threadIdx.x == 0) { s_bits = am->bits; s_chars = am->chars; }
+    __syncthreads();
     u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= d) return;
-    keys[u] = word_key(pool, uoff, uwords, (u32)u, 0);
+    const u32 bits = s_bits, chars = s_chars, len = ulen[u];
+    const u32 nc = len < chars ? len : chars;
+    u64 key = 0;
+    u64 v = 0;
+    for (u32 i = 0; i < nc; i++) {
+        if ((i & 7) == 0) v = __ldg(pool + uoff[u] + (i >> 3));
+        u32 c = (u32)(v >> (8 * (i & 7))) & 255u;
+        key |= (u64)lut[c] << (64 - bits * (i + 1));
+    }
+    keys[u] = key;
     vals[u] = (u32)u;
 }
 
-__global__ void rank_heads0_k(const u64 *__restrict__ ks, u64 d, u8 *__restrict__ head) {
+__global__ void rank_heads0_k(const u64 *__restrict__ ks, u64 d, const AlphaMap *__restrict__ am,
+                              u8 *__restrict__ head, u32 *__restrict__ depth) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d) return;
     head[i] = (i == 0 || ks[i] != ks[i - 1]) ? 1 : 0;
+    depth[i] = am->depth0;
 }
 
-__global__ void rank_active_k(const u8 *__restrict__ head, u64 d, u8 *__restrict__ act,
+// ---- tie groups ------------------------------------------------------------------------------------------
+constexpr u32 LOCAL_MAX = 2048;   // largest tie group finished inside one CTA
+constexpr u32 WARP_MAX = 32;      // largest tie group finished inside one warp
+
+// hp[k] = first position of group k (k < nheads), hp[nheads] = d; gid[i] = group of position i
+__global__ void groups_compact_k(const u8 *__restrict__ head, const u32 *__restrict__ hscan, u64 d,
+                                 const u32 *__restrict__ nheads, u32 *__restrict__ hp,
+                                 u32 *__restrict__ gid) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    u32 g = hscan[i] + head[i] - 1;
+    gid[i] = g;
+    if (head[i]) hp[g] = (u32)i;
+    if (i == 0) hp[*nheads] = (u32)d;
+}
+
+// positions in groups larger than LOCAL_MAX go through another global round
+__global__ void rank_active_k(const u8 *__restrict__ head, const u32 *__restrict__ gid,
+                              const u32 *__restrict__ hp, u64 d, u8 *__restrict__ act,
                               u8 *__restrict__ gh) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d) return;
-    // first position at or before i that is a head == start of my group; I am alone iff I am a
-    // head and my successor is one too
-    bool single = head[i] && (i + 1 == d || head[i + 1]);
-    act[i] = single ? 0 : 1;
-    gh[i] = (!single && head[i]) ? 1 : 0;
+    u32 g = gid[i];
+    bool big = (hp[g + 1] - hp[g]) > LOCAL_MAX;
+    act[i] = big ? 1 : 0;
+    gh[i] = (big && head[i]) ? 1 : 0;
 }
 
 __global__ void rank_compact_k(const u8 *__restrict__ act, const u8 *__restrict__ gh,
                                const u32 *__restrict__ ascan, const u32 *__restrict__ gscan,
-                               const u32 *__restrict__ ord, u64 d, u32 r, const u64 *pool,
-                               const u64 *uoff, const u32 *uwords, u32 *__restrict__ apos,
-                               u64 *__restrict__ keys, u32 *__restrict__ vals,
+                               const u32 *__restrict__ ord, const u32 *__restrict__ gid,
+                               const u32 *__restrict__ hp, const u32 *__restrict__ depth, u64 d,
+                               const u64 *pool, const u64 *uoff, const u32 *uwords,
+                               u32 *__restrict__ apos, u64 *__restrict__ keys, u32 *__restrict__ vals,
                                u32 *__restrict__ gid_of_u) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d || !act[i]) return;
     u32 j = ascan[i];
     u32 u = ord[i];
+    u32 r = depth[hp[gid[i]]];          // chunks this group is known to share
     apos[j] = (u32)i;
     keys[j] = word_key(pool, uoff, uwords, u, r);
     vals[j] = u;
@@ -68,60 +167,211 @@ __global__ void rank_gidkeys_k(const u32 *__restrict__ vs, const u32 *__restrict
     if (j < m) keys2[j] = gid_of_u[vs[j]];
 }
 
+// new heads where the chunk changes inside an old group; every (old or new) head of a group that
+// took part now shares one more chunk
 __global__ void rank_writeback_k(const u32 *__restrict__ apos, const u64 *__restrict__ gk,
-                                 const u32 *__restrict__ vs, u64 m, u32 r, const u64 *pool,
-                                 const u64 *uoff, const u32 *uwords, u32 *__restrict__ ord,
-                                 u8 *__restrict__ head) {
+                                 const u32 *__restrict__ vs, u64 m, const u32 *__restrict__ gid,
+                                 const u32 *__restrict__ hp, const u32 *__restrict__ depth_in,
+                                 const u64 *pool, const u64 *uoff, const u32 *uwords,
+                                 u32 *__restrict__ ord, u8 *__restrict__ head,
+                                 u32 *__restrict__ depth_out) {
     u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     u32 i = apos[j];
     u32 u = vs[j];
+    u32 r = depth_in[hp[gid[i]]];
     ord[i] = u;
+    bool newhead = false;
     if (j > 0 && gk[j] == gk[j - 1]) {
         u32 up = vs[j - 1];
-        if (word_key(pool, uoff, uwords, u, r) != word_key(pool, uoff, uwords, up, r)) head[i] = 1;
+        newhead = word_key(pool, uoff, uwords, u, r) != word_key(pool, uoff, uwords, up, r);
+        if (newhead) head[i] = 1;
+    }
+    if (newhead || head[i]) depth_out[i] = r + 1;
+}
+
+// ---- local refinement: one warp per small tie group ---------------------------------------------------
+// Lanes are the positions of the group.  Each round every still-tied lane loads the next 8-byte
+// chunk of its word and counts, inside its tie range [lo,hi), the lanes with a smaller chunk and
+// the equal ones in front of it: that is its new position; ties shrink until all are singletons.
+__global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
+                                                   const u32 *__restrict__ nheads,
+                                                   const u32 *__restrict__ depth,
+                                                   const u64 *pool, const u64 *uoff, const u32 *uwords,
+                                                   u32 max_chunks, u32 *__restrict__ ord,
+                                                   u64 *__restrict__ flags) {
+    __shared__ u32 s_uid[8][32];
+    __shared__ u16 s_lo[8][32], s_hi[8][32];
+    const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const u32 ng = *nheads;
+    const u32 nwarps = gridDim.x * 8;
+    for (u32 g = blockIdx.x * 8 + wp; g < ng; g += nwarps) {
+        const u32 s = hp[g], m = hp[g + 1] - s;
+        if (m < 2 || m > WARP_MAX) continue;
+        u32 r = depth[s];
+        u32 uid = lane < m ? ord[s + lane] : 0;
+        u32 lo = lane < m ? 0 : lane, hi = lane < m ? m : lane + 1;
+        for (;;) {
+            bool active = (hi - lo) > 1;
+            if (!__any_sync(0xffffffffu, active)) break;
+            if (r >= max_chunks) {
+                if (lane == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
+                break;
+            }
+            u64 key = active ? word_key(pool, uoff, uwords, uid, r) : 0ull;
+            u32 less = 0, eqb = 0, eq = 0;
+            for (u32 j = 0; j < m; j++) {
+                u64 kj = __shfl_sync(0xffffffffu, key, j);
+                bool in = (j >= lo) && (j < hi);
+                less += (in && kj < key) ? 1 : 0;
+                bool e = in && (kj == key);
+                eq += e ? 1 : 0;
+                eqb += (e && j < lane) ? 1 : 0;
+            }
+            u32 np = lane, nlo = lo, nhi = hi;
+            if (active) { nlo = lo + less; nhi = nlo + eq; np = nlo + eqb; }
+            __syncwarp();
+            s_uid[wp][np] = uid; s_lo[wp][np] = (u16)nlo; s_hi[wp][np] = (u16)nhi;
+            __syncwarp();
+            uid = s_uid[wp][lane]; lo = s_lo[wp][lane]; hi = s_hi[wp][lane];
+            r++;
+        }
+        if (lane < m) ord[s + lane] = uid;
+    }
+}
+
+// ---- local refinement: one CTA per medium tie group -----------------------------------------------------
+struct CtaSort {
+    u64 key[LOCAL_MAX];
+    u32 uid[2][LOCAL_MAX];
+    u16 lo[2][LOCAL_MAX];
+    u16 hi[2][LOCAL_MAX];
+};
+
+__global__ void rank_cta_list_k(const u32 *__restrict__ hp, const u32 *__restrict__ nheads, u64 d,
+                                u32 *__restrict__ list, u32 *__restrict__ count) {
+    u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d || g >= *nheads) return;
+    u32 m = hp[g + 1] - hp[g];
+    if (m > WARP_MAX && m <= LOCAL_MAX) list[atomicAdd(count, 1u)] = (u32)g;
+}
+
+__global__ void __launch_bounds__(256) rank_cta_k(const u32 *__restrict__ hp,
+                                                  const u32 *__restrict__ list,
+                                                  const u32 *__restrict__ count,
+                                                  const u32 *__restrict__ depth,
+                                                  const u64 *pool, const u64 *uoff, const u32 *uwords,
+                                                  u32 max_chunks, u32 *__restrict__ ord,
+                                                  u64 *__restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char cta_raw[];
+    CtaSort &S = *reinterpret_cast<CtaSort *>(cta_raw);
+    const u32 t = threadIdx.x;
+    const u32 n = *count;
+    for (u32 q = blockIdx.x; q < n; q += gridDim.x) {
+        const u32 g = list[q];
+        const u32 s = hp[g], m = hp[g + 1] - s;
+        u32 r = depth[s];
+        int cur = 0;
+        __syncthreads();
+        for (u32 i = t; i < m; i += 256) { S.uid[0][i] = ord[s + i]; S.lo[0][i] = 0; S.hi[0][i] = (u16)m; }
+        __syncthreads();
+        for (;;) {
+            int any = 0;
+            for (u32 i = t; i < m; i += 256) {
+                bool act = (u32)(S.hi[cur][i] - S.lo[cur][i]) > 1;
+                S.key[i] = act ? word_key(pool, uoff, uwords, S.uid[cur][i], r) : 0ull;
+                any |= act ? 1 : 0;
+            }
+            if (!__syncthreads_or(any)) break;
+            if (r >= max_chunks) {
+                if (t == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
+                break;
+            }
+            for (u32 i = t; i < m; i += 256) {
+                u32 l = S.lo[cur][i], h = S.hi[cur][i];
+                u32 np = i, nlo = l, nhi = h;
+                if (h - l > 1) {
+                    u64 key = S.key[i];
+                    u32 less = 0, eqb = 0, eq = 0;
+                    for (u32 j = l; j < h; j++) {
+                        u64 kj = S.key[j];
+                        less += (kj < key) ? 1 : 0;
+                        bool e = (kj == key);
+                        eq += e ? 1 : 0;
+                        eqb += (e && j < i) ? 1 : 0;
+                    }
+                    nlo = l + less; nhi = nlo + eq; np = nlo + eqb;
+                }
+                S.uid[cur ^ 1][np] = S.uid[cur][i];
+                S.lo[cur ^ 1][np] = (u16)nlo;
+                S.hi[cur ^ 1][np] = (u16)nhi;
+            }
+            __syncthreads();
+            cur ^= 1;
+            r++;
+        }
+        __syncthreads();
+        for (u32 i = t; i < m; i += 256) ord[s + i] = S.uid[cur][i];
     }
 }
 
 int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *rounds) {
     const int TB = 256;
     const u64 d = D.d;
+    const u32 nbd = pfp_blocks(d, TB);
+    const u32 max_chunks = (D.max_len + 7) / 8 + 1;
     u64 *k0 = nullptr, *k1 = nullptr, *ks = nullptr;
     u32 *v0 = nullptr, *v1 = nullptr, *vs = nullptr;
-    u32 *ord = nullptr;
+    u32 *ord = nullptr, *depth = nullptr, *hscan = nullptr, *hp = nullptr, *gid = nullptr;
+    u8 *head = nullptr;
+    AlphaMap *am = nullptr;
+    u32 *amask = nullptr;
     PFP_TRY(pfp_alloc_t(ctx, &k0, d));
     PFP_TRY(pfp_alloc_t(ctx, &k1, d));
     PFP_TRY(pfp_alloc_t(ctx, &v0, d));
     PFP_TRY(pfp_alloc_t(ctx, &v1, d));
     PFP_TRY(pfp_alloc_t(ctx, &ord, d));
-    u8 *head = nullptr, *act = nullptr, *gh = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &depth, d));
+    PFP_TRY(pfp_alloc_t(ctx, &hscan, d));
+    PFP_TRY(pfp_alloc_t(ctx, &hp, d + 1));
+    PFP_TRY(pfp_alloc_t(ctx, &gid, d));
     PFP_TRY(pfp_alloc_t(ctx, &head, d));
-    const u32 nbd = pfp_blocks(d, TB);
-    rank_keys0_k<<<nbd, TB, 0, ctx->stream>>>(D.pool, D.uoff, D.uwords, d, k0, v0);
+    PFP_TRY(pfp_alloc_t(ctx, &am, 1));
+    PFP_TRY(pfp_alloc_t(ctx, &amask, 8));
+    // first key: alphabet-compacted prefix, one global sort
+    PFP_CUDA(ctx, cudaMemsetAsync(amask, 0, 8 * sizeof(u32), ctx->stream));
+    alpha_presence_k<<<nbd, TB, 0, ctx->stream>>>(D.pool, D.uoff, D.ulen, d, amask);
+    PFP_LAUNCHED(ctx);
+    alpha_build_k<<<1, 32, 0, ctx->stream>>>(amask, am);
+    PFP_LAUNCHED(ctx);
+    rank_keys0_k<<<nbd, TB, 0, ctx->stream>>>(D.pool, D.uoff, D.ulen, d, am, k0, v0);
     PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, d, 0, 64, &ks, &vs));
-    rank_heads0_k<<<nbd, TB, 0, ctx->stream>>>(ks, d, head);
+    rank_heads0_k<<<nbd, TB, 0, ctx->stream>>>(ks, d, am, head, depth);
     PFP_LAUNCHED(ctx);
     PFP_CUDA(ctx, cudaMemcpyAsync(ord, vs, d * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
 
-    u32 *ascan = nullptr, *gscan = nullptr, *apos = nullptr, *gid_of_u = nullptr;
+    u8 *act = nullptr, *gh = nullptr;
+    u32 *ascan = nullptr, *gscan = nullptr, *apos = nullptr, *gid_of_u = nullptr, *depth2 = nullptr;
+    u32 *d_nheads = reinterpret_cast<u32 *>(&ctx->d_flags[4]);
     u32 r = 1;
-    const u32 max_rounds = (D.max_len + 7) / 8 + 1;
-    bool allocated = false;
+    bool big_bufs = false;
     for (;; r++) {
+        // group table from the head flags
+        PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 4 * sizeof(u64), ctx->stream));
+        PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, head, hscan, d, d_nheads));
+        groups_compact_k<<<nbd, TB, 0, ctx->stream>>>(head, hscan, d, d_nheads, hp, gid);
+        PFP_LAUNCHED(ctx);
         if (d < 2) break;
-        if (!allocated) {
+        if (!big_bufs) {
             PFP_TRY(pfp_alloc_t(ctx, &act, d));
             PFP_TRY(pfp_alloc_t(ctx, &gh, d));
             PFP_TRY(pfp_alloc_t(ctx, &ascan, d));
             PFP_TRY(pfp_alloc_t(ctx, &gscan, d));
-            PFP_TRY(pfp_alloc_t(ctx, &apos, d));
-            PFP_TRY(pfp_alloc_t(ctx, &gid_of_u, d));
-            allocated = true;
+            big_bufs = true;
         }
-        rank_active_k<<<nbd, TB, 0, ctx->stream>>>(head, d, act, gh);
+        rank_active_k<<<nbd, TB, 0, ctx->stream>>>(head, gid, hp, d, act, gh);
         PFP_LAUNCHED(ctx);
-        PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 2 * sizeof(u64), ctx->stream));
         PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, act, ascan, d, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
         PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, gh, gscan, d, reinterpret_cast<u32 *>(&ctx->d_flags[2])));
         PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 3 * sizeof(u64),
@@ -129,12 +379,17 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         u64 m = (u32)ctx->h_flags[1], ng = (u32)ctx->h_flags[2];
         if (m == 0) break;
-        if (r > max_rounds)
+        if (r > max_chunks + 1)
             return pfp_fail(ctx, PFPB200_E_INTERNAL,
                             "ranking did not separate %llu words after %u rounds (duplicate words?)",
                             (unsigned long long)m, r);
-        rank_compact_k<<<nbd, TB, 0, ctx->stream>>>(act, gh, ascan, gscan, ord, d, r, D.pool, D.uoff,
-                                                    D.uwords, apos, k0, v0, gid_of_u);
+        if (!apos) {
+            PFP_TRY(pfp_alloc_t(ctx, &apos, d));
+            PFP_TRY(pfp_alloc_t(ctx, &gid_of_u, d));
+            PFP_TRY(pfp_alloc_t(ctx, &depth2, d));
+        }
+        rank_compact_k<<<nbd, TB, 0, ctx->stream>>>(act, gh, ascan, gscan, ord, gid, hp, depth, d, D.pool,
+                                                    D.uoff, D.uwords, apos, k0, v0, gid_of_u);
         PFP_LAUNCHED(ctx);
         PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, m, 0, 64, &ks, &vs));
         // second key: the tie group, stable, only as many bits as there are groups
@@ -148,23 +403,46 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
         u64 *gs = nullptr;
         u32 *vs2 = nullptr;
         PFP_TRY(pfp_radix_sort_pairs(ctx, g_in, vs, ks, v_other, m, 0, bits, &gs, &vs2));
-        rank_writeback_k<<<nbm, TB, 0, ctx->stream>>>(apos, gs, vs2, m, r, D.pool, D.uoff, D.uwords,
-                                                      ord, head);
+        PFP_CUDA(ctx, cudaMemcpyAsync(depth2, depth, d * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        rank_writeback_k<<<nbm, TB, 0, ctx->stream>>>(apos, gs, vs2, m, gid, hp, depth, D.pool, D.uoff,
+                                                      D.uwords, ord, head, depth2);
         PFP_LAUNCHED(ctx);
+        u32 *tdp = depth; depth = depth2; depth2 = tdp;
+    }
+    // finish every remaining tie group on chip
+    if (d >= 2) {
+        static bool attr = false;
+        if (!attr) {
+            PFP_CUDA(ctx, cudaFuncSetAttribute(rank_cta_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)sizeof(CtaSort)));
+            attr = true;
+        }
+        u32 *cta_list = v1;                      // sort buffers are free again
+        u32 *cta_count = reinterpret_cast<u32 *>(&ctx->d_flags[5]);
+        PFP_CUDA(ctx, cudaMemsetAsync(cta_count, 0, sizeof(u32), ctx->stream));
+        rank_cta_list_k<<<nbd, TB, 0, ctx->stream>>>(hp, d_nheads, d, cta_list, cta_count);
+        PFP_LAUNCHED(ctx);
+        u64 want = (d / 2 + 7) / 8;
+        u64 maxb = (u64)ctx->sm_count * 16;
+        u32 nbw = (u32)(want < maxb ? want : maxb);
+        if (nbw == 0) nbw = 1;
+        rank_warp_k<<<nbw, 256, 0, ctx->stream>>>(hp, d_nheads, depth, D.pool, D.uoff, D.uwords, max_chunks,
+                                                  ord, ctx->d_flags);
+        PFP_LAUNCHED(ctx);
+        rank_cta_k<<<ctx->sm_count * 4, 256, sizeof(CtaSort), ctx->stream>>>(
+            hp, cta_list, cta_count, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
+        PFP_LAUNCHED(ctx);
+        PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(u64), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_flags[0] & PFP_ERRBIT_INTERNAL)
+            return pfp_fail(ctx, PFPB200_E_INTERNAL, "ranking found words that never differ (duplicates?)");
     }
     *rounds = r;
     *order = ord;
-    PFP_TRY(pfp_free_now(ctx, k0));
-    PFP_TRY(pfp_free_now(ctx, k1));
-    PFP_TRY(pfp_free_now(ctx, v0));
-    PFP_TRY(pfp_free_now(ctx, v1));
-    PFP_TRY(pfp_free_now(ctx, head));
-    PFP_TRY(pfp_free_now(ctx, act));
-    PFP_TRY(pfp_free_now(ctx, gh));
-    PFP_TRY(pfp_free_now(ctx, ascan));
-    PFP_TRY(pfp_free_now(ctx, gscan));
-    PFP_TRY(pfp_free_now(ctx, apos));
-    PFP_TRY(pfp_free_now(ctx, gid_of_u));
+    void *to_free[] = {k0, k1, v0, v1, depth, depth2, hscan, hp, gid, head, am, amask, act, gh, ascan,
+                       gscan, apos, gid_of_u};
+    for (void *q : to_free) PFP_TRY(pfp_free_now(ctx, q));
     return PFPB200_OK;
 }
 
