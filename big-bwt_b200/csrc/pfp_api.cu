@@ -19,6 +19,27 @@ static double wall_sec() {
 
 __global__ void set_u64_k(u64 *p, u64 v) { *p = v; }
 
+// first position holding a byte <= 0x02 (newscan.cpp:364), or n: 16-byte loads, the classic
+// "has a byte below k" word test, exact position only in the rare word that trips it
+__global__ void __launch_bounds__(256) first_invalid_k(const u8 *__restrict__ t, u64 n,
+                                                       unsigned long long *__restrict__ first) {
+    const u64 stride = (u64)gridDim.x * blockDim.x * 16;
+    for (u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n; i += stride) {
+        bool hit = false;
+        if (i + 16 <= n && (((uintptr_t)(t + i)) & 15) == 0) {
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(t + i));
+            u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) hit |= ((w[k] - 0x03030303u) & ~w[k] & 0x80808080u) != 0;
+        } else hit = true;
+        if (hit) {
+            u64 e = i + 16 < n ? i + 16 : n;
+            for (u64 j = i; j < e; j++)
+                if (t[j] <= PFP_DOLLAR) { atomicMin(first, (unsigned long long)j); break; }
+        }
+    }
+}
+
 extern "C" int pfpb200_abi_version(void) { return PFPB200_ABI_VERSION; }
 
 extern "C" const char *pfpb200_strerror(int code) {
@@ -243,20 +264,6 @@ extern "C" int pfpb200_memcpy_d2h(pfpb200_ctx *ctx, void *dst_host, const void *
     return PFPB200_OK;
 }
 
-// number of leading valid text bytes (newscan.cpp:364: stop at the first byte <= Dollar)
-static u64 valid_prefix(const u8 *t, u64 n) {
-    u64 i = 0;
-    // 8 bytes at a time: a byte b <= 2 iff (b - 3) borrows
-    while (i + 8 <= n) {
-        u64 v;
-        memcpy(&v, t + i, 8);
-        if (((v - 0x0303030303030303ULL) & ~v & 0x8080808080808080ULL) != 0) break;
-        i += 8;
-    }
-    while (i < n && t[i] > PFP_DOLLAR) i++;
-    return i;
-}
-
 extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_t n_text,
                                   const pfpb200_opts *opts, pfpb200_outputs *host_out,
                                   pfpb200_stats *stats) {
@@ -265,16 +272,30 @@ extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_
     if (stats) memset(stats, 0, sizeof(*stats));
     memset(host_out, 0, sizeof(*host_out));
     PFP_TRY(begin_call(ctx));
-    u64 n = valid_prefix(text, n_text);
-    if (n < n_text && (opts->flags & PFPB200_F_VERBOSE))
-        fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     u8 *d_text = nullptr;
-    PFP_TRY(pfp_alloc(ctx, (void **)&d_text, n, true));
+    PFP_TRY(pfp_alloc(ctx, (void **)&d_text, n_text, true));
     cudaEventRecord(e0, ctx->stream);
-    if (n) PFP_CUDA(ctx, cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_text) PFP_CUDA(ctx, cudaMemcpyAsync(d_text, text, n_text, cudaMemcpyHostToDevice, ctx->stream));
+    // the cut at the first invalid byte is found on the device, at HBM speed
+    u64 n = n_text;
+    if (n_text) {
+        set_u64_k<<<1, 1, 0, ctx->stream>>>(&ctx->d_flags[14], n_text);
+        PFP_LAUNCHED(ctx);
+        first_invalid_k<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+            d_text, n_text, reinterpret_cast<unsigned long long *>(&ctx->d_flags[14]));
+        PFP_LAUNCHED(ctx);
+        PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[14], &ctx->d_flags[14], sizeof(u64),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    }
     cudaEventRecord(e1, ctx->stream);
+    if (n_text) {
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        n = ctx->h_flags[14];
+    }
+    if (n < n_text && (opts->flags & PFPB200_F_VERBOSE))
+        fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
     pfpb200_outputs dv;
     memset(&dv, 0, sizeof(dv));
     int rc = parse_device_impl(ctx, d_text, n, opts, &dv, stats);
