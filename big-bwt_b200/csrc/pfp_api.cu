@@ -56,6 +56,8 @@ extern "C" const char *pfpb200_strerror(int code) {
     }
 }
 
+extern "C" uint32_t pfpb200_launch_count(const pfpb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
 extern "C" const char *pfpb200_last_error(const pfpb200_ctx *ctx) { return ctx ? ctx->err : ""; }
 
 static u64 splitmix64(u64 &s) {
@@ -400,5 +402,184 @@ extern "C" int pfpb200_scan_triggers(pfpb200_ctx *ctx, const uint8_t *d_buf, uin
     *d_triggers = out;
     *n_triggers = k;
     if (ms) *ms = a;
+    return PFPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded parsing (one process per GPU drives these between its collectives)
+// ------------------------------------------------------------------------------------------------
+struct CallTimer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    explicit CallTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    float stop() {
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float t = 0;
+        cudaEventElapsedTime(&t, a, b);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        return t;
+    }
+};
+
+// what is still in the scratch list must survive until the next parse: move it to `held`
+static void promote_scratch(pfpb200_ctx *ctx) {
+    for (void *p : ctx->scratch) ctx->held.push_back(p);
+    ctx->scratch.clear();
+}
+
+extern "C" int pfpb200_shard_scan(pfpb200_ctx *ctx, const pfpb200_shard *shard, const pfpb200_opts *opts,
+                                  uint64_t *n_triggers, uint64_t *first_trigger, uint64_t *last_trigger,
+                                  float *ms) {
+    PFP_TRY(check_opts(ctx, opts));
+    if (!shard || !n_triggers || !first_trigger || !last_trigger) return pfp_fail(ctx, PFPB200_E_ARG, "null argument");
+    if (shard->own_lo > shard->own_hi || shard->own_hi > shard->n_global)
+        return pfp_fail(ctx, PFPB200_E_ARG, "bad shard range");
+    PFP_TRY(begin_call(ctx));
+    ctx->sh.desc = *shard;
+    ctx->sh.opts = *opts;
+    CallTimer tm(ctx->stream);
+    u64 *ends = nullptr, k = 0;
+    float a = 0, b = 0;
+    int rc = pfp_scan_stage(ctx, shard->d_buf, shard->n_buf, shard->buf_pos0, shard->own_lo, shard->own_hi,
+                            opts->w, opts->p, 1, true, &ends, &k, &a, &b);
+    if (rc == PFPB200_OK && k > 0) {
+        cudaMemcpyAsync(&ctx->h_flags[8], ends, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(&ctx->h_flags[9], ends + (k - 1), sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    float t = tm.stop();
+    pfp_release_scratch(ctx);
+    if (rc != PFPB200_OK) return rc;
+    PFP_CUDA(ctx, cudaGetLastError());
+    ctx->sh.ends = ends;
+    ctx->sh.n_trig = k;
+    *n_triggers = k;
+    *first_trigger = k ? ctx->h_flags[8] : 0;
+    *last_trigger = k ? ctx->h_flags[9] : 0;
+    if (ms) *ms = t;
+    return PFPB200_OK;
+}
+
+extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb200_words *out, float *ms) {
+    if (!ctx || !out) return PFPB200_E_ARG;
+    memset(out, 0, sizeof(*out));
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const pfpb200_shard &sh = ctx->sh.desc;
+    const pfpb200_opts &o = ctx->sh.opts;
+    const u32 w = o.w;
+    const u64 k = ctx->sh.n_trig;
+    const u64 P = k + (sh.is_last ? 1 : 0);
+    ctx->sh.P = P;
+    ctx->sh.d = 0;
+    ctx->sh.uid = nullptr;
+    if (ms) *ms = 0;
+    if (P == 0) return PFPB200_OK;
+    if (P >= 0xFFFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "the shard's parse has more than 2^32-2 words");
+    CallTimer tm(ctx->stream);
+    auto run = [&]() -> int {
+        u64 *ends = ctx->sh.ends;
+        if (sh.is_last) {
+            set_u64_k<<<1, 1, 0, ctx->stream>>>(ends + k, sh.n_global + w - 1);
+            PFP_LAUNCHED(ctx);
+        }
+        PhraseArrays ph{};
+        ph.ends = ends;
+        PFP_TRY(pfp_alloc_t(ctx, &ph.fpa, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.fpb, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.key, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.len, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
+        if (o.flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
+        TextView tv{sh.d_buf, sh.n_buf, (i64)sh.buf_pos0, (i64)sh.n_global};
+        PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, first_start, w));
+        DictArrays D;
+        PFP_TRY(pfp_dedup_stage(ctx, ph, P, &D));
+        u64 *wfpa = nullptr, *wfpb = nullptr;
+        PFP_TRY(pfp_alloc_t(ctx, &wfpa, D.d));
+        PFP_TRY(pfp_alloc_t(ctx, &wfpb, D.d));
+        PFP_TRY(pfp_gather_word_fp(ctx, D, ph, wfpa, wfpb));
+        PFP_TRY(pfp_free_now(ctx, ph.fpa));
+        PFP_TRY(pfp_free_now(ctx, ph.fpb));
+        PFP_TRY(pfp_free_now(ctx, ph.key));
+        PFP_TRY(pfp_pool_stage(ctx, tv, ends, first_start, w, &D));
+        PFP_TRY(pfp_free_now(ctx, ph.len));
+        PFP_TRY(pfp_free_now(ctx, D.rep));
+        PFP_TRY(pfp_free_now(ctx, D.uoff));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PFP_CUDA(ctx, cudaGetLastError());
+        ctx->sh.d = D.d;
+        ctx->sh.uid = D.uid;
+        out->n_words = D.d; out->n_phrases = P; out->pool_words = D.pool_words;
+        out->fpa = wfpa; out->fpb = wfpb; out->len = D.ulen; out->count = D.count;
+        out->uwords = D.uwords; out->pool = D.pool; out->last = ph.last; out->sai = ph.sai;
+        return PFPB200_OK;
+    };
+    int rc = run();
+    float t = tm.stop();
+    if (rc != PFPB200_OK) { pfp_release_scratch(ctx); return rc; }
+    promote_scratch(ctx);
+    if (ms) *ms = t;
+    return PFPB200_OK;
+}
+
+extern "C" int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_t *fpa, const uint64_t *fpb,
+                                  const uint32_t *len, const uint32_t *count, const uint32_t *uwords,
+                                  const uint64_t *pool, uint64_t pool_words, uint32_t w, uint32_t flags,
+                                  pfpb200_merged *out, float *ms) {
+    if (!ctx || !out) return PFPB200_E_ARG;
+    memset(out, 0, sizeof(*out));
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, PFP_FLAG_SLOTS * sizeof(u64), ctx->stream));
+    CallTimer tm(ctx->stream);
+    auto run = [&]() -> int {
+        if (n_in == 0) {
+            u8 *dict = nullptr;
+            PFP_TRY(pfp_alloc_t(ctx, &dict, 1, true));
+            PFP_CUDA(ctx, cudaMemsetAsync(dict, 0, 1, ctx->stream));
+            out->dict = dict; out->dict_bytes = 1;
+            return PFPB200_OK;
+        }
+        DictArrays D;
+        u32 *uid_of_entry = nullptr;
+        PFP_TRY(pfp_merge_stage(ctx, n_in, fpa, fpb, len, count, uwords, pool, pool_words, &D, &uid_of_entry));
+        u32 *order = nullptr, rounds = 0;
+        PFP_TRY(pfp_rank_stage(ctx, D, &order, &rounds));
+        u8 *dict = nullptr;
+        u32 *occ = nullptr, *rank_of_uid = nullptr, *rank_of_entry = nullptr;
+        u64 dict_bytes = 0;
+        PFP_TRY(pfp_dict_stage(ctx, D, order, (flags & PFPB200_F_COMPRESS) ? w : 0, &dict, &dict_bytes, &occ,
+                               &rank_of_uid));
+        PFP_TRY(pfp_alloc_t(ctx, &rank_of_entry, n_in, true));
+        PFP_TRY(pfp_remap_stage(ctx, uid_of_entry, rank_of_uid, n_in, rank_of_entry));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PFP_CUDA(ctx, cudaGetLastError());
+        out->n_distinct = D.d; out->dict_bytes = dict_bytes; out->sum_word_len = D.sum_len;
+        out->dict = dict; out->occ = occ; out->rank_of_entry = rank_of_entry;
+        return PFPB200_OK;
+    };
+    int rc = run();
+    float t = tm.stop();
+    pfp_release_scratch(ctx);
+    if (ms) *ms = t;
+    return rc;
+}
+
+extern "C" int pfpb200_shard_remap(pfpb200_ctx *ctx, const uint32_t *d_rank_of_word, const uint32_t **d_parse,
+                                   float *ms) {
+    if (!ctx || !d_parse) return PFPB200_E_ARG;
+    *d_parse = nullptr;
+    if (ms) *ms = 0;
+    const u64 P = ctx->sh.P;
+    if (P == 0) return PFPB200_OK;
+    if (!d_rank_of_word || !ctx->sh.uid) return pfp_fail(ctx, PFPB200_E_ARG, "shard_remap before shard_words");
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    CallTimer tm(ctx->stream);
+    u32 *parse = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &parse, P, true));
+    PFP_TRY(pfp_remap_stage(ctx, ctx->sh.uid, d_rank_of_word, P, parse));
+    float t = tm.stop();
+    PFP_CUDA(ctx, cudaGetLastError());
+    *d_parse = parse;
+    if (ms) *ms = t;
     return PFPB200_OK;
 }

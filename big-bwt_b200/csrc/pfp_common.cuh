@@ -41,8 +41,14 @@ struct pfpb200_ctx {
     u32 *d_keys = nullptr;         // NH key table (phrase fingerprints)
     u64 *d_flags = nullptr;        // [0] error bits, [1..] counters read back by the host
     u64 *h_flags = nullptr;        // pinned mirror
-    // scan-stage result kept for pfpb200_scan_triggers callers
-    u64 *trig_hold = nullptr;
+    // state carried between the pfpb200_shard_* calls of one sharded parse
+    struct {
+        pfpb200_shard desc;
+        pfpb200_opts opts;
+        u64 *ends = nullptr;
+        u64 n_trig = 0, P = 0, d = 0;
+        u32 *uid = nullptr;
+    } sh;
 };
 
 #define PFP_FLAG_SLOTS 16

@@ -402,3 +402,135 @@ int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 fi
     PFP_LAUNCHED(ctx);
     return PFPB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// dictionary merge: words (fingerprint, length, count, pool bytes) coming from several shards
+// ------------------------------------------------------------------------------------------
+__global__ void merge_keys_k(const u64 *__restrict__ fpa, const u64 *__restrict__ fpb,
+                             const u32 *__restrict__ len, u64 n, u64 *__restrict__ keys,
+                             u32 *__restrict__ vals) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = sort_key_of(fpa[i], fpb[i], len[i]);
+    vals[i] = (u32)i;
+}
+
+// occurrences of a merged word = sum over the entries of its run; plus the per-word tables
+__global__ void merge_words_k(const u32 *__restrict__ headpos, const u32 *__restrict__ sidx,
+                              const u32 *__restrict__ rep, const u32 *__restrict__ count_in,
+                              const u32 *__restrict__ len_in, const u32 *__restrict__ uwords_in,
+                              const u64 *__restrict__ in_off, u64 d, u64 n,
+                              u32 *__restrict__ count, u32 *__restrict__ ulen,
+                              u32 *__restrict__ uwords, u64 *__restrict__ uoff,
+                              u64 *__restrict__ flags) {
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 L = 0;
+    if (u < d) {
+        u32 a = headpos[u], b = (u + 1 < d) ? headpos[u + 1] : (u32)n;
+        u64 c = 0;
+        for (u32 q = a; q < b; q++) c += count_in[sidx[q]];
+        if (c > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);   // :277-281
+        count[u] = (u32)c;
+        u32 r = rep[u];
+        L = len_in[r];
+        ulen[u] = L;
+        uwords[u] = uwords_in[r];
+        uoff[u] = in_off[r];
+    }
+    u32 mx = L;
+    u64 sum = L;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && sum) {
+        atomicMax((unsigned long long *)&flags[2], (unsigned long long)mx);
+        atomicAdd((unsigned long long *)&flags[3], (unsigned long long)sum);
+    }
+}
+
+// per-word fingerprints of a shard's local dictionary (what a shard exports)
+__global__ void gather_word_fp_k(const u32 *__restrict__ rep, const u64 *__restrict__ fpa,
+                                 const u64 *__restrict__ fpb, u64 d, u64 *__restrict__ wfpa,
+                                 u64 *__restrict__ wfpb) {
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= d) return;
+    u32 j = rep[u];
+    wfpa[u] = fpa[j];
+    wfpb[u] = fpb[j];
+}
+
+int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays &ph, u64 *wfpa,
+                       u64 *wfpb) {
+    gather_word_fp_k<<<pfp_blocks(D.d, 256), 256, 0, ctx->stream>>>(D.rep, ph.fpa, ph.fpb, D.d, wfpa, wfpb);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
+// Merges n input words into the distinct set D (uid order = fingerprint-key order);
+// uid_of_entry[i] = merged word of input entry i.  Two synchronisations.
+int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, const u32 *len,
+                    const u32 *count_in, const u32 *uwords_in, const u64 *pool, u64 pool_words,
+                    DictArrays *D, u32 **uid_of_entry) {
+    const int TB = 256;
+    if (n >= 0xFFFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "too many words to merge");
+    u64 *k0 = nullptr, *k1 = nullptr, *sk = nullptr, *in_off = nullptr;
+    u32 *v0 = nullptr, *v1 = nullptr, *sv = nullptr, *hscan = nullptr, *headpos = nullptr;
+    u8 *head = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &k0, n));
+    PFP_TRY(pfp_alloc_t(ctx, &k1, n));
+    PFP_TRY(pfp_alloc_t(ctx, &v0, n));
+    PFP_TRY(pfp_alloc_t(ctx, &v1, n));
+    PFP_TRY(pfp_alloc_t(ctx, &head, n));
+    PFP_TRY(pfp_alloc_t(ctx, &hscan, n));
+    PFP_TRY(pfp_alloc_t(ctx, &in_off, n));
+    merge_keys_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(fpa, fpb, len, n, k0, v0);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, n, 0, 64, &sk, &sv));
+    PhraseArrays view{};
+    view.fpa = const_cast<u64 *>(fpa);
+    view.fpb = const_cast<u64 *>(fpb);
+    view.len = const_cast<u32 *>(len);
+    mark_heads_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(sk, sv, n, view, head, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
+    PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, head, hscan, n, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
+    PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, uwords_in, in_off, n, nullptr));
+    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(u64), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
+        return pfp_fail(ctx, PFPB200_E_COLLISION, "fingerprint collision between different phrases");
+    u64 d = (u32)ctx->h_flags[1];
+    if (d > 0x7FFFFFFEull)
+        return pfp_fail(ctx, PFPB200_E_LIMIT, "%llu distinct words exceed the limit 2^31-2",
+                        (unsigned long long)d);
+    D->d = d;
+    D->pool = const_cast<u64 *>(pool);
+    D->pool_words = pool_words;
+    PFP_TRY(pfp_alloc_t(ctx, uid_of_entry, n));
+    PFP_TRY(pfp_alloc_t(ctx, &D->rep, d));
+    PFP_TRY(pfp_alloc_t(ctx, &headpos, d));
+    PFP_TRY(pfp_alloc_t(ctx, &D->count, d));
+    PFP_TRY(pfp_alloc_t(ctx, &D->ulen, d));
+    PFP_TRY(pfp_alloc_t(ctx, &D->uwords, d));
+    PFP_TRY(pfp_alloc_t(ctx, &D->uoff, d));
+    D->uid = *uid_of_entry;
+    assign_uid_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(sv, head, hscan, n, *uid_of_entry, D->rep, headpos);
+    PFP_LAUNCHED(ctx);
+    merge_words_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(headpos, sv, D->rep, count_in, len, uwords_in,
+                                                             in_off, d, n, D->count, D->ulen, D->uwords,
+                                                             D->uoff, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(u64), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
+        return pfp_fail(ctx, PFPB200_E_LIMIT, "a word occurs more than 2^32-1 times");
+    D->max_len = (u32)ctx->h_flags[2];
+    D->sum_len = ctx->h_flags[3];
+    void *fr[] = {k0, k1, v0, v1, head, hscan, in_off, headpos};
+    for (void *q : fr) PFP_TRY(pfp_free_now(ctx, q));
+    return PFPB200_OK;
+}

@@ -65,3 +65,10 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
 int pfp_dict_stage(pfpb200_ctx *ctx, const DictArrays &D, const u32 *order, u32 strip_w,
                    u8 **dict, u64 *dict_bytes, u32 **occ, u32 **rank_of_uid);
 int pfp_remap_stage(pfpb200_ctx *ctx, const u32 *uid, const u32 *rank_of_uid, u64 P, u32 *parse);
+
+// ---- sharded parsing building blocks ------------------------------------------------------------------------
+int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays &ph, u64 *wfpa,
+                       u64 *wfpb);
+int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, const u32 *len,
+                    const u32 *count_in, const u32 *uwords_in, const u64 *pool, u64 pool_words,
+                    DictArrays *D, u32 **uid_of_entry);

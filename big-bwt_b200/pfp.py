@@ -76,7 +76,9 @@ _lib = None
 
 SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_parse_device",
            "pfpb200_parse_host", "pfpb200_parse_file", "pfpb200_fasta_extract",
-           "pfpb200_scan_triggers", "pfpb200_memcpy_d2h", "pfpb200_strerror", "pfpb200_last_error", "pfpb200_abi_version"]
+           "pfpb200_scan_triggers", "pfpb200_memcpy_d2h", "pfpb200_strerror",
+           "pfpb200_shard_scan", "pfpb200_shard_words", "pfpb200_dict_merge", "pfpb200_shard_remap",
+           "pfpb200_launch_count", "pfpb200_last_error", "pfpb200_abi_version"]
 
 
 def load_library():
@@ -112,6 +114,8 @@ def load_library():
     L.pfpb200_last_error.argtypes = [vp]
     L.pfpb200_last_error.restype = C.c_char_p
     L.pfpb200_abi_version.restype = C.c_int
+    L.pfpb200_launch_count.argtypes = [vp]
+    L.pfpb200_launch_count.restype = C.c_uint32
     _lib = L
     return L
 

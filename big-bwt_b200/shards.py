@@ -1,61 +1,379 @@
 """Sharded prefix-free parsing: one process per GPU, the text split into contiguous shards.
 
-World size 1 is the plain single-GPU parser.  (Multi-GPU: see ShardedParser docstring.)
+Reference analogue: the per-thread input ranges of pscan.hpp:114-165 / newscan.hpp:230-337 and
+the shared dictionary of pscan.cpp:137-205.  Protocol of one parse (rank g, G ranks):
+
+  1. halo     : rank g>0 receives the last HALO bytes of shard g-1 (>= w: w-1 for the window
+                that ends at its first position, 1 for that phrase's `.last` byte)
+  2. scan     : K1 on [halo|shard]; the rank owns the triggers whose END lies in its shard, with
+                the sequential first-window rule (e >= w-1), so the union over ranks is exactly
+                the sequential scanner's trigger set
+  3. seams    : all-gather of (trigger count, last trigger).  The first phrase ending in shard g
+                starts at (last trigger of any lower rank) - w + 1; if that lies before the halo,
+                the missing head bytes are fetched peer to peer from the ranks that own them
+  4. words    : K2 + K3 on the shard -> local dictionary (fingerprint, length, count, pool bytes),
+                `.last`/`.sai` of the shard
+  5. merge    : mode "replicate": all-gather of the local dictionaries, every rank runs the global
+                dedup + ranking (identical `.dict/.occ` everywhere).
+                mode "partition": words are routed to the rank owning their lexicographic range
+                (splitters from an all-gathered sample of first keys; identical words share a
+                range, so one all-to-all serves dedup AND ranking); each owner dedups and ranks
+                its range; global rank = local rank + number of distinct words in lower ranges;
+                ranks travel back with a second all-to-all.  `.dict/.occ` are the per-rank pieces
+                in rank order.
+  6. remap    : `.parse` of the shard from the global rank of each local word (K5)
+
+World size 1 short-circuits to the single-GPU parser.  The collectives are torch.distributed
+(NCCL on GPUs; the same code runs over gloo with the CPU mock backend of tests/).
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
+import torch
 
 from . import pfp
 
+HALO = 4096
+FRONT = 1 << 20
 
-class ShardedParser:
-    """Holds this rank's shard of the text in HBM and parses the whole text cooperatively.
 
-    Reference analogue: the per-thread input ranges of pscan.hpp:114-165 / newscan.hpp:230-337.
-    """
+# ------------------------------------------------------------------------------------------------
+# pure planning helpers (unit-tested on CPU)
+# ------------------------------------------------------------------------------------------------
+def first_phrase_start(rank: int, n_trig: list[int], last_trig: list[int], w: int) -> int:
+    """Global start of the first phrase that ends in shard `rank`: previous trigger - w + 1, or -1
+    (the virtual 0x02 in front of the text) when no lower rank has a trigger."""
+    for q in range(rank - 1, -1, -1):
+        if n_trig[q] > 0:
+            return last_trig[q] - w + 1
+    return -1
 
-    def __init__(self, device: int, world: int = 1, rank: int = 0):
-        self.device, self.world, self.rank = device, world, rank
+
+def head_requests(pos0: list[int], n_local: list[int], n_trig: list[int], last_trig: list[int],
+                  w: int, halo: int) -> list[tuple[int, int]]:
+    """For every rank the global byte range [a, b) it still needs in front of its halo (a == b:
+    nothing).  A rank without phrases (no trigger and not last) needs nothing."""
+    G = len(pos0)
+    out = []
+    for g in range(G):
+        has_phrase = n_trig[g] > 0 or g == G - 1
+        have_from = max(0, pos0[g] - halo)
+        a = b = have_from
+        if g > 0 and has_phrase:
+            fs = max(0, first_phrase_start(g, n_trig, last_trig, w))
+            if fs < have_from:
+                a = fs
+        out.append((a, b))
+    return out
+
+
+def transfers(requests: list[tuple[int, int]], pos0: list[int], n_local: list[int]):
+    """(src, dst, global_lo, global_hi) copies that satisfy the requests from the owning shards."""
+    ops = []
+    for dst, (a, b) in enumerate(requests):
+        if a >= b:
+            continue
+        for src in range(len(pos0)):
+            lo, hi = max(a, pos0[src]), min(b, pos0[src] + n_local[src])
+            if lo < hi:
+                ops.append((src, dst, lo, hi))
+    return ops
+
+
+class _DevView:
+    """Zero-copy torch view of library-owned device memory."""
+
+    def __init__(self, ptr, nbytes, typestr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+_TYPES = {torch.uint8: ("|u1", 1), torch.int32: ("<i4", 4), torch.int64: ("<i8", 8)}
+
+
+def dev_tensor(ptr, count, dtype, device):
+    if not ptr or count == 0:
+        return torch.empty(0, dtype=dtype, device=device)
+    ts, sz = _TYPES[dtype]
+    return torch.as_tensor(_DevView(ptr, count * sz, ts, count), device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU backend: the stage-level C ABI on torch tensors
+# ------------------------------------------------------------------------------------------------
+class CudaBackend:
+    def __init__(self, device: int):
         self.scanner = pfp.Scanner(device)
-        self.text = None
-        self.n_local = 0
-        self.n_global = 0
-        self.out = None
+        self.L, self.h = self.scanner.L, self.scanner.h
+        self.dev = torch.device("cuda", device)
+        self._declare()
+        self.ms = {}
 
+    def _declare(self):
+        L = self.L
+        vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+        L.pfpb200_shard_scan.argtypes = [vp, C.POINTER(Shard), C.POINTER(pfp.Opts), C.POINTER(u64),
+                                         C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float)]
+        L.pfpb200_shard_words.argtypes = [vp, C.c_int64, C.POINTER(Words), C.POINTER(C.c_float)]
+        L.pfpb200_dict_merge.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, u64, u32, u32,
+                                         C.POINTER(Merged), C.POINTER(C.c_float)]
+        L.pfpb200_shard_remap.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_float)]
+        for f in (L.pfpb200_shard_scan, L.pfpb200_shard_words, L.pfpb200_dict_merge, L.pfpb200_shard_remap):
+            f.restype = C.c_int
+
+    def shard_scan(self, buf, buf_pos0, own_lo, own_hi, n_global, is_last, w, p, sai):
+        sh = Shard(buf.data_ptr(), buf.numel(), buf_pos0, own_lo, own_hi, n_global, 1 if is_last else 0, 0)
+        o = pfp.Opts(w, p, pfp.F_SAI if sai else 0, 0)
+        n, first, last, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_float()
+        self.scanner._check(self.L.pfpb200_shard_scan(self.h, C.byref(sh), C.byref(o), C.byref(n),
+                                                      C.byref(first), C.byref(last), C.byref(ms)))
+        self.ms["scan"] = ms.value
+        return n.value, first.value, last.value
+
+    def shard_words(self, first_start):
+        wd, ms = Words(), C.c_float()
+        self.scanner._check(self.L.pfpb200_shard_words(self.h, first_start, C.byref(wd), C.byref(ms)))
+        self.ms["words"] = ms.value
+        d, dev = wd.n_words, self.dev
+        return {"n_words": d, "n_phrases": wd.n_phrases,
+                "fpa": dev_tensor(wd.fpa, d, torch.int64, dev), "fpb": dev_tensor(wd.fpb, d, torch.int64, dev),
+                "len": dev_tensor(wd.len, d, torch.int32, dev), "count": dev_tensor(wd.count, d, torch.int32, dev),
+                "uwords": dev_tensor(wd.uwords, d, torch.int32, dev),
+                "pool": dev_tensor(wd.pool, wd.pool_words, torch.int64, dev),
+                "last": dev_tensor(wd.last, wd.n_phrases, torch.uint8, dev),
+                "sai": dev_tensor(wd.sai, 5 * wd.n_phrases if wd.sai else 0, torch.uint8, dev)}
+
+    def dict_merge(self, fpa, fpb, ln, count, uwords, pool, w, compress=False):
+        m, ms = Merged(), C.c_float()
+        self.scanner._check(self.L.pfpb200_dict_merge(
+            self.h, fpa.numel(), fpa.data_ptr(), fpb.data_ptr(), ln.data_ptr(), count.data_ptr(),
+            uwords.data_ptr(), pool.data_ptr(), pool.numel(), w, pfp.F_COMPRESS if compress else 0,
+            C.byref(m), C.byref(ms)))
+        self.ms["merge"] = ms.value
+        dev = self.dev
+        return {"n_distinct": m.n_distinct, "sum_word_len": m.sum_word_len,
+                "dict": dev_tensor(m.dict, m.dict_bytes, torch.uint8, dev),
+                "occ": dev_tensor(m.occ, m.n_distinct, torch.int32, dev),
+                "rank_of_entry": dev_tensor(m.rank_of_entry, fpa.numel(), torch.int32, dev)}
+
+    def shard_remap(self, rank_of_word, n_phrases):
+        out, ms = C.c_void_p(), C.c_float()
+        self.scanner._check(self.L.pfpb200_shard_remap(self.h, rank_of_word.data_ptr(), C.byref(out), C.byref(ms)))
+        self.ms["remap"] = ms.value
+        return dev_tensor(out.value, n_phrases, torch.int32, self.dev)
+
+
+class Shard(C.Structure):
+    _fields_ = [("d_buf", C.c_void_p), ("n_buf", C.c_uint64), ("buf_pos0", C.c_uint64),
+                ("own_lo", C.c_uint64), ("own_hi", C.c_uint64), ("n_global", C.c_uint64),
+                ("is_last", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Words(C.Structure):
+    _fields_ = [("n_words", C.c_uint64), ("n_phrases", C.c_uint64), ("pool_words", C.c_uint64),
+                ("fpa", C.c_void_p), ("fpb", C.c_void_p), ("len", C.c_void_p), ("count", C.c_void_p),
+                ("uwords", C.c_void_p), ("pool", C.c_void_p), ("last", C.c_void_p), ("sai", C.c_void_p)]
+
+
+class Merged(C.Structure):
+    _fields_ = [("n_distinct", C.c_uint64), ("dict_bytes", C.c_uint64), ("sum_word_len", C.c_uint64),
+                ("dict", C.c_void_p), ("occ", C.c_void_p), ("rank_of_entry", C.c_void_p)]
+
+
+# ------------------------------------------------------------------------------------------------
+# the sharded parser
+# ------------------------------------------------------------------------------------------------
+class ShardedParser:
+    """Holds this rank's shard of the text and parses the whole text with the other ranks."""
+
+    def __init__(self, device: int | None, world: int = 1, rank: int = 0, backend=None, mode="replicate",
+                 halo: int = HALO, front: int = FRONT):
+        self.world, self.rank, self.mode = world, rank, mode
+        self.halo, self.front_cap = halo, front
+        self.backend = backend if backend is not None else CudaBackend(device)
+        self.scanner = getattr(self.backend, "scanner", None)
+        self.buf = None
+        self.n_local = self.n_global = self.pos0 = 0
+        self.result = None
+
+    # -- collectives --------------------------------------------------------------------------------
+    def _all_gather_i64(self, vals):
+        import torch.distributed as dist
+        t = torch.tensor(vals, dtype=torch.int64, device=self.buf.device)
+        out = torch.empty(self.world * len(vals), dtype=torch.int64, device=self.buf.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.view(self.world, len(vals)).tolist()
+
+    def _all_gather_v(self, t, counts):
+        """Concatenation over ranks of 1-D tensors of different lengths (padded all-gather)."""
+        import torch.distributed as dist
+        mx = max(counts) if counts else 0
+        if mx == 0:
+            return torch.empty(0, dtype=t.dtype, device=t.device)
+        send = t
+        if t.numel() != mx:
+            send = torch.empty(mx, dtype=t.dtype, device=t.device)
+            send[:t.numel()] = t
+        out = torch.empty(self.world * mx, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, send.contiguous())
+        if all(c == mx for c in counts):
+            return out
+        return torch.cat([out[q * mx:q * mx + c] for q, c in enumerate(counts)])
+
+    def _p2p(self, ops):
+        """ops: (src, dst, global_lo, global_hi) byte ranges; executes this rank's part."""
+        import torch.distributed as dist
+        todo = []
+        for src, dst, lo, hi in ops:
+            if src == dst:
+                continue
+            if self.rank == src:
+                a = self.front + (lo - self.pos0)
+                todo.append(dist.P2POp(dist.isend, self.buf[a:a + (hi - lo)], dst))
+            elif self.rank == dst:
+                a = self.front - (self.pos0 - lo)
+                if a < 0:
+                    raise RuntimeError(f"a phrase straddling into shard {dst} starts {self.pos0 - lo} bytes "
+                                       f"before it: more than the {self.front} bytes reserved")
+                todo.append(dist.P2POp(dist.irecv, self.buf[a:a + (hi - lo)], src))
+        if todo:
+            for r in dist.batch_isend_irecv(todo):
+                r.wait()
+
+    # -- text ------------------------------------------------------------------------------------------
     def set_text(self, text):
-        """text: CUDA uint8 tensor with this rank's contiguous shard of the global text."""
-        self.text = text
+        """text: this rank's contiguous shard (uint8 tensor on the compute device)."""
         self.n_local = int(text.numel())
+        dev = text.device
         if self.world == 1:
-            self.n_global = self.n_local
-        else:
-            import torch
-            import torch.distributed as dist
-            sizes = torch.zeros(self.world, dtype=torch.int64, device=text.device)
-            sizes[self.rank] = self.n_local
-            dist.all_reduce(sizes)
-            self.sizes = [int(x) for x in sizes.tolist()]
-            self.n_global = sum(self.sizes)
-            self.pos0 = sum(self.sizes[:self.rank])
+            self.buf, self.front = text, 0
+            self.n_global, self.pos0 = self.n_local, 0
+            self.sizes = [self.n_local]
+            return
+        import torch.distributed as dist
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        sizes[self.rank] = self.n_local
+        dist.all_reduce(sizes)
+        self.sizes = [int(x) for x in sizes.tolist()]
+        self.n_global = sum(self.sizes)
+        self.starts = [sum(self.sizes[:q]) for q in range(self.world)]
+        self.pos0 = self.starts[self.rank]
+        self.front = min(self.front_cap, self.pos0)
+        self.buf = torch.empty(self.front + self.n_local, dtype=torch.uint8, device=dev)
+        self.buf[self.front:].copy_(text)
 
     def release_text(self):
-        self.text = None
+        self.buf = None
 
-    def parse_device(self, w=10, p=100, sai=True) -> dict:
-        if self.world != 1:
-            raise NotImplementedError("multi-GPU parse not wired yet")
-        self.out = self.scanner.parse_device(self.text, w, p, sai=sai)
-        return self.scanner.stats.as_dict()
+    # -- parse --------------------------------------------------------------------------------------------
+    def parse_device(self, w=10, p=100, sai=True, compress=False) -> dict:
+        if self.world == 1 and self.scanner is not None:
+            self.out = self.scanner.parse_device(self.buf, w, p, sai=sai, compress=compress)
+            return self.scanner.stats.as_dict()
+        return self._parse_sharded(w, p, sai, compress)
 
     def parse_host(self, host_text, w=10, p=100, sai=True) -> dict:
-        """host_text: pinned CPU uint8 tensor (this rank's shard)."""
-        if self.world != 1:
-            raise NotImplementedError("multi-GPU parse not wired yet")
-        out = self.scanner.parse_host_ptr(host_text.data_ptr(), host_text.numel(), w, p, sai=sai)
-        st = self.scanner.stats.as_dict()
-        P, d = out.n_phrases, out.n_distinct
-        st["h2d_bytes"] = int(st["n_text"])
-        st["d2h_bytes"] = int(out.dict_bytes + 4 * d + 4 * P + P + (5 * P if sai else 0))
-        self.host_out = out
+        """host_text: pinned CPU uint8 tensor holding this rank's shard."""
+        if self.world == 1:
+            out = self.scanner.parse_host_ptr(host_text.data_ptr(), host_text.numel(), w, p, sai=sai)
+            st = self.scanner.stats.as_dict()
+            P, d = out.n_phrases, out.n_distinct
+            st["h2d_bytes"] = int(st["n_text"])
+            st["d2h_bytes"] = int(out.dict_bytes + 4 * d + 4 * P + P + (5 * P if sai else 0))
+            self.host_out = out
+            return st
+        # sharded: H2D of the shard, cooperative parse, D2H of this rank's output pieces
+        dev = self.backend.dev
+        if self.buf is None or self.buf.numel() != self.front + host_text.numel():
+            self.set_text(torch.empty(host_text.numel(), dtype=torch.uint8, device=dev))
+        self.buf[self.front:].copy_(host_text, non_blocking=True)
+        st = self._parse_sharded(w, p, sai, False)
+        r = self.result
+        outs = [r["parse"], r["last"], r["sai"]]
+        if self.mode == "partition" or self.rank == 0:
+            outs += [r["dict"], r["occ"]]
+        self.host_pieces = [t.cpu() for t in outs]
+        st["h2d_bytes"] = int(host_text.numel())
+        st["d2h_bytes"] = int(sum(t.numel() * t.element_size() for t in outs))
         return st
+
+    def _parse_sharded(self, w, p, sai, compress) -> dict:
+        be, G, g = self.backend, self.world, self.rank
+        if w > self.halo:
+            raise ValueError("window larger than the shard halo")
+        if min(self.sizes[:-1]) < self.halo:
+            raise ValueError("shards must be at least HALO bytes long")
+        # 1. halo
+        halo_reqs = [(max(0, self.starts[q] - self.halo), self.starts[q]) for q in range(G)]
+        self._p2p(transfers(halo_reqs, self.starts, self.sizes))
+        # 2. scan
+        n_trig, first, last = be.shard_scan(self.buf, self.pos0 - self.front, self.pos0,
+                                            self.pos0 + self.n_local, self.n_global, g == G - 1, w, p, sai)
+        # 3. seams
+        info = self._all_gather_i64([n_trig, last])
+        nts, lasts = [r[0] for r in info], [r[1] for r in info]
+        self._p2p(transfers(head_requests(self.starts, self.sizes, nts, lasts, w, self.halo),
+                            self.starts, self.sizes))
+        fs = first_phrase_start(g, nts, lasts, w)
+        # 4. words
+        wd = be.shard_words(fs)
+        # 5. merge
+        if self.mode == "replicate":
+            res = self._merge_replicated(wd, w, compress)
+        else:
+            res = self._merge_partitioned(wd, w, compress)
+        # 6. remap
+        parse = be.shard_remap(res["rank_of_word"], wd["n_phrases"])
+        self.result = {"dict": res["dict"], "occ": res["occ"], "parse": parse, "last": wd["last"],
+                       "sai": wd["sai"], "n_distinct": res["n_distinct"], "dict_offset": res.get("dict_offset", 0)}
+        tot = self._all_gather_i64([wd["n_phrases"], res["n_distinct_local"], res["dict_bytes_local"],
+                                    res["sum_len_local"]])
+        P = sum(r[0] for r in tot)
+        d = sum(r[1] for r in tot) if self.mode == "partition" else res["n_distinct"]
+        db = sum(r[2] for r in tot) if self.mode == "partition" else res["dict_bytes_local"]
+        sl = sum(r[3] for r in tot) if self.mode == "partition" else res["sum_len_local"]
+        ms = dict(getattr(be, "ms", {}))
+        st = {"n_text": self.n_global, "n_phrases": P, "n_distinct": d, "dict_bytes": db, "sum_word_len": sl,
+              "alg_bytes": self.n_global + 4 * P + P + (5 * P if sai else 0) + db + 4 * d,
+              "rank_rounds": 0,
+              "launches": int(be.L.pfpb200_launch_count(be.h)) if hasattr(be, "L") else 0,
+              "ms_scan": ms.get("scan", 0.0), "ms_hash": ms.get("words", 0.0), "ms_rank": ms.get("merge", 0.0),
+              "ms_remap": ms.get("remap", 0.0)}
+        return st
+
+    def _merge_replicated(self, wd, w, compress):
+        be, G, g = self.backend, self.world, self.rank
+        sizes = self._all_gather_i64([wd["n_words"], wd["pool"].numel()])
+        nw, npool = [r[0] for r in sizes], [r[1] for r in sizes]
+        cat = {k: self._all_gather_v(wd[k], nw) for k in ("fpa", "fpb", "len", "count", "uwords")}
+        pool = self._all_gather_v(wd["pool"], npool)
+        m = be.dict_merge(cat["fpa"], cat["fpb"], cat["len"], cat["count"], cat["uwords"], pool, w, compress)
+        base = sum(nw[:g])
+        return {"dict": m["dict"], "occ": m["occ"], "n_distinct": m["n_distinct"],
+                "rank_of_word": m["rank_of_entry"][base:base + nw[g]].contiguous(),
+                "n_distinct_local": m["n_distinct"], "dict_bytes_local": int(m["dict"].numel()),
+                "sum_len_local": m["sum_word_len"]}
+
+    def _merge_partitioned(self, wd, w, compress):
+        raise NotImplementedError("partitioned dictionary merge: next step")
+
+    # -- results ----------------------------------------------------------------------------------------------
+    def gather_files(self):
+        """All five streams of the whole text as bytes on every rank (tests / small inputs)."""
+        import torch.distributed as dist
+        r = self.result
+
+        def cat_over_ranks(t):
+            t = t.contiguous().view(torch.uint8) if t.dtype != torch.uint8 else t.contiguous()
+            n = self._all_gather_i64([t.numel()])
+            return bytes(self._all_gather_v(t, [x[0] for x in n]).cpu().numpy().tobytes())
+        out = {k: cat_over_ranks(r[k]) for k in ("parse", "last", "sai")}
+        if self.mode == "partition":
+            out["dict"] = cat_over_ranks(r["dict"])
+            out["occ"] = cat_over_ranks(r["occ"])
+        else:
+            out["dict"] = bytes(r["dict"].cpu().numpy().tobytes())
+            out["occ"] = bytes(r["occ"].contiguous().view(torch.uint8).cpu().numpy().tobytes())
+        return out

@@ -129,6 +129,58 @@ int pfpb200_scan_triggers(pfpb200_ctx *ctx, const uint8_t *d_buf, uint64_t n_buf
                           uint32_t w, uint32_t p, const uint64_t **d_triggers,
                           uint64_t *n_triggers, float *ms);
 
+/* ---- sharded parsing: the building blocks big-bwt_b200/shards.py drives, one process per GPU ---- *
+ * Reference analogue: the per-thread input ranges of pscan.hpp:114-165 / newscan.hpp:230-337 and
+ * the shared dictionary of pscan.cpp:137-205, with NCCL collectives between the calls.
+ *   1. pfpb200_shard_scan   : triggers owned by this shard (needs w bytes of left halo in d_buf)
+ *   2. (all-gather of last triggers -> first_start; fetch of the straddling phrase's head bytes)
+ *   3. pfpb200_shard_words  : phrase records + this shard's local dictionary (words, counts, pool)
+ *   4. (exchange of words)  -> pfpb200_dict_merge : global dedup + lexicographic ranks + .dict/.occ
+ *   5. pfpb200_shard_remap  : .parse of the shard from the global rank of each local word        */
+typedef struct pfpb200_shard {
+    const uint8_t *d_buf;   /* device buffer: halo/head bytes followed by the shard              */
+    uint64_t n_buf;         /* bytes in d_buf                                                     */
+    uint64_t buf_pos0;      /* global text position of d_buf[0]                                   */
+    uint64_t own_lo, own_hi;/* this shard owns the phrases whose END position e is in [lo, hi)    */
+    uint64_t n_global;      /* length of the whole text                                           */
+    uint32_t is_last;       /* 1: also emit the final phrase ending in the virtual 0x02^w         */
+    uint32_t reserved;
+} pfpb200_shard;
+
+typedef struct pfpb200_words {      /* a shard's local dictionary, device pointers               */
+    uint64_t n_words, n_phrases, pool_words;
+    const uint64_t *fpa, *fpb;      /* 128-bit fingerprint of each word                          */
+    const uint32_t *len, *count;    /* length in bytes, occurrences in this shard                */
+    const uint32_t *uwords;         /* length in 8-byte pool words                               */
+    const uint64_t *pool;           /* the words back to back, zero padded to 8 bytes            */
+    const uint8_t *last, *sai;      /* this shard's .last / .sai streams                         */
+} pfpb200_words;
+
+typedef struct pfpb200_merged {
+    uint64_t n_distinct, dict_bytes;
+    uint64_t sum_word_len;
+    const uint8_t *dict;            /* words in rank order + 0x01 each (+ final 0x00, counted)   */
+    const uint32_t *occ;
+    const uint32_t *rank_of_entry;  /* 1-based rank, inside this merge, of every input entry     */
+} pfpb200_merged;
+
+int pfpb200_shard_scan(pfpb200_ctx *ctx, const pfpb200_shard *shard, const pfpb200_opts *opts,
+                       uint64_t *n_triggers, uint64_t *first_trigger, uint64_t *last_trigger,
+                       float *ms);
+/* first_start: global position of the first byte of the first phrase ending in this shard
+ * (previous trigger - w + 1), or -1 when that phrase starts at the beginning of the text. */
+int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb200_words *out, float *ms);
+int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_t *fpa, const uint64_t *fpb,
+                       const uint32_t *len, const uint32_t *count, const uint32_t *uwords,
+                       const uint64_t *pool, uint64_t pool_words, uint32_t w, uint32_t flags,
+                       pfpb200_merged *out, float *ms);
+int pfpb200_shard_remap(pfpb200_ctx *ctx, const uint32_t *d_rank_of_word, const uint32_t **d_parse,
+                        float *ms);
+
+/* Kernels launched on this context since the start of the current parse (the last
+ * pfpb200_parse_* / pfpb200_shard_scan call). */
+uint32_t pfpb200_launch_count(const pfpb200_ctx *ctx);
+
 const char *pfpb200_strerror(int code);
 /* Message of the last failure on this context (CUDA error string, file name, ...). */
 const char *pfpb200_last_error(const pfpb200_ctx *ctx);

@@ -1,0 +1,108 @@
+"""CPU stand-in for the stage-level C ABI (big-bwt_b200/shards.py CudaBackend), built on numpy and
+the oracle's window hash.  It lets the multi-rank protocol of ShardedParser (halo / head fetch,
+seam resolution, dictionary merge, rank offsets) run over gloo without a GPU.  Test code only."""
+import hashlib
+
+import numpy as np
+import torch
+
+from oracle import pfp_oracle as orc
+
+
+def _fp(word: bytes):
+    h = hashlib.blake2b(word, digest_size=16).digest()
+    return (int.from_bytes(h[:8], "little", signed=True), int.from_bytes(h[8:], "little", signed=True))
+
+
+def _pack(words):
+    """zero padded 8-byte pool + per-word 8-byte word counts"""
+    uw = [(len(x) + 7) // 8 for x in words]
+    raw = b"".join(x + b"\0" * (8 * k - len(x)) for x, k in zip(words, uw))
+    return np.frombuffer(raw, dtype=np.int64).copy(), uw
+
+
+def _unpack(pool, uwords, lens):
+    raw = pool.tobytes()
+    out, off = [], 0
+    for k, ln in zip(uwords, lens):
+        out.append(raw[off:off + ln])
+        off += 8 * k
+    return out
+
+
+class MockBackend:
+    def __init__(self):
+        self.ms = {}
+
+    def shard_scan(self, buf, buf_pos0, own_lo, own_hi, n_global, is_last, w, p, sai):
+        self.buf = buf.numpy()
+        self.buf_pos0, self.own = buf_pos0, (own_lo, own_hi)
+        self.n_global, self.is_last, self.w, self.sai = n_global, is_last, w, sai
+        # windows need w-1 bytes in front of the first owned position
+        start = max(buf_pos0, own_lo - (w - 1))
+        seg = self.buf[start - buf_pos0: own_hi - buf_pos0].tobytes()
+        e = orc.triggers(seg, w, p, flags=orc.THREADED_RULE).astype(np.int64) + start
+        # the threaded rule drops only a trigger at the segment's very first window, which ends
+        # at start + w - 1: re-check it by hand when it is owned and not the text's zero-padded one
+        first = start + w - 1
+        if first < own_hi and len(seg) >= w and orc.window_hash(seg[:w]) % p == 0:
+            e = np.concatenate([[first], e])
+        e = e[(e >= own_lo) & (e < own_hi) & (e >= w - 1)]
+        self.trig = e
+        if len(e) == 0:
+            return 0, 0, 0
+        return len(e), int(e[0]), int(e[-1])
+
+    def _byte(self, g):
+        if g < 0 or g >= self.n_global:
+            return 2
+        return int(self.buf[g - self.buf_pos0])
+
+    def shard_words(self, first_start):
+        w = self.w
+        ends = list(self.trig) + ([self.n_global + w - 1] if self.is_last else [])
+        words, index, uid, last, sai = [], {}, [], bytearray(), bytearray()
+        prev = None
+        for j, e in enumerate(ends):
+            s0 = first_start if j == 0 else prev - w + 1
+            ph = bytes(self._byte(x) for x in range(s0, e + 1))
+            if ph not in index:
+                index[ph] = len(words)
+                words.append(ph)
+            uid.append(index[ph])
+            last.append(self._byte(e - w))
+            sai += int(e + 1).to_bytes(5, "little")
+            prev = e
+        self.uid = np.array(uid, dtype=np.int64)
+        cnt = np.bincount(self.uid, minlength=len(words)) if words else np.zeros(0, np.int64)
+        fps = [_fp(x) for x in words]
+        pool, uw = _pack(words)
+        t = torch.from_numpy
+        return {"n_words": len(words), "n_phrases": len(ends),
+                "fpa": t(np.array([f[0] for f in fps], dtype=np.int64)),
+                "fpb": t(np.array([f[1] for f in fps], dtype=np.int64)),
+                "len": t(np.array([len(x) for x in words], dtype=np.int32)),
+                "count": t(cnt.astype(np.int32)), "uwords": t(np.array(uw, dtype=np.int32)),
+                "pool": t(pool), "last": t(np.frombuffer(bytes(last), np.uint8).copy()),
+                "sai": t(np.frombuffer(bytes(sai) if self.sai else b"", np.uint8).copy())}
+
+    def dict_merge(self, fpa, fpb, ln, count, uwords, pool, w, compress=False):
+        lens = ln.numpy().tolist()
+        words = _unpack(pool.numpy(), uwords.numpy().tolist(), lens)
+        keys = list(zip(fpa.numpy().tolist(), fpb.numpy().tolist(), lens))
+        tot, rep = {}, {}
+        for k, c, wd in zip(keys, count.numpy().tolist(), words):
+            tot[k] = tot.get(k, 0) + c
+            assert rep.setdefault(k, wd) == wd, "fingerprint collision in the mock"
+        order = sorted(tot, key=lambda k: rep[k])
+        rank = {k: i + 1 for i, k in enumerate(order)}
+        d = b"".join(rep[k] + b"\x01" for k in order) + b"\x00"
+        t = torch.from_numpy
+        return {"n_distinct": len(order), "sum_word_len": sum(len(rep[k]) for k in order),
+                "dict": t(np.frombuffer(d, np.uint8).copy()),
+                "occ": t(np.array([tot[k] for k in order], dtype=np.int32)),
+                "rank_of_entry": t(np.array([rank[k] for k in keys], dtype=np.int32))}
+
+    def shard_remap(self, rank_of_word, n_phrases):
+        r = rank_of_word.numpy()
+        return torch.from_numpy(r[self.uid].astype(np.int32)) if n_phrases else torch.zeros(0, dtype=torch.int32)
