@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--cpu-haplotypes", type=int, default=4, help="prefix timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--merge", default="partition", choices=["partition", "replicate"],
+                    help="multi-GPU dictionary merge: range-partitioned all-to-all or replicated all-gather")
     return ap.parse_args()
 
 
@@ -222,7 +224,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from bigbwt_b200 import shards
-    job = shards.ShardedParser(local, world, rank)
+    job = shards.ShardedParser(local, world, rank, mode=a.merge)
 
     # ---- workload: this rank's shard of the text, generated in HBM ------------------------------
     if a.workload == "random":
@@ -344,7 +346,7 @@ def main():
                    "phrases": last_stats["n_phrases"], "distinct": last_stats["n_distinct"],
                    "dict_bytes": last_stats["dict_bytes"], "rank_rounds": last_stats["rank_rounds"],
                    "l2": "inputs larger than L2 (no flush needed)" if n_local > 256e6 else "input smaller than L2",
-                   "parallelism": f"{world} shard(s), one process per GPU"},
+                   "parallelism": f"{world} shard(s), one process per GPU" + (f", {a.merge} dictionary merge" if world > 1 else "")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         "stages_ms": stage_ms,
     }

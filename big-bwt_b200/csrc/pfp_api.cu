@@ -504,11 +504,13 @@ extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb20
         PFP_TRY(pfp_pool_stage(ctx, tv, ends, first_start, w, &D));
         PFP_TRY(pfp_free_now(ctx, ph.len));
         PFP_TRY(pfp_free_now(ctx, D.rep));
-        PFP_TRY(pfp_free_now(ctx, D.uoff));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         PFP_CUDA(ctx, cudaGetLastError());
         ctx->sh.d = D.d;
         ctx->sh.uid = D.uid;
+        ctx->sh.wfpa = wfpa; ctx->sh.wfpb = wfpb; ctx->sh.pool = D.pool; ctx->sh.uoff = D.uoff;
+        ctx->sh.pool_words = D.pool_words;
+        ctx->sh.ulen = D.ulen; ctx->sh.count = D.count; ctx->sh.uwords = D.uwords;
         out->n_words = D.d; out->n_phrases = P; out->pool_words = D.pool_words;
         out->fpa = wfpa; out->fpb = wfpb; out->len = D.ulen; out->count = D.count;
         out->uwords = D.uwords; out->pool = D.pool; out->last = ph.last; out->sai = ph.sai;
@@ -580,6 +582,48 @@ extern "C" int pfpb200_shard_remap(pfpb200_ctx *ctx, const uint32_t *d_rank_of_w
     float t = tm.stop();
     PFP_CUDA(ctx, cudaGetLastError());
     *d_parse = parse;
+    if (ms) *ms = t;
+    return PFPB200_OK;
+}
+
+// ---- routing of a shard's words to the owners of their lexicographic range -----------------------
+struct Splitters { u64 s[PFPB200_MAX_RANKS]; u32 n; };
+
+extern "C" int pfp_route_impl(pfpb200_ctx *ctx, const Splitters &sp, u32 n_ranks, pfpb200_routed *out);
+extern "C" int pfp_first_keys_impl(pfpb200_ctx *ctx, u64 **keys);
+
+extern "C" int pfpb200_shard_first_keys(pfpb200_ctx *ctx, const uint64_t **d_keys) {
+    if (!ctx || !d_keys) return PFPB200_E_ARG;
+    *d_keys = nullptr;
+    if (ctx->sh.d == 0) return PFPB200_OK;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    u64 *keys = nullptr;
+    int rc = pfp_first_keys_impl(ctx, &keys);
+    if (rc != PFPB200_OK) return rc;
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *d_keys = keys;
+    return PFPB200_OK;
+}
+
+extern "C" int pfpb200_shard_route(pfpb200_ctx *ctx, const uint64_t *splitters, uint32_t n_ranks,
+                                   pfpb200_routed *out, float *ms) {
+    if (!ctx || !out || n_ranks < 1 || n_ranks > PFPB200_MAX_RANKS || (n_ranks > 1 && !splitters))
+        return PFPB200_E_ARG;
+    memset(out, 0, sizeof(*out));
+    if (ms) *ms = 0;
+    if (ctx->sh.d == 0) return PFPB200_OK;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Splitters sp;
+    sp.n = n_ranks - 1;
+    for (u32 i = 0; i < sp.n; i++) {
+        sp.s[i] = splitters[i];
+        if (i && sp.s[i] < sp.s[i - 1]) return pfp_fail(ctx, PFPB200_E_ARG, "splitters not ascending");
+    }
+    CallTimer tm(ctx->stream);
+    int rc = pfp_route_impl(ctx, sp, n_ranks, out);
+    float t = tm.stop();
+    if (rc != PFPB200_OK) { pfp_release_scratch(ctx); return rc; }
+    promote_scratch(ctx);
     if (ms) *ms = t;
     return PFPB200_OK;
 }

@@ -48,6 +48,9 @@ struct pfpb200_ctx {
         u64 *ends = nullptr;
         u64 n_trig = 0, P = 0, d = 0;
         u32 *uid = nullptr;
+        // local dictionary of the shard (held until the next parse)
+        u64 *wfpa = nullptr, *wfpb = nullptr, *pool = nullptr, *uoff = nullptr, pool_words = 0;
+        u32 *ulen = nullptr, *count = nullptr, *uwords = nullptr;
     } sh;
 };
 

@@ -546,3 +546,122 @@ int pfp_remap_stage(pfpb200_ctx *ctx, const u32 *uid, const u32 *rank_of_uid, u6
     PFP_LAUNCHED(ctx);
     return PFPB200_OK;
 }
+
+// ---- routing (range-partitioned dictionary merge) ----------------------------------------------------
+struct Splitters { u64 s[PFPB200_MAX_RANKS]; u32 n; };
+
+__global__ void first_keys_k(const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
+                             const u32 *__restrict__ uwords, u64 d, u64 *__restrict__ keys) {
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < d) keys[u] = word_key(pool, uoff, uwords, (u32)u, 0);
+}
+
+__global__ void route_dest_k(const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
+                             const u32 *__restrict__ uwords, u64 d, Splitters sp,
+                             u64 *__restrict__ keys, u32 *__restrict__ vals,
+                             unsigned long long *__restrict__ cnt /* [2*MAX_RANKS] */) {
+    __shared__ unsigned long long sc[2 * PFPB200_MAX_RANKS];
+    for (int i = threadIdx.x; i < 2 * PFPB200_MAX_RANKS; i += blockDim.x) sc[i] = 0;
+    __syncthreads();
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < d) {
+        u64 k = word_key(pool, uoff, uwords, (u32)u, 0);
+        u32 dest = 0;
+        for (u32 i = 0; i < sp.n; i++) dest += (sp.s[i] <= k) ? 1u : 0u;
+        keys[u] = dest;
+        vals[u] = (u32)u;
+        atomicAdd(&sc[dest], 1ull);
+        atomicAdd(&sc[PFPB200_MAX_RANKS + dest], (unsigned long long)uwords[u]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * PFPB200_MAX_RANKS; i += blockDim.x)
+        if (sc[i]) atomicAdd(&cnt[i], sc[i]);
+}
+
+__global__ void route_gather_k(const u32 *__restrict__ perm, u64 d, const u64 *__restrict__ fpa,
+                               const u64 *__restrict__ fpb, const u32 *__restrict__ len,
+                               const u32 *__restrict__ count, const u32 *__restrict__ uwords,
+                               u64 *__restrict__ ofpa, u64 *__restrict__ ofpb, u32 *__restrict__ olen,
+                               u32 *__restrict__ ocount, u32 *__restrict__ ouwords) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    u32 u = perm[i];
+    ofpa[i] = fpa[u]; ofpb[i] = fpb[u]; olen[i] = len[u]; ocount[i] = count[u]; ouwords[i] = uwords[u];
+}
+
+__global__ void __launch_bounds__(256) route_pool_k(const u32 *__restrict__ perm, u64 d,
+                                                    const u64 *__restrict__ pool,
+                                                    const u64 *__restrict__ uoff,
+                                                    const u32 *__restrict__ uwords,
+                                                    const u64 *__restrict__ ooff,
+                                                    u64 *__restrict__ opool) {
+    const u32 li = threadIdx.x & 7;
+    for (u64 i = (u64)blockIdx.x * 32 + (threadIdx.x >> 3); i < d; i += (u64)gridDim.x * 32) {
+        u32 u = perm[i];
+        const u64 *src = pool + uoff[u];
+        u64 *dst = opool + ooff[i];
+        u32 nw = uwords[u];
+        for (u32 k = li; k < nw; k += 8) dst[k] = __ldg(src + k);
+    }
+}
+
+extern "C" int pfp_first_keys_impl(pfpb200_ctx *ctx, u64 **keys) {
+    const u64 d = ctx->sh.d;
+    PFP_TRY(pfp_alloc_t(ctx, keys, d, true));
+    first_keys_k<<<pfp_blocks(d, 256), 256, 0, ctx->stream>>>(ctx->sh.pool, ctx->sh.uoff, ctx->sh.uwords, d, *keys);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
+extern "C" int pfp_route_impl(pfpb200_ctx *ctx, const Splitters &sp, u32 n_ranks, pfpb200_routed *out) {
+    const u64 d = ctx->sh.d;
+    const u32 nbd = pfp_blocks(d, 256);
+    u64 *k0 = nullptr, *k1 = nullptr, *ks = nullptr, *ooff = nullptr;
+    u32 *v0 = nullptr, *v1 = nullptr, *perm = nullptr;
+    unsigned long long *cnt = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &k0, d));
+    PFP_TRY(pfp_alloc_t(ctx, &k1, d));
+    PFP_TRY(pfp_alloc_t(ctx, &v0, d));
+    PFP_TRY(pfp_alloc_t(ctx, &v1, d));
+    PFP_TRY(pfp_alloc_t(ctx, &cnt, 2 * PFPB200_MAX_RANKS));
+    PFP_CUDA(ctx, cudaMemsetAsync(cnt, 0, 2 * PFPB200_MAX_RANKS * sizeof(unsigned long long), ctx->stream));
+    route_dest_k<<<nbd, 256, 0, ctx->stream>>>(ctx->sh.pool, ctx->sh.uoff, ctx->sh.uwords, d, sp, k0, v0, cnt);
+    PFP_LAUNCHED(ctx);
+    int bits = 1;
+    while ((1u << bits) < n_ranks) bits++;
+    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, d, 0, bits, &ks, &perm));
+    u64 *ofpa = nullptr, *ofpb = nullptr, *opool = nullptr;
+    u32 *olen = nullptr, *ocount = nullptr, *ouwords = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &ofpa, d));
+    PFP_TRY(pfp_alloc_t(ctx, &ofpb, d));
+    PFP_TRY(pfp_alloc_t(ctx, &olen, d));
+    PFP_TRY(pfp_alloc_t(ctx, &ocount, d));
+    PFP_TRY(pfp_alloc_t(ctx, &ouwords, d));
+    PFP_TRY(pfp_alloc_t(ctx, &ooff, d));
+    PFP_TRY(pfp_alloc_t(ctx, &opool, (size_t)ctx->sh.pool_words));
+    route_gather_k<<<nbd, 256, 0, ctx->stream>>>(perm, d, ctx->sh.wfpa, ctx->sh.wfpb, ctx->sh.ulen, ctx->sh.count,
+                                                 ctx->sh.uwords, ofpa, ofpb, olen, ocount, ouwords);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, ouwords, ooff, d, nullptr));
+    u64 want = (d + 31) / 32, maxb = (u64)ctx->sm_count * 32;
+    u32 nb = (u32)(want < maxb ? want : maxb);
+    route_pool_k<<<nb ? nb : 1, 256, 0, ctx->stream>>>(perm, d, ctx->sh.pool, ctx->sh.uoff, ctx->sh.uwords, ooff, opool);
+    PFP_LAUNCHED(ctx);
+    unsigned long long hc[2 * PFPB200_MAX_RANKS];
+    PFP_CUDA(ctx, cudaMemcpyAsync(hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (u32 r = 0; r < PFPB200_MAX_RANKS; r++) {
+        out->words_to[r] = hc[r];
+        out->pool_to[r] = hc[PFPB200_MAX_RANKS + r];
+    }
+    out->fpa = ofpa; out->fpb = ofpb; out->len = olen; out->count = ocount; out->uwords = ouwords;
+    out->pool = opool; out->perm = perm;
+    // free what the caller does not need; the rest is promoted to `held` by the caller
+    u32 *perm_other = (perm == v0) ? v1 : v0;
+    PFP_TRY(pfp_free_now(ctx, k0));
+    PFP_TRY(pfp_free_now(ctx, k1));
+    PFP_TRY(pfp_free_now(ctx, perm_other));
+    PFP_TRY(pfp_free_now(ctx, cnt));
+    PFP_TRY(pfp_free_now(ctx, ooff));
+    return PFPB200_OK;
+}

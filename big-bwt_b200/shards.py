@@ -120,7 +120,10 @@ class CudaBackend:
         L.pfpb200_dict_merge.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, u64, u32, u32,
                                          C.POINTER(Merged), C.POINTER(C.c_float)]
         L.pfpb200_shard_remap.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_float)]
-        for f in (L.pfpb200_shard_scan, L.pfpb200_shard_words, L.pfpb200_dict_merge, L.pfpb200_shard_remap):
+        L.pfpb200_shard_first_keys.argtypes = [vp, C.POINTER(vp)]
+        L.pfpb200_shard_route.argtypes = [vp, vp, u32, C.POINTER(Routed), C.POINTER(C.c_float)]
+        for f in (L.pfpb200_shard_scan, L.pfpb200_shard_words, L.pfpb200_dict_merge, L.pfpb200_shard_remap,
+                  L.pfpb200_shard_first_keys, L.pfpb200_shard_route):
             f.restype = C.c_int
 
     def shard_scan(self, buf, buf_pos0, own_lo, own_hi, n_global, is_last, w, p, sai):
@@ -158,6 +161,26 @@ class CudaBackend:
                 "occ": dev_tensor(m.occ, m.n_distinct, torch.int32, dev),
                 "rank_of_entry": dev_tensor(m.rank_of_entry, fpa.numel(), torch.int32, dev)}
 
+    def first_keys(self, wd):
+        out = C.c_void_p()
+        self.scanner._check(self.L.pfpb200_shard_first_keys(self.h, C.byref(out)))
+        return dev_tensor(out.value, wd["n_words"], torch.int64, self.dev)
+
+    def route(self, wd, splitters: np.ndarray, n_ranks: int):
+        rt, ms = Routed(), C.c_float()
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        self.scanner._check(self.L.pfpb200_shard_route(self.h, C.c_void_p(sp.ctypes.data if sp.size else 0),
+                                                       n_ranks, C.byref(rt), C.byref(ms)))
+        self.ms["route"] = ms.value
+        d, dev = wd["n_words"], self.dev
+        return {"fpa": dev_tensor(rt.fpa, d, torch.int64, dev), "fpb": dev_tensor(rt.fpb, d, torch.int64, dev),
+                "len": dev_tensor(rt.len, d, torch.int32, dev), "count": dev_tensor(rt.count, d, torch.int32, dev),
+                "uwords": dev_tensor(rt.uwords, d, torch.int32, dev),
+                "pool": dev_tensor(rt.pool, wd["pool"].numel(), torch.int64, dev),
+                "perm": dev_tensor(rt.perm, d, torch.int32, dev),
+                "words_to": [int(rt.words_to[q]) for q in range(n_ranks)],
+                "pool_to": [int(rt.pool_to[q]) for q in range(n_ranks)]}
+
     def shard_remap(self, rank_of_word, n_phrases):
         out, ms = C.c_void_p(), C.c_float()
         self.scanner._check(self.L.pfpb200_shard_remap(self.h, rank_of_word.data_ptr(), C.byref(out), C.byref(ms)))
@@ -175,6 +198,12 @@ class Words(C.Structure):
     _fields_ = [("n_words", C.c_uint64), ("n_phrases", C.c_uint64), ("pool_words", C.c_uint64),
                 ("fpa", C.c_void_p), ("fpb", C.c_void_p), ("len", C.c_void_p), ("count", C.c_void_p),
                 ("uwords", C.c_void_p), ("pool", C.c_void_p), ("last", C.c_void_p), ("sai", C.c_void_p)]
+
+
+class Routed(C.Structure):
+    _fields_ = [("fpa", C.c_void_p), ("fpb", C.c_void_p), ("len", C.c_void_p), ("count", C.c_void_p),
+                ("uwords", C.c_void_p), ("pool", C.c_void_p), ("perm", C.c_void_p),
+                ("words_to", C.c_uint64 * 64), ("pool_to", C.c_uint64 * 64)]
 
 
 class Merged(C.Structure):
@@ -356,8 +385,80 @@ class ShardedParser:
                 "n_distinct_local": m["n_distinct"], "dict_bytes_local": int(m["dict"].numel()),
                 "sum_len_local": m["sum_word_len"]}
 
+    def _all_to_all_v(self, send, send_counts, recv_counts):
+        """Variable-size all-to-all of a 1-D tensor grouped by destination (grouped P2P)."""
+        import torch.distributed as dist
+        out = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+        so = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64)
+        ro = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
+        todo = []
+        for q in range(self.world):
+            if q == self.rank:
+                out[ro[q]:ro[q + 1]] = send[so[q]:so[q + 1]]
+                continue
+            if send_counts[q]:
+                todo.append(dist.P2POp(dist.isend, send[so[q]:so[q + 1]], q))
+            if recv_counts[q]:
+                todo.append(dist.P2POp(dist.irecv, out[ro[q]:ro[q + 1]], q))
+        if todo:
+            for r in dist.batch_isend_irecv(todo):
+                r.wait()
+        return out
+
+    SAMPLE = 1024
+
+    def _splitters(self, wd):
+        """G-1 range splitters (big-endian first-8-byte keys) from an all-gathered sample."""
+        be, G = self.backend, self.world
+        d = wd["n_words"]
+        dev = self.buf.device
+        samp = torch.zeros(self.SAMPLE, dtype=torch.int64, device=dev)
+        k = 0
+        if d:
+            keys = be.first_keys(wd)          # uid order = fingerprint order: any stride is a random sample
+            step = max(1, d // self.SAMPLE)
+            pick = keys[::step][:self.SAMPLE]
+            k = int(pick.numel())
+            samp[:k] = pick
+        ks = [r[0] for r in self._all_gather_i64([k])]
+        import torch.distributed as dist
+        allv = torch.empty(G * self.SAMPLE, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allv, samp)
+        a = allv.cpu().numpy().view(np.uint64).reshape(G, self.SAMPLE)
+        vals = np.sort(np.concatenate([a[q, :ks[q]] for q in range(G)])) if sum(ks) else np.zeros(0, np.uint64)
+        if vals.size == 0:
+            return np.zeros(G - 1, dtype=np.uint64)
+        return np.array([vals[min(vals.size - 1, (q + 1) * vals.size // G)] for q in range(G - 1)], dtype=np.uint64)
+
     def _merge_partitioned(self, wd, w, compress):
-        raise NotImplementedError("partitioned dictionary merge: next step")
+        be, G, g = self.backend, self.world, self.rank
+        sp = self._splitters(wd)
+        rt = be.route(wd, sp, G) if wd["n_words"] else None
+        words_to = rt["words_to"] if rt else [0] * G
+        pool_to = rt["pool_to"] if rt else [0] * G
+        M = self._all_gather_i64(list(words_to) + list(pool_to))           # M[src] = [words_to.., pool_to..]
+        recv_w = [M[q][g] for q in range(G)]
+        recv_p = [M[q][G + g] for q in range(G)]
+        dev = self.buf.device
+        empty = {"fpa": torch.int64, "fpb": torch.int64, "len": torch.int32, "count": torch.int32,
+                 "uwords": torch.int32, "pool": torch.int64}
+        got = {}
+        for key, dt in empty.items():
+            send = rt[key] if rt else torch.empty(0, dtype=dt, device=dev)
+            sc, rc = (pool_to, recv_p) if key == "pool" else (words_to, recv_w)
+            got[key] = self._all_to_all_v(send, sc, rc)
+        m = be.dict_merge(got["fpa"], got["fpb"], got["len"], got["count"], got["uwords"], got["pool"], w, compress)
+        piece = m["dict"] if g == G - 1 else m["dict"][:-1]                 # only the last piece ends in 0x00
+        nd = [r[0] for r in self._all_gather_i64([m["n_distinct"]])]
+        offset = sum(nd[:g])
+        ranks = m["rank_of_entry"] + offset if m["rank_of_entry"].numel() else m["rank_of_entry"]
+        back = self._all_to_all_v(ranks.to(torch.int32), recv_w, words_to)  # routed order
+        rank_of_word = torch.empty(wd["n_words"], dtype=torch.int32, device=dev)
+        if rt:
+            rank_of_word[rt["perm"].long()] = back
+        return {"dict": piece, "occ": m["occ"], "n_distinct": sum(nd), "rank_of_word": rank_of_word,
+                "n_distinct_local": m["n_distinct"], "dict_bytes_local": int(piece.numel()),
+                "sum_len_local": m["sum_word_len"]}
 
     # -- results ----------------------------------------------------------------------------------------------
     def gather_files(self):

@@ -177,6 +177,29 @@ int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_t *fpa, con
 int pfpb200_shard_remap(pfpb200_ctx *ctx, const uint32_t *d_rank_of_word, const uint32_t **d_parse,
                         float *ms);
 
+/* ---- range-partitioned dictionary merge (mode "partition" of shards.py) -------------------- *
+ * Words are routed to the rank that owns their lexicographic range, identified by the big-endian
+ * first 8 bytes of the word; equal words have equal keys, so a single exchange serves the global
+ * dedup and the global ranking (the reference's analogue: hash % (3*threads) map shards,
+ * pscan.cpp:137-205 -- here the partition is by order, so ranks need no second exchange).     */
+#define PFPB200_MAX_RANKS 64
+/* Device array with the big-endian first 8 bytes (zero padded) of every word of the last
+ * pfpb200_shard_words call; used to sample range splitters. */
+int pfpb200_shard_first_keys(pfpb200_ctx *ctx, const uint64_t **d_keys);
+
+typedef struct pfpb200_routed {     /* the local dictionary regrouped by destination rank        */
+    const uint64_t *fpa, *fpb;
+    const uint32_t *len, *count, *uwords;
+    const uint64_t *pool;
+    const uint32_t *perm;           /* perm[i] = local word stored at routed position i          */
+    uint64_t words_to[PFPB200_MAX_RANKS];   /* words / pool words going to each rank             */
+    uint64_t pool_to[PFPB200_MAX_RANKS];
+} pfpb200_routed;
+
+/* Word u goes to rank  #{ s : splitters[s] <= key(u) }  (n_ranks-1 ascending host keys). */
+int pfpb200_shard_route(pfpb200_ctx *ctx, const uint64_t *splitters, uint32_t n_ranks,
+                        pfpb200_routed *out, float *ms);
+
 /* Kernels launched on this context since the start of the current parse (the last
  * pfpb200_parse_* / pfpb200_shard_scan call). */
 uint32_t pfpb200_launch_count(const pfpb200_ctx *ctx);

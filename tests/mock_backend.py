@@ -73,6 +73,7 @@ class MockBackend:
             last.append(self._byte(e - w))
             sai += int(e + 1).to_bytes(5, "little")
             prev = e
+        self.words = words
         self.uid = np.array(uid, dtype=np.int64)
         cnt = np.bincount(self.uid, minlength=len(words)) if words else np.zeros(0, np.int64)
         fps = [_fp(x) for x in words]
@@ -85,6 +86,23 @@ class MockBackend:
                 "count": t(cnt.astype(np.int32)), "uwords": t(np.array(uw, dtype=np.int32)),
                 "pool": t(pool), "last": t(np.frombuffer(bytes(last), np.uint8).copy()),
                 "sai": t(np.frombuffer(bytes(sai) if self.sai else b"", np.uint8).copy())}
+
+    def first_keys(self, wd):
+        ks = [int.from_bytes(x[:8].ljust(8, b"\0"), "big") for x in self.words]
+        return torch.from_numpy(np.array(ks, dtype=np.uint64).view(np.int64))
+
+    def route(self, wd, splitters, n_ranks):
+        ks = self.first_keys(wd).numpy().view(np.uint64)
+        dest = np.array([int(np.sum(splitters <= k)) for k in ks], dtype=np.int64)
+        perm = np.argsort(dest, kind="stable")
+        words = [self.words[i] for i in perm]
+        pool, uw = _pack(words)
+        t = torch.from_numpy
+        g = lambda key: t(wd[key].numpy()[perm].copy())
+        return {"fpa": g("fpa"), "fpb": g("fpb"), "len": g("len"), "count": g("count"),
+                "uwords": t(np.array(uw, dtype=np.int32)), "pool": t(pool), "perm": t(perm.astype(np.int32)),
+                "words_to": [int(np.sum(dest == q)) for q in range(n_ranks)],
+                "pool_to": [int(sum(uw[i] for i in range(len(uw)) if dest[perm[i]] == q)) for q in range(n_ranks)]}
 
     def dict_merge(self, fpa, fpb, ln, count, uwords, pool, w, compress=False):
         lens = ln.numpy().tolist()

@@ -73,12 +73,15 @@ def run_sharded(text, cuts, w, p, mode="replicate"):
     return files, st
 
 
-@pytest.mark.parametrize("world,w,p", [(2, 10, 100), (3, 10, 100), (2, 4, 10), (3, 6, 50)])
-def test_sharded_protocol_matches_oracle(pkg, world, w, p):
+@pytest.mark.parametrize("world,w,p,mode", [(2, 10, 100, "replicate"), (3, 10, 100, "replicate"),
+                                             (2, 4, 10, "replicate"), (3, 6, 50, "replicate"),
+                                             (2, 10, 100, "partition"), (3, 10, 100, "partition"),
+                                             (3, 4, 10, "partition")])
+def test_sharded_protocol_matches_oracle(pkg, world, w, p, mode):
     text = pkg.synth.pangenome_text(1500, 6, 7).numpy().tobytes()
     n = len(text)
     cuts = [0] + [n * k // world + 3 * k for k in range(1, world)] + [n]
-    files, st = run_sharded(text, cuts, w, p)
+    files, st = run_sharded(text, cuts, w, p, mode)
     want = orc.parse(text, w, p)
     for ext in FILES:
         assert files[ext] == getattr(want, ext), f".{ext} differs (world {world})"
@@ -91,7 +94,7 @@ def test_sharded_seam_without_triggers(pkg):
     a = pkg.synth.random_dna(3000, 3).numpy().tobytes()
     text = a + b"N" * 2500 + a[:2000]
     cuts = [0, 3200, 5000, len(text)]          # shard 1 lies inside the N run
-    files, _ = run_sharded(text, cuts, 10, 100)
+    files, _ = run_sharded(text, cuts, 10, 100, "partition")
     want = orc.parse(text, 10, 100)
     for ext in FILES:
         assert files[ext] == getattr(want, ext), f".{ext} differs"
