@@ -239,7 +239,6 @@ def main():
     n_total = job.n_global
 
     stream = torch.cuda.Stream(device=dev)
-    job.scanner.set_stream(stream.cuda_stream)
 
     def barrier():
         if world > 1:

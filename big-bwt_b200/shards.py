@@ -110,6 +110,16 @@ class CudaBackend:
         self.dev = torch.device("cuda", device)
         self._declare()
         self.ms = {}
+        self._stream = None
+        self.use_current_stream()
+
+    def use_current_stream(self):
+        """Run the library on torch's current stream so that its kernels are ordered with the
+        collectives and tensor ops around them."""
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        if s != self._stream:
+            self.scanner.set_stream(s)
+            self._stream = s
 
     def _declare(self):
         L = self.L
@@ -299,6 +309,7 @@ class ShardedParser:
     # -- parse --------------------------------------------------------------------------------------------
     def parse_device(self, w=10, p=100, sai=True, compress=False) -> dict:
         if self.world == 1 and self.scanner is not None:
+            self.backend.use_current_stream()
             self.out = self.scanner.parse_device(self.buf, w, p, sai=sai, compress=compress)
             return self.scanner.stats.as_dict()
         return self._parse_sharded(w, p, sai, compress)
@@ -306,6 +317,7 @@ class ShardedParser:
     def parse_host(self, host_text, w=10, p=100, sai=True) -> dict:
         """host_text: pinned CPU uint8 tensor holding this rank's shard."""
         if self.world == 1:
+            self.backend.use_current_stream()
             out = self.scanner.parse_host_ptr(host_text.data_ptr(), host_text.numel(), w, p, sai=sai)
             st = self.scanner.stats.as_dict()
             P, d = out.n_phrases, out.n_distinct
@@ -330,6 +342,8 @@ class ShardedParser:
 
     def _parse_sharded(self, w, p, sai, compress) -> dict:
         be, G, g = self.backend, self.world, self.rank
+        if hasattr(be, "use_current_stream"):
+            be.use_current_stream()
         if w > self.halo:
             raise ValueError("window larger than the shard halo")
         if min(self.sizes[:-1]) < self.halo:
