@@ -186,10 +186,7 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
         // K2
         PhraseArrays ph{};
         ph.ends = ends;
-        PFP_TRY(pfp_alloc_t(ctx, &ph.fpa, P));
-        PFP_TRY(pfp_alloc_t(ctx, &ph.fpb, P));
-        PFP_TRY(pfp_alloc_t(ctx, &ph.key, P));
-        PFP_TRY(pfp_alloc_t(ctx, &ph.len, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.rec, P));
         PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
         if (o->flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
         TextView tv{d_text, n, 0, (i64)n};
@@ -198,9 +195,7 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
         // K3
         DictArrays D;
         PFP_TRY(pfp_dedup_stage(ctx, ph, P, &D));
-        PFP_TRY(pfp_free_now(ctx, ph.fpa));
-        PFP_TRY(pfp_free_now(ctx, ph.fpb));
-        PFP_TRY(pfp_free_now(ctx, ph.key));
+        PFP_TRY(pfp_free_now(ctx, ph.rec));
         PFP_TRY(pfp_pool_stage(ctx, tv, ends, -1, w, &D));
         tm.mark(ctx->stream);                                           // 3
         // K4
@@ -484,10 +479,7 @@ extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb20
         }
         PhraseArrays ph{};
         ph.ends = ends;
-        PFP_TRY(pfp_alloc_t(ctx, &ph.fpa, P));
-        PFP_TRY(pfp_alloc_t(ctx, &ph.fpb, P));
-        PFP_TRY(pfp_alloc_t(ctx, &ph.key, P));
-        PFP_TRY(pfp_alloc_t(ctx, &ph.len, P));
+        PFP_TRY(pfp_alloc_t(ctx, &ph.rec, P));
         PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
         if (o.flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
         TextView tv{sh.d_buf, sh.n_buf, (i64)sh.buf_pos0, (i64)sh.n_global};
@@ -498,11 +490,8 @@ extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb20
         PFP_TRY(pfp_alloc_t(ctx, &wfpa, D.d));
         PFP_TRY(pfp_alloc_t(ctx, &wfpb, D.d));
         PFP_TRY(pfp_gather_word_fp(ctx, D, ph, wfpa, wfpb));
-        PFP_TRY(pfp_free_now(ctx, ph.fpa));
-        PFP_TRY(pfp_free_now(ctx, ph.fpb));
-        PFP_TRY(pfp_free_now(ctx, ph.key));
+        PFP_TRY(pfp_free_now(ctx, ph.rec));
         PFP_TRY(pfp_pool_stage(ctx, tv, ends, first_start, w, &D));
-        PFP_TRY(pfp_free_now(ctx, ph.len));
         PFP_TRY(pfp_free_now(ctx, D.rep));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         PFP_CUDA(ctx, cudaGetLastError());

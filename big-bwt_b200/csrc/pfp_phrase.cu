@@ -27,15 +27,21 @@ __device__ __forceinline__ u64 fmix64(u64 k) {
 // fast path: aligned 32-bit loads + funnel shift by the byte misalignment of the phrase start
 __device__ __forceinline__ void load_chunk(const TextView &tv, i64 s0, u64 len, u64 o, bool special,
                                            u32 x[4]) {
-    u32 nbv = (u32)((len - o) < 16 ? (len - o) : 16);
+    const u32 nbv = (u32)((len - o) < 16 ? (len - o) : 16);
     if (!special) {
-        const u8 *p = tv.T + (s0 + (i64)o - tv.pos0);
-        u32 bs = (u32)((uintptr_t)p & 3);
+        const i64 loc = s0 + (i64)o - tv.pos0;            // offset of the chunk in the buffer
+        const u8 *p = tv.T + loc;
+        const u32 bs = (u32)((uintptr_t)p & 3);
         const u32 *p4 = reinterpret_cast<const u32 *>(p - bs);
-        u32 need = bs + nbv;   // bytes needed counted from p4
         u32 W[5];
+        if ((u64)loc + 20 <= tv.n_buf) {                  // interior: five unconditional loads
 #pragma unroll
-        for (int j = 0; j < 5; j++) W[j] = (4u * j < need) ? __ldg(p4 + j) : 0u;
+            for (int j = 0; j < 5; j++) W[j] = __ldg(p4 + j);
+        } else {
+            const u32 need = bs + nbv;                    // bytes needed counted from p4
+#pragma unroll
+            for (int j = 0; j < 5; j++) W[j] = (4u * j < need) ? __ldg(p4 + j) : 0u;
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) x[j] = __funnelshift_r(W[j], W[j + 1], 8 * bs);
     } else {
@@ -49,11 +55,13 @@ __device__ __forceinline__ void load_chunk(const TextView &tv, i64 s0, u64 len, 
             x[j] = v;
         }
     }
+    if (nbv < 16) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        u32 lo = 4u * j;
-        u32 nb = nbv > lo ? nbv - lo : 0;
-        if (nb < 4) x[j] &= (nb == 0) ? 0u : ((1u << (8 * nb)) - 1u);
+        for (int j = 0; j < 4; j++) {
+            u32 lo = 4u * j;
+            u32 nb = nbv > lo ? nbv - lo : 0;
+            if (nb < 4) x[j] &= (nb == 0) ? 0u : ((1u << (8 * nb)) - 1u);
+        }
     }
 }
 
@@ -65,24 +73,38 @@ __device__ __forceinline__ void nh_chunk(const u32 *__restrict__ sk, u32 c, cons
     pb += (u64)(x[0] + k1.x) * (u64)(x[1] + k1.y) + (u64)(x[2] + k1.z) * (u64)(x[3] + k1.w);
 }
 
+// never 0: 0 marks an empty slot of the dictionary table
 __device__ __forceinline__ u64 sort_key_of(u64 fa, u64 fb, u32 len) {
-    return fmix64(fa ^ rotl64(fb, 32) ^ ((u64)len * 0x9E3779B97F4A7C15ULL));
+    u64 k = fmix64(fa ^ rotl64(fb, 32) ^ ((u64)len * 0x9E3779B97F4A7C15ULL));
+    return k ? k : 0x9E3779B97F4A7C15ULL;
 }
 
-__device__ __forceinline__ void write_records(const PhraseArrays &ph, const TextView &tv, u64 j,
-                                              i64 e, u32 w) {
-    ph.last[j] = tv_byte(tv, e - (i64)w);                       // newscan.cpp:296
-    if (ph.sai) {                                               // newscan.cpp:299-301
+__device__ __forceinline__ void store_rec(PhraseFp *rec, u64 j, u64 fa, u64 fb, u32 len) {
+    uint4 *q = reinterpret_cast<uint4 *>(rec + j);
+    u64 key = sort_key_of(fa, fb, len);
+    q[0] = make_uint4((u32)fa, (u32)(fa >> 32), (u32)fb, (u32)(fb >> 32));
+    q[1] = make_uint4(len, 0u, (u32)key, (u32)(key >> 32));
+}
+
+// .last and .sai of every phrase: one thread per phrase, coalesced stores
+__global__ void phrase_records_k(TextView tv, const u64 *__restrict__ ends, u64 P, u32 w,
+                                 u8 *__restrict__ last, u8 *__restrict__ sai) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P) return;
+    i64 e = (i64)ends[j];
+    last[j] = tv_byte(tv, e - (i64)w);                          // newscan.cpp:296
+    if (sai) {                                                  // newscan.cpp:299-301
         u64 pos = (u64)(e + 1);
-        u8 *d = ph.sai + j * PFP_IBYTES;
+        u8 *d = sai + j * PFP_IBYTES;
 #pragma unroll
         for (int b = 0; b < PFP_IBYTES; b++) d[b] = (u8)(pos >> (8 * b));
     }
 }
 
 constexpr int PH_T = 256;
-constexpr int PH_GROUP = 8;                          // lanes per phrase
-constexpr int PH_PER_BLOCK = PH_T / PH_GROUP;        // 32 phrases per CTA iteration
+constexpr int PH_GROUP = 4;                          // lanes per phrase
+constexpr int PH_PER_WARP = 32 / PH_GROUP;
+constexpr int PH_PER_BLOCK = PH_T / PH_GROUP;        // 64 phrases per CTA iteration
 
 __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays ph, u64 P,
                                                       i64 first_start, u32 w,
@@ -93,32 +115,26 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
     __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
     for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
     __syncthreads();
-    const u32 lane = threadIdx.x & 31, li = lane & 7, grp = lane >> 3;
-    const u32 gmask = 0xFFu << (8 * grp);
+    const u32 lane = threadIdx.x & 31, li = lane & (PH_GROUP - 1), grp = lane / PH_GROUP;
+    const u32 gmask = ((1u << PH_GROUP) - 1u) << (PH_GROUP * grp);
     const u32 warp = threadIdx.x >> 5;
-    for (u64 jw = ((u64)blockIdx.x * (PH_T / 32) + warp) * 4; jw < P;
+    for (u64 jw = ((u64)blockIdx.x * (PH_T / 32) + warp) * PH_PER_WARP; jw < P;
          jw += (u64)gridDim.x * PH_PER_BLOCK) {
         u64 j = jw + grp;
         if (j >= P) continue;                                  // whole group leaves together
         i64 e = (i64)ph.ends[j];
         i64 s0 = (j == 0) ? first_start : (i64)ph.ends[j - 1] - (i64)w + 1;
         u64 len = (u64)(e - s0 + 1);
-        if (len > 0xFFFFFFFFull) {
-            if (li == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
-            continue;
-        }
-        if (li == 0) write_records(ph, tv, j, e, w);
         if (len > PHRASE_LONG) {
             if (li == 0) {
-                u32 slot = atomicAdd(long_count, 1u);
-                long_list[slot] = (u32)j;
-                ph.len[j] = (u32)len;
+                if (len > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
+                else long_list[atomicAdd(long_count, 1u)] = (u32)j;
             }
             continue;
         }
-        bool special = (s0 < 0) || (e >= tv.n_global);
+        const bool special = (s0 < 0) || (e >= tv.n_global);
         u64 fa = 0, fb = 0;
-        u32 nseg = (u32)((len + NH_SEG_BYTES - 1) / NH_SEG_BYTES);
+        const u32 nseg = (u32)((len + NH_SEG_BYTES - 1) / NH_SEG_BYTES);
         for (u32 s = 0; s < nseg; s++) {
             u64 so = (u64)s * NH_SEG_BYTES;
             u32 segb = (u32)((len - so) < NH_SEG_BYTES ? (len - so) : NH_SEG_BYTES);
@@ -133,20 +149,17 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
             fb = fb * NH_FOLD_B + pb;
         }
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = PH_GROUP / 2; o > 0; o >>= 1) {
             fa += __shfl_xor_sync(gmask, fa, o);
             fb += __shfl_xor_sync(gmask, fb, o);
         }
-        if (li == 0) {
-            ph.fpa[j] = fa;
-            ph.fpb[j] = fb;
-            ph.len[j] = (u32)len;
-            ph.key[j] = sort_key_of(fa, fb, (u32)len);
-        }
+        if (li == 0) store_rec(ph.rec, j, fa, fb, (u32)len);
     }
 }
 
-// phrases longer than PHRASE_LONG: one CTA per phrase, 32 groups stride over the segments
+// phrases longer than PHRASE_LONG: one CTA per phrase, 32 groups of 8 lanes stride over the segments
+constexpr int PL_GROUP = 8;
+constexpr int PL_GROUPS = PH_T / PL_GROUP;
 __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseArrays ph,
                                                            i64 first_start, u32 w,
                                                            const u32 *__restrict__ keytab,
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
     __shared__ u64 red[2][PH_T / 32];
     for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
     __syncthreads();
-    const u32 li = threadIdx.x & 7, g = threadIdx.x >> 3;   // 32 groups
+    const u32 li = threadIdx.x & (PL_GROUP - 1), g = threadIdx.x / PL_GROUP;
     const u32 nlong = *long_count;
     for (u32 q = blockIdx.x; q < nlong; q += gridDim.x) {
         u64 j = long_list[q];
@@ -168,17 +181,17 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
         u64 nseg = (len + NH_SEG_BYTES - 1) / NH_SEG_BYTES;
         u64 fa = 0, fb = 0;
         i64 s_last = -1;
-        for (u64 s = g; s < nseg; s += PH_PER_BLOCK) {
+        for (u64 s = g; s < nseg; s += PL_GROUPS) {
             u64 so = s * NH_SEG_BYTES;
             u32 segb = (u32)((len - so) < NH_SEG_BYTES ? (len - so) : NH_SEG_BYTES);
             u32 nch = (segb + 15) >> 4;
             u64 pa = 0, pb = 0;
-            for (u32 c = li; c < nch; c += PH_GROUP) {
+            for (u32 c = li; c < nch; c += PL_GROUP) {
                 u32 x[4];
                 load_chunk(tv, s0, len, so + 16ull * c, special, x);
                 nh_chunk(sk, c, x, pa, pb);
             }
-            fa = fa * fold_a32 + pa;     // Horner with stride 32 segments
+            fa = fa * fold_a32 + pa;     // Horner with stride PL_GROUPS segments
             fb = fb * fold_b32 + pb;
             s_last = (i64)s;
         }
@@ -196,9 +209,7 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
         if (threadIdx.x == 0) {
             u64 a = 0, b = 0;
             for (int i = 0; i < PH_T / 32; i++) { a += red[0][i]; b += red[1][i]; }
-            ph.fpa[j] = a;
-            ph.fpb[j] = b;
-            ph.key[j] = sort_key_of(a, b, (u32)len);
+            store_rec(ph.rec, j, a, b, (u32)len);
         }
     }
 }
@@ -208,41 +219,58 @@ __global__ void iota_u32_k(u32 *v, u64 n) {
     if (i < n) v[i] = (u32)i;
 }
 
-// run heads of the sorted keys + fingerprint agreement inside runs
-__global__ void mark_heads_k(const u64 *__restrict__ skey, const u32 *__restrict__ sidx, u64 P,
-                             PhraseArrays ph, u8 *__restrict__ head, u64 *__restrict__ flags) {
+// ---- K3: dictionary table ----------------------------------------------------------------------------
+// Open addressing, linear probing, 16-byte slots {key, first phrase, occurrences}; key 0 = empty.
+// A warp first groups its lanes by key (match.any) so that runs of identical phrases cost one
+// atomic per warp instead of 32.
+struct __align__(16) DictSlot { u64 key; u32 rep; u32 cnt; };
+
+__global__ void table_init_k(DictSlot *__restrict__ tab, u64 cap) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    bool h = (i == 0) || (skey[i] != skey[i - 1]);
-    if (!h) {
-        u32 a = sidx[i], b = sidx[i - 1];
-        if (ph.fpa[a] != ph.fpa[b] || ph.fpb[a] != ph.fpb[b] || ph.len[a] != ph.len[b])
-            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+    if (i < cap) *reinterpret_cast<uint4 *>(tab + i) = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+}
+
+__global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict__ rec, u64 P,
+                                                      DictSlot *__restrict__ tab, u64 mask, int shift,
+                                                      u32 *__restrict__ slot_of) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < P;
+    u64 k = active ? rec[j].key : 0ull;
+    u32 peers = __match_any_sync(0xffffffffu, k);
+    const u32 lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    u64 slot = 0;
+    if (active && (int)lane == leader) {
+        slot = k >> shift;
+        for (;;) {
+            u64 prev = atomicCAS((unsigned long long *)&tab[slot].key, 0ull, (unsigned long long)k);
+            if (prev == 0ull || prev == k) break;
+            slot = (slot + 1) & mask;
+        }
+        atomicAdd(&tab[slot].cnt, (u32)__popc(peers));
+        atomicMin(&tab[slot].rep, (u32)j);          // lowest lane of the group = smallest index
     }
-    head[i] = h ? 1 : 0;
+    slot = __shfl_sync(0xffffffffu, slot, leader);
+    if (active) slot_of[j] = (u32)slot;
 }
 
-__global__ void assign_uid_k(const u32 *__restrict__ sidx, const u8 *__restrict__ head,
-                             const u32 *__restrict__ hscan, u64 P, u32 *__restrict__ uid,
-                             u32 *__restrict__ rep, u32 *__restrict__ headpos) {
+__global__ void table_flags_k(const DictSlot *__restrict__ tab, u64 cap, u8 *__restrict__ occ) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    u32 u = hscan[i] + head[i] - 1;     // inclusive scan - 1
-    u32 j = sidx[i];
-    uid[j] = u;
-    if (head[i]) { rep[u] = j; headpos[u] = (u32)i; }
+    if (i < cap) occ[i] = tab[i].key != 0ull ? 1 : 0;
 }
 
-__global__ void word_stats_k(const u32 *__restrict__ headpos, const u32 *__restrict__ rep,
-                             const u32 *__restrict__ plen, u64 d, u64 P, u32 *__restrict__ count,
-                             u32 *__restrict__ ulen, u32 *__restrict__ uwords,
-                             u64 *__restrict__ flags /* [2]=max len, [3]=sum len */) {
-    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void table_emit_k(const DictSlot *__restrict__ tab, const u8 *__restrict__ occ,
+                             const u32 *__restrict__ umap, u64 cap, const PhraseFp *__restrict__ rec,
+                             u32 *__restrict__ rep, u32 *__restrict__ count, u32 *__restrict__ ulen,
+                             u32 *__restrict__ uwords, u64 *__restrict__ flags) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 L = 0;
-    if (u < d) {
-        u32 nxt = (u + 1 < d) ? headpos[u + 1] : (u32)P;
-        count[u] = nxt - headpos[u];
-        L = plen[rep[u]];
+    if (i < cap && occ[i]) {
+        u32 u = umap[i];
+        DictSlot s = tab[i];
+        rep[u] = s.rep;
+        count[u] = s.cnt;
+        L = rec[s.rep].len;
         ulen[u] = L;
         uwords[u] = (L + 7) >> 3;
     }
@@ -259,16 +287,66 @@ __global__ void word_stats_k(const u32 *__restrict__ headpos, const u32 *__restr
     }
 }
 
+// phrase -> word id, and the collision check: every phrase agrees with its word's first
+// occurrence on the full fingerprint and the length (newscan.cpp:282-286 compares the strings)
+__global__ void table_uid_k(const PhraseFp *__restrict__ rec, const u32 *__restrict__ slot_of,
+                            const DictSlot *__restrict__ tab, const u32 *__restrict__ umap, u64 P,
+                            u32 *__restrict__ uid, u64 *__restrict__ flags) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P) return;
+    u32 s = slot_of[j];
+    uid[j] = umap[s];
+    u32 r = tab[s].rep;
+    if (r != (u32)j) {
+        const uint4 *a = reinterpret_cast<const uint4 *>(rec + j);
+        const uint4 *b = reinterpret_cast<const uint4 *>(rec + r);
+        uint4 a0 = __ldg(a), b0 = __ldg(b);
+        u32 la = __ldg(&rec[j].len), lb = __ldg(&rec[r].len);
+        if (a0.x != b0.x || a0.y != b0.y || a0.z != b0.z || a0.w != b0.w || la != lb)
+            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+    }
+}
+
+// run heads of sorted keys + fingerprint agreement inside runs (dictionary merge)
+__global__ void mark_heads_k(const u64 *__restrict__ skey, const u32 *__restrict__ sidx, u64 n,
+                             const u64 *__restrict__ fpa, const u64 *__restrict__ fpb,
+                             const u32 *__restrict__ len, u8 *__restrict__ head,
+                             u64 *__restrict__ flags) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool h = (i == 0) || (skey[i] != skey[i - 1]);
+    if (!h) {
+        u32 a = sidx[i], b = sidx[i - 1];
+        if (fpa[a] != fpa[b] || fpb[a] != fpb[b] || len[a] != len[b])
+            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+    }
+    head[i] = h ? 1 : 0;
+}
+
+__global__ void assign_uid_k(const u32 *__restrict__ sidx, const u8 *__restrict__ head,
+                             const u32 *__restrict__ hscan, u64 P, u32 *__restrict__ uid,
+                             u32 *__restrict__ rep, u32 *__restrict__ headpos) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    u32 u = hscan[i] + head[i] - 1;     // inclusive scan - 1
+    u32 j = sidx[i];
+    uid[j] = u;
+    if (head[i]) { rep[u] = j; headpos[u] = (u32)i; }
+}
+
 // phrase pool: every distinct word once, zero padded to 8 bytes, 8-byte aligned
+constexpr int PC_GROUP = 8;                          // lanes per word
+constexpr int PC_PER_BLOCK = PH_T / PC_GROUP;
+
 __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__restrict__ ends,
                                                     i64 first_start, u32 w,
                                                     const u32 *__restrict__ rep,
                                                     const u32 *__restrict__ ulen,
                                                     const u64 *__restrict__ uoff, u64 d,
                                                     u64 *__restrict__ pool) {
-    const u32 li = threadIdx.x & 7;
-    for (u64 u = (u64)blockIdx.x * PH_PER_BLOCK + (threadIdx.x >> 3); u < d;
-         u += (u64)gridDim.x * PH_PER_BLOCK) {
+    const u32 li = threadIdx.x & (PC_GROUP - 1);
+    for (u64 u = (u64)blockIdx.x * PC_PER_BLOCK + (threadIdx.x / PC_GROUP); u < d;
+         u += (u64)gridDim.x * PC_PER_BLOCK) {
         u64 j = rep[u];
         i64 e = (i64)ends[j];
         i64 s0 = (j == 0) ? first_start : (i64)ends[j - 1] - (i64)w + 1;
@@ -276,7 +354,7 @@ __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__re
         bool special = (s0 < 0) || (e >= tv.n_global);
         u64 nw = (len + 7) >> 3;
         u64 *dst = pool + uoff[u];
-        for (u64 k = li; k < nw; k += PH_GROUP) {
+        for (u64 k = li; k < nw; k += PC_GROUP) {
             u64 o = 8 * k;
             u32 nbv = (u32)((len - o) < 8 ? (len - o) : 8);
             u64 v = 0;
@@ -308,6 +386,8 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     PFP_TRY(pfp_alloc_t(ctx, &long_list, (size_t)cap));
     PFP_TRY(pfp_alloc_t(ctx, &long_count, 1));
     PFP_CUDA(ctx, cudaMemsetAsync(long_count, 0, sizeof(u32), ctx->stream));
+    phrase_records_k<<<pfp_blocks(P, 256), 256, 0, ctx->stream>>>(tv, ph.ends, P, w, ph.last, ph.sai);
+    PFP_LAUNCHED(ctx);
     u64 want = (P + PH_PER_BLOCK - 1) / PH_PER_BLOCK;
     u64 maxb = (u64)ctx->sm_count * 32;
     u32 nb = (u32)(want < maxb ? want : maxb);
@@ -316,7 +396,7 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
                                                 long_count, ctx->d_flags);
     PFP_LAUNCHED(ctx);
     u64 fa32 = 1, fb32 = 1;
-    for (int i = 0; i < PH_PER_BLOCK; i++) { fa32 *= NH_FOLD_A; fb32 *= NH_FOLD_B; }
+    for (int i = 0; i < PL_GROUPS; i++) { fa32 *= NH_FOLD_A; fb32 *= NH_FOLD_B; }
     u32 nlb = (u32)(cap < (u64)ctx->sm_count ? cap : (u64)ctx->sm_count);
     phrase_hash_long_k<<<nlb, PH_T, 0, ctx->stream>>>(tv, ph, first_start, w, ctx->d_keys, long_list,
                                                       long_count, fa32, fb32);
@@ -326,57 +406,54 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     return PFPB200_OK;
 }
 
-// Sorts phrases by fingerprint key and derives the dictionary.  Reads d (and length stats)
-// back to the host: one synchronisation.
+// Inserts every phrase into the dictionary table and derives the dictionary arrays.
+// Reads d (and length stats) back to the host: one synchronisation.
 int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D) {
     const int TB = 256;
-    u64 *k1 = nullptr, *sk = nullptr;
-    u32 *v0 = nullptr, *v1 = nullptr, *sv = nullptr;
-    PFP_TRY(pfp_alloc_t(ctx, &k1, P));
-    PFP_TRY(pfp_alloc_t(ctx, &v0, P));
-    PFP_TRY(pfp_alloc_t(ctx, &v1, P));
-    iota_u32_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(v0, P);
+    // capacity: power of two >= 1.5 P  (load factor <= 2/3 even if every phrase is distinct)
+    u64 cap = 1024;
+    while (cap < P + P / 2) cap <<= 1;
+    int kbits = 0;
+    while ((1ull << kbits) < cap) kbits++;
+    DictSlot *tab = nullptr;
+    u32 *slot_of = nullptr, *umap = nullptr;
+    u8 *occ = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &tab, cap));
+    PFP_TRY(pfp_alloc_t(ctx, &slot_of, P));
+    table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
     PFP_LAUNCHED(ctx);
-    PFP_TRY(pfp_radix_sort_pairs(ctx, ph.key, v0, k1, v1, P, 0, 64, &sk, &sv));
-    u8 *head = nullptr;
-    u32 *hscan = nullptr;
-    PFP_TRY(pfp_alloc_t(ctx, &head, P));
-    PFP_TRY(pfp_alloc_t(ctx, &hscan, P));
-    mark_heads_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(sk, sv, P, ph, head, ctx->d_flags);
+    table_insert_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(ph.rec, P, tab, cap - 1, 64 - kbits, slot_of);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_alloc_t(ctx, &occ, cap));
+    PFP_TRY(pfp_alloc_t(ctx, &umap, cap));
+    table_flags_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap, occ);
     PFP_LAUNCHED(ctx);
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
-    u32 *d_total = reinterpret_cast<u32 *>(&ctx->d_flags[1]);
-    PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, head, hscan, P, d_total));
+    PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, occ, umap, cap, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
     PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(u64), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
         return pfp_fail(ctx, PFPB200_E_LIMIT, "a phrase is longer than 2^32-1 bytes");
-    if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
-        return pfp_fail(ctx, PFPB200_E_COLLISION, "fingerprint collision between different phrases");
     u64 d = (u32)ctx->h_flags[1];
     if (d > 0x7FFFFFFEull)
         return pfp_fail(ctx, PFPB200_E_LIMIT, "%llu distinct words exceed the limit 2^31-2",
                         (unsigned long long)d);
     D->d = d;
-    u32 *headpos = nullptr;
     PFP_TRY(pfp_alloc_t(ctx, &D->uid, P));
     PFP_TRY(pfp_alloc_t(ctx, &D->rep, d));
-    PFP_TRY(pfp_alloc_t(ctx, &headpos, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->count, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->ulen, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->uwords, d));
-    assign_uid_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(sv, head, hscan, P, D->uid, D->rep, headpos);
+    table_emit_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, occ, umap, cap, ph.rec, D->rep, D->count,
+                                                              D->ulen, D->uwords, ctx->d_flags);
     PFP_LAUNCHED(ctx);
-    word_stats_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(headpos, D->rep, ph.len, d, P, D->count,
-                                                            D->ulen, D->uwords, ctx->d_flags);
+    table_uid_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(ph.rec, slot_of, tab, umap, P, D->uid, ctx->d_flags);
     PFP_LAUNCHED(ctx);
-    PFP_TRY(pfp_free_now(ctx, k1));
-    PFP_TRY(pfp_free_now(ctx, v0));
-    PFP_TRY(pfp_free_now(ctx, v1));
-    PFP_TRY(pfp_free_now(ctx, head));
-    PFP_TRY(pfp_free_now(ctx, hscan));
-    PFP_TRY(pfp_free_now(ctx, headpos));
+    PFP_TRY(pfp_free_now(ctx, tab));
+    PFP_TRY(pfp_free_now(ctx, slot_of));
+    PFP_TRY(pfp_free_now(ctx, occ));
+    PFP_TRY(pfp_free_now(ctx, umap));
     return PFPB200_OK;
 }
 
@@ -389,11 +466,13 @@ int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 fi
     PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(u64), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
+        return pfp_fail(ctx, PFPB200_E_COLLISION, "fingerprint collision between different phrases");
     D->pool_words = ctx->h_flags[1];
     D->max_len = (u32)ctx->h_flags[2];
     D->sum_len = ctx->h_flags[3];
     PFP_TRY(pfp_alloc_t(ctx, &D->pool, (size_t)D->pool_words));
-    u64 want = (d + PH_PER_BLOCK - 1) / PH_PER_BLOCK;
+    u64 want = (d + PC_PER_BLOCK - 1) / PC_PER_BLOCK;
     u64 maxb = (u64)ctx->sm_count * 32;
     u32 nb = (u32)(want < maxb ? want : maxb);
     if (nb == 0) nb = 1;
@@ -451,19 +530,18 @@ __global__ void merge_words_k(const u32 *__restrict__ headpos, const u32 *__rest
 }
 
 // per-word fingerprints of a shard's local dictionary (what a shard exports)
-__global__ void gather_word_fp_k(const u32 *__restrict__ rep, const u64 *__restrict__ fpa,
-                                 const u64 *__restrict__ fpb, u64 d, u64 *__restrict__ wfpa,
-                                 u64 *__restrict__ wfpb) {
+__global__ void gather_word_fp_k(const u32 *__restrict__ rep, const PhraseFp *__restrict__ rec,
+                                 u64 d, u64 *__restrict__ wfpa, u64 *__restrict__ wfpb) {
     u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= d) return;
     u32 j = rep[u];
-    wfpa[u] = fpa[j];
-    wfpb[u] = fpb[j];
+    wfpa[u] = rec[j].fpa;
+    wfpb[u] = rec[j].fpb;
 }
 
 int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays &ph, u64 *wfpa,
                        u64 *wfpb) {
-    gather_word_fp_k<<<pfp_blocks(D.d, 256), 256, 0, ctx->stream>>>(D.rep, ph.fpa, ph.fpb, D.d, wfpa, wfpb);
+    gather_word_fp_k<<<pfp_blocks(D.d, 256), 256, 0, ctx->stream>>>(D.rep, ph.rec, D.d, wfpa, wfpb);
     PFP_LAUNCHED(ctx);
     return PFPB200_OK;
 }
@@ -488,11 +566,7 @@ int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, con
     merge_keys_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(fpa, fpb, len, n, k0, v0);
     PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, n, 0, 64, &sk, &sv));
-    PhraseArrays view{};
-    view.fpa = const_cast<u64 *>(fpa);
-    view.fpb = const_cast<u64 *>(fpb);
-    view.len = const_cast<u32 *>(len);
-    mark_heads_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(sk, sv, n, view, head, ctx->d_flags);
+    mark_heads_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(sk, sv, n, fpa, fpb, len, head, ctx->d_flags);
     PFP_LAUNCHED(ctx);
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
     PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, head, hscan, n, reinterpret_cast<u32 *>(&ctx->d_flags[1])));

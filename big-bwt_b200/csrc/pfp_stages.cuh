@@ -18,14 +18,19 @@ __device__ __forceinline__ u8 tv_byte(const TextView &tv, i64 g) {
 }
 
 // ---- per-phrase arrays (P entries, text order) ----------------------------------------------------
+// 32-byte fingerprint record of a phrase: one sector, written once by K2, read by K3
+struct __align__(32) PhraseFp {
+    u64 fpa, fpb;   // 128-bit NH fingerprint
+    u32 len;        // phrase length in bytes, including the w-byte overlap and virtual borders
+    u32 pad;
+    u64 key;        // table key derived from (fpa, fpb, len); never 0
+};
+
 struct PhraseArrays {
-    u64 *ends;   // inclusive global END position of the phrase (trigger position; n+w-1 for the last)
-    u64 *fpa;    // fingerprint half A
-    u64 *fpb;    // fingerprint half B
-    u64 *key;    // sort key derived from (fpa, fpb, len)
-    u32 *len;    // phrase length in bytes, including the w-byte overlap and virtual borders
-    u8 *last;    // .last stream
-    u8 *sai;     // .sai stream (5 bytes per phrase) or null
+    u64 *ends;      // inclusive global END position of the phrase (trigger position; n+w-1 for the last)
+    PhraseFp *rec;  // fingerprint records
+    u8 *last;       // .last stream
+    u8 *sai;        // .sai stream (5 bytes per phrase) or null
 };
 
 // ---- dictionary arrays (d entries, in fingerprint-key order = "uid" order) ---------------------------
