@@ -102,10 +102,15 @@ __global__ void phrase_records_k(TextView tv, const u64 *__restrict__ ends, u64 
 }
 
 constexpr int PH_T = 256;
-constexpr int PH_GROUP = 4;                          // lanes per phrase
-constexpr int PH_PER_WARP = 32 / PH_GROUP;
-constexpr int PH_PER_BLOCK = PH_T / PH_GROUP;        // 64 phrases per CTA iteration
+constexpr int PH_WARPS = PH_T / 32;
+constexpr int PH_PER_BLOCK = PH_T;                   // one phrase per thread of a warp block
 
+// A warp takes 32 consecutive phrases, flattens them into their 16-byte chunks and gives every
+// lane the same number of consecutive chunks (phrase lengths are geometric: giving lanes whole
+// phrases would leave most of the warp idle).  NH sums are additive, so a lane adds what it
+// accumulated to the phrase's shared-memory accumulator whenever it crosses a phrase boundary
+// (dealing chunks round-robin instead costs two shared atomics per chunk: measured 1.6x slower).
+// Phrases longer than one NH segment (8 KB) go to phrase_hash_long_k.
 __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays ph, u64 P,
                                                       i64 first_start, u32 w,
                                                       const u32 *__restrict__ keytab,
@@ -113,51 +118,83 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
                                                       u32 *__restrict__ long_count,
                                                       u64 *__restrict__ flags) {
     __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
+    __shared__ i64 s_s0[PH_WARPS][32];
+    __shared__ u32 s_len[PH_WARPS][32];
+    __shared__ u32 s_pre[PH_WARPS][33];
+    __shared__ unsigned long long s_acc[PH_WARPS][32][2];
     for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
     __syncthreads();
-    const u32 lane = threadIdx.x & 31, li = lane & (PH_GROUP - 1), grp = lane / PH_GROUP;
-    const u32 gmask = ((1u << PH_GROUP) - 1u) << (PH_GROUP * grp);
-    const u32 warp = threadIdx.x >> 5;
-    for (u64 jw = ((u64)blockIdx.x * (PH_T / 32) + warp) * PH_PER_WARP; jw < P;
-         jw += (u64)gridDim.x * PH_PER_BLOCK) {
-        u64 j = jw + grp;
-        if (j >= P) continue;                                  // whole group leaves together
-        i64 e = (i64)ph.ends[j];
-        i64 s0 = (j == 0) ? first_start : (i64)ph.ends[j - 1] - (i64)w + 1;
-        u64 len = (u64)(e - s0 + 1);
-        if (len > PHRASE_LONG) {
-            if (li == 0) {
-                if (len > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
-                else long_list[atomicAdd(long_count, 1u)] = (u32)j;
-            }
-            continue;
+    const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (u64 j0 = ((u64)blockIdx.x * PH_WARPS + wp) * 32; j0 < P; j0 += (u64)gridDim.x * PH_PER_BLOCK) {
+        const u64 j = j0 + lane;
+        const bool valid = j < P;
+        i64 e = valid ? (i64)ph.ends[j] : 0;
+        i64 prev = __shfl_up_sync(0xffffffffu, e, 1);
+        if (lane == 0) prev = (j0 > 0) ? (i64)ph.ends[j0 - 1] : 0;
+        const i64 s0 = (j == 0) ? first_start : prev - (i64)w + 1;
+        const u64 len = valid ? (u64)(e - s0 + 1) : 0;
+        const bool is_long = len > NH_SEG_BYTES;
+        if (is_long) {
+            if (len > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
+            else long_list[atomicAdd(long_count, 1u)] = (u32)j;
         }
-        const bool special = (s0 < 0) || (e >= tv.n_global);
-        u64 fa = 0, fb = 0;
-        const u32 nseg = (u32)((len + NH_SEG_BYTES - 1) / NH_SEG_BYTES);
-        for (u32 s = 0; s < nseg; s++) {
-            u64 so = (u64)s * NH_SEG_BYTES;
-            u32 segb = (u32)((len - so) < NH_SEG_BYTES ? (len - so) : NH_SEG_BYTES);
-            u32 nch = (segb + 15) >> 4;
+        const u32 mylen = is_long ? 0u : (u32)len;
+        const u32 nch = (mylen + 15) >> 4;
+        const u32 incl = warp_incl_scan(nch);
+        const u32 T = __shfl_sync(0xffffffffu, incl, 31);
+        s_s0[wp][lane] = s0;
+        s_len[wp][lane] = mylen;
+        s_pre[wp][lane] = incl - nch;
+        if (lane == 31) s_pre[wp][32] = T;
+        s_acc[wp][lane][0] = 0ull;
+        s_acc[wp][lane][1] = 0ull;
+        __syncwarp();
+        const u32 K = (T + 31) >> 5;
+        u32 g = lane * K;
+        const u32 g1 = (g + K < T) ? g + K : T;
+        if (g < g1) {
+            u32 lo = 0, hi = 32;              // phrase holding chunk g: pre[lo] <= g < pre[lo+1]
+            while (hi - lo > 1) {
+                u32 mid = (lo + hi) >> 1;
+                if (s_pre[wp][mid] <= g) lo = mid; else hi = mid;
+            }
+            u32 q = lo;
+            u32 c = g - s_pre[wp][q];
+            i64 qs0 = s_s0[wp][q];
+            u32 qlen = s_len[wp][q];
+            u32 qnch = (qlen + 15) >> 4;
+            bool special = (qs0 < 0) || (qs0 + (i64)qlen - 1 >= tv.n_global);
             u64 pa = 0, pb = 0;
-            for (u32 c = li; c < nch; c += PH_GROUP) {
+            for (; g < g1; g++) {
                 u32 x[4];
-                load_chunk(tv, s0, len, so + 16ull * c, special, x);
+                load_chunk(tv, qs0, qlen, 16ull * c, special, x);
                 nh_chunk(sk, c, x, pa, pb);
+                if (++c == qnch) {
+                    atomicAdd(&s_acc[wp][q][0], (unsigned long long)pa);
+                    atomicAdd(&s_acc[wp][q][1], (unsigned long long)pb);
+                    pa = pb = 0;
+                    c = 0;
+                    do { q++; } while (q < 32 && s_len[wp][q] == 0);
+                    if (q < 32) {
+                        qs0 = s_s0[wp][q];
+                        qlen = s_len[wp][q];
+                        qnch = (qlen + 15) >> 4;
+                        special = (qs0 < 0) || (qs0 + (i64)qlen - 1 >= tv.n_global);
+                    }
+                }
             }
-            fa = fa * NH_FOLD_A + pa;
-            fb = fb * NH_FOLD_B + pb;
+            if (c != 0) {
+                atomicAdd(&s_acc[wp][q][0], (unsigned long long)pa);
+                atomicAdd(&s_acc[wp][q][1], (unsigned long long)pb);
+            }
         }
-#pragma unroll
-        for (int o = PH_GROUP / 2; o > 0; o >>= 1) {
-            fa += __shfl_xor_sync(gmask, fa, o);
-            fb += __shfl_xor_sync(gmask, fb, o);
-        }
-        if (li == 0) store_rec(ph.rec, j, fa, fb, (u32)len);
+        __syncwarp();
+        if (valid && !is_long) store_rec(ph.rec, j, s_acc[wp][lane][0], s_acc[wp][lane][1], (u32)len);
+        __syncwarp();
     }
 }
 
-// phrases longer than PHRASE_LONG: one CTA per phrase, 32 groups of 8 lanes stride over the segments
+// phrases longer than one NH segment: one CTA per phrase, 32 groups of 8 lanes stride over the segments
 constexpr int PL_GROUP = 8;
 constexpr int PL_GROUPS = PH_T / PL_GROUP;
 __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseArrays ph,
@@ -220,23 +257,44 @@ __global__ void iota_u32_k(u32 *v, u64 n) {
 }
 
 // ---- K3: dictionary table ----------------------------------------------------------------------------
-// Open addressing, linear probing, 16-byte slots {key, first phrase, occurrences}; key 0 = empty.
+// Open addressing, linear probing, 16-byte slots {key, occurrences, check}; key 0 = empty.
 // A warp first groups its lanes by key (match.any) so that runs of identical phrases cost one
-// atomic per warp instead of 32.
-struct __align__(16) DictSlot { u64 key; u32 rep; u32 cnt; };
+// atomic per warp instead of 32.  `chk` is a 32-bit digest of the full 128-bit fingerprint and
+// the length, independent of the key: every phrase that lands in a slot must agree with it, or
+// the parse stops with PFPB200_E_COLLISION (the reference compares strings, newscan.cpp:282-286).
+struct __align__(16) DictSlot { u64 key; u32 cnt; u32 chk; };
+
+__device__ __forceinline__ u32 check_of(const PhraseFp &r) {
+    u64 x = (r.fpa + 0x632BE59BD9B4E019ULL) * 0xD1342543DE82EF95ULL;
+    x ^= rotl64(r.fpb, 23) * 0xAF251AF3B0F025B5ULL;
+    x ^= (u64)r.len << 32;
+    x ^= x >> 29;
+    u32 c = (u32)(x ^ (x >> 32));
+    return c ? c : 1u;
+}
 
 __global__ void table_init_k(DictSlot *__restrict__ tab, u64 cap) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap) *reinterpret_cast<uint4 *>(tab + i) = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+    if (i < cap) *reinterpret_cast<uint4 *>(tab + i) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict__ rec, u64 P,
                                                       DictSlot *__restrict__ tab, u64 mask, int shift,
-                                                      u32 *__restrict__ slot_of) {
+                                                      u32 *__restrict__ slot_of,
+                                                      u64 *__restrict__ flags) {
     u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < P;
-    u64 k = active ? rec[j].key : 0ull;
-    u32 peers = __match_any_sync(0xffffffffu, k);
+    PhraseFp r;
+    r.key = 0;
+    if (active) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(rec + j);
+        uint4 a = __ldg(q), b = __ldg(q + 1);
+        r.fpa = ((u64)a.y << 32) | a.x; r.fpb = ((u64)a.w << 32) | a.z;
+        r.len = b.x; r.key = ((u64)b.w << 32) | b.z;
+    }
+    const u64 k = r.key;
+    const u32 chk = active ? check_of(r) : 0u;
+    const u32 peers = __match_any_sync(0xffffffffu, k);
     const u32 lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
     u64 slot = 0;
@@ -248,10 +306,15 @@ __global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict
             slot = (slot + 1) & mask;
         }
         atomicAdd(&tab[slot].cnt, (u32)__popc(peers));
-        atomicMin(&tab[slot].rep, (u32)j);          // lowest lane of the group = smallest index
+        u32 pc = atomicCAS(&tab[slot].chk, 0u, chk);
+        if (pc != 0u && pc != chk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
     }
     slot = __shfl_sync(0xffffffffu, slot, leader);
-    if (active) slot_of[j] = (u32)slot;
+    const u32 lchk = __shfl_sync(0xffffffffu, chk, leader);
+    if (active) {
+        slot_of[j] = (u32)slot;
+        if (chk != lchk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+    }
 }
 
 __global__ void table_flags_k(const DictSlot *__restrict__ tab, u64 cap, u8 *__restrict__ occ) {
@@ -260,17 +323,39 @@ __global__ void table_flags_k(const DictSlot *__restrict__ tab, u64 cap, u8 *__r
 }
 
 __global__ void table_emit_k(const DictSlot *__restrict__ tab, const u8 *__restrict__ occ,
-                             const u32 *__restrict__ umap, u64 cap, const PhraseFp *__restrict__ rec,
-                             u32 *__restrict__ rep, u32 *__restrict__ count, u32 *__restrict__ ulen,
-                             u32 *__restrict__ uwords, u64 *__restrict__ flags) {
+                             const u32 *__restrict__ umap, u64 cap, u32 *__restrict__ count,
+                             u32 *__restrict__ rep) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 L = 0;
     if (i < cap && occ[i]) {
         u32 u = umap[i];
-        DictSlot s = tab[i];
-        rep[u] = s.rep;
-        count[u] = s.cnt;
-        L = rec[s.rep].len;
+        count[u] = tab[i].cnt;
+        rep[u] = 0xFFFFFFFFu;
+    }
+}
+
+// phrase -> word id; the first phrase of every word becomes its representative occurrence
+__global__ void table_uid_k(const u32 *__restrict__ slot_of, const u32 *__restrict__ umap, u64 P,
+                            u32 *__restrict__ uid, u32 *__restrict__ rep) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < P;
+    u32 u = active ? umap[slot_of[j]] : 0xFFFFFFFFu;
+    if (active) uid[j] = u;
+    // lanes of a warp hold increasing j: the lowest lane of each group carries the minimum
+    u32 peers = __match_any_sync(0xffffffffu, u);
+    if (active && (peers & lanemask_lt()) == 0) atomicMin(&rep[u], (u32)j);
+}
+
+__global__ void word_stats_k(const u32 *__restrict__ rep, const PhraseFp *__restrict__ rec, u64 d,
+                             u32 *__restrict__ ulen, u32 *__restrict__ uwords,
+                             u64 *__restrict__ flags /* [2]=max len, [3]=sum len */) {
+    __shared__ unsigned long long s_sum;
+    __shared__ u32 s_max;
+    if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }
+    __syncthreads();
+    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 L = 0;
+    if (u < d) {
+        L = rec[rep[u]].len;
         ulen[u] = L;
         uwords[u] = (L + 7) >> 3;
     }
@@ -281,29 +366,11 @@ __global__ void table_emit_k(const DictSlot *__restrict__ tab, const u8 *__restr
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
     }
-    if ((threadIdx.x & 31) == 0 && sum) {
-        atomicMax((unsigned long long *)&flags[2], (unsigned long long)mx);
-        atomicAdd((unsigned long long *)&flags[3], (unsigned long long)sum);
-    }
-}
-
-// phrase -> word id, and the collision check: every phrase agrees with its word's first
-// occurrence on the full fingerprint and the length (newscan.cpp:282-286 compares the strings)
-__global__ void table_uid_k(const PhraseFp *__restrict__ rec, const u32 *__restrict__ slot_of,
-                            const DictSlot *__restrict__ tab, const u32 *__restrict__ umap, u64 P,
-                            u32 *__restrict__ uid, u64 *__restrict__ flags) {
-    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P) return;
-    u32 s = slot_of[j];
-    uid[j] = umap[s];
-    u32 r = tab[s].rep;
-    if (r != (u32)j) {
-        const uint4 *a = reinterpret_cast<const uint4 *>(rec + j);
-        const uint4 *b = reinterpret_cast<const uint4 *>(rec + r);
-        uint4 a0 = __ldg(a), b0 = __ldg(b);
-        u32 la = __ldg(&rec[j].len), lb = __ldg(&rec[r].len);
-        if (a0.x != b0.x || a0.y != b0.y || a0.z != b0.z || a0.w != b0.w || la != lb)
-            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum, (unsigned long long)sum); atomicMax(&s_max, mx); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) {
+        atomicMax((unsigned long long *)&flags[2], (unsigned long long)s_max);
+        atomicAdd((unsigned long long *)&flags[3], s_sum);
     }
 }
 
@@ -382,7 +449,7 @@ __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__re
 int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 P,
                    i64 first_start, u32 w) {
     u32 *long_list = nullptr, *long_count = nullptr;
-    u64 cap = tv.n_buf / PHRASE_LONG + 4;    // at most this many phrases exceed PHRASE_LONG
+    u64 cap = tv.n_buf / NH_SEG_BYTES + 4;   // at most this many phrases exceed one NH segment
     PFP_TRY(pfp_alloc_t(ctx, &long_list, (size_t)cap));
     PFP_TRY(pfp_alloc_t(ctx, &long_count, 1));
     PFP_CUDA(ctx, cudaMemsetAsync(long_count, 0, sizeof(u32), ctx->stream));
@@ -422,7 +489,8 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays 
     PFP_TRY(pfp_alloc_t(ctx, &slot_of, P));
     table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
     PFP_LAUNCHED(ctx);
-    table_insert_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(ph.rec, P, tab, cap - 1, 64 - kbits, slot_of);
+    table_insert_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(ph.rec, P, tab, cap - 1, 64 - kbits, slot_of,
+                                                              ctx->d_flags);
     PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_alloc_t(ctx, &occ, cap));
     PFP_TRY(pfp_alloc_t(ctx, &umap, cap));
@@ -445,10 +513,11 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays 
     PFP_TRY(pfp_alloc_t(ctx, &D->count, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->ulen, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->uwords, d));
-    table_emit_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, occ, umap, cap, ph.rec, D->rep, D->count,
-                                                              D->ulen, D->uwords, ctx->d_flags);
+    table_emit_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, occ, umap, cap, D->count, D->rep);
     PFP_LAUNCHED(ctx);
-    table_uid_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(ph.rec, slot_of, tab, umap, P, D->uid, ctx->d_flags);
+    table_uid_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(slot_of, umap, P, D->uid, D->rep);
+    PFP_LAUNCHED(ctx);
+    word_stats_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(D->rep, ph.rec, d, D->ulen, D->uwords, ctx->d_flags);
     PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_free_now(ctx, tab));
     PFP_TRY(pfp_free_now(ctx, slot_of));

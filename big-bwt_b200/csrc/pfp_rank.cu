@@ -475,6 +475,9 @@ __global__ void dict_layout_k(const u32 *__restrict__ ord, u64 d, const DictArra
 constexpr int DC_T = 256;
 constexpr int DC_GROUP = 8;
 
+// One 8-lane group per word.  The source (pool) is 8-byte aligned, the destination is not: the
+// bytes up to the destination's next 8-byte boundary and the last <8 bytes go out as byte
+// stores, everything between as aligned 8-byte stores of funnel-shifted pool words.
 __global__ void __launch_bounds__(DC_T) dict_copy_k(const u32 *__restrict__ ord,
                                                     const u64 *__restrict__ doff, u64 d,
                                                     const DictArrays D, u32 strip_w, u64 total,
@@ -483,24 +486,29 @@ __global__ void __launch_bounds__(DC_T) dict_copy_k(const u32 *__restrict__ ord,
     if (blockIdx.x == 0 && threadIdx.x == 0) dict[total] = (u8)PFP_END_OF_DICT;   // :438
     for (u64 i = (u64)blockIdx.x * (DC_T / DC_GROUP) + (threadIdx.x / DC_GROUP); i < d;
          i += (u64)gridDim.x * (DC_T / DC_GROUP)) {
-        u32 u = ord[i];
+        const u32 u = ord[i];
         u32 skip, outlen;
-        u64 off = D.uoff[u];
+        const u64 off = D.uoff[u];
         out_span(D.pool, off, D.ulen[u], strip_w, &skip, &outlen);
-        const u8 *src = reinterpret_cast<const u8 *>(D.pool + off) + skip;
+        const u64 *src64 = D.pool + off;
+        const u8 *src = reinterpret_cast<const u8 *>(src64) + skip;
         u8 *dst = dict + doff[i];
-        if (skip == 0) {
-            // aligned 8-byte source words, byte stores (destination is unaligned)
-            u32 nw = (outlen + 7) >> 3;
-            for (u32 k = li; k < nw; k += DC_GROUP) {
-                u64 v = __ldg(D.pool + off + k);
-                u32 nb = outlen - 8 * k < 8 ? outlen - 8 * k : 8;
-                for (u32 b = 0; b < nb; b++) dst[8 * k + b] = (u8)(v >> (8 * b));
-            }
-        } else {
-            for (u32 b = li; b < outlen; b += DC_GROUP) dst[b] = src[b];
+        u32 head = (u32)((8 - ((uintptr_t)dst & 7)) & 7);
+        if (head > outlen) head = outlen;
+        if (li < head) dst[li] = src[li];
+        const u32 nbody = (outlen - head) >> 3;
+        u64 *dst64 = reinterpret_cast<u64 *>(dst + head);
+        for (u32 k = li; k < nbody; k += DC_GROUP) {
+            u32 so = skip + head + 8 * k;
+            u32 sh = (so & 7) * 8;
+            u64 w0 = __ldg(src64 + (so >> 3));
+            u64 v = w0;
+            if (sh) v = (w0 >> sh) | (__ldg(src64 + (so >> 3) + 1) << (64 - sh));
+            dst64[k] = v;
         }
-        if (li == 0) dst[outlen] = (u8)PFP_END_OF_WORD;
+        const u32 done = head + 8 * nbody;
+        if (li < outlen - done) dst[done + li] = src[done + li];
+        if (li == DC_GROUP - 1) dst[outlen] = (u8)PFP_END_OF_WORD;                 // :416
     }
 }
 

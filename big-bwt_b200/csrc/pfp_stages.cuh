@@ -51,7 +51,6 @@ struct DictArrays {
 // ---- fingerprint parameters ---------------------------------------------------------------------------
 constexpr u32 NH_SEG_BYTES = 8192;                 // NH key table covers one segment
 constexpr u32 NH_KEY_WORDS = NH_SEG_BYTES / 4 + 8; // + Toeplitz shift for the second sum
-constexpr u64 PHRASE_LONG = 65536;                 // longer phrases get a CTA of their own
 constexpr u64 NH_FOLD_A = 0x9E3779B97F4A7C15ULL;   // odd multipliers folding segment sums
 constexpr u64 NH_FOLD_B = 0xD6E8FEB86659FD93ULL;
 
