@@ -117,6 +117,8 @@ class CudaBackend:
         """Run the library on torch's current stream so that its kernels are ordered with the
         collectives and tensor ops around them."""
         s = torch.cuda.current_stream(self.dev).cuda_stream
+        if s == 0:
+            s = 1          # cudaStreamLegacy: the handle 0 would mean "the library's own stream"
         if s != self._stream:
             self.scanner.set_stream(s)
             self._stream = s
