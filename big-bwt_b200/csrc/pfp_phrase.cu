@@ -65,6 +65,27 @@ __device__ __forceinline__ void load_chunk(const TextView &tv, i64 s0, u64 len, 
     }
 }
 
+// same from a shared-memory window that mirrors the text with the same 16-byte alignment
+__device__ __forceinline__ void load_chunk_win(const u8 *p, u32 len, u32 o, u32 x[4]) {
+    const u32 nbv = (len - o) < 16 ? (len - o) : 16;
+    p += o;
+    const u32 bs = (u32)((uintptr_t)p & 3);
+    const u32 *p4 = reinterpret_cast<const u32 *>(p - bs);
+    u32 W[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) W[j] = p4[j];
+#pragma unroll
+    for (int j = 0; j < 4; j++) x[j] = __funnelshift_r(W[j], W[j + 1], 8 * bs);
+    if (nbv < 16) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            u32 lo = 4u * j;
+            u32 nb = nbv > lo ? nbv - lo : 0;
+            if (nb < 4) x[j] &= (nb == 0) ? 0u : ((1u << (8 * nb)) - 1u);
+        }
+    }
+}
+
 __device__ __forceinline__ void nh_chunk(const u32 *__restrict__ sk, u32 c, const u32 x[4], u64 &pa,
                                          u64 &pb) {
     const uint4 k0 = *reinterpret_cast<const uint4 *>(sk + 4 * c);
@@ -104,6 +125,7 @@ __global__ void phrase_records_k(TextView tv, const u64 *__restrict__ ends, u64 
 constexpr int PH_T = 256;
 constexpr int PH_WARPS = PH_T / 32;
 constexpr int PH_PER_BLOCK = PH_T;                   // one phrase per thread of a warp block
+constexpr int PH_WIN = 6144;                         // shared-memory text window per warp
 
 // A warp takes 32 consecutive phrases, flattens them into their 16-byte chunks and gives every
 // lane the same number of consecutive chunks (phrase lengths are geometric: giving lanes whole
@@ -122,9 +144,11 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
     __shared__ u32 s_len[PH_WARPS][32];
     __shared__ u32 s_pre[PH_WARPS][33];
     __shared__ unsigned long long s_acc[PH_WARPS][32][2];
+    extern __shared__ __align__(16) unsigned char ph_win[];     // PH_WARPS windows of PH_WIN bytes
     for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
     __syncthreads();
     const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    unsigned char *win = ph_win + wp * PH_WIN;
     for (u64 j0 = ((u64)blockIdx.x * PH_WARPS + wp) * 32; j0 < P; j0 += (u64)gridDim.x * PH_PER_BLOCK) {
         const u64 j = j0 + lane;
         const bool valid = j < P;
@@ -148,6 +172,33 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
         if (lane == 31) s_pre[wp][32] = T;
         s_acc[wp][lane][0] = 0ull;
         s_acc[wp][lane][1] = 0ull;
+        // text window of the warp's phrases (those lying wholly inside the buffer): one coalesced
+        // pass of 16-byte loads into shared memory, so the per-lane chunk walks below hit
+        // shared memory instead of 32 different cache lines per load instruction
+        const bool inside = mylen > 0 && s0 >= tv.pos0 && e < tv.n_global &&
+                            (u64)(e - tv.pos0) < tv.n_buf;
+        i64 wlo = inside ? s0 - tv.pos0 : (i64)0x7fffffffffffffffLL;
+        i64 whi = inside ? e - tv.pos0 + 1 : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+            whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+        }
+        const u8 *gbase = nullptr;      // 16-byte aligned text address mirrored at win[0]
+        bool use_win = false;
+        if (whi > wlo) {
+            gbase = reinterpret_cast<const u8 *>(reinterpret_cast<uintptr_t>(tv.T + wlo) & ~(uintptr_t)15);
+            const u64 wbytes = (u64)((tv.T + whi) - gbase) + 24;    // + reach of the last 20-byte read
+            if (wbytes <= PH_WIN) {
+                use_win = true;
+                const u8 *gend = tv.T + tv.n_buf;
+                for (u32 o = lane * 16; o < wbytes; o += 512) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (gbase + o < gend) v = __ldg(reinterpret_cast<const uint4 *>(gbase + o));
+                    *reinterpret_cast<uint4 *>(win + o) = v;
+                }
+            }
+        }
         __syncwarp();
         const u32 K = (T + 31) >> 5;
         u32 g = lane * K;
@@ -164,10 +215,12 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
             u32 qlen = s_len[wp][q];
             u32 qnch = (qlen + 15) >> 4;
             bool special = (qs0 < 0) || (qs0 + (i64)qlen - 1 >= tv.n_global);
+            bool in_win = use_win && qs0 >= tv.pos0 && !special;
             u64 pa = 0, pb = 0;
             for (; g < g1; g++) {
                 u32 x[4];
-                load_chunk(tv, qs0, qlen, 16ull * c, special, x);
+                if (in_win) load_chunk_win(win + ((tv.T + (qs0 - tv.pos0)) - gbase), qlen, 16u * c, x);
+                else load_chunk(tv, qs0, qlen, 16ull * c, special, x);
                 nh_chunk(sk, c, x, pa, pb);
                 if (++c == qnch) {
                     atomicAdd(&s_acc[wp][q][0], (unsigned long long)pa);
@@ -180,6 +233,7 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
                         qlen = s_len[wp][q];
                         qnch = (qlen + 15) >> 4;
                         special = (qs0 < 0) || (qs0 + (i64)qlen - 1 >= tv.n_global);
+                        in_win = use_win && qs0 >= tv.pos0 && !special;
                     }
                 }
             }
@@ -459,8 +513,14 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     u64 maxb = (u64)ctx->sm_count * 32;
     u32 nb = (u32)(want < maxb ? want : maxb);
     if (nb == 0) nb = 1;
-    phrase_hash_k<<<nb, PH_T, 0, ctx->stream>>>(tv, ph, P, first_start, w, ctx->d_keys, long_list,
-                                                long_count, ctx->d_flags);
+    static bool attr = false;
+    if (!attr) {
+        PFP_CUDA(ctx, cudaFuncSetAttribute(phrase_hash_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           PH_WARPS * PH_WIN));
+        attr = true;
+    }
+    phrase_hash_k<<<nb, PH_T, PH_WARPS * PH_WIN, ctx->stream>>>(tv, ph, P, first_start, w, ctx->d_keys,
+                                                                 long_list, long_count, ctx->d_flags);
     PFP_LAUNCHED(ctx);
     u64 fa32 = 1, fb32 = 1;
     for (int i = 0; i < PL_GROUPS; i++) { fa32 *= NH_FOLD_A; fb32 *= NH_FOLD_B; }

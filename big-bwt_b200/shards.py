@@ -334,12 +334,26 @@ class ShardedParser:
         self.buf[self.front:].copy_(host_text, non_blocking=True)
         st = self._parse_sharded(w, p, sai, False)
         r = self.result
-        outs = [r["parse"], r["last"], r["sai"]]
+        outs = {"parse": r["parse"], "last": r["last"], "sai": r["sai"]}
         if self.mode == "partition" or self.rank == 0:
-            outs += [r["dict"], r["occ"]]
-        self.host_pieces = [t.cpu() for t in outs]
+            outs.update({"dict": r["dict"], "occ": r["occ"]})
+        # device -> pinned host buffers kept across calls (grown on demand), one sync at the end
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        self.host_pieces = {}
+        nbytes = 0
+        for k, t in outs.items():
+            t = t.contiguous().view(torch.uint8) if t.dtype != torch.uint8 else t.contiguous()
+            buf = self._pinned.get(k)
+            if buf is None or buf.numel() < t.numel():
+                buf = torch.empty(int(t.numel() * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+                self._pinned[k] = buf
+            buf[:t.numel()].copy_(t, non_blocking=True)
+            self.host_pieces[k] = buf[:t.numel()]
+            nbytes += t.numel()
+        torch.cuda.current_stream(dev).synchronize()
         st["h2d_bytes"] = int(host_text.numel())
-        st["d2h_bytes"] = int(sum(t.numel() * t.element_size() for t in outs))
+        st["d2h_bytes"] = int(nbytes)
         return st
 
     def _parse_sharded(self, w, p, sai, compress) -> dict:
