@@ -32,6 +32,7 @@ struct pfpb200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     u32 launches = 0;
+    double dedup_ratio = 0.0;      // distinct words / phrases of the previous parse (table sizing hint)
     char err[512] = {0};
     std::vector<void *> scratch;   // freed at the end of every call
     std::vector<void *> held;      // outputs: freed at the start of the next call / destroy
@@ -58,6 +59,7 @@ struct pfpb200_ctx {
 #define PFP_ERRBIT_COLLISION 1ull
 #define PFP_ERRBIT_LIMIT 2ull
 #define PFP_ERRBIT_INTERNAL 4ull
+#define PFP_ERRBIT_TABLE_FULL 8ull
 
 int pfp_fail(pfpb200_ctx *ctx, int code, const char *fmt, ...);
 

@@ -14,6 +14,7 @@
 // the run = representative occurrence.
 #include "pfp_common.cuh"
 #include "pfp_stages.cuh"
+#include <stdlib.h>
 
 __device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
 __device__ __forceinline__ u64 fmix64(u64 k) {
@@ -65,9 +66,10 @@ __device__ __forceinline__ void load_chunk(const TextView &tv, i64 s0, u64 len, 
     }
 }
 
-// same from a shared-memory window that mirrors the text with the same 16-byte alignment
-__device__ __forceinline__ void load_chunk_win(const u8 *p, u32 len, u32 o, u32 x[4]) {
-    const u32 nbv = (len - o) < 16 ? (len - o) : 16;
+// 16 bytes at phrase offset o through a generic pointer (shared-memory window or global text),
+// bytes past the phrase end zeroed without branches; the caller guarantees 20 readable bytes
+__device__ __forceinline__ void load_chunk_ptr(const u8 *p, u32 len, u32 o, u32 x[4]) {
+    const u32 rem = len - o;                         // >= 1
     p += o;
     const u32 bs = (u32)((uintptr_t)p & 3);
     const u32 *p4 = reinterpret_cast<const u32 *>(p - bs);
@@ -75,14 +77,12 @@ __device__ __forceinline__ void load_chunk_win(const u8 *p, u32 len, u32 o, u32 
 #pragma unroll
     for (int j = 0; j < 5; j++) W[j] = p4[j];
 #pragma unroll
-    for (int j = 0; j < 4; j++) x[j] = __funnelshift_r(W[j], W[j + 1], 8 * bs);
-    if (nbv < 16) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            u32 lo = 4u * j;
-            u32 nb = nbv > lo ? nbv - lo : 0;
-            if (nb < 4) x[j] &= (nb == 0) ? 0u : ((1u << (8 * nb)) - 1u);
-        }
+    for (int j = 0; j < 4; j++) {
+        u32 v = __funnelshift_r(W[j], W[j + 1], 8 * bs);
+        // valid bytes of word j: clamp(rem - 4j, 0, 4) -> mask = 0xFFFFFFFF >> 8*(4 - nb)
+        int nb = (int)rem - 4 * j;
+        nb = nb < 0 ? 0 : (nb > 4 ? 4 : nb);
+        x[j] = v & __funnelshift_rc(0xFFFFFFFFu, 0u, 8u * (4u - (u32)nb));
     }
 }
 
@@ -127,6 +127,7 @@ constexpr int PH_WARPS = PH_T / 32;
 constexpr int PH_PER_BLOCK = PH_T;                   // one phrase per thread of a warp block
 constexpr int PH_WIN = 6144;                         // shared-memory text window per warp
 
+
 // A warp takes 32 consecutive phrases, flattens them into their 16-byte chunks and gives every
 // lane the same number of consecutive chunks (phrase lengths are geometric: giving lanes whole
 // phrases would leave most of the warp idle).  NH sums are additive, so a lane adds what it
@@ -138,9 +139,9 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
                                                       const u32 *__restrict__ keytab,
                                                       u32 *__restrict__ long_list,
                                                       u32 *__restrict__ long_count,
-                                                      u64 *__restrict__ flags) {
+                                                      u64 *__restrict__ flags, int use_window) {
     __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
-    __shared__ i64 s_s0[PH_WARPS][32];
+    __shared__ const u8 *s_ptr[PH_WARPS][32];
     __shared__ u32 s_len[PH_WARPS][32];
     __shared__ u32 s_pre[PH_WARPS][33];
     __shared__ unsigned long long s_acc[PH_WARPS][32][2];
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
     __syncthreads();
     const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     unsigned char *win = ph_win + wp * PH_WIN;
+    const u8 *gend = tv.T + tv.n_buf;
     for (u64 j0 = ((u64)blockIdx.x * PH_WARPS + wp) * 32; j0 < P; j0 += (u64)gridDim.x * PH_PER_BLOCK) {
         const u64 j = j0 + lane;
         const bool valid = j < P;
@@ -157,93 +159,103 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
         if (lane == 0) prev = (j0 > 0) ? (i64)ph.ends[j0 - 1] : 0;
         const i64 s0 = (j == 0) ? first_start : prev - (i64)w + 1;
         const u64 len = valid ? (u64)(e - s0 + 1) : 0;
-        const bool is_long = len > NH_SEG_BYTES;
-        if (is_long) {
+        // the long kernel takes phrases beyond one NH segment, phrases touching the virtual
+        // borders of the text, and phrases within 20 bytes of the end of the buffer
+        const bool slow = valid && (len > NH_SEG_BYTES || s0 < tv.pos0 || e >= tv.n_global ||
+                                    (u64)(e - tv.pos0) + 24 > tv.n_buf);
+        if (slow) {
             if (len > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
             else long_list[atomicAdd(long_count, 1u)] = (u32)j;
         }
-        const u32 mylen = is_long ? 0u : (u32)len;
+        const u32 mylen = slow ? 0u : (u32)len;
         const u32 nch = (mylen + 15) >> 4;
         const u32 incl = warp_incl_scan(nch);
         const u32 T = __shfl_sync(0xffffffffu, incl, 31);
-        s_s0[wp][lane] = s0;
-        s_len[wp][lane] = mylen;
-        s_pre[wp][lane] = incl - nch;
-        if (lane == 31) s_pre[wp][32] = T;
-        s_acc[wp][lane][0] = 0ull;
-        s_acc[wp][lane][1] = 0ull;
-        // text window of the warp's phrases (those lying wholly inside the buffer): one coalesced
-        // pass of 16-byte loads into shared memory, so the per-lane chunk walks below hit
-        // shared memory instead of 32 different cache lines per load instruction
-        const bool inside = mylen > 0 && s0 >= tv.pos0 && e < tv.n_global &&
-                            (u64)(e - tv.pos0) < tv.n_buf;
-        i64 wlo = inside ? s0 - tv.pos0 : (i64)0x7fffffffffffffffLL;
-        i64 whi = inside ? e - tv.pos0 + 1 : -1;
+        // text window of the warp's phrases: one coalesced pass of 16-byte loads into shared
+        // memory, so that the per-lane chunk walks do not touch 32 cache lines per instruction
+        i64 wlo = mylen ? s0 - tv.pos0 : (i64)0x7fffffffffffffffLL;
+        i64 whi = mylen ? e - tv.pos0 + 1 : -1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
             whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
         }
-        const u8 *gbase = nullptr;      // 16-byte aligned text address mirrored at win[0]
-        bool use_win = false;
-        if (whi > wlo) {
-            gbase = reinterpret_cast<const u8 *>(reinterpret_cast<uintptr_t>(tv.T + wlo) & ~(uintptr_t)15);
+        const u8 *myptr = tv.T + (s0 - tv.pos0);
+        if (use_window && whi > wlo) {
+            const u8 *gbase = reinterpret_cast<const u8 *>(reinterpret_cast<uintptr_t>(tv.T + wlo) & ~(uintptr_t)15);
             const u64 wbytes = (u64)((tv.T + whi) - gbase) + 24;    // + reach of the last 20-byte read
             if (wbytes <= PH_WIN) {
-                use_win = true;
-                const u8 *gend = tv.T + tv.n_buf;
                 for (u32 o = lane * 16; o < wbytes; o += 512) {
                     uint4 v = make_uint4(0u, 0u, 0u, 0u);
                     if (gbase + o < gend) v = __ldg(reinterpret_cast<const uint4 *>(gbase + o));
                     *reinterpret_cast<uint4 *>(win + o) = v;
                 }
+                myptr = win + (myptr - gbase);
             }
         }
+        s_ptr[wp][lane] = myptr;
+        s_len[wp][lane] = mylen;
+        s_pre[wp][lane] = incl - nch;
+        if (lane == 31) s_pre[wp][32] = T;
+        s_acc[wp][lane][0] = 0ull;
+        s_acc[wp][lane][1] = 0ull;
         __syncwarp();
         const u32 K = (T + 31) >> 5;
         u32 g = lane * K;
         const u32 g1 = (g + K < T) ? g + K : T;
+        // A phrase finished inside the lane that started it is stored at once.  A phrase that
+        // spans lanes is the sum of: the tail partial of the lane where it starts, the whole sum
+        // of every lane lying inside it (pass-through), the head partial of the lane where it
+        // ends -- combined by one segmented warp scan, no atomics.
+        u64 head_a = 0, head_b = 0, tail_a = 0, tail_b = 0;
+        u32 head_q = 0xFFFFFFFFu;
+        bool pass = false;
         if (g < g1) {
             u32 lo = 0, hi = 32;              // phrase holding chunk g: pre[lo] <= g < pre[lo+1]
-            while (hi - lo > 1) {
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
                 u32 mid = (lo + hi) >> 1;
                 if (s_pre[wp][mid] <= g) lo = mid; else hi = mid;
             }
             u32 q = lo;
             u32 c = g - s_pre[wp][q];
-            i64 qs0 = s_s0[wp][q];
+            bool cont = c != 0;               // the first partial continues an earlier lane's phrase
+            const u8 *qp = s_ptr[wp][q];
             u32 qlen = s_len[wp][q];
             u32 qnch = (qlen + 15) >> 4;
-            bool special = (qs0 < 0) || (qs0 + (i64)qlen - 1 >= tv.n_global);
-            bool in_win = use_win && qs0 >= tv.pos0 && !special;
             u64 pa = 0, pb = 0;
             for (; g < g1; g++) {
                 u32 x[4];
-                if (in_win) load_chunk_win(win + ((tv.T + (qs0 - tv.pos0)) - gbase), qlen, 16u * c, x);
-                else load_chunk(tv, qs0, qlen, 16ull * c, special, x);
+                load_chunk_ptr(qp, qlen, 16u * c, x);
                 nh_chunk(sk, c, x, pa, pb);
                 if (++c == qnch) {
-                    atomicAdd(&s_acc[wp][q][0], (unsigned long long)pa);
-                    atomicAdd(&s_acc[wp][q][1], (unsigned long long)pb);
+                    if (cont) { head_a = pa; head_b = pb; head_q = q; cont = false; }
+                    else { s_acc[wp][q][0] = pa; s_acc[wp][q][1] = pb; }
                     pa = pb = 0;
                     c = 0;
-                    do { q++; } while (q < 32 && s_len[wp][q] == 0);
-                    if (q < 32) {
-                        qs0 = s_s0[wp][q];
-                        qlen = s_len[wp][q];
-                        qnch = (qlen + 15) >> 4;
-                        special = (qs0 < 0) || (qs0 + (i64)qlen - 1 >= tv.n_global);
-                        in_win = use_win && qs0 >= tv.pos0 && !special;
-                    }
+                    do { q++; } while (q < 31 && s_len[wp][q] == 0);
+                    qp = s_ptr[wp][q & 31];
+                    qlen = s_len[wp][q & 31];
+                    qnch = (qlen + 15) >> 4;
                 }
             }
-            if (c != 0) {
-                atomicAdd(&s_acc[wp][q][0], (unsigned long long)pa);
-                atomicAdd(&s_acc[wp][q][1], (unsigned long long)pb);
-            }
+            if (c != 0) { tail_a = pa; tail_b = pb; pass = cont; }
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 ta = __shfl_up_sync(0xffffffffu, tail_a, o);
+            u64 tb = __shfl_up_sync(0xffffffffu, tail_b, o);
+            int tp = __shfl_up_sync(0xffffffffu, (int)pass, o);
+            if (lane >= (u32)o && pass) { tail_a += ta; tail_b += tb; pass = tp != 0; }
+        }
+        u64 ca = __shfl_up_sync(0xffffffffu, tail_a, 1);
+        u64 cb = __shfl_up_sync(0xffffffffu, tail_b, 1);
+        if (head_q != 0xFFFFFFFFu) {
+            s_acc[wp][head_q][0] = head_a + (lane ? ca : 0ull);
+            s_acc[wp][head_q][1] = head_b + (lane ? cb : 0ull);
         }
         __syncwarp();
-        if (valid && !is_long) store_rec(ph.rec, j, s_acc[wp][lane][0], s_acc[wp][lane][1], (u32)len);
+        if (valid && !slow) store_rec(ph.rec, j, s_acc[wp][lane][0], s_acc[wp][lane][1], (u32)len);
         __syncwarp();
     }
 }
@@ -317,6 +329,7 @@ __global__ void iota_u32_k(u32 *v, u64 n) {
 // the length, independent of the key: every phrase that lands in a slot must agree with it, or
 // the parse stops with PFPB200_E_COLLISION (the reference compares strings, newscan.cpp:282-286).
 struct __align__(16) DictSlot { u64 key; u32 cnt; u32 chk; };
+constexpr u32 TABLE_MAX_PROBES = 2048;
 
 __device__ __forceinline__ u32 check_of(const PhraseFp &r) {
     u64 x = (r.fpa + 0x632BE59BD9B4E019ULL) * 0xD1342543DE82EF95ULL;
@@ -354,14 +367,22 @@ __global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict
     u64 slot = 0;
     if (active && (int)lane == leader) {
         slot = k >> shift;
+        u32 probes = 0;
+        bool placed = false;
         for (;;) {
             u64 prev = atomicCAS((unsigned long long *)&tab[slot].key, 0ull, (unsigned long long)k);
-            if (prev == 0ull || prev == k) break;
+            if (prev == 0ull || prev == k) { placed = true; break; }
+            if (++probes > TABLE_MAX_PROBES) break;           // table too small for this input
             slot = (slot + 1) & mask;
         }
-        atomicAdd(&tab[slot].cnt, (u32)__popc(peers));
-        u32 pc = atomicCAS(&tab[slot].chk, 0u, chk);
-        if (pc != 0u && pc != chk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+        if (placed) {
+            atomicAdd(&tab[slot].cnt, (u32)__popc(peers));
+            u32 pc = atomicCAS(&tab[slot].chk, 0u, chk);
+            if (pc != 0u && pc != chk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+        } else {
+            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_TABLE_FULL);
+            slot = 0;
+        }
     }
     slot = __shfl_sync(0xffffffffu, slot, leader);
     const u32 lchk = __shfl_sync(0xffffffffu, chk, leader);
@@ -503,7 +524,7 @@ __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__re
 int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 P,
                    i64 first_start, u32 w) {
     u32 *long_list = nullptr, *long_count = nullptr;
-    u64 cap = tv.n_buf / NH_SEG_BYTES + 4;   // at most this many phrases exceed one NH segment
+    u64 cap = tv.n_buf / NH_SEG_BYTES + 8;   // phrases beyond one NH segment + the few at the borders
     PFP_TRY(pfp_alloc_t(ctx, &long_list, (size_t)cap));
     PFP_TRY(pfp_alloc_t(ctx, &long_count, 1));
     PFP_CUDA(ctx, cudaMemsetAsync(long_count, 0, sizeof(u32), ctx->stream));
@@ -519,8 +540,13 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
                                            PH_WARPS * PH_WIN));
         attr = true;
     }
-    phrase_hash_k<<<nb, PH_T, PH_WARPS * PH_WIN, ctx->stream>>>(tv, ph, P, first_start, w, ctx->d_keys,
-                                                                 long_list, long_count, ctx->d_flags);
+    static int use_window = -1;
+    if (use_window < 0) {
+        const char *ev = getenv("PFPB200_K2_WINDOW");
+        use_window = ev ? atoi(ev) : 0;      // measured: no gain on B200 once the atomics were gone
+    }
+    phrase_hash_k<<<nb, PH_T, use_window ? PH_WARPS * PH_WIN : 0, ctx->stream>>>(
+        tv, ph, P, first_start, w, ctx->d_keys, long_list, long_count, ctx->d_flags, use_window);
     PFP_LAUNCHED(ctx);
     u64 fa32 = 1, fb32 = 1;
     for (int i = 0; i < PL_GROUPS; i++) { fa32 *= NH_FOLD_A; fb32 *= NH_FOLD_B; }
@@ -537,33 +563,57 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
 // Reads d (and length stats) back to the host: one synchronisation.
 int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D) {
     const int TB = 256;
-    // capacity: power of two >= 1.5 P  (load factor <= 2/3 even if every phrase is distinct)
-    u64 cap = 1024;
-    while (cap < P + P / 2) cap <<= 1;
-    int kbits = 0;
-    while ((1ull << kbits) < cap) kbits++;
+    // Capacity: a power of two.  Without a hint 1.5 P (load factor <= 2/3 even if every phrase
+    // is distinct).  The distinct/phrase ratio of the previous parse on this context sizes the
+    // table ~2.5x the expected dictionary instead, which keeps it (and the passes over it) several
+    // times smaller on repetitive inputs; if that guess turns out too small the insert kernel says
+    // so and the stage reruns with the safe size.
     DictSlot *tab = nullptr;
     u32 *slot_of = nullptr, *umap = nullptr;
     u8 *occ = nullptr;
-    PFP_TRY(pfp_alloc_t(ctx, &tab, cap));
+    u64 cap = 0, d = 0;
     PFP_TRY(pfp_alloc_t(ctx, &slot_of, P));
-    table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
-    PFP_LAUNCHED(ctx);
-    table_insert_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(ph.rec, P, tab, cap - 1, 64 - kbits, slot_of,
-                                                              ctx->d_flags);
-    PFP_LAUNCHED(ctx);
-    PFP_TRY(pfp_alloc_t(ctx, &occ, cap));
-    PFP_TRY(pfp_alloc_t(ctx, &umap, cap));
-    table_flags_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap, occ);
-    PFP_LAUNCHED(ctx);
-    PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
-    PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, occ, umap, cap, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
-    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(u64), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
-        return pfp_fail(ctx, PFPB200_E_LIMIT, "a phrase is longer than 2^32-1 bytes");
-    u64 d = (u32)ctx->h_flags[1];
+    for (int attempt = 0;; attempt++) {
+        double want = (double)P * 1.5;
+        if (attempt == 0 && ctx->dedup_ratio > 0.0) {
+            double guess = ctx->dedup_ratio * (double)P * 2.5;
+            if (guess < want) want = guess;
+        }
+        cap = 1024;
+        while ((double)cap < want) cap <<= 1;
+        int kbits = 0;
+        while ((1ull << kbits) < cap) kbits++;
+        PFP_TRY(pfp_alloc_t(ctx, &tab, cap));
+        table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
+        PFP_LAUNCHED(ctx);
+        table_insert_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(ph.rec, P, tab, cap - 1, 64 - kbits, slot_of,
+                                                                  ctx->d_flags);
+        PFP_LAUNCHED(ctx);
+        PFP_TRY(pfp_alloc_t(ctx, &occ, cap));
+        PFP_TRY(pfp_alloc_t(ctx, &umap, cap));
+        table_flags_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap, occ);
+        PFP_LAUNCHED(ctx);
+        PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
+        PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, occ, umap, cap, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
+        PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(u64), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
+            return pfp_fail(ctx, PFPB200_E_LIMIT, "a phrase is longer than 2^32-1 bytes");
+        d = (u32)ctx->h_flags[1];
+        const bool full = (ctx->h_flags[0] & PFP_ERRBIT_TABLE_FULL) != 0 || (double)d > 0.85 * (double)cap;
+        if (!full) break;
+        if (attempt > 0) return pfp_fail(ctx, PFPB200_E_INTERNAL, "dictionary table overflow");
+        // undo and retry with the safe capacity
+        PFP_TRY(pfp_free_now(ctx, tab));
+        PFP_TRY(pfp_free_now(ctx, occ));
+        PFP_TRY(pfp_free_now(ctx, umap));
+        ctx->dedup_ratio = 0.0;
+        const u64 keep = ctx->h_flags[0] & ~PFP_ERRBIT_TABLE_FULL;
+        PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->d_flags[0], &keep, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->dedup_ratio = (double)d / (double)P;
     if (d > 0x7FFFFFFEull)
         return pfp_fail(ctx, PFPB200_E_LIMIT, "%llu distinct words exceed the limit 2^31-2",
                         (unsigned long long)d);

@@ -192,8 +192,10 @@ __global__ void rank_writeback_k(const u32 *__restrict__ apos, const u64 *__rest
 
 // ---- local refinement: one warp per small tie group ---------------------------------------------------
 // Lanes are the positions of the group.  Each round every still-tied lane loads the next 8-byte
-// chunk of its word and counts, inside its tie range [lo,hi), the lanes with a smaller chunk and
-// the equal ones in front of it: that is its new position; ties shrink until all are singletons.
+// chunk of its word; if no lane differs from the first lane of its tie range the round is a
+// shared prefix and is skipped at once.  Otherwise every lane counts, inside its tie range
+// [lo,hi), the lanes with a smaller chunk and the equal ones in front of it: that is its new
+// position; ties shrink until all are singletons.
 __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
                                                    const u32 *__restrict__ nheads,
                                                    const u32 *__restrict__ depth,
@@ -211,6 +213,9 @@ __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
         u32 r = depth[s];
         u32 uid = lane < m ? ord[s + lane] : 0;
         u32 lo = lane < m ? 0 : lane, hi = lane < m ? m : lane + 1;
+        const u64 woff = lane < m ? uoff[uid] : 0;
+        u32 wn = lane < m ? uwords[uid] : 0;
+        u64 myoff = woff;
         for (;;) {
             bool active = (hi - lo) > 1;
             if (!__any_sync(0xffffffffu, active)) break;
@@ -218,7 +223,9 @@ __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
                 if (lane == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
                 break;
             }
-            u64 key = active ? word_key(pool, uoff, uwords, uid, r) : 0ull;
+            u64 key = (active && r < wn) ? bswap64(__ldg(pool + myoff + r)) : 0ull;
+            u64 headkey = __shfl_sync(0xffffffffu, key, lo & 31);
+            if (!__any_sync(0xffffffffu, active && key != headkey)) { r++; continue; }   // shared prefix
             u32 less = 0, eqb = 0, eq = 0;
             for (u32 j = 0; j < m; j++) {
                 u64 kj = __shfl_sync(0xffffffffu, key, j);
@@ -234,26 +241,117 @@ __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
             s_uid[wp][np] = uid; s_lo[wp][np] = (u16)nlo; s_hi[wp][np] = (u16)nhi;
             __syncwarp();
             uid = s_uid[wp][lane]; lo = s_lo[wp][lane]; hi = s_hi[wp][lane];
+            if (lane < m) { myoff = uoff[uid]; wn = uwords[uid]; }
             r++;
         }
         if (lane < m) ord[s + lane] = uid;
     }
 }
 
-// ---- local refinement: one CTA per medium tie group -----------------------------------------------------
-struct CtaSort {
-    u64 key[LOCAL_MAX];
-    u32 uid[2][LOCAL_MAX];
-    u16 lo[2][LOCAL_MAX];
-    u16 hi[2][LOCAL_MAX];
+// ---- local refinement of larger tie groups in shared memory ---------------------------------------------
+// The same refinement with the group's positions in shared memory, worked on by NT threads:
+// NT = 32 (one warp per group of up to MID_MAX words, eight groups per CTA) or NT = 256 (one CTA
+// per group of up to LOCAL_MAX words).
+constexpr u32 MID_MAX = 256;
+
+template <u32 CAP>
+struct TieSort {
+    u64 key[CAP];
+    u32 uid[2][CAP];
+    u16 lo[2][CAP];
+    u16 hi[2][CAP];
 };
 
-__global__ void rank_cta_list_k(const u32 *__restrict__ hp, const u32 *__restrict__ nheads, u64 d,
-                                u32 *__restrict__ list, u32 *__restrict__ count) {
+template <int NT>
+__device__ __forceinline__ void tie_sync() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+}
+template <int NT>
+__device__ __forceinline__ int tie_any(int x) {
+    if (NT == 32) { int r = __any_sync(0xffffffffu, x); __syncwarp(); return r; }
+    return __syncthreads_or(x);
+}
+
+template <int NT, u32 CAP>
+__device__ void tie_refine(TieSort<CAP> &S, u32 t, u32 s, u32 m, u32 r, const u64 *pool, const u64 *uoff,
+                           const u32 *uwords, u32 max_chunks, u32 *__restrict__ ord,
+                           u64 *__restrict__ flags) {
+    int cur = 0;
+    tie_sync<NT>();
+    for (u32 i = t; i < m; i += NT) { S.uid[0][i] = ord[s + i]; S.lo[0][i] = 0; S.hi[0][i] = (u16)m; }
+    tie_sync<NT>();
+    for (;;) {
+        int any = 0;
+        for (u32 i = t; i < m; i += NT) {
+            bool act = (u32)(S.hi[cur][i] - S.lo[cur][i]) > 1;
+            S.key[i] = act ? word_key(pool, uoff, uwords, S.uid[cur][i], r) : 0ull;
+            any |= act ? 1 : 0;
+        }
+        if (!tie_any<NT>(any)) break;
+        if (r >= max_chunks) {
+            if (t == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
+            break;
+        }
+        int differs = 0;
+        for (u32 i = t; i < m; i += NT) {
+            u32 l = S.lo[cur][i];
+            differs |= ((u32)(S.hi[cur][i] - l) > 1 && S.key[i] != S.key[l]) ? 1 : 0;
+        }
+        if (!tie_any<NT>(differs)) { r++; continue; }      // shared prefix: nothing moves
+        for (u32 i = t; i < m; i += NT) {
+            u32 l = S.lo[cur][i], h = S.hi[cur][i];
+            u32 np = i, nlo = l, nhi = h;
+            if (h - l > 1) {
+                u64 key = S.key[i];
+                u32 less = 0, eqb = 0, eq = 0;
+                for (u32 j = l; j < h; j++) {
+                    u64 kj = S.key[j];
+                    less += (kj < key) ? 1 : 0;
+                    bool e = (kj == key);
+                    eq += e ? 1 : 0;
+                    eqb += (e && j < i) ? 1 : 0;
+                }
+                nlo = l + less; nhi = nlo + eq; np = nlo + eqb;
+            }
+            S.uid[cur ^ 1][np] = S.uid[cur][i];
+            S.lo[cur ^ 1][np] = (u16)nlo;
+            S.hi[cur ^ 1][np] = (u16)nhi;
+        }
+        tie_sync<NT>();
+        cur ^= 1;
+        r++;
+    }
+    tie_sync<NT>();
+    for (u32 i = t; i < m; i += NT) ord[s + i] = S.uid[cur][i];
+}
+
+// lists of the groups for the two shared-memory kernels
+__global__ void rank_lists_k(const u32 *__restrict__ hp, const u32 *__restrict__ nheads, u64 d,
+                             u32 *__restrict__ mid_list, u32 *__restrict__ big_list,
+                             u32 *__restrict__ counts /* [0]=mid, [1]=big */) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d || g >= *nheads) return;
     u32 m = hp[g + 1] - hp[g];
-    if (m > WARP_MAX && m <= LOCAL_MAX) list[atomicAdd(count, 1u)] = (u32)g;
+    if (m > WARP_MAX && m <= MID_MAX) mid_list[atomicAdd(&counts[0], 1u)] = (u32)g;
+    else if (m > MID_MAX && m <= LOCAL_MAX) big_list[atomicAdd(&counts[1], 1u)] = (u32)g;
+}
+
+__global__ void __launch_bounds__(256) rank_mid_k(const u32 *__restrict__ hp,
+                                                  const u32 *__restrict__ list,
+                                                  const u32 *__restrict__ count,
+                                                  const u32 *__restrict__ depth,
+                                                  const u64 *pool, const u64 *uoff, const u32 *uwords,
+                                                  u32 max_chunks, u32 *__restrict__ ord,
+                                                  u64 *__restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char mid_raw[];
+    const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    TieSort<MID_MAX> &S = reinterpret_cast<TieSort<MID_MAX> *>(mid_raw)[wp];
+    const u32 n = *count;
+    for (u32 q = blockIdx.x * 8 + wp; q < n; q += gridDim.x * 8) {
+        const u32 g = list[q];
+        const u32 s = hp[g], m = hp[g + 1] - s;
+        tie_refine<32, MID_MAX>(S, lane, s, m, depth[s], pool, uoff, uwords, max_chunks, ord, flags);
+    }
 }
 
 __global__ void __launch_bounds__(256) rank_cta_k(const u32 *__restrict__ hp,
@@ -264,54 +362,12 @@ __global__ void __launch_bounds__(256) rank_cta_k(const u32 *__restrict__ hp,
                                                   u32 max_chunks, u32 *__restrict__ ord,
                                                   u64 *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char cta_raw[];
-    CtaSort &S = *reinterpret_cast<CtaSort *>(cta_raw);
-    const u32 t = threadIdx.x;
+    TieSort<LOCAL_MAX> &S = *reinterpret_cast<TieSort<LOCAL_MAX> *>(cta_raw);
     const u32 n = *count;
     for (u32 q = blockIdx.x; q < n; q += gridDim.x) {
         const u32 g = list[q];
         const u32 s = hp[g], m = hp[g + 1] - s;
-        u32 r = depth[s];
-        int cur = 0;
-        __syncthreads();
-        for (u32 i = t; i < m; i += 256) { S.uid[0][i] = ord[s + i]; S.lo[0][i] = 0; S.hi[0][i] = (u16)m; }
-        __syncthreads();
-        for (;;) {
-            int any = 0;
-            for (u32 i = t; i < m; i += 256) {
-                bool act = (u32)(S.hi[cur][i] - S.lo[cur][i]) > 1;
-                S.key[i] = act ? word_key(pool, uoff, uwords, S.uid[cur][i], r) : 0ull;
-                any |= act ? 1 : 0;
-            }
-            if (!__syncthreads_or(any)) break;
-            if (r >= max_chunks) {
-                if (t == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
-                break;
-            }
-            for (u32 i = t; i < m; i += 256) {
-                u32 l = S.lo[cur][i], h = S.hi[cur][i];
-                u32 np = i, nlo = l, nhi = h;
-                if (h - l > 1) {
-                    u64 key = S.key[i];
-                    u32 less = 0, eqb = 0, eq = 0;
-                    for (u32 j = l; j < h; j++) {
-                        u64 kj = S.key[j];
-                        less += (kj < key) ? 1 : 0;
-                        bool e = (kj == key);
-                        eq += e ? 1 : 0;
-                        eqb += (e && j < i) ? 1 : 0;
-                    }
-                    nlo = l + less; nhi = nlo + eq; np = nlo + eqb;
-                }
-                S.uid[cur ^ 1][np] = S.uid[cur][i];
-                S.lo[cur ^ 1][np] = (u16)nlo;
-                S.hi[cur ^ 1][np] = (u16)nhi;
-            }
-            __syncthreads();
-            cur ^= 1;
-            r++;
-        }
-        __syncthreads();
-        for (u32 i = t; i < m; i += 256) ord[s + i] = S.uid[cur][i];
+        tie_refine<256, LOCAL_MAX>(S, threadIdx.x, s, m, depth[s], pool, uoff, uwords, max_chunks, ord, flags);
     }
 }
 
@@ -414,13 +470,15 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
         static bool attr = false;
         if (!attr) {
             PFP_CUDA(ctx, cudaFuncSetAttribute(rank_cta_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)sizeof(CtaSort)));
+                                               (int)sizeof(TieSort<LOCAL_MAX>)));
+            PFP_CUDA(ctx, cudaFuncSetAttribute(rank_mid_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(8 * sizeof(TieSort<MID_MAX>))));
             attr = true;
         }
-        u32 *cta_list = v1;                      // sort buffers are free again
-        u32 *cta_count = reinterpret_cast<u32 *>(&ctx->d_flags[5]);
-        PFP_CUDA(ctx, cudaMemsetAsync(cta_count, 0, sizeof(u32), ctx->stream));
-        rank_cta_list_k<<<nbd, TB, 0, ctx->stream>>>(hp, d_nheads, d, cta_list, cta_count);
+        u32 *mid_list = v1, *big_list = v0;      // sort buffers are free again
+        u32 *counts = reinterpret_cast<u32 *>(&ctx->d_flags[5]);
+        PFP_CUDA(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(u32), ctx->stream));
+        rank_lists_k<<<nbd, TB, 0, ctx->stream>>>(hp, d_nheads, d, mid_list, big_list, counts);
         PFP_LAUNCHED(ctx);
         u64 want = (d / 2 + 7) / 8;
         u64 maxb = (u64)ctx->sm_count * 16;
@@ -429,8 +487,11 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
         rank_warp_k<<<nbw, 256, 0, ctx->stream>>>(hp, d_nheads, depth, D.pool, D.uoff, D.uwords, max_chunks,
                                                   ord, ctx->d_flags);
         PFP_LAUNCHED(ctx);
-        rank_cta_k<<<ctx->sm_count * 4, 256, sizeof(CtaSort), ctx->stream>>>(
-            hp, cta_list, cta_count, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
+        rank_mid_k<<<ctx->sm_count * 4, 256, 8 * sizeof(TieSort<MID_MAX>), ctx->stream>>>(
+            hp, mid_list, counts, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
+        PFP_LAUNCHED(ctx);
+        rank_cta_k<<<ctx->sm_count * 4, 256, sizeof(TieSort<LOCAL_MAX>), ctx->stream>>>(
+            hp, big_list, counts + 1, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
         PFP_LAUNCHED(ctx);
         PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(u64), cudaMemcpyDeviceToHost,
                                       ctx->stream));

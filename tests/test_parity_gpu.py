@@ -113,6 +113,18 @@ def test_low_complexity_vs_oracle(sc):
         assert_same_files(sc.parse_host(text, w, p), orc.parse(text, w, p), f"lowcx w{w}")
 
 
+def test_dictionary_table_resize_retry(pkg):
+    """The dictionary table is sized from the previous parse's distinct/phrase ratio; an input
+    with far more distinct words than that guess must trigger the overflow retry and still be exact."""
+    s = pkg.pfp.Scanner(0)
+    rep = (pkg.synth.random_dna(2000, 77).numpy().tobytes()) * 400        # ~1% distinct
+    assert_same_files(s.parse_host(rep, 10, 100), orc.parse(rep, 10, 100), "repetitive")
+    rnd = pkg.synth.random_dna(800_000, 78).numpy().tobytes()              # ~100% distinct
+    assert_same_files(s.parse_host(rnd, 10, 100), orc.parse(rnd, 10, 100), "random after repetitive")
+    assert_same_files(s.parse_host(rep, 10, 100), orc.parse(rep, 10, 100), "repetitive again")
+    s.close()
+
+
 def test_invalid_byte_truncates(sc):
     text = b"ACGT" * 5000 + b"\x01" + b"ACGT" * 100
     got = sc.parse_host(text, 10, 100)
