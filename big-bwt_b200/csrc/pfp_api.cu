@@ -555,6 +555,28 @@ extern "C" int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_
     return rc;
 }
 
+extern "C" int pfp_unpack_words(pfpb200_ctx *ctx, const pfpb200_word *in, u64 n, u64 *fpa, u64 *fpb,
+                                u32 *len, u32 *count, u32 *uwords);
+
+extern "C" int pfpb200_dict_merge_words(pfpb200_ctx *ctx, uint64_t n_in, const pfpb200_word *words,
+                                        const uint64_t *pool, uint64_t pool_words, uint32_t w,
+                                        uint32_t flags, pfpb200_merged *out, float *ms) {
+    if (!ctx || !out || (n_in && !words)) return PFPB200_E_ARG;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    u64 *fpa = nullptr, *fpb = nullptr;
+    u32 *len = nullptr, *count = nullptr, *uwords = nullptr;
+    if (n_in) {
+        // the separate arrays must outlive the merge's own scratch release: hold them
+        PFP_TRY(pfp_alloc_t(ctx, &fpa, n_in, true));
+        PFP_TRY(pfp_alloc_t(ctx, &fpb, n_in, true));
+        PFP_TRY(pfp_alloc_t(ctx, &len, n_in, true));
+        PFP_TRY(pfp_alloc_t(ctx, &count, n_in, true));
+        PFP_TRY(pfp_alloc_t(ctx, &uwords, n_in, true));
+        PFP_TRY(pfp_unpack_words(ctx, words, n_in, fpa, fpb, len, count, uwords));
+    }
+    return pfpb200_dict_merge(ctx, n_in, fpa, fpb, len, count, uwords, pool, pool_words, w, flags, out, ms);
+}
+
 extern "C" int pfpb200_shard_remap(pfpb200_ctx *ctx, const uint32_t *d_rank_of_word, const uint32_t **d_parse,
                                    float *ms) {
     if (!ctx || !d_parse) return PFPB200_E_ARG;

@@ -650,12 +650,36 @@ __global__ void route_dest_k(const u64 *__restrict__ pool, const u64 *__restrict
 __global__ void route_gather_k(const u32 *__restrict__ perm, u64 d, const u64 *__restrict__ fpa,
                                const u64 *__restrict__ fpb, const u32 *__restrict__ len,
                                const u32 *__restrict__ count, const u32 *__restrict__ uwords,
-                               u64 *__restrict__ ofpa, u64 *__restrict__ ofpb, u32 *__restrict__ olen,
-                               u32 *__restrict__ ocount, u32 *__restrict__ ouwords) {
+                               pfpb200_word *__restrict__ out, u32 *__restrict__ ouwords) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d) return;
     u32 u = perm[i];
-    ofpa[i] = fpa[u]; ofpb[i] = fpb[u]; olen[i] = len[u]; ocount[i] = count[u]; ouwords[i] = uwords[u];
+    u64 a = fpa[u], b = fpb[u];
+    u32 uw = uwords[u];
+    uint4 *q = reinterpret_cast<uint4 *>(out + i);
+    q[0] = make_uint4((u32)a, (u32)(a >> 32), (u32)b, (u32)(b >> 32));
+    q[1] = make_uint4(len[u], count[u], uw, 0u);
+    ouwords[i] = uw;
+}
+
+// wire records -> the separate arrays the merge stage works on
+__global__ void unpack_words_k(const pfpb200_word *__restrict__ in, u64 n, u64 *__restrict__ fpa,
+                               u64 *__restrict__ fpb, u32 *__restrict__ len, u32 *__restrict__ count,
+                               u32 *__restrict__ uwords) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *q = reinterpret_cast<const uint4 *>(in + i);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    fpa[i] = ((u64)a.y << 32) | a.x;
+    fpb[i] = ((u64)a.w << 32) | a.z;
+    len[i] = b.x; count[i] = b.y; uwords[i] = b.z;
+}
+
+extern "C" int pfp_unpack_words(pfpb200_ctx *ctx, const pfpb200_word *in, u64 n, u64 *fpa, u64 *fpb,
+                                u32 *len, u32 *count, u32 *uwords) {
+    unpack_words_k<<<pfp_blocks(n, 256), 256, 0, ctx->stream>>>(in, n, fpa, fpb, len, count, uwords);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
 }
 
 __global__ void __launch_bounds__(256) route_pool_k(const u32 *__restrict__ perm, u64 d,
@@ -699,17 +723,15 @@ extern "C" int pfp_route_impl(pfpb200_ctx *ctx, const Splitters &sp, u32 n_ranks
     int bits = 1;
     while ((1u << bits) < n_ranks) bits++;
     PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, d, 0, bits, &ks, &perm));
-    u64 *ofpa = nullptr, *ofpb = nullptr, *opool = nullptr;
-    u32 *olen = nullptr, *ocount = nullptr, *ouwords = nullptr;
-    PFP_TRY(pfp_alloc_t(ctx, &ofpa, d));
-    PFP_TRY(pfp_alloc_t(ctx, &ofpb, d));
-    PFP_TRY(pfp_alloc_t(ctx, &olen, d));
-    PFP_TRY(pfp_alloc_t(ctx, &ocount, d));
+    u64 *opool = nullptr;
+    pfpb200_word *owords = nullptr;
+    u32 *ouwords = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &owords, d));
     PFP_TRY(pfp_alloc_t(ctx, &ouwords, d));
     PFP_TRY(pfp_alloc_t(ctx, &ooff, d));
     PFP_TRY(pfp_alloc_t(ctx, &opool, (size_t)ctx->sh.pool_words));
     route_gather_k<<<nbd, 256, 0, ctx->stream>>>(perm, d, ctx->sh.wfpa, ctx->sh.wfpb, ctx->sh.ulen, ctx->sh.count,
-                                                 ctx->sh.uwords, ofpa, ofpb, olen, ocount, ouwords);
+                                                 ctx->sh.uwords, owords, ouwords);
     PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, ouwords, ooff, d, nullptr));
     u64 want = (d + 31) / 32, maxb = (u64)ctx->sm_count * 32;
@@ -723,7 +745,7 @@ extern "C" int pfp_route_impl(pfpb200_ctx *ctx, const Splitters &sp, u32 n_ranks
         out->words_to[r] = hc[r];
         out->pool_to[r] = hc[PFPB200_MAX_RANKS + r];
     }
-    out->fpa = ofpa; out->fpb = ofpb; out->len = olen; out->count = ocount; out->uwords = ouwords;
+    out->words = owords;
     out->pool = opool; out->perm = perm;
     // free what the caller does not need; the rest is promoted to `held` by the caller
     u32 *perm_other = (perm == v0) ? v1 : v0;
@@ -732,5 +754,6 @@ extern "C" int pfp_route_impl(pfpb200_ctx *ctx, const Splitters &sp, u32 n_ranks
     PFP_TRY(pfp_free_now(ctx, perm_other));
     PFP_TRY(pfp_free_now(ctx, cnt));
     PFP_TRY(pfp_free_now(ctx, ooff));
+    PFP_TRY(pfp_free_now(ctx, ouwords));
     return PFPB200_OK;
 }

@@ -134,6 +134,9 @@ class CudaBackend:
         L.pfpb200_shard_remap.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_float)]
         L.pfpb200_shard_first_keys.argtypes = [vp, C.POINTER(vp)]
         L.pfpb200_shard_route.argtypes = [vp, vp, u32, C.POINTER(Routed), C.POINTER(C.c_float)]
+        L.pfpb200_dict_merge_words.argtypes = [vp, u64, vp, vp, u64, u32, u32, C.POINTER(Merged),
+                                               C.POINTER(C.c_float)]
+        L.pfpb200_dict_merge_words.restype = C.c_int
         for f in (L.pfpb200_shard_scan, L.pfpb200_shard_words, L.pfpb200_dict_merge, L.pfpb200_shard_remap,
                   L.pfpb200_shard_first_keys, L.pfpb200_shard_route):
             f.restype = C.c_int
@@ -185,13 +188,24 @@ class CudaBackend:
                                                        n_ranks, C.byref(rt), C.byref(ms)))
         self.ms["route"] = ms.value
         d, dev = wd["n_words"], self.dev
-        return {"fpa": dev_tensor(rt.fpa, d, torch.int64, dev), "fpb": dev_tensor(rt.fpb, d, torch.int64, dev),
-                "len": dev_tensor(rt.len, d, torch.int32, dev), "count": dev_tensor(rt.count, d, torch.int32, dev),
-                "uwords": dev_tensor(rt.uwords, d, torch.int32, dev),
+        return {"words": dev_tensor(rt.words, 32 * d, torch.uint8, dev),     # pfpb200_word records
                 "pool": dev_tensor(rt.pool, wd["pool"].numel(), torch.int64, dev),
                 "perm": dev_tensor(rt.perm, d, torch.int32, dev),
                 "words_to": [int(rt.words_to[q]) for q in range(n_ranks)],
                 "pool_to": [int(rt.pool_to[q]) for q in range(n_ranks)]}
+
+    def dict_merge_words(self, words, pool, w, compress=False):
+        m, ms = Merged(), C.c_float()
+        n_in = words.numel() // 32
+        self.scanner._check(self.L.pfpb200_dict_merge_words(
+            self.h, n_in, words.data_ptr(), pool.data_ptr(), pool.numel(), w,
+            pfp.F_COMPRESS if compress else 0, C.byref(m), C.byref(ms)))
+        self.ms["merge"] = ms.value
+        dev = self.dev
+        return {"n_distinct": m.n_distinct, "sum_word_len": m.sum_word_len,
+                "dict": dev_tensor(m.dict, m.dict_bytes, torch.uint8, dev),
+                "occ": dev_tensor(m.occ, m.n_distinct, torch.int32, dev),
+                "rank_of_entry": dev_tensor(m.rank_of_entry, n_in, torch.int32, dev)}
 
     def shard_remap(self, rank_of_word, n_phrases):
         out, ms = C.c_void_p(), C.c_float()
@@ -213,8 +227,7 @@ class Words(C.Structure):
 
 
 class Routed(C.Structure):
-    _fields_ = [("fpa", C.c_void_p), ("fpb", C.c_void_p), ("len", C.c_void_p), ("count", C.c_void_p),
-                ("uwords", C.c_void_p), ("pool", C.c_void_p), ("perm", C.c_void_p),
+    _fields_ = [("words", C.c_void_p), ("pool", C.c_void_p), ("perm", C.c_void_p),
                 ("words_to", C.c_uint64 * 64), ("pool_to", C.c_uint64 * 64)]
 
 
@@ -387,12 +400,8 @@ class ShardedParser:
         parse = be.shard_remap(res["rank_of_word"], wd["n_phrases"])
         self.result = {"dict": res["dict"], "occ": res["occ"], "parse": parse, "last": wd["last"],
                        "sai": wd["sai"], "n_distinct": res["n_distinct"], "dict_offset": res.get("dict_offset", 0)}
-        tot = self._all_gather_i64([wd["n_phrases"], res["n_distinct_local"], res["dict_bytes_local"],
-                                    res["sum_len_local"]])
-        P = sum(r[0] for r in tot)
-        d = sum(r[1] for r in tot) if self.mode == "partition" else res["n_distinct"]
-        db = sum(r[2] for r in tot) if self.mode == "partition" else res["dict_bytes_local"]
-        sl = sum(r[3] for r in tot) if self.mode == "partition" else res["sum_len_local"]
+        t = res["totals"]
+        P, d, db, sl = t["n_phrases"], t["n_distinct"], t["dict_bytes"], t["sum_word_len"]
         ms = dict(getattr(be, "ms", {}))
         st = {"n_text": self.n_global, "n_phrases": P, "n_distinct": d, "dict_bytes": db, "sum_word_len": sl,
               "alg_bytes": self.n_global + 4 * P + P + (5 * P if sai else 0) + db + 4 * d,
@@ -410,10 +419,11 @@ class ShardedParser:
         pool = self._all_gather_v(wd["pool"], npool)
         m = be.dict_merge(cat["fpa"], cat["fpb"], cat["len"], cat["count"], cat["uwords"], pool, w, compress)
         base = sum(nw[:g])
+        P = sum(r[0] for r in self._all_gather_i64([wd["n_phrases"]]))
         return {"dict": m["dict"], "occ": m["occ"], "n_distinct": m["n_distinct"],
                 "rank_of_word": m["rank_of_entry"][base:base + nw[g]].contiguous(),
-                "n_distinct_local": m["n_distinct"], "dict_bytes_local": int(m["dict"].numel()),
-                "sum_len_local": m["sum_word_len"]}
+                "totals": {"n_phrases": P, "n_distinct": m["n_distinct"],
+                           "dict_bytes": int(m["dict"].numel()), "sum_word_len": m["sum_word_len"]}}
 
     def _all_to_all_v(self, send, send_counts, recv_counts):
         """Variable-size all-to-all of a 1-D tensor grouped by destination (grouped P2P)."""
@@ -442,7 +452,7 @@ class ShardedParser:
         be, G = self.backend, self.world
         d = wd["n_words"]
         dev = self.buf.device
-        samp = torch.zeros(self.SAMPLE, dtype=torch.int64, device=dev)
+        samp = torch.zeros(self.SAMPLE + 1, dtype=torch.int64, device=dev)
         k = 0
         if d:
             keys = be.first_keys(wd)          # uid order = fingerprint order: any stride is a random sample
@@ -450,11 +460,12 @@ class ShardedParser:
             pick = keys[::step][:self.SAMPLE]
             k = int(pick.numel())
             samp[:k] = pick
-        ks = [r[0] for r in self._all_gather_i64([k])]
+        samp[self.SAMPLE] = k
         import torch.distributed as dist
-        allv = torch.empty(G * self.SAMPLE, dtype=torch.int64, device=dev)
+        allv = torch.empty(G * (self.SAMPLE + 1), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allv, samp)
-        a = allv.cpu().numpy().view(np.uint64).reshape(G, self.SAMPLE)
+        a = allv.cpu().numpy().view(np.uint64).reshape(G, self.SAMPLE + 1)
+        ks = [int(a[q, self.SAMPLE]) for q in range(G)]
         vals = np.sort(np.concatenate([a[q, :ks[q]] for q in range(G)])) if sum(ks) else np.zeros(0, np.uint64)
         if vals.size == 0:
             return np.zeros(G - 1, dtype=np.uint64)
@@ -462,6 +473,7 @@ class ShardedParser:
 
     def _merge_partitioned(self, wd, w, compress):
         be, G, g = self.backend, self.world, self.rank
+        dev = self.buf.device
         sp = self._splitters(wd)
         rt = be.route(wd, sp, G) if wd["n_words"] else None
         words_to = rt["words_to"] if rt else [0] * G
@@ -469,17 +481,15 @@ class ShardedParser:
         M = self._all_gather_i64(list(words_to) + list(pool_to))           # M[src] = [words_to.., pool_to..]
         recv_w = [M[q][g] for q in range(G)]
         recv_p = [M[q][G + g] for q in range(G)]
-        dev = self.buf.device
-        empty = {"fpa": torch.int64, "fpb": torch.int64, "len": torch.int32, "count": torch.int32,
-                 "uwords": torch.int32, "pool": torch.int64}
-        got = {}
-        for key, dt in empty.items():
-            send = rt[key] if rt else torch.empty(0, dtype=dt, device=dev)
-            sc, rc = (pool_to, recv_p) if key == "pool" else (words_to, recv_w)
-            got[key] = self._all_to_all_v(send, sc, rc)
-        m = be.dict_merge(got["fpa"], got["fpb"], got["len"], got["count"], got["uwords"], got["pool"], w, compress)
+        # two exchanges: the 32-byte word records and the pool bytes
+        send_words = rt["words"] if rt else torch.empty(0, dtype=torch.uint8, device=dev)
+        send_pool = rt["pool"] if rt else torch.empty(0, dtype=torch.int64, device=dev)
+        got_words = self._all_to_all_v(send_words, [32 * c for c in words_to], [32 * c for c in recv_w])
+        got_pool = self._all_to_all_v(send_pool, pool_to, recv_p)
+        m = be.dict_merge_words(got_words, got_pool, w, compress)
         piece = m["dict"] if g == G - 1 else m["dict"][:-1]                 # only the last piece ends in 0x00
-        nd = [r[0] for r in self._all_gather_i64([m["n_distinct"]])]
+        tot = self._all_gather_i64([m["n_distinct"], int(piece.numel()), m["sum_word_len"], wd["n_phrases"]])
+        nd = [r[0] for r in tot]
         offset = sum(nd[:g])
         ranks = m["rank_of_entry"] + offset if m["rank_of_entry"].numel() else m["rank_of_entry"]
         back = self._all_to_all_v(ranks.to(torch.int32), recv_w, words_to)  # routed order
@@ -487,8 +497,8 @@ class ShardedParser:
         if rt:
             rank_of_word[rt["perm"].long()] = back
         return {"dict": piece, "occ": m["occ"], "n_distinct": sum(nd), "rank_of_word": rank_of_word,
-                "n_distinct_local": m["n_distinct"], "dict_bytes_local": int(piece.numel()),
-                "sum_len_local": m["sum_word_len"]}
+                "totals": {"n_phrases": sum(r[3] for r in tot), "n_distinct": sum(nd),
+                           "dict_bytes": sum(r[1] for r in tot), "sum_word_len": sum(r[2] for r in tot)}}
 
     # -- results ----------------------------------------------------------------------------------------------
     def gather_files(self):

@@ -187,10 +187,15 @@ int pfpb200_shard_remap(pfpb200_ctx *ctx, const uint32_t *d_rank_of_word, const 
  * pfpb200_shard_words call; used to sample range splitters. */
 int pfpb200_shard_first_keys(pfpb200_ctx *ctx, const uint64_t **d_keys);
 
+typedef struct pfpb200_word {       /* one dictionary word on the wire: 32 bytes                 */
+    uint64_t fpa, fpb;              /* 128-bit fingerprint                                       */
+    uint32_t len, count, uwords;    /* bytes, occurrences, 8-byte pool words                     */
+    uint32_t pad;
+} pfpb200_word;
+
 typedef struct pfpb200_routed {     /* the local dictionary regrouped by destination rank        */
-    const uint64_t *fpa, *fpb;
-    const uint32_t *len, *count, *uwords;
-    const uint64_t *pool;
+    const pfpb200_word *words;      /* n_words records, grouped by destination                   */
+    const uint64_t *pool;           /* their bytes in the same order                             */
     const uint32_t *perm;           /* perm[i] = local word stored at routed position i          */
     uint64_t words_to[PFPB200_MAX_RANKS];   /* words / pool words going to each rank             */
     uint64_t pool_to[PFPB200_MAX_RANKS];
@@ -199,6 +204,11 @@ typedef struct pfpb200_routed {     /* the local dictionary regrouped by destina
 /* Word u goes to rank  #{ s : splitters[s] <= key(u) }  (n_ranks-1 ascending host keys). */
 int pfpb200_shard_route(pfpb200_ctx *ctx, const uint64_t *splitters, uint32_t n_ranks,
                         pfpb200_routed *out, float *ms);
+
+/* pfpb200_dict_merge for words received as pfpb200_word records (the all-to-all payload). */
+int pfpb200_dict_merge_words(pfpb200_ctx *ctx, uint64_t n_in, const pfpb200_word *words,
+                             const uint64_t *pool, uint64_t pool_words, uint32_t w, uint32_t flags,
+                             pfpb200_merged *out, float *ms);
 
 /* Kernels launched on this context since the start of the current parse (the last
  * pfpb200_parse_* / pfpb200_shard_scan call). */

@@ -97,12 +97,22 @@ class MockBackend:
         perm = np.argsort(dest, kind="stable")
         words = [self.words[i] for i in perm]
         pool, uw = _pack(words)
+        rec = np.zeros(len(words), dtype=[("fpa", "<i8"), ("fpb", "<i8"), ("len", "<u4"), ("count", "<u4"),
+                                          ("uwords", "<u4"), ("pad", "<u4")])
+        for key in ("fpa", "fpb", "len", "count"):
+            rec[key] = wd[key].numpy()[perm]
+        rec["uwords"] = uw
         t = torch.from_numpy
-        g = lambda key: t(wd[key].numpy()[perm].copy())
-        return {"fpa": g("fpa"), "fpb": g("fpb"), "len": g("len"), "count": g("count"),
-                "uwords": t(np.array(uw, dtype=np.int32)), "pool": t(pool), "perm": t(perm.astype(np.int32)),
+        return {"words": t(rec.view(np.uint8).copy()), "pool": t(pool), "perm": t(perm.astype(np.int32)),
                 "words_to": [int(np.sum(dest == q)) for q in range(n_ranks)],
                 "pool_to": [int(sum(uw[i] for i in range(len(uw)) if dest[perm[i]] == q)) for q in range(n_ranks)]}
+
+    def dict_merge_words(self, words, pool, w, compress=False):
+        rec = words.numpy().view([("fpa", "<i8"), ("fpb", "<i8"), ("len", "<u4"), ("count", "<u4"),
+                                  ("uwords", "<u4"), ("pad", "<u4")])
+        t = torch.from_numpy
+        return self.dict_merge(t(rec["fpa"].copy()), t(rec["fpb"].copy()), t(rec["len"].astype(np.int32)),
+                               t(rec["count"].astype(np.int32)), t(rec["uwords"].astype(np.int32)), pool, w, compress)
 
     def dict_merge(self, fpa, fpb, ln, count, uwords, pool, w, compress=False):
         lens = ln.numpy().tolist()

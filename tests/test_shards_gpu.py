@@ -57,15 +57,13 @@ def emulate(pkg, text: bytes, cuts, w, p, mode, halo=64, front=4096):
         rts = [bes[g].route(wds[g], sp, G) for g in range(G)]
         merged, dict_b, occ_b = [], b"", b""
         for o in range(G):                     # owner o receives slice o of every source
-            got = {}
-            for key in ("fpa", "fpb", "len", "count", "uwords", "pool"):
-                parts = []
-                for src in range(G):
-                    cnt = rts[src]["pool_to"] if key == "pool" else rts[src]["words_to"]
-                    a = sum(cnt[:o])
-                    parts.append(rts[src][key][a:a + cnt[o]])
-                got[key] = torch.cat(parts).contiguous()
-            m = bes[o].dict_merge(got["fpa"], got["fpb"], got["len"], got["count"], got["uwords"], got["pool"], w)
+            wparts, pparts = [], []
+            for src in range(G):
+                a = sum(rts[src]["words_to"][:o])
+                wparts.append(rts[src]["words"][32 * a:32 * (a + rts[src]["words_to"][o])])
+                b = sum(rts[src]["pool_to"][:o])
+                pparts.append(rts[src]["pool"][b:b + rts[src]["pool_to"][o]])
+            m = bes[o].dict_merge_words(torch.cat(wparts).contiguous(), torch.cat(pparts).contiguous(), w)
             merged.append(m)
             d = m["dict"].cpu().numpy().tobytes()
             dict_b += d if o == G - 1 else d[:-1]
