@@ -66,21 +66,24 @@ __device__ __forceinline__ void load_chunk(const TextView &tv, i64 s0, u64 len, 
     }
 }
 
-// 16 bytes at phrase offset o through a generic pointer (shared-memory window or global text),
-// bytes past the phrase end zeroed without branches; the caller guarantees 20 readable bytes
-__device__ __forceinline__ void load_chunk_ptr(const u8 *p, u32 len, u32 o, u32 x[4]) {
-    const u32 rem = len - o;                         // >= 1
-    p += o;
-    const u32 bs = (u32)((uintptr_t)p & 3);
-    const u32 *p4 = reinterpret_cast<const u32 *>(p - bs);
-    u32 W[5];
+// 16 bytes of a phrase at p (20 readable bytes guaranteed by the caller), in two halves so that
+// the loads of the next chunk can be in flight while the current one is hashed:
+// fetch = five aligned 32-bit loads; finish = funnel shift by the misalignment and zero the
+// bytes past the phrase end (rem = bytes left from p), without branches
+struct ChunkRaw { u32 W[5]; u32 bs; };
+
+__device__ __forceinline__ void chunk_fetch(const u8 *p, ChunkRaw &r) {
+    r.bs = (u32)((uintptr_t)p & 3);
+    const u32 *p4 = reinterpret_cast<const u32 *>(p - r.bs);
 #pragma unroll
-    for (int j = 0; j < 5; j++) W[j] = p4[j];
+    for (int j = 0; j < 5; j++) r.W[j] = __ldg(p4 + j);
+}
+
+__device__ __forceinline__ void chunk_finish(const ChunkRaw &r, u32 rem, u32 x[4]) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        u32 v = __funnelshift_r(W[j], W[j + 1], 8 * bs);
-        // valid bytes of word j: clamp(rem - 4j, 0, 4) -> mask = 0xFFFFFFFF >> 8*(4 - nb)
-        int nb = (int)rem - 4 * j;
+        u32 v = __funnelshift_r(r.W[j], r.W[j + 1], 8 * r.bs);
+        int nb = (int)rem - 4 * j;                    // valid bytes of word j, clamped to 0..4
         nb = nb < 0 ? 0 : (nb > 4 ? 4 : nb);
         x[j] = v & __funnelshift_rc(0xFFFFFFFFu, 0u, 8u * (4u - (u32)nb));
     }
@@ -224,20 +227,32 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
             u32 qlen = s_len[wp][q];
             u32 qnch = (qlen + 15) >> 4;
             u64 pa = 0, pb = 0;
+            ChunkRaw cur;
+            chunk_fetch(qp + 16u * c, cur);
             for (; g < g1; g++) {
+                // where the next chunk lives: same phrase, or the start of the next one
+                u32 nq = q, nc = c + 1, nlen = qlen, nnch = qnch;
+                const u8 *np = qp;
+                const bool ends = nc == qnch;
+                if (ends) {
+                    nc = 0;
+                    do { nq++; } while (nq < 31 && s_len[wp][nq] == 0);
+                    np = s_ptr[wp][nq & 31];
+                    nlen = s_len[wp][nq & 31];
+                    nnch = (nlen + 15) >> 4;
+                }
+                ChunkRaw nxt;
+                if (g + 1 < g1) chunk_fetch(np + 16u * nc, nxt);      // in flight during the hashing below
                 u32 x[4];
-                load_chunk_ptr(qp, qlen, 16u * c, x);
+                chunk_finish(cur, qlen - 16u * c, x);
                 nh_chunk(sk, c, x, pa, pb);
-                if (++c == qnch) {
+                if (ends) {
                     if (cont) { head_a = pa; head_b = pb; head_q = q; cont = false; }
                     else { s_acc[wp][q][0] = pa; s_acc[wp][q][1] = pb; }
                     pa = pb = 0;
-                    c = 0;
-                    do { q++; } while (q < 31 && s_len[wp][q] == 0);
-                    qp = s_ptr[wp][q & 31];
-                    qlen = s_len[wp][q & 31];
-                    qnch = (qlen + 15) >> 4;
                 }
+                q = nq; c = nc; qp = np; qlen = nlen; qnch = nnch;
+                cur = nxt;
             }
             if (c != 0) { tail_a = pa; tail_b = pb; pass = cont; }
         }
