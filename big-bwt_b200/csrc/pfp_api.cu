@@ -78,6 +78,7 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     pfpb200_ctx *ctx = new (std::nothrow) pfpb200_ctx();
     if (!ctx) return PFPB200_E_NOMEM;
     ctx->device = device;
+    { const char *ev = getenv("PFPB200_LEGACY_K2"); ctx->legacy_k2 = ev && atoi(ev) != 0; }
     auto bail = [&](int code) { pfpb200_destroy(ctx); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(PFPB200_E_CUDA);
     cudaDeviceProp prop;
@@ -172,25 +173,34 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
     int rc = PFPB200_OK;
     auto run = [&]() -> int {
         tm.mark(ctx->stream);                                           // 0
-        // K1
-        u64 *ends = nullptr, k = 0;
+        // K1: trigger bits
+        ScanBits sb;
         float ms_scan = 0, ms_emit = 0;
-        PFP_TRY(pfp_scan_stage(ctx, d_text, n, 0, 0, n, w, p, 1, false, &ends, &k, &ms_scan, &ms_emit));
+        PFP_TRY(pfp_scan_bits(ctx, d_text, n, 0, 0, n, w, p, false, &sb, &ms_scan));
+        const u64 k = sb.total;
         const u64 P = k + 1;
         if (P >= 0xFFFFFFFFull)
             return pfp_fail(ctx, PFPB200_E_LIMIT, "the parse contains %llu words, more than 2^32-2",
                             (unsigned long long)P);                     // bigbwt:110-114
+        u64 *ends = nullptr;
+        PFP_TRY(pfp_alloc_t(ctx, &ends, P));
         set_u64_k<<<1, 1, 0, ctx->stream>>>(ends + k, n + w - 1);       // final word (:376-377)
         PFP_LAUNCHED(ctx);
         tm.mark(ctx->stream);                                           // 1
-        // K2
+        // K2: positions, .last, .sai and fingerprints in one pass over text + bits
         PhraseArrays ph{};
         ph.ends = ends;
         PFP_TRY(pfp_alloc_t(ctx, &ph.rec, P));
         PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
         if (o->flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
         TextView tv{d_text, n, 0, (i64)n};
-        PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, -1, w));
+        if (pfp_stream_ok(sb, w) && !ctx->legacy_k2) {
+            PFP_TRY(pfp_stream_stage(ctx, sb, tv, ph, P, -1, w, true));
+        } else {                                                        // any window size
+            PFP_TRY(pfp_scan_emit(ctx, sb, ends));
+            PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, -1, w));
+        }
+        PFP_TRY(pfp_scan_bits_free(ctx, &sb));
         tm.mark(ctx->stream);                                           // 2
         // K3
         DictArrays D;
@@ -435,9 +445,16 @@ extern "C" int pfpb200_shard_scan(pfpb200_ctx *ctx, const pfpb200_shard *shard, 
     ctx->sh.opts = *opts;
     CallTimer tm(ctx->stream);
     u64 *ends = nullptr, k = 0;
-    float a = 0, b = 0;
-    int rc = pfp_scan_stage(ctx, shard->d_buf, shard->n_buf, shard->buf_pos0, shard->own_lo, shard->own_hi,
-                            opts->w, opts->p, 1, true, &ends, &k, &a, &b);
+    float a = 0;
+    ScanBits sb;
+    int rc = pfp_scan_bits(ctx, shard->d_buf, shard->n_buf, shard->buf_pos0, shard->own_lo, shard->own_hi,
+                           opts->w, opts->p, true, &sb, &a);
+    if (rc == PFPB200_OK) {
+        k = sb.total;
+        rc = pfp_alloc_t(ctx, &ends, k + 1, true);
+    }
+    if (rc == PFPB200_OK) rc = pfp_scan_emit(ctx, sb, ends);
+    ctx->sh.bits = sb;
     if (rc == PFPB200_OK && k > 0) {
         cudaMemcpyAsync(&ctx->h_flags[8], ends, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(&ctx->h_flags[9], ends + (k - 1), sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
@@ -483,7 +500,8 @@ extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb20
         PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
         if (o.flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
         TextView tv{sh.d_buf, sh.n_buf, (i64)sh.buf_pos0, (i64)sh.n_global};
-        PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, first_start, w));
+        if (pfp_stream_ok(ctx->sh.bits, w) && !ctx->legacy_k2) PFP_TRY(pfp_stream_stage(ctx, ctx->sh.bits, tv, ph, P, first_start, w, false));
+        else PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, first_start, w));
         DictArrays D;
         PFP_TRY(pfp_dedup_stage(ctx, ph, P, &D));
         u64 *wfpa = nullptr, *wfpb = nullptr;

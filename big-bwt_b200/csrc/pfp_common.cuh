@@ -25,6 +25,25 @@ struct PfpArena {
     size_t in_use = 0, peak = 0, total = 0;
 };
 
+// ---- trigger bits of a buffer (K1a output) ------------------------------------------------------
+// Positions are counted in "q" coordinates: byte offsets from the 16-byte aligned address A at
+// or below the buffer start; global text position = q + pos_bias.  Bit q of `mask` (little
+// endian 32-bit words) is set iff an owned trigger ends at q.  Tiles of PFP_TILE positions.
+constexpr int PFP_TILE_T = 256;                        // threads per tile CTA
+constexpr int PFP_TILE_RUN = 128;                      // positions per thread
+constexpr int PFP_TILE = PFP_TILE_T * PFP_TILE_RUN;    // 32768 positions per tile
+struct ScanBits {
+    const uint4 *A;
+    u64 q_end;          // q of the first byte behind the buffer
+    u64 pos_bias;       // global position of q = 0 (may wrap below zero; arithmetic is modular)
+    u32 ntiles;         // 0: nothing was scanned (empty range)
+    uint4 *mask;        // [ntiles * 256] = 128 bits per thread run
+    u32 *tile_cnt;      // [ntiles] triggers per tile
+    u64 *tile_off;      // [ntiles] triggers before the tile
+    u64 total;          // all triggers
+    u32 max_tile_cnt;   // largest tile_cnt
+};
+
 struct pfpb200_ctx {
     int device = 0;
     PfpArena arena;
@@ -32,6 +51,7 @@ struct pfpb200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     u32 launches = 0;
+    bool legacy_k2 = false;        // PFPB200_LEGACY_K2=1: per-phrase K2 kernels (A/B measurements)
     double dedup_ratio = 0.0;      // distinct words / phrases of the previous parse (table sizing hint)
     char err[512] = {0};
     std::vector<void *> scratch;   // freed at the end of every call
@@ -47,6 +67,7 @@ struct pfpb200_ctx {
         pfpb200_shard desc;
         pfpb200_opts opts;
         u64 *ends = nullptr;
+        ScanBits bits;                 // trigger bits of the shard, kept from shard_scan to shard_words
         u64 n_trig = 0, P = 0, d = 0;
         u32 *uid = nullptr;
         // local dictionary of the shard (held until the next parse)

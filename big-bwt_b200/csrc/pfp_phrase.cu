@@ -14,15 +14,8 @@
 // the run = representative occurrence.
 #include "pfp_common.cuh"
 #include "pfp_stages.cuh"
+#include "pfp_fp.cuh"
 #include <stdlib.h>
-
-__device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
-__device__ __forceinline__ u64 fmix64(u64 k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
-    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
-    k ^= k >> 33;
-    return k;
-}
 
 // 16 bytes of a phrase at phrase offset o (multiple of 16), zero beyond the phrase end.
 // fast path: aligned 32-bit loads + funnel shift by the byte misalignment of the phrase start
@@ -97,23 +90,10 @@ __device__ __forceinline__ void nh_chunk(const u32 *__restrict__ sk, u32 c, cons
     pb += (u64)(x[0] + k1.x) * (u64)(x[1] + k1.y) + (u64)(x[2] + k1.z) * (u64)(x[3] + k1.w);
 }
 
-// never 0: 0 marks an empty slot of the dictionary table
-__device__ __forceinline__ u64 sort_key_of(u64 fa, u64 fb, u32 len) {
-    u64 k = fmix64(fa ^ rotl64(fb, 32) ^ ((u64)len * 0x9E3779B97F4A7C15ULL));
-    return k ? k : 0x9E3779B97F4A7C15ULL;
-}
-
-__device__ __forceinline__ void store_rec(PhraseFp *rec, u64 j, u64 fa, u64 fb, u32 len) {
-    uint4 *q = reinterpret_cast<uint4 *>(rec + j);
-    u64 key = sort_key_of(fa, fb, len);
-    q[0] = make_uint4((u32)fa, (u32)(fa >> 32), (u32)fb, (u32)(fb >> 32));
-    q[1] = make_uint4(len, 0u, (u32)key, (u32)(key >> 32));
-}
-
 // .last and .sai of every phrase: one thread per phrase, coalesced stores
-__global__ void phrase_records_k(TextView tv, const u64 *__restrict__ ends, u64 P, u32 w,
+__global__ void phrase_records_k(TextView tv, const u64 *__restrict__ ends, u64 j0, u64 P, u32 w,
                                  u8 *__restrict__ last, u8 *__restrict__ sai) {
-    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 j = j0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P) return;
     i64 e = (i64)ends[j];
     last[j] = tv_byte(tv, e - (i64)w);                          // newscan.cpp:296
@@ -275,7 +255,8 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
     }
 }
 
-// phrases longer than one NH segment: one CTA per phrase, 32 groups of 8 lanes stride over the segments
+// phrases longer than one NH segment or touching the text borders: one CTA per phrase, 32 groups
+// of 8 lanes stride over the segments; segment s enters the sum with weight FOLD^s (pfp_fp.cuh)
 constexpr int PL_GROUP = 8;
 constexpr int PL_GROUPS = PH_T / PL_GROUP;
 __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseArrays ph,
@@ -298,7 +279,7 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
         bool special = (s0 < 0) || (e >= tv.n_global);
         u64 nseg = (len + NH_SEG_BYTES - 1) / NH_SEG_BYTES;
         u64 fa = 0, fb = 0;
-        i64 s_last = -1;
+        u64 wa = fold_pow(NH_FOLD_A, g), wb = fold_pow(NH_FOLD_B, g);   // weight of segment g
         for (u64 s = g; s < nseg; s += PL_GROUPS) {
             u64 so = s * NH_SEG_BYTES;
             u32 segb = (u32)((len - so) < NH_SEG_BYTES ? (len - so) : NH_SEG_BYTES);
@@ -309,12 +290,10 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
                 load_chunk(tv, s0, len, so + 16ull * c, special, x);
                 nh_chunk(sk, c, x, pa, pb);
             }
-            fa = fa * fold_a32 + pa;     // Horner with stride PL_GROUPS segments
-            fb = fb * fold_b32 + pb;
-            s_last = (i64)s;
-        }
-        if (s_last >= 0) {               // bring to the common power FOLD^(nseg-1-s)
-            for (u64 k = (u64)s_last; k + 1 < nseg; k++) { fa *= NH_FOLD_A; fb *= NH_FOLD_B; }
+            fa += wa * pa;
+            fb += wb * pb;
+            wa *= fold_a32;              // FOLD^PL_GROUPS: on to segment s + PL_GROUPS
+            wb *= fold_b32;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -536,6 +515,27 @@ __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__re
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
+// fingerprints of the phrases listed in long_list[0..*long_count): any length, any position
+int pfp_hash_list(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, i64 first_start, u32 w,
+                  const u32 *long_list, const u32 *long_count, u64 max_count) {
+    u64 fa32 = 1, fb32 = 1;
+    for (int i = 0; i < PL_GROUPS; i++) { fa32 *= NH_FOLD_A; fb32 *= NH_FOLD_B; }
+    u32 nlb = (u32)(max_count < (u64)ctx->sm_count ? max_count : (u64)ctx->sm_count);
+    if (nlb == 0) nlb = 1;
+    phrase_hash_long_k<<<nlb, PH_T, 0, ctx->stream>>>(tv, ph, first_start, w, ctx->d_keys, long_list,
+                                                      long_count, fa32, fb32);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
+// .last/.sai of the phrases [j0, P)
+int pfp_records_range(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 j0, u64 P, u32 w) {
+    if (j0 >= P) return PFPB200_OK;
+    phrase_records_k<<<pfp_blocks(P - j0, 256), 256, 0, ctx->stream>>>(tv, ph.ends, j0, P, w, ph.last, ph.sai);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
 int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 P,
                    i64 first_start, u32 w) {
     u32 *long_list = nullptr, *long_count = nullptr;
@@ -543,7 +543,7 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     PFP_TRY(pfp_alloc_t(ctx, &long_list, (size_t)cap));
     PFP_TRY(pfp_alloc_t(ctx, &long_count, 1));
     PFP_CUDA(ctx, cudaMemsetAsync(long_count, 0, sizeof(u32), ctx->stream));
-    phrase_records_k<<<pfp_blocks(P, 256), 256, 0, ctx->stream>>>(tv, ph.ends, P, w, ph.last, ph.sai);
+    phrase_records_k<<<pfp_blocks(P, 256), 256, 0, ctx->stream>>>(tv, ph.ends, 0, P, w, ph.last, ph.sai);
     PFP_LAUNCHED(ctx);
     u64 want = (P + PH_PER_BLOCK - 1) / PH_PER_BLOCK;
     u64 maxb = (u64)ctx->sm_count * 32;
@@ -563,12 +563,7 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     phrase_hash_k<<<nb, PH_T, use_window ? PH_WARPS * PH_WIN : 0, ctx->stream>>>(
         tv, ph, P, first_start, w, ctx->d_keys, long_list, long_count, ctx->d_flags, use_window);
     PFP_LAUNCHED(ctx);
-    u64 fa32 = 1, fb32 = 1;
-    for (int i = 0; i < PL_GROUPS; i++) { fa32 *= NH_FOLD_A; fb32 *= NH_FOLD_B; }
-    u32 nlb = (u32)(cap < (u64)ctx->sm_count ? cap : (u64)ctx->sm_count);
-    phrase_hash_long_k<<<nlb, PH_T, 0, ctx->stream>>>(tv, ph, first_start, w, ctx->d_keys, long_list,
-                                                      long_count, fa32, fb32);
-    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_hash_list(ctx, tv, ph, first_start, w, long_list, long_count, cap));
     PFP_TRY(pfp_free_now(ctx, long_list));
     PFP_TRY(pfp_free_now(ctx, long_count));
     return PFPB200_OK;

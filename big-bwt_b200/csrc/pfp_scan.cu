@@ -12,11 +12,12 @@
 // slots (moves the PRMT extractions from the ALU pipe, 63 % busy, to the idle LSU pipe) with a
 // predicated OR for the mask: 3.05 ms vs 2.86 ms for this version (56 registers, fewer CTAs).
 #include "pfp_common.cuh"
+#include "pfp_stages.cuh"
 #include <stdlib.h>
 
-constexpr int K1_T = 256;                    // threads per CTA
-constexpr int K1_RUN = 128;                  // positions per thread
-constexpr int K1_TILE = K1_T * K1_RUN;       // 32768 positions per CTA
+constexpr int K1_T = PFP_TILE_T;             // threads per CTA
+constexpr int K1_RUN = PFP_TILE_RUN;         // positions per thread
+constexpr int K1_TILE = PFP_TILE;            // 32768 positions per CTA
 constexpr int K1_SLOT = K1_RUN + 16;         // padded slot: LDS.128 of 8 lanes hits 32 banks
 constexpr int K1_SMEM = (K1_T + 1) * K1_SLOT;
 constexpr int K1_CHUNKS = K1_TILE / 16;
@@ -191,6 +192,17 @@ __global__ void __launch_bounds__(K1_T) kr_emit_k(const uint4 *__restrict__ mask
     }
 }
 
+// largest number of triggers in one tile (the streaming K2 pass has a per-tile capacity)
+__global__ void __launch_bounds__(256) tile_max_k(const u32 *__restrict__ tile_cnt, u32 ntiles,
+                                                  unsigned long long *__restrict__ out) {
+    u32 m = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < ntiles; i += gridDim.x * blockDim.x)
+        m = max(m, tile_cnt[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, (unsigned long long)m);
+}
+
 template <int W>
 static void launch_scan(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
                         const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
@@ -204,6 +216,88 @@ static void launch_scan(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end,
 
 #define K1_CASE(W) case W: launch_scan<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
 
+// K1a + the scan over tiles.  On return sb describes the trigger bits of the buffer, sb->total
+// is the number of triggers and sb->max_tile_cnt the largest per-tile count (read back: one
+// synchronisation).
+int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u64 own_lo, u64 own_hi,
+                  u32 w, u32 p, bool held, ScanBits *sb, float *ms_scan) {
+    memset(sb, 0, sizeof(*sb));
+    pfp_scan_consts C = pfp_make_scan_consts(w, p);
+    uintptr_t addr = (uintptr_t)d_buf;
+    u64 delta = addr & 15;
+    const uint4 *A = reinterpret_cast<const uint4 *>(addr - delta);
+    u64 q_end = delta + n_buf;
+    sb->A = A;
+    sb->q_end = q_end;
+    sb->pos_bias = buf_pos0 - delta;
+    // first position whose whole window lies in the text and in the buffer
+    u64 lo = own_lo;
+    if (lo < (u64)w - 1) lo = (u64)w - 1;
+    if (lo < buf_pos0 + w - 1) lo = buf_pos0 + w - 1;
+    u64 hi = own_hi;
+    if (hi > buf_pos0 + n_buf) hi = buf_pos0 + n_buf;
+    if (ms_scan) *ms_scan = 0;
+    if (!(lo < hi && n_buf > 0)) return PFPB200_OK;
+    u64 q_lo = lo - buf_pos0 + delta, q_hi = hi - buf_pos0 + delta;
+    u64 nt64 = (q_end + K1_TILE - 1) / K1_TILE;
+    if (nt64 > 0x7FFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "shard too large");
+    u32 ntiles = (u32)nt64;
+    uint4 *mask = nullptr;
+    u32 *tile_cnt = nullptr;
+    u64 *tile_off = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &mask, (size_t)ntiles * K1_T, held));
+    PFP_TRY(pfp_alloc_t(ctx, &tile_cnt, ntiles, held));
+    PFP_TRY(pfp_alloc_t(ctx, &tile_off, ntiles, held));
+    cudaEvent_t e0, e1;
+    PFP_CUDA(ctx, cudaEventCreate(&e0));
+    PFP_CUDA(ctx, cudaEventCreate(&e1));
+    PFP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    switch (w <= K1_MAXW_FAST ? (int)w : 0) {
+        K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7) K1_CASE(8) K1_CASE(9) K1_CASE(10)
+        K1_CASE(11) K1_CASE(12) K1_CASE(13) K1_CASE(14) K1_CASE(15) K1_CASE(16)
+        K1_CASE(20) K1_CASE(24) K1_CASE(28) K1_CASE(31) K1_CASE(32)
+        default:
+            kr_scan_generic_k<<<ntiles, K1_T, 0, ctx->stream>>>(
+                reinterpret_cast<const unsigned char *>(A), q_end, q_lo, q_hi, C, mask, tile_cnt);
+    }
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[5], 0, sizeof(u64), ctx->stream));
+    PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, tile_cnt, tile_off, ntiles, &ctx->d_flags[1]));
+    tile_max_k<<<ctx->sm_count, 256, 0, ctx->stream>>>(tile_cnt, ntiles,
+                                                       reinterpret_cast<unsigned long long *>(&ctx->d_flags[5]));
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[1], &ctx->d_flags[1], 5 * sizeof(u64),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float a = 0;
+    cudaEventElapsedTime(&a, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_scan) *ms_scan = a;
+    sb->ntiles = ntiles;
+    sb->mask = mask; sb->tile_cnt = tile_cnt; sb->tile_off = tile_off;
+    sb->total = ctx->h_flags[1];
+    sb->max_tile_cnt = (u32)ctx->h_flags[5];
+    return PFPB200_OK;
+}
+
+int pfp_scan_bits_free(pfpb200_ctx *ctx, ScanBits *sb) {
+    PFP_TRY(pfp_free_now(ctx, sb->mask));
+    PFP_TRY(pfp_free_now(ctx, sb->tile_cnt));
+    PFP_TRY(pfp_free_now(ctx, sb->tile_off));
+    sb->mask = nullptr; sb->tile_cnt = nullptr; sb->tile_off = nullptr;
+    return PFPB200_OK;
+}
+
+// K1c alone: bits -> ascending positions in out[0..total)
+int pfp_scan_emit(pfpb200_ctx *ctx, const ScanBits &sb, u64 *out) {
+    if (sb.ntiles == 0 || sb.total == 0) return PFPB200_OK;
+    kr_emit_k<<<sb.ntiles, K1_T, 0, ctx->stream>>>(sb.mask, sb.tile_off, sb.pos_bias, out);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
 // Runs K1a+scan+K1c.  On return *d_out (scratch, or held when `held`) holds *n_out positions;
 // `extra_slots` more u64 are allocated behind them for the caller (final virtual trigger).
 int pfp_scan_stage(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u64 own_lo,
@@ -211,72 +305,24 @@ int pfp_scan_stage(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u
                    float *ms_scan, float *ms_emit) {
     *d_out = nullptr;
     *n_out = 0;
-    pfp_scan_consts C = pfp_make_scan_consts(w, p);
-    uintptr_t addr = (uintptr_t)d_buf;
-    u64 delta = addr & 15;
-    const uint4 *A = reinterpret_cast<const uint4 *>(addr - delta);
-    u64 q_end = delta + n_buf;
-    // first position whose whole window lies in the text and in the buffer
-    u64 lo = own_lo;
-    if (lo < (u64)w - 1) lo = (u64)w - 1;
-    if (lo < buf_pos0 + w - 1) lo = buf_pos0 + w - 1;
-    u64 hi = own_hi;
-    if (hi > buf_pos0 + n_buf) hi = buf_pos0 + n_buf;
-    cudaEvent_t e0, e1, e2;
-    PFP_CUDA(ctx, cudaEventCreate(&e0));
+    ScanBits sb;
+    PFP_TRY(pfp_scan_bits(ctx, d_buf, n_buf, buf_pos0, own_lo, own_hi, w, p, false, &sb, ms_scan));
+    u64 *out = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &out, (size_t)(sb.total + extra_slots), held));
+    cudaEvent_t e1, e2;
     PFP_CUDA(ctx, cudaEventCreate(&e1));
     PFP_CUDA(ctx, cudaEventCreate(&e2));
-    u64 total = 0;
-    u64 *out = nullptr;
-    if (lo < hi && n_buf > 0) {
-        u64 q_lo = lo - buf_pos0 + delta, q_hi = hi - buf_pos0 + delta;
-        u64 nt64 = (q_end + K1_TILE - 1) / K1_TILE;
-        if (nt64 > 0x7FFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "shard too large");
-        u32 ntiles = (u32)nt64;
-        uint4 *mask = nullptr;
-        u32 *tile_cnt = nullptr;
-        u64 *tile_off = nullptr;
-        PFP_TRY(pfp_alloc_t(ctx, &mask, (size_t)ntiles * K1_T));
-        PFP_TRY(pfp_alloc_t(ctx, &tile_cnt, ntiles));
-        PFP_TRY(pfp_alloc_t(ctx, &tile_off, ntiles));
-        PFP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-        switch (w <= K1_MAXW_FAST ? (int)w : 0) {
-            K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7) K1_CASE(8) K1_CASE(9) K1_CASE(10)
-            K1_CASE(11) K1_CASE(12) K1_CASE(13) K1_CASE(14) K1_CASE(15) K1_CASE(16)
-            K1_CASE(20) K1_CASE(24) K1_CASE(28) K1_CASE(31) K1_CASE(32)
-            default:
-                kr_scan_generic_k<<<ntiles, K1_T, 0, ctx->stream>>>(
-                    reinterpret_cast<const unsigned char *>(A), q_end, q_lo, q_hi, C, mask, tile_cnt);
-        }
-        PFP_LAUNCHED(ctx);
-        PFP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
-        PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, tile_cnt, tile_off, ntiles, &ctx->d_flags[1]));
-        PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[1], &ctx->d_flags[1], sizeof(u64),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        total = ctx->h_flags[1];
-        PFP_TRY(pfp_alloc_t(ctx, &out, (size_t)(total + extra_slots), held));
-        kr_emit_k<<<ntiles, K1_T, 0, ctx->stream>>>(mask, tile_off, buf_pos0 - delta, out);
-        PFP_LAUNCHED(ctx);
-        PFP_CUDA(ctx, cudaEventRecord(e2, ctx->stream));
-        PFP_TRY(pfp_free_now(ctx, mask));
-        PFP_TRY(pfp_free_now(ctx, tile_cnt));
-        PFP_TRY(pfp_free_now(ctx, tile_off));
-        PFP_CUDA(ctx, cudaEventSynchronize(e2));
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, e0, e1);
-        cudaEventElapsedTime(&b, e1, e2);
-        if (ms_scan) *ms_scan = a;
-        if (ms_emit) *ms_emit = b;
-    } else {
-        PFP_TRY(pfp_alloc_t(ctx, &out, (size_t)extra_slots, held));
-        if (ms_scan) *ms_scan = 0;
-        if (ms_emit) *ms_emit = 0;
-    }
-    cudaEventDestroy(e0);
+    PFP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    PFP_TRY(pfp_scan_emit(ctx, sb, out));
+    PFP_CUDA(ctx, cudaEventRecord(e2, ctx->stream));
+    PFP_TRY(pfp_scan_bits_free(ctx, &sb));
+    PFP_CUDA(ctx, cudaEventSynchronize(e2));
+    float b = 0;
+    cudaEventElapsedTime(&b, e1, e2);
+    if (ms_emit) *ms_emit = b;
     cudaEventDestroy(e1);
     cudaEventDestroy(e2);
     *d_out = out;
-    *n_out = total;
+    *n_out = sb.total;
     return PFPB200_OK;
 }

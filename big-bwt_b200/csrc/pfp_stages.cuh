@@ -58,8 +58,20 @@ constexpr u64 NH_FOLD_B = 0xD6E8FEB86659FD93ULL;
 int pfp_scan_stage(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u64 own_lo,
                    u64 own_hi, u32 w, u32 p, u64 extra_slots, bool held, u64 **d_out, u64 *n_out,
                    float *ms_scan, float *ms_emit);
+int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u64 own_lo, u64 own_hi,
+                  u32 w, u32 p, bool held, ScanBits *sb, float *ms_scan);
+int pfp_scan_emit(pfpb200_ctx *ctx, const ScanBits &sb, u64 *out);
+int pfp_scan_bits_free(pfpb200_ctx *ctx, ScanBits *sb);
 int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 P,
                    i64 first_start, u32 w);
+int pfp_hash_list(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, i64 first_start, u32 w,
+                  const u32 *long_list, const u32 *long_count, u64 max_count);
+int pfp_records_range(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 j0, u64 P, u32 w);
+// K2 streaming: one pass over text + trigger bits writes ends (optional), .last, .sai and the
+// fingerprint records of all P phrases (ph.ends[P-1] must already hold a final virtual end, if any)
+bool pfp_stream_ok(const ScanBits &sb, u32 w);   // false: w > 32 or a tile too dense -> per-phrase kernels
+int pfp_stream_stage(pfpb200_ctx *ctx, const ScanBits &sb, const TextView &tv, const PhraseArrays &ph,
+                     u64 P, i64 first_start, u32 w, bool emit_ends);
 int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D);
 int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w,
                    DictArrays *D);

@@ -142,6 +142,37 @@ def test_device_entry_matches_host_entry(pkg, sc):
     assert not out.sai
 
 
+def test_stream_k2_misaligned_buffers_and_dense_triggers(pkg, sc):
+    """The streaming K2 pass (pfp_stream.cu): device buffers that start at every alignment within
+    16 bytes, phrases crossing run / warp / tile borders, runs holding many phrases (small p) and
+    tiles holding none (N runs)."""
+    a = pkg.synth.random_dna(150_000, 131).numpy()
+    text = np.concatenate([a, np.full(100_000, ord("N"), np.uint8), a[:70_000],
+                           np.frombuffer(b"ACGTTGCA" * 4000, np.uint8), a[5_000:90_000]])
+    for (w, p) in [(10, 100), (4, 10), (7, 11), (32, 50), (16, 1000)]:
+        want = orc.parse(text.tobytes(), w, p)
+        for off in (0, 3, 9):
+            buf = torch.from_numpy(np.concatenate([np.full(off, 65, np.uint8), text])).cuda()
+            got = sc.fetch(sc.parse_device(buf[off:], w, p, sai=True))
+            assert_same_files(got, want, f"stream w{w} p{p} off{off}")
+
+
+def test_stream_k2_equals_per_phrase_k2_64mb(pkg):
+    """Same files from the streaming K2 and from the per-phrase K2 kernels it replaced
+    (PFPB200_LEGACY_K2=1), at a size the oracle is too slow for."""
+    t = pkg.synth.pangenome_text(4_000_000, 16, 133).cuda()
+    res = []
+    for legacy in ("0", "1"):
+        os.environ["PFPB200_LEGACY_K2"] = legacy
+        try:
+            s = pkg.pfp.Scanner(0)
+        finally:
+            os.environ.pop("PFPB200_LEGACY_K2", None)
+        res.append(s.fetch(s.parse_device(t, 10, 100, sai=True)))
+        s.close()
+    assert_same_files(res[0], res[1], "stream vs per-phrase K2")
+
+
 def test_compress_mode_dicz(pkg, sc):
     """-c: words lose their last w bytes and the leading 0x02 (newscan.cpp:410-413)."""
     text = pkg.synth.pangenome_text(30_000, 5, 82).numpy().tobytes()
