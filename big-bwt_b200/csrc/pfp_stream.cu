@@ -23,6 +23,7 @@
 #include "pfp_common.cuh"
 #include "pfp_stages.cuh"
 #include "pfp_fp.cuh"
+#include "pfp_tma.cuh"
 
 constexpr int K2_T = PFP_TILE_T;
 constexpr int K2_TILE = PFP_TILE;
@@ -99,24 +100,43 @@ __global__ void __launch_bounds__(K2_T, 4) phrase_stream_k(const StreamArgs a) {
     const i64 q0 = (i64)(tile * (u64)K2_TILE);
     const u32 w = a.w;
 
-    // ---- stage keys, text (+halos) and trigger bits ------------------------------------------------
-    for (int i = t; i < NH_KEY_WORDS / 4; i += K2_T)
-        reinterpret_cast<uint4 *>(sk)[i] = __ldg(reinterpret_cast<const uint4 *>(a.keytab) + i);
-    for (int c = t; c < K2_TEXT / 16; c += K2_T) {
-        const i64 qc = q0 - K2_HALO + 16 * (i64)c;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (qc >= 0 && (u64)qc + 16 <= a.q_end) v = __ldg(a.A + (qc >> 4));
-        else if (qc >= 0 && (u64)qc < a.q_end)
-            v = k2_partial_chunk(reinterpret_cast<const unsigned char *>(a.A) + qc, (int)(a.q_end - (u64)qc));
-        reinterpret_cast<uint4 *>(sT)[c] = v;
+    // ---- stage text (+halos), trigger bits and keys ----------------------------------------------------
+    // interior tiles: three bulk copies (TMA) on one mbarrier; the first/last tiles of the buffer
+    // (halo before the buffer, partial 16-byte chunk at its end) take the explicit path
+    __shared__ __align__(8) u64 s_bar;
+    const i64 qs = q0 - K2_HALO;
+    const bool bulk = qs >= 0 && (u64)qs + K2_TEXT <= (a.q_end & ~(u64)15) &&
+                      (tile * (u64)K2_T + K2_MWORDS / 4) <= (u64)a.ntiles * K2_T;
+    if (bulk) {
+        if (t == 0) { mbar_init(&s_bar, 1); mbar_init_fence(); }
+        __syncthreads();
+        if (t == 0) {
+            mbar_expect_tx(&s_bar, (u32)(K2_TEXT + K2_MWORDS * 4 + NH_KEY_WORDS * 4));
+            bulk_copy_g2s(sT, a.A + (qs >> 4), K2_TEXT, &s_bar);
+            bulk_copy_g2s(sM, a.mask + tile * (u64)K2_T, K2_MWORDS * 4, &s_bar);
+            bulk_copy_g2s(sk, a.keytab, NH_KEY_WORDS * 4, &s_bar);
+        }
+        if (t < K2_NBIN) { s_hist[t] = 0; }
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = t; i < NH_KEY_WORDS / 4; i += K2_T)
+            reinterpret_cast<uint4 *>(sk)[i] = __ldg(reinterpret_cast<const uint4 *>(a.keytab) + i);
+        for (int c = t; c < K2_TEXT / 16; c += K2_T) {
+            const i64 qc = qs + 16 * (i64)c;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (qc >= 0 && (u64)qc + 16 <= a.q_end) v = __ldg(a.A + (qc >> 4));
+            else if (qc >= 0 && (u64)qc < a.q_end)
+                v = k2_partial_chunk(reinterpret_cast<const unsigned char *>(a.A) + qc, (int)(a.q_end - (u64)qc));
+            reinterpret_cast<uint4 *>(sT)[c] = v;
+        }
+        for (int i = t; i < K2_MWORDS / 4; i += K2_T) {
+            const u64 gi = tile * (u64)K2_T + (u64)i;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (gi < (u64)a.ntiles * K2_T) v = __ldg(a.mask + gi);
+            reinterpret_cast<uint4 *>(sM)[i] = v;
+        }
+        if (t < K2_NBIN) { s_hist[t] = 0; }
     }
-    for (int i = t; i < K2_MWORDS / 4; i += K2_T) {
-        const u64 gi = tile * (u64)K2_T + (u64)i;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (gi < (u64)a.ntiles * K2_T) v = __ldg(a.mask + gi);
-        reinterpret_cast<uint4 *>(sM)[i] = v;
-    }
-    if (t < K2_NBIN) { s_hist[t] = 0; }
     __syncthreads();
 
     // ---- trigger bits -> tile-local positions se[0..tot), se[tot] = first trigger behind the tile ----
