@@ -322,7 +322,7 @@ __global__ void iota_u32_k(u32 *v, u64 n) {
 // atomic per warp instead of 32.  `chk` is a 32-bit digest of the full 128-bit fingerprint and
 // the length, independent of the key: every phrase that lands in a slot must agree with it, or
 // the parse stops with PFPB200_E_COLLISION (the reference compares strings, newscan.cpp:282-286).
-struct __align__(16) DictSlot { u64 key; u32 cnt; u32 chk; };
+struct __align__(16) DictSlot { u64 key; u32 rep; u32 chk; };
 constexpr u32 TABLE_MAX_PROBES = 2048;
 
 __device__ __forceinline__ u32 check_of(const PhraseFp &r) {
@@ -339,50 +339,84 @@ __global__ void table_init_k(DictSlot *__restrict__ tab, u64 cap) {
     if (i < cap) *reinterpret_cast<uint4 *>(tab + i) = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// One probe sequence: a plain 16-byte load of the slot first -- on repetitive inputs nine phrases
+// in ten find their word already there and finish with one fire-and-forget add -- and a CAS only
+// on an empty slot.  The thread that wins the CAS (the word's creator) records itself as the
+// word's representative occurrence and the word's length next to the table.
+struct Probe { u64 slot; bool placed; bool creator; u32 seen_chk; };
+
+__device__ __forceinline__ Probe table_probe(DictSlot *__restrict__ tab, u64 cap, u64 slot, uint4 sv, u64 k) {
+    Probe r{slot, false, false, 0u};
+    u32 probes = 0;
+    for (;;) {
+        const u64 key = ((u64)sv.y << 32) | sv.x;
+        if (key == k) { r.placed = true; r.seen_chk = sv.w; break; }
+        if (key == 0ull) {
+            const u64 prev = atomicCAS((unsigned long long *)&tab[r.slot].key, 0ull, (unsigned long long)k);
+            if (prev == 0ull) { r.placed = true; r.creator = true; break; }
+            if (prev == k) { r.placed = true; break; }
+        }
+        if (++probes > TABLE_MAX_PROBES) break;               // table too small for this input
+        r.slot = (r.slot + 1 == cap) ? 0 : r.slot + 1;
+        sv = __ldcg(reinterpret_cast<const uint4 *>(tab + r.slot));
+    }
+    return r;
+}
+
+constexpr int TI_ITEMS = 2;      // phrases per thread: their first probes are in flight together
+
 __global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict__ rec, u64 P,
-                                                      DictSlot *__restrict__ tab, u64 mask, int shift,
+                                                      DictSlot *__restrict__ tab, u64 cap,
                                                       u32 *__restrict__ slot_of,
+                                                      u32 *__restrict__ len_slot,
                                                       u64 *__restrict__ flags) {
-    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = j < P;
-    PhraseFp r;
-    r.key = 0;
-    if (active) {
-        const uint4 *q = reinterpret_cast<const uint4 *>(rec + j);
-        uint4 a = __ldg(q), b = __ldg(q + 1);
-        r.fpa = ((u64)a.y << 32) | a.x; r.fpb = ((u64)a.w << 32) | a.z;
-        r.len = b.x; r.key = ((u64)b.w << 32) | b.z;
-    }
-    const u64 k = r.key;
-    const u32 chk = active ? check_of(r) : 0u;
-    const u32 peers = __match_any_sync(0xffffffffu, k);
     const u32 lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    u64 slot = 0;
-    if (active && (int)lane == leader) {
-        slot = k >> shift;
-        u32 probes = 0;
-        bool placed = false;
-        for (;;) {
-            u64 prev = atomicCAS((unsigned long long *)&tab[slot].key, 0ull, (unsigned long long)k);
-            if (prev == 0ull || prev == k) { placed = true; break; }
-            if (++probes > TABLE_MAX_PROBES) break;           // table too small for this input
-            slot = (slot + 1) & mask;
+    const u64 base = (u64)blockIdx.x * (256 * TI_ITEMS) + threadIdx.x;
+    u64 k[TI_ITEMS];
+    u32 chk[TI_ITEMS], len[TI_ITEMS], peers[TI_ITEMS];
+    uint4 sv[TI_ITEMS];
+    bool lead[TI_ITEMS];
+#pragma unroll
+    for (int it = 0; it < TI_ITEMS; it++) {
+        const u64 j = base + (u64)it * 256;
+        PhraseFp r;
+        r.key = 0; r.len = 0; r.fpa = r.fpb = 0;
+        if (j < P) {                                  // streamed once: keep it out of the table's way in L2
+            const uint4 *q = reinterpret_cast<const uint4 *>(rec + j);
+            uint4 a = __ldcs(q), b = __ldcs(q + 1);
+            r.fpa = ((u64)a.y << 32) | a.x; r.fpb = ((u64)a.w << 32) | a.z;
+            r.len = b.x; r.key = ((u64)b.w << 32) | b.z;
         }
-        if (placed) {
-            atomicAdd(&tab[slot].cnt, (u32)__popc(peers));
-            u32 pc = atomicCAS(&tab[slot].chk, 0u, chk);
-            if (pc != 0u && pc != chk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
-        } else {
-            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_TABLE_FULL);
-            slot = 0;
-        }
+        k[it] = r.key;
+        len[it] = r.len;
+        chk[it] = j < P ? check_of(r) : 0u;
+        peers[it] = __match_any_sync(0xffffffffu, k[it]);
+        lead[it] = j < P && (int)lane == __ffs(peers[it]) - 1;
+        if (lead[it]) sv[it] = __ldcg(reinterpret_cast<const uint4 *>(tab + __umul64hi(k[it], cap)));
     }
-    slot = __shfl_sync(0xffffffffu, slot, leader);
-    const u32 lchk = __shfl_sync(0xffffffffu, chk, leader);
-    if (active) {
-        slot_of[j] = (u32)slot;
-        if (chk != lchk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+#pragma unroll
+    for (int it = 0; it < TI_ITEMS; it++) {
+        const u64 j = base + (u64)it * 256;
+        u64 slot = 0;
+        if (lead[it]) {
+            const Probe pr = table_probe(tab, cap, __umul64hi(k[it], cap), sv[it], k[it]);
+            if (pr.placed) {
+                slot = pr.slot;
+                u32 seen = pr.seen_chk;
+                if (pr.creator) { tab[slot].rep = (u32)j; len_slot[slot] = len[it]; }
+                if (seen == 0u) seen = atomicCAS(&tab[slot].chk, 0u, chk[it]);   // creator, or racing with it
+                if (seen != 0u && seen != chk[it]) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+            } else {
+                atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_TABLE_FULL);
+            }
+        }
+        const int leader = __ffs(peers[it]) - 1;
+        slot = __shfl_sync(0xffffffffu, slot, leader);
+        const u32 lchk = __shfl_sync(0xffffffffu, chk[it], leader);
+        if (j < P) {
+            __stcs(slot_of + j, (u32)slot);
+            if (chk[it] != lchk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+        }
     }
 }
 
@@ -391,40 +425,24 @@ __global__ void table_flags_k(const DictSlot *__restrict__ tab, u64 cap, u8 *__r
     if (i < cap) occ[i] = tab[i].key != 0ull ? 1 : 0;
 }
 
-__global__ void table_emit_k(const DictSlot *__restrict__ tab, const u8 *__restrict__ occ,
-                             const u32 *__restrict__ umap, u64 cap, u32 *__restrict__ count,
-                             u32 *__restrict__ rep) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap && occ[i]) {
-        u32 u = umap[i];
-        count[u] = tab[i].cnt;
-        rep[u] = 0xFFFFFFFFu;
-    }
-}
-
-// phrase -> word id; the first phrase of every word becomes its representative occurrence
-__global__ void table_uid_k(const u32 *__restrict__ slot_of, const u32 *__restrict__ umap, u64 P,
-                            u32 *__restrict__ uid, u32 *__restrict__ rep) {
-    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = j < P;
-    u32 u = active ? umap[slot_of[j]] : 0xFFFFFFFFu;
-    if (active) uid[j] = u;
-    // lanes of a warp hold increasing j: the lowest lane of each group carries the minimum
-    u32 peers = __match_any_sync(0xffffffffu, u);
-    if (active && (peers & lanemask_lt()) == 0) atomicMin(&rep[u], (u32)j);
-}
-
-__global__ void word_stats_k(const u32 *__restrict__ rep, const PhraseFp *__restrict__ rec, u64 d,
-                             u32 *__restrict__ ulen, u32 *__restrict__ uwords,
-                             u64 *__restrict__ flags /* [2]=max len, [3]=sum len */) {
+// per distinct word (= occupied slot): occurrences, representative phrase, length; max / total length
+__global__ void __launch_bounds__(256) table_emit_k(const DictSlot *__restrict__ tab, const u8 *__restrict__ occ,
+                                                    const u32 *__restrict__ umap,
+                                                    const u32 *__restrict__ len_slot, u64 cap,
+                                                    u32 *__restrict__ count, u32 *__restrict__ rep,
+                                                    u32 *__restrict__ ulen, u32 *__restrict__ uwords,
+                                                    u64 *__restrict__ flags /* [2]=max len, [3]=sum len */) {
     __shared__ unsigned long long s_sum;
     __shared__ u32 s_max;
     if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }
     __syncthreads();
-    u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 L = 0;
-    if (u < d) {
-        L = rec[rep[u]].len;
+    if (i < cap && occ[i]) {
+        u32 u = umap[i];
+        count[u] = 0;                                 // occurrences are counted by table_uid_k
+        rep[u] = tab[i].rep;
+        L = len_slot[i];
         ulen[u] = L;
         uwords[u] = (L + 7) >> 3;
     }
@@ -435,12 +453,24 @@ __global__ void word_stats_k(const u32 *__restrict__ rep, const PhraseFp *__rest
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
     }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum, (unsigned long long)sum); atomicMax(&s_max, mx); }
+    if ((threadIdx.x & 31) == 0 && sum) { atomicAdd(&s_sum, (unsigned long long)sum); atomicMax(&s_max, mx); }
     __syncthreads();
     if (threadIdx.x == 0 && s_sum) {
         atomicMax((unsigned long long *)&flags[2], (unsigned long long)s_max);
         atomicAdd((unsigned long long *)&flags[3], s_sum);
     }
+}
+
+// phrase -> word id, and the occurrence counts: the adds go to the d-entry count array, which
+// stays in L2, instead of dirtying the (much larger) table
+__global__ void table_uid_k(const u32 *__restrict__ slot_of, const u32 *__restrict__ umap, u64 P,
+                            u32 *__restrict__ uid, u32 *__restrict__ count) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < P;
+    u32 u = active ? umap[__ldcs(slot_of + j)] : 0xFFFFFFFFu;
+    if (active) uid[j] = u;
+    const u32 peers = __match_any_sync(0xffffffffu, u);
+    if (active && (peers & lanemask_lt()) == 0) atomicAdd(&count[u], (u32)__popc(peers));
 }
 
 // run heads of sorted keys + fingerprint agreement inside runs (dictionary merge)
@@ -573,31 +603,30 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
 // Reads d (and length stats) back to the host: one synchronisation.
 int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D) {
     const int TB = 256;
-    // Capacity: a power of two.  Without a hint 1.5 P (load factor <= 2/3 even if every phrase
-    // is distinct).  The distinct/phrase ratio of the previous parse on this context sizes the
-    // table ~2.5x the expected dictionary instead, which keeps it (and the passes over it) several
-    // times smaller on repetitive inputs; if that guess turns out too small the insert kernel says
-    // so and the stage reruns with the safe size.
+    // Capacity: without a hint 1.5 P (load factor <= 2/3 even if every phrase is distinct).  The
+    // distinct/phrase ratio of the previous parse on this context sizes the table 2x the expected
+    // dictionary instead, which keeps it (and the passes over it) several times smaller on
+    // repetitive inputs -- small enough to live in L2; if that guess turns out too small the
+    // insert kernel says so and the stage reruns with the safe size.  Slots are addressed by
+    // fastrange (mulhi(key, cap)), so the capacity need not be a power of two.
     DictSlot *tab = nullptr;
-    u32 *slot_of = nullptr, *umap = nullptr;
+    u32 *slot_of = nullptr, *umap = nullptr, *len_slot = nullptr;
     u8 *occ = nullptr;
     u64 cap = 0, d = 0;
     PFP_TRY(pfp_alloc_t(ctx, &slot_of, P));
     for (int attempt = 0;; attempt++) {
         double want = (double)P * 1.5;
         if (attempt == 0 && ctx->dedup_ratio > 0.0) {
-            double guess = ctx->dedup_ratio * (double)P * 2.5;
+            double guess = ctx->dedup_ratio * (double)P * 2.0;
             if (guess < want) want = guess;
         }
-        cap = 1024;
-        while ((double)cap < want) cap <<= 1;
-        int kbits = 0;
-        while ((1ull << kbits) < cap) kbits++;
+        cap = (u64)want + 1024;
         PFP_TRY(pfp_alloc_t(ctx, &tab, cap));
+        PFP_TRY(pfp_alloc_t(ctx, &len_slot, cap));
         table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
         PFP_LAUNCHED(ctx);
-        table_insert_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(ph.rec, P, tab, cap - 1, 64 - kbits, slot_of,
-                                                                  ctx->d_flags);
+        table_insert_k<<<pfp_blocks(P, TB * TI_ITEMS), TB, 0, ctx->stream>>>(ph.rec, P, tab, cap, slot_of, len_slot,
+                                                                            ctx->d_flags);
         PFP_LAUNCHED(ctx);
         PFP_TRY(pfp_alloc_t(ctx, &occ, cap));
         PFP_TRY(pfp_alloc_t(ctx, &umap, cap));
@@ -616,6 +645,7 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays 
         if (attempt > 0) return pfp_fail(ctx, PFPB200_E_INTERNAL, "dictionary table overflow");
         // undo and retry with the safe capacity
         PFP_TRY(pfp_free_now(ctx, tab));
+        PFP_TRY(pfp_free_now(ctx, len_slot));
         PFP_TRY(pfp_free_now(ctx, occ));
         PFP_TRY(pfp_free_now(ctx, umap));
         ctx->dedup_ratio = 0.0;
@@ -633,13 +663,13 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays 
     PFP_TRY(pfp_alloc_t(ctx, &D->count, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->ulen, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->uwords, d));
-    table_emit_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, occ, umap, cap, D->count, D->rep);
+    table_emit_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, occ, umap, len_slot, cap, D->count, D->rep,
+                                                              D->ulen, D->uwords, ctx->d_flags);
     PFP_LAUNCHED(ctx);
-    table_uid_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(slot_of, umap, P, D->uid, D->rep);
-    PFP_LAUNCHED(ctx);
-    word_stats_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(D->rep, ph.rec, d, D->ulen, D->uwords, ctx->d_flags);
+    table_uid_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(slot_of, umap, P, D->uid, D->count);
     PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_free_now(ctx, tab));
+    PFP_TRY(pfp_free_now(ctx, len_slot));
     PFP_TRY(pfp_free_now(ctx, slot_of));
     PFP_TRY(pfp_free_now(ctx, occ));
     PFP_TRY(pfp_free_now(ctx, umap));
