@@ -191,19 +191,19 @@ __global__ void rank_writeback_k(const u32 *__restrict__ apos, const u64 *__rest
 }
 
 // ---- local refinement: one warp per small tie group ---------------------------------------------------
-// Lanes are the positions of the group.  Each round every still-tied lane loads the next 8-byte
-// chunk of its word; if no lane differs from the first lane of its tie range the round is a
-// shared prefix and is skipped at once.  Otherwise every lane counts, inside its tie range
-// [lo,hi), the lanes with a smaller chunk and the equal ones in front of it: that is its new
-// position; ties shrink until all are singletons.
+// Lanes are the words of the group and never move.  A lane knows the tie range it is in as
+// (lo, sz): the rank of the range's first word and its size.  Four 8-byte chunks per word are
+// fetched at once (independent loads: one memory round trip per 32 bytes of depth); for every
+// chunk, if no lane differs from the first lane of its range the chunk is a shared prefix and
+// costs one compare.  Otherwise each lane counts, among the lanes of its range, those with a
+// smaller chunk (its range moves up by that many) and those with an equal one (the new size).
+// When all ranges are singletons, lo is the word's rank inside the group.
 __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
                                                    const u32 *__restrict__ nheads,
                                                    const u32 *__restrict__ depth,
                                                    const u64 *pool, const u64 *uoff, const u32 *uwords,
                                                    u32 max_chunks, u32 *__restrict__ ord,
                                                    u64 *__restrict__ flags) {
-    __shared__ u32 s_uid[8][32];
-    __shared__ u16 s_lo[8][32], s_hi[8][32];
     const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const u32 ng = *nheads;
     const u32 nwarps = gridDim.x * 8;
@@ -211,40 +211,42 @@ __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
         const u32 s = hp[g], m = hp[g + 1] - s;
         if (m < 2 || m > WARP_MAX) continue;
         u32 r = depth[s];
-        u32 uid = lane < m ? ord[s + lane] : 0;
-        u32 lo = lane < m ? 0 : lane, hi = lane < m ? m : lane + 1;
-        const u64 woff = lane < m ? uoff[uid] : 0;
-        u32 wn = lane < m ? uwords[uid] : 0;
-        u64 myoff = woff;
-        for (;;) {
-            bool active = (hi - lo) > 1;
-            if (!__any_sync(0xffffffffu, active)) break;
+        const bool mem = lane < m;
+        const u32 uid = mem ? ord[s + lane] : 0;
+        const u64 *wptr = pool + (mem ? uoff[uid] : 0);
+        const u32 wn = mem ? uwords[uid] : 0;
+        u32 lo = mem ? 0u : 0xFFFF0000u + lane;      // lanes outside the group: ranges of their own
+        u32 sz = mem ? m : 1u;
+        bool done = false;
+        while (!done) {
             if (r >= max_chunks) {
                 if (lane == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
                 break;
             }
-            u64 key = (active && r < wn) ? bswap64(__ldg(pool + myoff + r)) : 0ull;
-            u64 headkey = __shfl_sync(0xffffffffu, key, lo & 31);
-            if (!__any_sync(0xffffffffu, active && key != headkey)) { r++; continue; }   // shared prefix
-            u32 less = 0, eqb = 0, eq = 0;
-            for (u32 j = 0; j < m; j++) {
-                u64 kj = __shfl_sync(0xffffffffu, key, j);
-                bool in = (j >= lo) && (j < hi);
-                less += (in && kj < key) ? 1 : 0;
-                bool e = in && (kj == key);
-                eq += e ? 1 : 0;
-                eqb += (e && j < lane) ? 1 : 0;
+            u64 k[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) k[c] = (sz > 1 && r + c < wn) ? bswap64(__ldg(wptr + r + c)) : 0ull;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const u32 peers = __match_any_sync(0xffffffffu, lo);
+                const u64 key = k[c];
+                const u64 headkey = __shfl_sync(0xffffffffu, key, __ffs(peers) - 1);
+                if (__any_sync(0xffffffffu, sz > 1 && key != headkey)) {
+                    u32 less = 0, eq = 0;
+                    for (u32 j = 0; j < m; j++) {
+                        const u64 kj = __shfl_sync(0xffffffffu, key, j);
+                        const bool in = (peers >> j) & 1u;
+                        less += (in && kj < key) ? 1 : 0;
+                        eq += (in && kj == key) ? 1 : 0;
+                    }
+                    lo += less;
+                    sz = eq;
+                    if (!__any_sync(0xffffffffu, sz > 1)) { done = true; break; }
+                }
             }
-            u32 np = lane, nlo = lo, nhi = hi;
-            if (active) { nlo = lo + less; nhi = nlo + eq; np = nlo + eqb; }
-            __syncwarp();
-            s_uid[wp][np] = uid; s_lo[wp][np] = (u16)nlo; s_hi[wp][np] = (u16)nhi;
-            __syncwarp();
-            uid = s_uid[wp][lane]; lo = s_lo[wp][lane]; hi = s_hi[wp][lane];
-            if (lane < m) { myoff = uoff[uid]; wn = uwords[uid]; }
-            r++;
+            r += 4;
         }
-        if (lane < m) ord[s + lane] = uid;
+        if (mem) ord[s + lo] = uid;
     }
 }
 
