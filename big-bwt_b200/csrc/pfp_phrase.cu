@@ -255,58 +255,49 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
     }
 }
 
-// phrases longer than one NH segment or touching the text borders: one CTA per phrase, 32 groups
-// of 8 lanes stride over the segments; segment s enters the sum with weight FOLD^s (pfp_fp.cuh)
-constexpr int PL_GROUP = 8;
-constexpr int PL_GROUPS = PH_T / PL_GROUP;
+// Listed phrases (longer than one NH segment, touching the text borders, or left over by the
+// streaming pass): one warp per phrase, lanes stride over its 16-byte chunks; the chunks of
+// segment s enter the sum with weight FOLD^s (pfp_fp.cuh).
 __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseArrays ph,
                                                            i64 first_start, u32 w,
                                                            const u32 *__restrict__ keytab,
                                                            const u32 *__restrict__ long_list,
                                                            const u32 *__restrict__ long_count,
-                                                           u64 fold_a32, u64 fold_b32) {
+                                                           u64 *__restrict__ flags) {
     __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
-    __shared__ u64 red[2][PH_T / 32];
     for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
     __syncthreads();
-    const u32 li = threadIdx.x & (PL_GROUP - 1), g = threadIdx.x / PL_GROUP;
+    const u32 lane = threadIdx.x & 31;
     const u32 nlong = *long_count;
-    for (u32 q = blockIdx.x; q < nlong; q += gridDim.x) {
-        u64 j = long_list[q];
-        i64 e = (i64)ph.ends[j];
-        i64 s0 = (j == 0) ? first_start : (i64)ph.ends[j - 1] - (i64)w + 1;
-        u64 len = (u64)(e - s0 + 1);
-        bool special = (s0 < 0) || (e >= tv.n_global);
-        u64 nseg = (len + NH_SEG_BYTES - 1) / NH_SEG_BYTES;
-        u64 fa = 0, fb = 0;
-        u64 wa = fold_pow(NH_FOLD_A, g), wb = fold_pow(NH_FOLD_B, g);   // weight of segment g
-        for (u64 s = g; s < nseg; s += PL_GROUPS) {
-            u64 so = s * NH_SEG_BYTES;
-            u32 segb = (u32)((len - so) < NH_SEG_BYTES ? (len - so) : NH_SEG_BYTES);
-            u32 nch = (segb + 15) >> 4;
-            u64 pa = 0, pb = 0;
-            for (u32 c = li; c < nch; c += PL_GROUP) {
-                u32 x[4];
-                load_chunk(tv, s0, len, so + 16ull * c, special, x);
-                nh_chunk(sk, c, x, pa, pb);
+    for (u32 q = blockIdx.x * PH_WARPS + (threadIdx.x >> 5); q < nlong; q += gridDim.x * PH_WARPS) {
+        const u64 j = long_list[q];
+        const i64 e = (i64)ph.ends[j];
+        const i64 s0 = (j == 0) ? first_start : (i64)ph.ends[j - 1] - (i64)w + 1;
+        const u64 len = (u64)(e - s0 + 1);
+        const bool special = (s0 < 0) || (e >= tv.n_global);
+        const u64 nch = (len + 15) >> 4;
+        u64 fa = 0, fb = 0, pa = 0, pb = 0, wa = 1, wb = 1;
+        u64 seg = 0;
+        for (u64 c = lane; c < nch; c += 32) {
+            const u64 sg = c >> 9;
+            if (sg != seg) {                       // leave segment `seg`: weigh what was gathered in it
+                fa += wa * pa; fb += wb * pb;
+                pa = pb = 0;
+                for (; seg < sg; seg++) { wa *= NH_FOLD_A; wb *= NH_FOLD_B; }
             }
-            fa += wa * pa;
-            fb += wb * pb;
-            wa *= fold_a32;              // FOLD^PL_GROUPS: on to segment s + PL_GROUPS
-            wb *= fold_b32;
+            u32 x[4];
+            load_chunk(tv, s0, len, 16ull * c, special, x);
+            nh_chunk(sk, (u32)(c & 511u), x, pa, pb);
         }
+        fa += wa * pa; fb += wb * pb;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             fa += __shfl_xor_sync(0xffffffffu, fa, o);
             fb += __shfl_xor_sync(0xffffffffu, fb, o);
         }
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = fa; red[1][threadIdx.x >> 5] = fb; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u64 a = 0, b = 0;
-            for (int i = 0; i < PH_T / 32; i++) { a += red[0][i]; b += red[1][i]; }
-            store_rec(ph.rec, j, a, b, (u32)len);
+        if (lane == 0) {
+            if (len > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
+            store_rec(ph.rec, j, fa, fb, (u32)len);
         }
     }
 }
@@ -548,12 +539,12 @@ __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__re
 // fingerprints of the phrases listed in long_list[0..*long_count): any length, any position
 int pfp_hash_list(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, i64 first_start, u32 w,
                   const u32 *long_list, const u32 *long_count, u64 max_count) {
-    u64 fa32 = 1, fb32 = 1;
-    for (int i = 0; i < PL_GROUPS; i++) { fa32 *= NH_FOLD_A; fb32 *= NH_FOLD_B; }
-    u32 nlb = (u32)(max_count < (u64)ctx->sm_count ? max_count : (u64)ctx->sm_count);
+    u64 want = (max_count + PH_WARPS - 1) / PH_WARPS;
+    u64 maxb = (u64)ctx->sm_count * 8;
+    u32 nlb = (u32)(want < maxb ? want : maxb);
     if (nlb == 0) nlb = 1;
     phrase_hash_long_k<<<nlb, PH_T, 0, ctx->stream>>>(tv, ph, first_start, w, ctx->d_keys, long_list,
-                                                      long_count, fa32, fb32);
+                                                      long_count, ctx->d_flags);
     PFP_LAUNCHED(ctx);
     return PFPB200_OK;
 }

@@ -2,13 +2,13 @@
 //
 // Replaces save_update_word() + kr_hash() of the reference (newscan.cpp:229-304) for all phrases
 // at once.  Input: the text and the trigger bits of K1a (one bit per position).  A CTA takes the
-// same 32 KB tile as K1 and stages its text (+32 B left halo, +1 KB to the right) and trigger
+// same 32 KB tile as K1 and stages its text (+32 B left halo, +4 KB to the right) and trigger
 // bits in shared memory.  It then
 //   1. compacts the trigger bits into tile-local positions and writes, per trigger, its global
 //      position (ends[]), the `.last` byte (newscan.cpp:296) and the `.sai` value (:299-301) --
 //      one thread per trigger, coalesced stores;
 //   2. owns every phrase that STARTS at one of its triggers (phrase j = text from e_{j-1}-w+1 to
-//      e_j); its end is the next trigger, in the tile or in the 1 KB behind it;
+//      e_j); its end is the next trigger, in the tile or in the 4 KB behind it;
 //   3. counting-sorts those phrases by their number of 16-byte chunks, longest first, so that the
 //      32 phrases of a warp have (almost) the same length -- phrase lengths are geometric, and
 //      giving lanes arbitrary phrases leaves two thirds of a warp idle;
@@ -17,7 +17,7 @@
 //      chunk's last word and second key carried in registers), one warp per longer phrase.
 // Every phrase is hashed by exactly one lane or warp, so there are no partial sums to join.
 // Left to the list kernel (phrase_hash_long_k): the buffer's first phrase, a final phrase ending
-// at the virtual text border, phrases that do not end within 1 KB of their tile or are longer
+// at the virtual text border, phrases that do not end within 4 KB of their tile or are longer
 // than one key segment (8 KB).  Tiles with more triggers than K2_CAP (p < ~40) are not handled
 // here at all: pfp_stream_stage reports them and the caller uses the per-phrase kernels.
 #include "pfp_common.cuh"
@@ -28,7 +28,7 @@
 constexpr int K2_T = PFP_TILE_T;
 constexpr int K2_TILE = PFP_TILE;
 constexpr int K2_HALO = 32;                                   // >= w (w <= 32 on this path)
-constexpr int K2_EXT = 1024;                                  // text staged behind the tile
+constexpr int K2_EXT = 4096;                                  // text staged behind the tile
 constexpr int K2_TEXT = K2_HALO + K2_TILE + K2_EXT + 32;      // staged text bytes
 constexpr int K2_MWORDS = (K2_TILE + K2_EXT) / 32;            // staged trigger-bit words
 constexpr int K2_CAP = 1024;                                  // triggers per tile handled here
@@ -161,12 +161,18 @@ __global__ void __launch_bounds__(K2_T, 4) phrase_stream_k(const StreamArgs a) {
             }
         }
     }
-    if (wp == 0) {                      // the 32 words behind the tile
-        const u32 x = sM[K2_TILE / 32 + lane];
-        const u32 nz = __ballot_sync(0xffffffffu, x != 0);
-        const int fl = __ffs(nz) - 1;
-        if (nz == 0) { if (lane == 0) se[tot] = (u16)K2_NONE; }
-        else if ((int)lane == fl) se[tot] = (u16)(K2_TILE + 32 * lane + __ffs(x) - 1);
+    if (wp == 0) {                      // first trigger in the K2_EXT / 32 words behind the tile
+        u32 found = K2_NONE;
+        for (int b0 = 0; b0 < K2_EXT / 32 && found == K2_NONE; b0 += 32) {
+            const u32 x = sM[K2_TILE / 32 + b0 + lane];
+            const u32 nz = __ballot_sync(0xffffffffu, x != 0);
+            if (nz) {
+                const int fl = __ffs(nz) - 1;
+                const u32 xf = __shfl_sync(0xffffffffu, x, fl);
+                found = (u32)(K2_TILE + 32 * (b0 + fl) + __ffs(xf) - 1);
+            }
+        }
+        if (lane == 0) se[tot] = (u16)found;
     }
     __syncthreads();
 

@@ -1,0 +1,138 @@
+#!/usr/bin/env python3
+"""Full-size property checks of BASELINE.json configs 2, 4 and 5 on one GPU.
+
+At these sizes the CPU oracle would take minutes to hours, so parity is checked through
+size-independent properties of the five output streams (all computed on the device, plus a
+host reconstruction of a text prefix from .dict + .parse):
+  * sum(.occ) == #phrases, bincount(.parse) == .occ, every rank in 1..d
+  * .sai strictly increasing, last value n + w; .last[j] == T[sai[j] - w - 1]
+  * every phrase end is a trigger: T[sai-w .. sai) hashes to 0 mod p (re-computed with torch)
+  * .dict: d words, strictly increasing (sampled adjacent pairs), 0x01 terminators, final 0x00
+  * unparse of the first 200 000 phrases == the text prefix
+usage: fullsize_check.py [--config pangenome|random|sweep|all] [--small]
+Prints one JSON line per case; exit status 1 on any failed property.
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+PW = 1999999973
+
+
+class DevView:
+    """torch view of a raw device pointer (no copy) through __cuda_array_interface__."""
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def view(ptr, n, typestr="|u1"):
+    return torch.as_tensor(DevView(ptr, n, typestr), device="cuda")
+
+
+def window_hash_mod_p(text, ends, w, p):
+    """(KR hash of T[e-w+1..e]) % p for int64 tensor of end positions (newscan.cpp:194-202)."""
+    h = torch.zeros_like(ends)
+    for i in range(w):
+        c = text[ends - w + 1 + i].to(torch.int64)
+        h = (h * 256 + c) % PW
+    return h % p
+
+
+def check_case(sc, text, w, p, name, sample_pairs=200_000, prefix_phrases=200_000):
+    n = text.numel()
+    sc.parse_device(text, w, p, sai=True)               # warm-up: arena growth, table sizing hint
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = sc.parse_device(text, w, p, sai=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = sc.stats.as_dict()
+    P, d = out.n_phrases, out.n_distinct
+    res = {"case": name, "n": n, "w": w, "p": p, "phrases": P, "distinct": d, "dict_bytes": out.dict_bytes,
+           "ms_gpu": round(st["ms_total"], 3), "GBps": round(n / st["ms_total"] / 1e6, 1), "wall_s": round(dt, 3),
+           "stages_ms": {k[3:]: round(v, 2) for k, v in st.items() if k.startswith("ms_") and k not in ("ms_total", "ms_h2d", "ms_d2h")},
+           "rank_rounds": st["rank_rounds"]}
+    fails = []
+    parse = view(out.parse, P, "<u4").to(torch.int64)
+    occ = view(out.occ, d, "<u4").to(torch.int64)
+    last = view(out.last, P)
+    sai = view(out.sai, 5 * P).view(P, 5).to(torch.int64)
+    pos = sai[:, 0] | (sai[:, 1] << 8) | (sai[:, 2] << 16) | (sai[:, 3] << 24) | (sai[:, 4] << 32)
+    if int(occ.sum()) != P: fails.append("sum(occ) != phrases")
+    if int(parse.min()) < 1 or int(parse.max()) > d: fails.append("rank out of range")
+    if not torch.equal(torch.bincount(parse, minlength=d + 1)[1:], occ): fails.append("bincount(parse) != occ")
+    if P > 1 and not bool((pos[1:] > pos[:-1]).all()): fails.append(".sai not increasing")
+    if int(pos[-1]) != n + w: fails.append(".sai last != n + w")
+    e = pos[:-1] - 1                                     # trigger positions
+    if e.numel():
+        lidx = e - w
+        ok = torch.where(lidx >= 0, text[lidx.clamp(min=0)], torch.full_like(last[:-1], 2)) == last[:-1]
+        if not bool(ok.all()): fails.append(".last mismatch")
+        if int(last[-1]) != int(text[n - 1]): fails.append(".last final mismatch")
+        step = max(1, e.numel() // 2_000_000)             # sampled trigger re-computation
+        if int(window_hash_mod_p(text, e[::step], w, p).abs().sum()) != 0: fails.append("phrase end is not a trigger")
+    # trigger count cross-check on a 64 MB slice: every trigger in the slice must be a phrase end
+    m = min(n, 1 << 26)
+    allpos = torch.arange(w - 1, m, dtype=torch.int64, device=text.device)
+    trig = allpos[window_hash_mod_p(text, allpos, w, p) == 0]
+    mine = e[e < m]
+    if not torch.equal(trig, mine): fails.append("trigger set differs on the first 64 MB")
+    # dictionary (host): terminators, order of sampled adjacent pairs, prefix reconstruction
+    dic = view(out.dict, out.dict_bytes).cpu().numpy()
+    if dic[-1] != 0: fails.append(".dict does not end with 0x00")
+    seps = np.flatnonzero(dic == 1)
+    if seps.size != d: fails.append("#0x01 != distinct")
+    starts = np.concatenate([[0], seps[:-1] + 1])
+    rng = np.random.default_rng(7)
+    idx = np.unique(rng.integers(0, max(d - 1, 1), min(sample_pairs, max(d - 1, 0))))
+    bad = 0
+    for i in idx:
+        a = dic[starts[i]:seps[i]].tobytes(); b = dic[starts[i + 1]:seps[i + 1]].tobytes()
+        bad += not (a < b)
+    if bad: fails.append(f".dict order violated in {bad} sampled pairs")
+    k = min(P, prefix_phrases)
+    ranks = parse[:k].cpu().numpy()
+    parts = []
+    for j, r in enumerate(ranks):
+        wd = dic[starts[r - 1]:seps[r - 1]]
+        parts.append(wd if j == 0 else wd[w:])
+    rec = np.concatenate(parts)[1:]
+    if k == P: rec = rec[:len(rec) - w]
+    if not np.array_equal(rec, text[:rec.size].cpu().numpy()): fails.append("unparse(prefix) != text prefix")
+    res["ok"] = not fails
+    res["fails"] = fails
+    print(json.dumps(res), flush=True)
+    return not fails
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="all", choices=["pangenome", "random", "sweep", "all"])
+    ap.add_argument("--small", action="store_true", help="1/16 of the sizes (smoke run)")
+    a = ap.parse_args()
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    sc = pkg.pfp.Scanner(0)
+    scale = 16 if a.small else 1
+    ok = True
+    if a.config in ("pangenome", "sweep", "all"):
+        text = pkg.synth.pangenome_text(40_000_000 // scale, 100, 2, device="cuda")
+        if a.config in ("pangenome", "all"):
+            ok &= check_case(sc, text, 10, 100, "config2 pangenome 100 x 40 Mbp")
+        if a.config in ("sweep", "all"):
+            for w in (6, 10, 16, 32):
+                for p in (50, 100, 500, 1000):
+                    ok &= check_case(sc, text, w, p, "config5 sweep")
+        del text
+        torch.cuda.empty_cache()
+    if a.config in ("random", "all"):
+        text = pkg.synth.random_dna(8_000_000_000 // scale, 4, device="cuda")
+        ok &= check_case(sc, text, 10, 100, "config4 random ACGT 8 GB")
+    sc.close()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
