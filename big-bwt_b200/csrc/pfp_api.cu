@@ -79,6 +79,7 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     if (!ctx) return PFPB200_E_NOMEM;
     ctx->device = device;
     { const char *ev = getenv("PFPB200_LEGACY_K2"); ctx->legacy_k2 = ev && atoi(ev) != 0; }
+    { const char *ev = getenv("PFPB200_K1"); ctx->k1_mode = (ev && strcmp(ev, "rolling") == 0) ? 1 : 0; }
     auto bail = [&](int code) { pfpb200_destroy(ctx); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(PFPB200_E_CUDA);
     cudaDeviceProp prop;
@@ -116,6 +117,7 @@ extern "C" void pfpb200_destroy(pfpb200_ctx *ctx) {
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->d_keys) cudaFree(ctx->d_keys);
+    if (ctx->dna_table) cudaFree(ctx->dna_table);
     for (int i = 0; i < 5; i++)
         if (ctx->pin_buf[i]) cudaFreeHost(ctx->pin_buf[i]);
     delete ctx;

@@ -51,6 +51,9 @@ struct pfpb200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     u32 launches = 0;
+    int k1_mode = 0;               // PFPB200_K1=rolling: always the rolling-arithmetic scan kernel (A/B)
+    u32 *dna_table = nullptr;      // 4^w-bit trigger table of (dna_w, dna_p) for the DNA scan (w <= 10)
+    u32 dna_w = 0, dna_p = 0;
     bool legacy_k2 = false;        // PFPB200_LEGACY_K2=1: per-phrase K2 kernels (A/B measurements)
     double dedup_ratio = 0.0;      // distinct words / phrases of the previous parse (table sizing hint)
     char err[512] = {0};

@@ -165,6 +165,152 @@ __global__ void __launch_bounds__(K1_T) kr_scan_generic_k(const unsigned char *_
     if (t == 0) tile_cnt[tile] = s_cnt;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1a, DNA form (w <= 10).  For a window of w symbols from {A,C,G,T} the answer to "is this
+// window a trigger" is a function of 2w bits: a bit table of 4^w entries (128 KB for w = 10),
+// built once per (w, p) on the device from the SAME exact arithmetic, lives in shared memory.
+// One persistent CTA per SM; a warp takes 1 KB rows of the text, a lane 32 consecutive
+// positions: two coalesced 16-byte loads, 2-bit codes ((c >> 1) & 3: A=0 C=1 T=2 G=3) packed
+// four at a time with one multiply, the 9 symbols in front taken from the neighbour lane's
+// packed word by shuffle, and per position one funnel shift, one table word and one bit.
+// Exactness: every loaded byte is checked against the letter its code stands for (PRMT
+// decode + compare); a row with any other byte (N, lower case, text that is not DNA at all)
+// is redone by the same warp with the rolling arithmetic of kr_scan_k -- same trigger set for
+// every input, DNA or not.
+// ------------------------------------------------------------------------------------------------
+constexpr int KD_T = 1024;                    // threads per CTA (one CTA per SM)
+constexpr int KD_MAXW = 10;
+constexpr u32 KD_LETTERS = 0x47544341u;       // code -> letter: 0 'A', 1 'C', 2 'T', 3 'G'
+
+__global__ void dna_table_k(pfp_scan_consts C, u32 *__restrict__ table, u32 nwords) {
+    const u32 wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    u32 bits = 0;
+    for (u32 b = 0; b < 32; b++) {
+        const u32 idx = wi * 32 + b;          // symbol k of the window (k = 0 oldest) at bits [2k, 2k+2)
+        if (C.w < 16 && (idx >> (2 * C.w)) != 0) break;
+        u32 h = 0;
+        for (u32 k = 0; k < C.w; k++) h = pfp_push(h, (KD_LETTERS >> (8 * ((idx >> (2 * k)) & 3u))) & 255u);
+        if (pfp_is_trigger(h, C.pinv, C.pshift, C.plimit)) bits |= 1u << b;
+    }
+    table[wi] = bits;
+}
+
+// four text bytes -> their four 2-bit codes in bits 0..7 (first byte lowest); `bad` collects
+// every bit in which a byte differs from the letter of its code
+__device__ __forceinline__ u32 dna_pack4(u32 x, u32 &bad) {
+    const u32 y = (x >> 1) & 0x03030303u;
+    const u32 z = y | (y >> 4);                               // nibbles: (c0,c1) in byte 0, (c2,c3) in byte 2
+    const u32 sel = __byte_perm(z, 0u, 0x4420u);              // c0,c1,c2,c3 as the low four nibbles
+    bad |= __byte_perm(KD_LETTERS, 0u, sel) ^ x;
+    return (y * 0x01041040u) >> 24;
+}
+__device__ __forceinline__ u32 dna_pack16(const uint4 &v, u32 &bad) {
+    return dna_pack4(v.x, bad) | (dna_pack4(v.y, bad) << 8) | (dna_pack4(v.z, bad) << 16) | (dna_pack4(v.w, bad) << 24);
+}
+
+__device__ __forceinline__ uint4 kd_load_unit(const uint4 *__restrict__ A, u64 q_end, i64 qc) {
+    if (qc >= 0 && (u64)qc + 16 <= q_end) return __ldg(A + (qc >> 4));
+    if (qc >= 0 && (u64)qc < q_end)
+        return k1_partial_chunk(reinterpret_cast<const unsigned char *>(A) + qc, (int)(q_end - (u64)qc));
+    return make_uint4(0, 0, 0, 0);
+}
+
+// byte j (-12 <= j < 32) of {three words in front, eight words of the lane}
+#define KD_BYTE(wd, j) (__byte_perm((wd)[((j) + 12) >> 2], 0u, 0x4440u | (((j) + 12) & 3)))
+
+// Rows overlap by one lane: row r covers the 32-position words 31r .. 31r+31 of the bit array,
+// lane 0 only supplies the symbols in front of lane 1 (its word belongs to lane 31 of row r-1).
+// Costs 1/32 of redundant work and removes every special case for "the bytes before my row".
+template <int W>
+__global__ void __launch_bounds__(KD_T, 1) kr_scan_dna_k(const uint4 *__restrict__ A, u64 q_end, u64 q_lo,
+                                                         u64 q_hi, pfp_scan_consts C,
+                                                         const u32 *__restrict__ table_g,
+                                                         u32 *__restrict__ mask32,
+                                                         u32 *__restrict__ tile_cnt, u64 nwords) {
+    extern __shared__ __align__(16) u32 tab[];
+    constexpr u32 TWORDS = ((1u << (2 * W)) + 31) / 32;
+    for (u32 i = threadIdx.x; i < TWORDS; i += KD_T) tab[i] = table_g[i];
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31;
+    const u64 nrows = (nwords + 30) / 31;
+    const u64 wstride = (u64)gridDim.x * (KD_T / 32);
+    u64 row = (u64)blockIdx.x * (KD_T / 32) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const u64 q_full = q_end & ~(u64)15;               // whole 16-byte units end here
+    // software prefetch: the loads of the next row are in flight while this one is worked on
+    uint4 n0, n1;
+    {
+        const u64 q = (row * 31 + lane) * 32;
+        n0 = kd_load_unit(A, q_end, (i64)q);
+        n1 = kd_load_unit(A, q_end, (i64)q + 16);
+    }
+    for (; row < nrows; row += wstride) {
+        const uint4 u0 = n0, u1 = n1;
+        const u64 word = row * 31 + lane;               // my 32 positions = bit-array word `word`
+        const u64 q = word * 32;
+        const u64 nrow = row + wstride;
+        if (nrow < nrows) {
+            const u64 nq = (nrow * 31 + lane) * 32;
+            if ((nrow * 31 + 32) * 32 <= q_full) {      // interior row: no bounds to check
+                n0 = __ldg(A + (nq >> 4));
+                n1 = __ldg(A + (nq >> 4) + 1);
+            } else {
+                n0 = kd_load_unit(A, q_end, (i64)nq);
+                n1 = kd_load_unit(A, q_end, (i64)nq + 16);
+            }
+        }
+        u32 bad = 0;
+        const u32 S1 = dna_pack16(u0, bad), S2 = dna_pack16(u1, bad);
+        const u32 S0 = __shfl_up_sync(0xffffffffu, S2, 1);      // the 16 symbols in front of my run
+        u32 m = 0;
+        if (!__any_sync(0xffffffffu, bad != 0)) {
+            const u32 S[3] = {S0, S1, S2};
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const int b = 2 * (i + 16 - (W - 1));            // first stream bit of the window ending at i
+                const int k = b >> 5, sh = b & 31;
+                const int kh = (sh + 2 * W > 32) ? k + 1 : k;    // the window reaches into the next word
+                const u32 v = sh ? __funnelshift_r(S[k], S[kh], sh) : S[k];
+                const u32 idx = v & ((1u << (2 * W)) - 1u);
+                const u32 wd = tab[idx >> 5];
+                m = __funnelshift_r(m, wd >> (idx & 31), 1);      // bit i after 32 steps
+            }
+        } else {
+            // exact arithmetic on the bytes (kr_scan_k's inner loop on a 32-position run)
+            u32 wd[11];
+            wd[0] = __shfl_up_sync(0xffffffffu, u1.y, 1);
+            wd[1] = __shfl_up_sync(0xffffffffu, u1.z, 1);
+            wd[2] = __shfl_up_sync(0xffffffffu, u1.w, 1);
+            if (lane == 0) { wd[0] = 0; wd[1] = 0; wd[2] = 0; }   // only used by word 0: nothing in front
+            wd[3] = u0.x; wd[4] = u0.y; wd[5] = u0.z; wd[6] = u0.w;
+            wd[7] = u1.x; wd[8] = u1.y; wd[9] = u1.z; wd[10] = u1.w;
+            u32 h = 0;
+#pragma unroll
+            for (int j = -W; j < 0; j++) h = pfp_push(h, KD_BYTE(wd, j));
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                h = pfp_roll(h, KD_BYTE(wd, i), KD_BYTE(wd, i - W), C.negw);
+                if (pfp_is_trigger(h, C.pinv, C.pshift, C.plimit)) m |= 1u << i;
+            }
+        }
+        const bool mine = (lane != 0 || row == 0) && word < nwords;
+        if (q < q_lo || q + 32 > q_hi) m &= range_mask32(q, q_lo, q_hi);
+        if (!mine) m = 0;
+        if (mine) mask32[word] = m;
+        // per-tile counts: the words of a row lie in at most two tiles
+        const u32 c = __popc(m);
+        const u64 t0 = (row * 31 + 1) >> 10;
+        const bool in0 = (word >> 10) == t0 || lane == 0;
+        const u32 c0 = __reduce_add_sync(0xffffffffu, in0 ? c : 0u);
+        const u32 c1 = __reduce_add_sync(0xffffffffu, in0 ? 0u : c);
+        if (lane == 0) {
+            if (c0) atomicAdd(&tile_cnt[row == 0 ? 0 : t0], c0);
+            if (c1) atomicAdd(&tile_cnt[t0 + 1], c1);
+        }
+    }
+}
+
 // K1c: bits -> ascending global positions
 __global__ void __launch_bounds__(K1_T) kr_emit_k(const uint4 *__restrict__ mask,
                                                   const u64 *__restrict__ tile_off,
@@ -216,6 +362,35 @@ static void launch_scan(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end,
 
 #define K1_CASE(W) case W: launch_scan<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
 
+template <int W>
+static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
+                                   const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
+    const size_t smem = (((size_t)1 << (2 * W)) + 31) / 32 * 4;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kr_scan_dna_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const u64 nwords = (u64)ntiles * (K1_TILE / 32);      // every word of every tile gets written
+    kr_scan_dna_k<W><<<ctx->sm_count, KD_T, smem, ctx->stream>>>(A, q_end, q_lo, q_hi, C, ctx->dna_table,
+                                                                reinterpret_cast<u32 *>(mask), tile_cnt, nwords);
+    return cudaGetLastError();
+}
+#define KD_CASE(W) case W: le = launch_scan_dna<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
+
+// the 4^w-bit trigger table of (w, p), cached in the context
+static int ensure_dna_table(pfpb200_ctx *ctx, const pfp_scan_consts &C) {
+    if (ctx->dna_table && ctx->dna_w == C.w && ctx->dna_p == C.p) return PFPB200_OK;
+    if (!ctx->dna_table) PFP_CUDA(ctx, cudaMalloc(&ctx->dna_table, ((size_t)1 << (2 * KD_MAXW)) / 8));
+    const u32 nwords = (u32)((((size_t)1 << (2 * C.w)) + 31) / 32);
+    dna_table_k<<<pfp_blocks(nwords, 256), 256, 0, ctx->stream>>>(C, ctx->dna_table, nwords);
+    PFP_LAUNCHED(ctx);
+    ctx->dna_w = C.w;
+    ctx->dna_p = C.p;
+    return PFPB200_OK;
+}
+
 // K1a + the scan over tiles.  On return sb describes the trigger bits of the buffer, sb->total
 // is the number of triggers and sb->max_tile_cnt the largest per-tile count (read back: one
 // synchronisation).
@@ -251,16 +426,31 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
     cudaEvent_t e0, e1;
     PFP_CUDA(ctx, cudaEventCreate(&e0));
     PFP_CUDA(ctx, cudaEventCreate(&e1));
+    const bool dna = w <= (u32)KD_MAXW && ctx->k1_mode != 1;
+    if (dna) PFP_TRY(ensure_dna_table(ctx, C));
     PFP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    switch (w <= K1_MAXW_FAST ? (int)w : 0) {
-        K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7) K1_CASE(8) K1_CASE(9) K1_CASE(10)
-        K1_CASE(11) K1_CASE(12) K1_CASE(13) K1_CASE(14) K1_CASE(15) K1_CASE(16)
-        K1_CASE(20) K1_CASE(24) K1_CASE(28) K1_CASE(31) K1_CASE(32)
-        default:
-            kr_scan_generic_k<<<ntiles, K1_T, 0, ctx->stream>>>(
-                reinterpret_cast<const unsigned char *>(A), q_end, q_lo, q_hi, C, mask, tile_cnt);
+    if (dna) {
+        // the table form: bits and per-tile counts (added up by the warps) for every row
+        PFP_CUDA(ctx, cudaMemsetAsync(tile_cnt, 0, (size_t)ntiles * sizeof(u32), ctx->stream));
+        cudaError_t le = cudaSuccess;
+        switch ((int)w) {
+            KD_CASE(4) KD_CASE(5) KD_CASE(6) KD_CASE(7) KD_CASE(8) KD_CASE(9) KD_CASE(10)
+            default: le = cudaErrorInvalidValue;
+        }
+        ctx->launches++;
+        if (le != cudaSuccess)
+            return pfp_fail(ctx, PFPB200_E_CUDA, "kr_scan_dna_k launch: %s", cudaGetErrorString(le));
+    } else {
+        switch (w <= K1_MAXW_FAST ? (int)w : 0) {
+            K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7) K1_CASE(8) K1_CASE(9) K1_CASE(10)
+            K1_CASE(11) K1_CASE(12) K1_CASE(13) K1_CASE(14) K1_CASE(15) K1_CASE(16)
+            K1_CASE(20) K1_CASE(24) K1_CASE(28) K1_CASE(31) K1_CASE(32)
+            default:
+                kr_scan_generic_k<<<ntiles, K1_T, 0, ctx->stream>>>(
+                    reinterpret_cast<const unsigned char *>(A), q_end, q_lo, q_hi, C, mask, tile_cnt);
+        }
+        PFP_LAUNCHED(ctx);
     }
-    PFP_LAUNCHED(ctx);
     PFP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[5], 0, sizeof(u64), ctx->stream));
     PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, tile_cnt, tile_off, ntiles, &ctx->d_flags[1]));
