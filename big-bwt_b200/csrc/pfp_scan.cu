@@ -182,6 +182,14 @@ constexpr int KD_T = 1024;                    // threads per CTA (one CTA per SM
 constexpr int KD_MAXW = 10;
 constexpr u32 KD_LETTERS = 0x47544341u;       // code -> letter: 0 'A', 1 'C', 2 'T', 3 'G'
 
+// Powers of two kept in constant memory on purpose: a shift by a compile-time amount written as
+// a multiplication by an operand the compiler cannot see through is issued on the FMA pipe
+// (IMAD / IMAD.HI), which this kernel leaves idle, instead of the ALU pipe (SHF), which bounds it.
+__constant__ u32 kd_pow2[33];
+__device__ __forceinline__ u32 shr_fma(u32 x, int s) { return s ? __umulhi(x, kd_pow2[32 - s]) : x; }
+// low 32 bits of (hi:lo) >> s, 0 < s < 32
+__device__ __forceinline__ u32 funnel_r_fma(u32 lo, u32 hi, int s) { return hi * kd_pow2[32 - s] + __umulhi(lo, kd_pow2[32 - s]); }
+
 __global__ void dna_table_k(pfp_scan_consts C, u32 *__restrict__ table, u32 nwords) {
     const u32 wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwords) return;
@@ -198,15 +206,18 @@ __global__ void dna_table_k(pfp_scan_consts C, u32 *__restrict__ table, u32 nwor
 
 // four text bytes -> their four 2-bit codes in bits 0..7 (first byte lowest); `bad` collects
 // every bit in which a byte differs from the letter of its code
+// returns a word whose TOP byte holds the four codes
 __device__ __forceinline__ u32 dna_pack4(u32 x, u32 &bad) {
-    const u32 y = (x >> 1) & 0x03030303u;
-    const u32 z = y | (y >> 4);                               // nibbles: (c0,c1) in byte 0, (c2,c3) in byte 2
+    const u32 y = shr_fma(x, 1) & 0x03030303u;
+    const u32 z = y | shr_fma(y, 4);                          // nibbles: (c0,c1) in byte 0, (c2,c3) in byte 2
     const u32 sel = __byte_perm(z, 0u, 0x4420u);              // c0,c1,c2,c3 as the low four nibbles
     bad |= __byte_perm(KD_LETTERS, 0u, sel) ^ x;
-    return (y * 0x01041040u) >> 24;
+    return y * 0x01041040u;
 }
 __device__ __forceinline__ u32 dna_pack16(const uint4 &v, u32 &bad) {
-    return dna_pack4(v.x, bad) | (dna_pack4(v.y, bad) << 8) | (dna_pack4(v.z, bad) << 16) | (dna_pack4(v.w, bad) << 24);
+    const u32 a = __byte_perm(dna_pack4(v.x, bad), dna_pack4(v.y, bad), 0x0073u);   // top bytes of both
+    const u32 b = __byte_perm(dna_pack4(v.z, bad), dna_pack4(v.w, bad), 0x0073u);
+    return __byte_perm(a, b, 0x5410u);
 }
 
 __device__ __forceinline__ uint4 kd_load_unit(const uint4 *__restrict__ A, u64 q_end, i64 qc) {
@@ -227,7 +238,8 @@ __global__ void __launch_bounds__(KD_T, 1) kr_scan_dna_k(const uint4 *__restrict
                                                          u64 q_hi, pfp_scan_consts C,
                                                          const u32 *__restrict__ table_g,
                                                          u32 *__restrict__ mask32,
-                                                         u32 *__restrict__ tile_cnt, u64 nwords) {
+                                                         u32 *__restrict__ tile_cnt, u64 nwords,
+                                                         u32 mix /* every mix-th row by arithmetic; 0: none */) {
     extern __shared__ __align__(16) u32 tab[];
     constexpr u32 TWORDS = ((1u << (2 * W)) + 31) / 32;
     for (u32 i = threadIdx.x; i < TWORDS; i += KD_T) tab[i] = table_g[i];
@@ -264,17 +276,21 @@ __global__ void __launch_bounds__(KD_T, 1) kr_scan_dna_k(const uint4 *__restrict
         const u32 S1 = dna_pack16(u0, bad), S2 = dna_pack16(u1, bad);
         const u32 S0 = __shfl_up_sync(0xffffffffu, S2, 1);      // the 16 symbols in front of my run
         u32 m = 0;
-        if (!__any_sync(0xffffffffu, bad != 0)) {
+        // mix > 0 gives every mix-th row to the arithmetic (table rows are bound by shared-memory
+        // bank conflicts, arithmetic rows by the ALU/FMA pipes).  Measured on B200, 4 GB, w=10:
+        // mix 0: 2.27 ms, 5: 2.68 ms, 3/6: 2.87 ms -- the slower rows only lengthen the tail. Off.
+        const bool by_table = !__any_sync(0xffffffffu, bad != 0) && !(mix && (row % mix) == mix - 1);
+        if (by_table) {
             const u32 S[3] = {S0, S1, S2};
 #pragma unroll
             for (int i = 0; i < 32; i++) {
                 const int b = 2 * (i + 16 - (W - 1));            // first stream bit of the window ending at i
                 const int k = b >> 5, sh = b & 31;
                 const int kh = (sh + 2 * W > 32) ? k + 1 : k;    // the window reaches into the next word
-                const u32 v = sh ? __funnelshift_r(S[k], S[kh], sh) : S[k];
-                const u32 idx = v & ((1u << (2 * W)) - 1u);
-                const u32 wd = tab[idx >> 5];
-                m = __funnelshift_r(m, wd >> (idx & 31), 1);      // bit i after 32 steps
+                const u32 v = sh ? funnel_r_fma(S[k], S[kh], sh) : S[k];     // window in the low 2W bits
+                const u32 wd = *reinterpret_cast<const u32 *>(reinterpret_cast<const unsigned char *>(tab) +
+                                                              (shr_fma(v, 3) & (((1u << (2 * W)) - 1u) >> 5 << 2)));
+                m = __funnelshift_r(m, wd >> (v & 31), 1);        // bit i after 32 steps
             }
         } else {
             // exact arithmetic on the bytes (kr_scan_k's inner loop on a 32-position run)
@@ -373,14 +389,29 @@ static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A,
         attr = true;
     }
     const u64 nwords = (u64)ntiles * (K1_TILE / 32);      // every word of every tile gets written
+    static int mix = -1;
+    if (mix < 0) {
+        const char *ev = getenv("PFPB200_K1_MIX");
+        mix = ev ? atoi(ev) : 0;
+    }
     kr_scan_dna_k<W><<<ctx->sm_count, KD_T, smem, ctx->stream>>>(A, q_end, q_lo, q_hi, C, ctx->dna_table,
-                                                                reinterpret_cast<u32 *>(mask), tile_cnt, nwords);
+                                                                reinterpret_cast<u32 *>(mask), tile_cnt, nwords,
+                                                                (u32)mix);
     return cudaGetLastError();
 }
 #define KD_CASE(W) case W: le = launch_scan_dna<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
 
 // the 4^w-bit trigger table of (w, p), cached in the context
 static int ensure_dna_table(pfpb200_ctx *ctx, const pfp_scan_consts &C) {
+    static int pow_dev = -1;                 // constant memory is per device
+    if (pow_dev != ctx->device) {
+        u32 h[33];
+        for (int i = 0; i < 32; i++) h[i] = 1u << i;
+        h[32] = 0;
+        PFP_CUDA(ctx, cudaMemcpyToSymbolAsync(kd_pow2, h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pow_dev = ctx->device;
+    }
     if (ctx->dna_table && ctx->dna_w == C.w && ctx->dna_p == C.p) return PFPB200_OK;
     if (!ctx->dna_table) PFP_CUDA(ctx, cudaMalloc(&ctx->dna_table, ((size_t)1 << (2 * KD_MAXW)) / 8));
     const u32 nwords = (u32)((((size_t)1 << (2 * C.w)) + 31) / 32);
