@@ -251,17 +251,33 @@ __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
 }
 
 // ---- local refinement of larger tie groups in shared memory ---------------------------------------------
-// The same refinement with the group's positions in shared memory, worked on by NT threads:
-// NT = 32 (one warp per group of up to MID_MAX words, eight groups per CTA) or NT = 256 (one CTA
-// per group of up to LOCAL_MAX words).
+// A group's words sit in shared memory in their current order, worked on by NT threads: NT = 32
+// (one warp per group of up to MID_MAX words, eight groups per CTA) or NT = 256 (one CTA per
+// group of up to LOCAL_MAX words).  Every word knows the tie range [lo, hi) it is in and the
+// depth (8-byte chunk index) up to which that range is known to agree.  One pass:
+//   * every word of a range of more than one word loads its chunk at the range's depth;
+//   * the range is split three ways around the chunk of its FIRST word: smaller | equal | larger
+//     (multikey quicksort).  The equal part moves one chunk deeper, the other two keep their
+//     depth and are split again in the next pass;
+//   * the position of a word inside its part is its rank among the words of the same class in
+//     front of it in the range: one segmented scan over the positions (three 16-bit counters in
+//     one 64-bit word), so a pass costs O(m) -- not O(range^2) as counting against every other
+//     word of the range did.  Families of near-identical words (a thousand haplotypes' variants
+//     of one phrase: long shared prefixes, one or two words leaving per chunk) are exactly the
+//     case where that difference is a factor of the family size.
 constexpr u32 MID_MAX = 256;
+constexpr u32 TIE_EMAX = 8;       // positions per thread at most: CAP / NT
 
 template <u32 CAP>
 struct TieSort {
     u64 key[CAP];
+    u64 tot[CAP];                 // class totals of a range, stored at its lo
     u32 uid[2][CAP];
+    u32 off[2][CAP];              // pool offset of the word (8-byte words)
+    u32 wn[2][CAP];               // its length in 8-byte words
     u16 lo[2][CAP];
     u16 hi[2][CAP];
+    u16 dep[2][CAP];
 };
 
 template <int NT>
@@ -274,57 +290,146 @@ __device__ __forceinline__ int tie_any(int x) {
     return __syncthreads_or(x);
 }
 
-template <int NT, u32 CAP>
-__device__ void tie_refine(TieSort<CAP> &S, u32 t, u32 s, u32 m, u32 r, const u64 *pool, const u64 *uoff,
-                           const u32 *uwords, u32 max_chunks, u32 *__restrict__ ord,
-                           u64 *__restrict__ flags) {
+// exclusive segmented scan across the NT threads: v = sum of my block behind its last segment
+// start (or of the whole block), f = my block holds a segment start.  Returns the sum over the
+// preceding threads back to the most recent start.
+template <int NT>
+__device__ __forceinline__ u64 tie_carry(u64 v, bool f, u64 *sm_v, u32 *sm_f) {
+    const u32 lane = threadIdx.x & 31;
+    u64 iv = v;
+    int fl = f ? 1 : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 uv = __shfl_up_sync(0xffffffffu, iv, o);
+        const int uf = __shfl_up_sync(0xffffffffu, fl, o);
+        if (lane >= (u32)o && !fl) { iv += uv; fl = uf; }
+    }
+    u64 ex = __shfl_up_sync(0xffffffffu, iv, 1);        // inclusive value of the lane in front
+    int exf = __shfl_up_sync(0xffffffffu, fl, 1);        // ... and whether it already saw a start
+    if (lane == 0) { ex = 0; exf = 0; }
+    if (NT == 32) return ex;
+    // NT == 256: join the eight warps
+    const u32 wp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 31) { sm_v[wp] = iv; sm_f[wp] = (u32)fl; }
+    __syncthreads();
+    u64 cin = 0;
+    for (u32 k = 0; k < wp; k++) {
+        if (sm_f[k]) cin = 0;
+        cin += sm_v[k];
+    }
+    return exf ? ex : ex + cin;
+}
+
+// TIE_E: compile-time bound of the positions per thread (2, 4 or 8), so that small groups do not
+// pay for eight predicated-off copies of every loop body
+template <int NT, u32 CAP, u32 TIE_E>
+__device__ __noinline__ void tie_refine_e(TieSort<CAP> &S, u64 *sm_v, u32 *sm_f, u32 t, u32 s, u32 m, u32 r0,
+                                          const u64 *pool, const u64 *uoff, const u32 *uwords, u32 max_chunks,
+                                          u32 *__restrict__ ord, u64 *__restrict__ flags) {
+    static_assert(CAP == NT * TIE_EMAX && TIE_E <= TIE_EMAX, "blocked layout: up to TIE_EMAX positions per thread");
     int cur = 0;
     tie_sync<NT>();
-    for (u32 i = t; i < m; i += NT) { S.uid[0][i] = ord[s + i]; S.lo[0][i] = 0; S.hi[0][i] = (u16)m; }
+    for (u32 i = t; i < m; i += NT) {
+        const u32 u = ord[s + i];
+        S.uid[0][i] = u; S.off[0][i] = (u32)uoff[u]; S.wn[0][i] = uwords[u];
+        S.lo[0][i] = 0; S.hi[0][i] = (u16)m; S.dep[0][i] = (u16)(r0 < 0xFFFFu ? r0 : 0xFFFFu);
+    }
     tie_sync<NT>();
+    const u32 E = (m + NT - 1) / NT;                     // positions per thread for this group (<= TIE_E)
+    const u32 p0 = t * E;                                // my positions: p0 .. p0 + E - 1
     for (;;) {
-        int any = 0;
-        for (u32 i = t; i < m; i += NT) {
-            bool act = (u32)(S.hi[cur][i] - S.lo[cur][i]) > 1;
-            S.key[i] = act ? word_key(pool, uoff, uwords, S.uid[cur][i], r) : 0ull;
-            any |= act ? 1 : 0;
+        // ---- chunks at the ranges' depths ---------------------------------------------------------------
+        int any = 0, bad = 0;
+#pragma unroll
+        for (u32 e = 0; e < TIE_E; e++) {
+            const u32 p = p0 + e;
+            if (e < E && p < m) {
+                const bool act = (u32)(S.hi[cur][p] - S.lo[cur][p]) > 1;
+                const u32 r = S.dep[cur][p];
+                S.key[p] = (act && r < S.wn[cur][p]) ? bswap64(__ldg(pool + S.off[cur][p] + r)) : 0ull;
+                any |= act ? 1 : 0;
+                bad |= (act && r >= max_chunks) ? 1 : 0;
+            }
         }
-        if (!tie_any<NT>(any)) break;
-        if (r >= max_chunks) {
+        if (!tie_any<NT>(any | (bad << 1))) break;
+        if (tie_any<NT>(bad)) {
             if (t == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
             break;
         }
-        int differs = 0;
-        for (u32 i = t; i < m; i += NT) {
-            u32 l = S.lo[cur][i];
-            differs |= ((u32)(S.hi[cur][i] - l) > 1 && S.key[i] != S.key[l]) ? 1 : 0;
-        }
-        if (!tie_any<NT>(differs)) { r++; continue; }      // shared prefix: nothing moves
-        for (u32 i = t; i < m; i += NT) {
-            u32 l = S.lo[cur][i], h = S.hi[cur][i];
-            u32 np = i, nlo = l, nhi = h;
-            if (h - l > 1) {
-                u64 key = S.key[i];
-                u32 less = 0, eqb = 0, eq = 0;
-                for (u32 j = l; j < h; j++) {
-                    u64 kj = S.key[j];
-                    less += (kj < key) ? 1 : 0;
-                    bool e = (kj == key);
-                    eq += e ? 1 : 0;
-                    eqb += (e && j < i) ? 1 : 0;
-                }
-                nlo = l + less; nhi = nlo + eq; np = nlo + eqb;
+        // ---- classes and the segmented scan of their counters ----------------------------------------
+        u64 incl[TIE_E];
+        u32 cls[TIE_E];
+        u64 run = 0;
+        bool started = false;                            // a range starts inside my block
+#pragma unroll
+        for (u32 e = 0; e < TIE_E; e++) {
+            const u32 p = p0 + e;
+            incl[e] = 0; cls[e] = 1;
+            if (e < E && p < m) {
+                const u32 l = S.lo[cur][p];
+                if (l == p) { started = true; run = 0; }
+                const bool act = (u32)(S.hi[cur][p] - l) > 1;
+                const u64 k = S.key[p], hk = S.key[l];
+                cls[e] = !act ? 1u : (k < hk ? 0u : (k == hk ? 1u : 2u));
+                run += 1ull << (16 * cls[e]);
+                incl[e] = run;
             }
-            S.uid[cur ^ 1][np] = S.uid[cur][i];
-            S.lo[cur ^ 1][np] = (u16)nlo;
-            S.hi[cur ^ 1][np] = (u16)nhi;
+        }
+        // run = my block behind its last range start (or all of it): what the next threads continue
+        const u64 carry = tie_carry<NT>(run, started, sm_v, sm_f);
+        // ---- totals of every range, left at its lo by its last word ---------------------------------------
+        started = false;
+#pragma unroll
+        for (u32 e = 0; e < TIE_E; e++) {
+            const u32 p = p0 + e;
+            if (e < E && p < m) {
+                const u32 l = S.lo[cur][p];
+                if (l == p) started = true;
+                if (!started) incl[e] += carry;         // still in the range the previous threads began
+                if (p + 1 == S.hi[cur][p]) S.tot[l] = incl[e];
+            }
+        }
+        tie_sync<NT>();
+        // ---- move ------------------------------------------------------------------------------------------
+#pragma unroll
+        for (u32 e = 0; e < TIE_E; e++) {
+            const u32 p = p0 + e;
+            if (e < E && p < m) {
+                const u32 l = S.lo[cur][p], h = S.hi[cur][p], r = S.dep[cur][p];
+                u32 np = p, nlo = l, nhi = h, nr = r;
+                if (h - l > 1) {
+                    const u64 T = S.tot[l];
+                    const u32 n0 = (u32)(T & 0xFFFFu), n1 = (u32)((T >> 16) & 0xFFFFu);
+                    const u32 idx = (u32)((incl[e] >> (16 * cls[e])) & 0xFFFFu) - 1u;
+                    if (cls[e] == 0) { nlo = l; nhi = l + n0; }
+                    else if (cls[e] == 1) { nlo = l + n0; nhi = l + n0 + n1; nr = r + 1; }
+                    else { nlo = l + n0 + n1; nhi = h; }
+                    np = nlo + idx;
+                }
+                S.uid[cur ^ 1][np] = S.uid[cur][p];
+                S.off[cur ^ 1][np] = S.off[cur][p];
+                S.wn[cur ^ 1][np] = S.wn[cur][p];
+                S.lo[cur ^ 1][np] = (u16)nlo;
+                S.hi[cur ^ 1][np] = (u16)nhi;
+                S.dep[cur ^ 1][np] = (u16)nr;
+            }
         }
         tie_sync<NT>();
         cur ^= 1;
-        r++;
     }
     tie_sync<NT>();
     for (u32 i = t; i < m; i += NT) ord[s + i] = S.uid[cur][i];
+}
+
+template <int NT, u32 CAP>
+__device__ __forceinline__ void tie_refine(TieSort<CAP> &S, u64 *sm_v, u32 *sm_f, u32 t, u32 s, u32 m, u32 r0,
+                                           const u64 *pool, const u64 *uoff, const u32 *uwords, u32 max_chunks,
+                                           u32 *__restrict__ ord, u64 *__restrict__ flags) {
+    const u32 E = (m + NT - 1) / NT;
+    if (E <= 2) tie_refine_e<NT, CAP, 2>(S, sm_v, sm_f, t, s, m, r0, pool, uoff, uwords, max_chunks, ord, flags);
+    else if (E <= 4) tie_refine_e<NT, CAP, 4>(S, sm_v, sm_f, t, s, m, r0, pool, uoff, uwords, max_chunks, ord, flags);
+    else tie_refine_e<NT, CAP, 8>(S, sm_v, sm_f, t, s, m, r0, pool, uoff, uwords, max_chunks, ord, flags);
 }
 
 // lists of the groups for the two shared-memory kernels
@@ -348,11 +453,13 @@ __global__ void __launch_bounds__(256) rank_mid_k(const u32 *__restrict__ hp,
     extern __shared__ __align__(16) unsigned char mid_raw[];
     const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     TieSort<MID_MAX> &S = reinterpret_cast<TieSort<MID_MAX> *>(mid_raw)[wp];
+    u64 *sm_v = nullptr;
+    u32 *sm_f = nullptr;
     const u32 n = *count;
     for (u32 q = blockIdx.x * 8 + wp; q < n; q += gridDim.x * 8) {
         const u32 g = list[q];
         const u32 s = hp[g], m = hp[g + 1] - s;
-        tie_refine<32, MID_MAX>(S, lane, s, m, depth[s], pool, uoff, uwords, max_chunks, ord, flags);
+        tie_refine<32, MID_MAX>(S, sm_v, sm_f, lane, s, m, depth[s], pool, uoff, uwords, max_chunks, ord, flags);
     }
 }
 
@@ -365,11 +472,14 @@ __global__ void __launch_bounds__(256) rank_cta_k(const u32 *__restrict__ hp,
                                                   u64 *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char cta_raw[];
     TieSort<LOCAL_MAX> &S = *reinterpret_cast<TieSort<LOCAL_MAX> *>(cta_raw);
+    __shared__ u64 sm_v[8];
+    __shared__ u32 sm_f[8];
     const u32 n = *count;
     for (u32 q = blockIdx.x; q < n; q += gridDim.x) {
         const u32 g = list[q];
         const u32 s = hp[g], m = hp[g + 1] - s;
-        tie_refine<256, LOCAL_MAX>(S, threadIdx.x, s, m, depth[s], pool, uoff, uwords, max_chunks, ord, flags);
+        tie_refine<256, LOCAL_MAX>(S, sm_v, sm_f, threadIdx.x, s, m, depth[s], pool, uoff, uwords, max_chunks, ord,
+                                   flags);
     }
 }
 

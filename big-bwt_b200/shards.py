@@ -369,10 +369,19 @@ class ShardedParser:
         st["d2h_bytes"] = int(nbytes)
         return st
 
+    def _mark(self, name):
+        """Phase boundary for the timeline in the returned stats (CUDA events, no synchronisation)."""
+        if self.buf is not None and self.buf.is_cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.buf.device))
+            self._marks.append((name, ev))
+
     def _parse_sharded(self, w, p, sai, compress) -> dict:
         be, G, g = self.backend, self.world, self.rank
         if hasattr(be, "use_current_stream"):
             be.use_current_stream()
+        self._marks = []
+        self._mark("start")
         if w > self.halo:
             raise ValueError("window larger than the shard halo")
         if min(self.sizes[:-1]) < self.halo:
@@ -380,17 +389,21 @@ class ShardedParser:
         # 1. halo
         halo_reqs = [(max(0, self.starts[q] - self.halo), self.starts[q]) for q in range(G)]
         self._p2p(transfers(halo_reqs, self.starts, self.sizes))
+        self._mark("halo")
         # 2. scan
         n_trig, first, last = be.shard_scan(self.buf, self.pos0 - self.front, self.pos0,
                                             self.pos0 + self.n_local, self.n_global, g == G - 1, w, p, sai)
+        self._mark("scan")
         # 3. seams
         info = self._all_gather_i64([n_trig, last])
         nts, lasts = [r[0] for r in info], [r[1] for r in info]
         self._p2p(transfers(head_requests(self.starts, self.sizes, nts, lasts, w, self.halo),
                             self.starts, self.sizes))
         fs = first_phrase_start(g, nts, lasts, w)
+        self._mark("seams")
         # 4. words
         wd = be.shard_words(fs)
+        self._mark("words")
         # 5. merge
         if self.mode == "replicate":
             res = self._merge_replicated(wd, w, compress)
@@ -398,6 +411,7 @@ class ShardedParser:
             res = self._merge_partitioned(wd, w, compress)
         # 6. remap
         parse = be.shard_remap(res["rank_of_word"], wd["n_phrases"])
+        self._mark("remap")
         self.result = {"dict": res["dict"], "occ": res["occ"], "parse": parse, "last": wd["last"],
                        "sai": wd["sai"], "n_distinct": res["n_distinct"], "dict_offset": res.get("dict_offset", 0)}
         t = res["totals"]
@@ -409,6 +423,10 @@ class ShardedParser:
               "launches": int(be.L.pfpb200_launch_count(be.h)) if hasattr(be, "L") else 0,
               "ms_scan": ms.get("scan", 0.0), "ms_hash": ms.get("words", 0.0), "ms_rank": ms.get("merge", 0.0),
               "ms_remap": ms.get("remap", 0.0)}
+        if self._marks:
+            self._marks[-1][1].synchronize()
+            for (_, a), (name, b) in zip(self._marks[:-1], self._marks[1:]):
+                st["ms_phase_" + name] = st.get("ms_phase_" + name, 0.0) + a.elapsed_time(b)
         return st
 
     def _merge_replicated(self, wd, w, compress):
@@ -475,7 +493,9 @@ class ShardedParser:
         be, G, g = self.backend, self.world, self.rank
         dev = self.buf.device
         sp = self._splitters(wd)
+        self._mark("splitters")
         rt = be.route(wd, sp, G) if wd["n_words"] else None
+        self._mark("route")
         words_to = rt["words_to"] if rt else [0] * G
         pool_to = rt["pool_to"] if rt else [0] * G
         M = self._all_gather_i64(list(words_to) + list(pool_to))           # M[src] = [words_to.., pool_to..]
@@ -486,7 +506,9 @@ class ShardedParser:
         send_pool = rt["pool"] if rt else torch.empty(0, dtype=torch.int64, device=dev)
         got_words = self._all_to_all_v(send_words, [32 * c for c in words_to], [32 * c for c in recv_w])
         got_pool = self._all_to_all_v(send_pool, pool_to, recv_p)
+        self._mark("exchange")
         m = be.dict_merge_words(got_words, got_pool, w, compress)
+        self._mark("merge")
         piece = m["dict"] if g == G - 1 else m["dict"][:-1]                 # only the last piece ends in 0x00
         tot = self._all_gather_i64([m["n_distinct"], int(piece.numel()), m["sum_word_len"], wd["n_phrases"]])
         nd = [r[0] for r in tot]
@@ -496,6 +518,7 @@ class ShardedParser:
         rank_of_word = torch.empty(wd["n_words"], dtype=torch.int32, device=dev)
         if rt:
             rank_of_word[rt["perm"].long()] = back
+        self._mark("ranks_back")
         return {"dict": piece, "occ": m["occ"], "n_distinct": sum(nd), "rank_of_word": rank_of_word,
                 "totals": {"n_phrases": sum(r[3] for r in tot), "n_distinct": sum(nd),
                            "dict_bytes": sum(r[1] for r in tot), "sum_word_len": sum(r[2] for r in tot)}}
