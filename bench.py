@@ -192,12 +192,17 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def scan_kernel_name():
+    """K1 of the benchmarked configuration (w=10): the table form unless PFPB200_K1=rolling."""
+    return "kr_scan_k<10>" if os.environ.get("PFPB200_K1") == "rolling" else "kr_scan_dna_k<10>"
+
+
 def load_traffic(n_text):
     """dram bytes per launch of the scan kernel from the committed ncu --set full capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        per_byte = t["kr_scan_k"]["dram_bytes_per_text_byte"]
+        per_byte = t[scan_kernel_name().split("<")[0]]["dram_bytes_per_text_byte"]
         return per_byte * n_text
     except Exception:
         return None
@@ -276,6 +281,11 @@ def main():
         ms = float(t.item())
     value = n_total * a.steps / (ms * 1e-3) / 1e9
     last_stats = st
+    per_rank = None
+    if world > 1:                      # every rank's phase timeline (who waits for whom)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: round(v, 3) for k, v in stage_ms.items() if k.startswith("ms_phase_")})
+        per_rank = {k: [g.get(k, 0.0) for g in gathered] for k in gathered[0]}
 
     # ---- e2e: host buffers in, host buffers out ------------------------------------------------
     e2e = None
@@ -316,7 +326,7 @@ def main():
     scan_bytes = n_local * (1.0 + 1.0 / 8.0)
     achieved = scan_bytes / (scan_ms_avg * 1e-3) / 1e9
     traffic = load_traffic(n_local)
-    roofline = {"kernel": "kr_scan_k<10>", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": scan_kernel_name(), "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms_avg,
                 "share_of_step": scan_ms_avg / (ms / a.steps),
@@ -349,6 +359,8 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         "stages_ms": stage_ms,
     }
+    if per_rank:
+        line["per_rank_phase_ms"] = per_rank
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
