@@ -190,14 +190,80 @@ __global__ void rank_writeback_k(const u32 *__restrict__ apos, const u64 *__rest
     if (newhead || head[i]) depth_out[i] = r + 1;
 }
 
-// ---- local refinement: one warp per small tie group ---------------------------------------------------
-// Lanes are the words of the group and never move.  A lane knows the tie range it is in as
-// (lo, sz): the rank of the range's first word and its size.  Four 8-byte chunks per word are
-// fetched at once (independent loads: one memory round trip per 32 bytes of depth); for every
-// chunk, if no lane differs from the first lane of its range the chunk is a shared prefix and
-// costs one compare.  Otherwise each lane counts, among the lanes of its range, those with a
-// smaller chunk (its range moves up by that many) and those with an equal one (the new size).
-// When all ranges are singletons, lo is the word's rank inside the group.
+// ---- local refinement of small tie groups inside a warp -----------------------------------------------
+// Lanes are words and never move.  A lane knows the tie range it is in as (lo, sz): the rank of
+// the range's first word and its size, and the depth r (8-byte chunk index) up to which the
+// range is known to agree; lanes with the same lo are the same range (`match.any` finds them).
+// One pass is a three-way split of every range around the chunk of its first lane (multikey
+// quicksort): smaller | equal | larger, counted with two ballots -- the equal part goes one
+// chunk deeper, the others keep their depth.  When every range is a singleton, lo is the rank.
+// Nothing in a pass depends on the size of a group, so one warp refines all the groups that lie
+// inside a window of 32 consecutive positions at once (rank_window_k); the groups straddling a
+// window border get a warp of their own (rank_warp_k).
+__device__ __forceinline__ u32 warp_refine(const u64 *__restrict__ wptr, u32 wn, u32 lo, u32 sz, u32 r,
+                                           u32 max_chunks, u64 *__restrict__ flags) {
+    u64 k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+    u32 have = 0;                                   // chunks r .. r+have-1 are in k0..
+    for (;;) {
+        const bool active = sz > 1;
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (__any_sync(0xffffffffu, active && r >= max_chunks)) {
+            if ((threadIdx.x & 31) == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
+            break;
+        }
+        if (active && have == 0) {                  // four independent loads: one round trip per 32 bytes
+            k0 = (r + 0 < wn) ? bswap64(__ldg(wptr + r + 0)) : 0ull;
+            k1 = (r + 1 < wn) ? bswap64(__ldg(wptr + r + 1)) : 0ull;
+            k2 = (r + 2 < wn) ? bswap64(__ldg(wptr + r + 2)) : 0ull;
+            k3 = (r + 3 < wn) ? bswap64(__ldg(wptr + r + 3)) : 0ull;
+            have = 4;
+        }
+        const u64 key = active ? k0 : 0ull;
+        const u32 peers = __match_any_sync(0xffffffffu, lo);
+        const u64 hk = __shfl_sync(0xffffffffu, key, __ffs(peers) - 1);
+        const u32 b0 = __ballot_sync(0xffffffffu, active && key < hk) & peers;
+        const u32 b1 = __ballot_sync(0xffffffffu, active && key == hk) & peers;
+        if (active) {
+            const u32 n0 = __popc(b0), n1 = __popc(b1);
+            if (key < hk) sz = n0;
+            else if (key == hk) { lo += n0; sz = n1; r++; k0 = k1; k1 = k2; k2 = k3; have--; }
+            else { lo += n0 + n1; sz -= n0 + n1; }
+        }
+    }
+    return lo;
+}
+
+// all groups of 2..32 words that lie inside one window of 32 consecutive positions
+__global__ void __launch_bounds__(256) rank_window_k(const u32 *__restrict__ hp, const u32 *__restrict__ gid,
+                                                     const u32 *__restrict__ depth, const u64 *pool,
+                                                     const u64 *uoff, const u32 *uwords, u64 d, u32 max_chunks,
+                                                     u32 shift /* 0, or 16: the groups pass 0 left over */,
+                                                     u32 *__restrict__ ord, u64 *__restrict__ flags) {
+    const u32 lane = threadIdx.x & 31;
+    const u64 nwin = (d + 31) / 32 + (shift ? 1 : 0);
+    const u64 nwarps = (u64)gridDim.x * 8;
+    for (u64 k = (u64)blockIdx.x * 8 + (threadIdx.x >> 5); k < nwin; k += nwarps) {
+        const i64 w0 = (i64)(k * 32) - (i64)shift;              // first position of the window
+        const i64 pos = w0 + lane;
+        u32 s = 0, m = 0;
+        if (pos >= 0 && (u64)pos < d) {
+            const u32 g = gid[pos];
+            s = hp[g];
+            m = hp[g + 1] - s;
+        }
+        bool in = m >= 2 && (i64)s >= w0 && (i64)s + m <= w0 + 32;
+        if (shift) in = in && (s >> 5) != ((s + m - 1) >> 5);   // inside an unshifted window: done already
+        if (!__any_sync(0xffffffffu, in)) continue;
+        const u32 uid = in ? ord[pos] : 0;
+        const u64 *wptr = pool + (in ? uoff[uid] : 0);
+        const u32 wn = in ? uwords[uid] : 0;
+        const u32 lo0 = in ? (u32)((i64)s - w0) : 0xFFFF0000u + lane;
+        const u32 lo = warp_refine(wptr, wn, lo0, in ? m : 1u, in ? depth[s] : 0u, max_chunks, flags);
+        if (in) ord[w0 + lo] = uid;
+    }
+}
+
+// groups of 2..32 words that straddle a window border: one warp each
 __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
                                                    const u32 *__restrict__ nheads,
                                                    const u32 *__restrict__ depth,
@@ -209,43 +275,12 @@ __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
     const u32 nwarps = gridDim.x * 8;
     for (u32 g = blockIdx.x * 8 + wp; g < ng; g += nwarps) {
         const u32 s = hp[g], m = hp[g + 1] - s;
-        if (m < 2 || m > WARP_MAX) continue;
-        u32 r = depth[s];
+        if (m < 2 || m > WARP_MAX || (s >> 5) == ((s + m - 1) >> 5)) continue;   // inside a window: done
         const bool mem = lane < m;
         const u32 uid = mem ? ord[s + lane] : 0;
         const u64 *wptr = pool + (mem ? uoff[uid] : 0);
         const u32 wn = mem ? uwords[uid] : 0;
-        u32 lo = mem ? 0u : 0xFFFF0000u + lane;      // lanes outside the group: ranges of their own
-        u32 sz = mem ? m : 1u;
-        bool done = false;
-        while (!done) {
-            if (r >= max_chunks) {
-                if (lane == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
-                break;
-            }
-            u64 k[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) k[c] = (sz > 1 && r + c < wn) ? bswap64(__ldg(wptr + r + c)) : 0ull;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const u32 peers = __match_any_sync(0xffffffffu, lo);
-                const u64 key = k[c];
-                const u64 headkey = __shfl_sync(0xffffffffu, key, __ffs(peers) - 1);
-                if (__any_sync(0xffffffffu, sz > 1 && key != headkey)) {
-                    u32 less = 0, eq = 0;
-                    for (u32 j = 0; j < m; j++) {
-                        const u64 kj = __shfl_sync(0xffffffffu, key, j);
-                        const bool in = (peers >> j) & 1u;
-                        less += (in && kj < key) ? 1 : 0;
-                        eq += (in && kj == key) ? 1 : 0;
-                    }
-                    lo += less;
-                    sz = eq;
-                    if (!__any_sync(0xffffffffu, sz > 1)) { done = true; break; }
-                }
-            }
-            r += 4;
-        }
+        const u32 lo = warp_refine(wptr, wn, mem ? 0u : 0xFFFF0000u + lane, mem ? m : 1u, depth[s], max_chunks, flags);
         if (mem) ord[s + lo] = uid;
     }
 }
@@ -596,6 +631,11 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
         u64 maxb = (u64)ctx->sm_count * 16;
         u32 nbw = (u32)(want < maxb ? want : maxb);
         if (nbw == 0) nbw = 1;
+        rank_window_k<<<nbw, 256, 0, ctx->stream>>>(hp, gid, depth, D.pool, D.uoff, D.uwords, d, max_chunks, 0, ord,
+                                                    ctx->d_flags);
+        PFP_LAUNCHED(ctx);
+        // (a second pass over windows shifted by 16 for the groups straddling a border was measured:
+        //  it costs what it saves -- the kernels are bound by their chains of dependent loads)
         rank_warp_k<<<nbw, 256, 0, ctx->stream>>>(hp, d_nheads, depth, D.pool, D.uoff, D.uwords, max_chunks,
                                                   ord, ctx->d_flags);
         PFP_LAUNCHED(ctx);
