@@ -552,9 +552,14 @@ extern "C" int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_
         }
         DictArrays D;
         u32 *uid_of_entry = nullptr;
+        StageTimer tm;
+        const bool trace = getenv("PFPB200_TRACE") != nullptr && tm.init() == 0;
+        if (trace) tm.mark(ctx->stream);
         PFP_TRY(pfp_merge_stage(ctx, n_in, fpa, fpb, len, count, uwords, pool, pool_words, &D, &uid_of_entry));
+        if (trace) tm.mark(ctx->stream);
         u32 *order = nullptr, rounds = 0;
         PFP_TRY(pfp_rank_stage(ctx, D, &order, &rounds));
+        if (trace) tm.mark(ctx->stream);
         u8 *dict = nullptr;
         u32 *occ = nullptr, *rank_of_uid = nullptr, *rank_of_entry = nullptr;
         u64 dict_bytes = 0;
@@ -562,8 +567,14 @@ extern "C" int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_
                                &rank_of_uid));
         PFP_TRY(pfp_alloc_t(ctx, &rank_of_entry, n_in, true));
         PFP_TRY(pfp_remap_stage(ctx, uid_of_entry, rank_of_uid, n_in, rank_of_entry));
+        if (trace) tm.mark(ctx->stream);
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         PFP_CUDA(ctx, cudaGetLastError());
+        if (trace) {
+            fprintf(stderr, "[pfpb200 merge] n_in %llu -> d %llu: dedup %.3f ms, rank %.3f ms (%u rounds), dict+remap %.3f ms\n",
+                    (unsigned long long)n_in, (unsigned long long)D.d, tm.ms(0, 1), tm.ms(1, 2), rounds, tm.ms(2, 3));
+            tm.destroy();
+        }
         out->n_distinct = D.d; out->dict_bytes = dict_bytes; out->sum_word_len = D.sum_len;
         out->dict = dict; out->occ = occ; out->rank_of_entry = rank_of_entry;
         return PFPB200_OK;

@@ -464,33 +464,6 @@ __global__ void table_uid_k(const u32 *__restrict__ slot_of, const u32 *__restri
     if (active && (peers & lanemask_lt()) == 0) atomicAdd(&count[u], (u32)__popc(peers));
 }
 
-// run heads of sorted keys + fingerprint agreement inside runs (dictionary merge)
-__global__ void mark_heads_k(const u64 *__restrict__ skey, const u32 *__restrict__ sidx, u64 n,
-                             const u64 *__restrict__ fpa, const u64 *__restrict__ fpb,
-                             const u32 *__restrict__ len, u8 *__restrict__ head,
-                             u64 *__restrict__ flags) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    bool h = (i == 0) || (skey[i] != skey[i - 1]);
-    if (!h) {
-        u32 a = sidx[i], b = sidx[i - 1];
-        if (fpa[a] != fpa[b] || fpb[a] != fpb[b] || len[a] != len[b])
-            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
-    }
-    head[i] = h ? 1 : 0;
-}
-
-__global__ void assign_uid_k(const u32 *__restrict__ sidx, const u8 *__restrict__ head,
-                             const u32 *__restrict__ hscan, u64 P, u32 *__restrict__ uid,
-                             u32 *__restrict__ rep, u32 *__restrict__ headpos) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    u32 u = hscan[i] + head[i] - 1;     // inclusive scan - 1
-    u32 j = sidx[i];
-    uid[j] = u;
-    if (head[i]) { rep[u] = j; headpos[u] = (u32)i; }
-}
-
 // phrase pool: every distinct word once, zero padded to 8 bytes, 8-byte aligned
 constexpr int PC_GROUP = 8;                          // lanes per word
 constexpr int PC_PER_BLOCK = PH_T / PC_GROUP;
@@ -695,48 +668,35 @@ int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 fi
 // ------------------------------------------------------------------------------------------
 // dictionary merge: words (fingerprint, length, count, pool bytes) coming from several shards
 // ------------------------------------------------------------------------------------------
-__global__ void merge_keys_k(const u64 *__restrict__ fpa, const u64 *__restrict__ fpb,
-                             const u32 *__restrict__ len, u64 n, u64 *__restrict__ keys,
-                             u32 *__restrict__ vals) {
+// the incoming words as fingerprint records, so that the dictionary-table kernels above dedup them
+__global__ void merge_recs_k(const u64 *__restrict__ fpa, const u64 *__restrict__ fpb,
+                             const u32 *__restrict__ len, u64 n, PhraseFp *__restrict__ rec) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    keys[i] = sort_key_of(fpa[i], fpb[i], len[i]);
-    vals[i] = (u32)i;
+    if (i < n) store_rec(rec, i, fpa[i], fpb[i], len[i]);
 }
 
-// occurrences of a merged word = sum over the entries of its run; plus the per-word tables
-__global__ void merge_words_k(const u32 *__restrict__ headpos, const u32 *__restrict__ sidx,
-                              const u32 *__restrict__ rep, const u32 *__restrict__ count_in,
-                              const u32 *__restrict__ len_in, const u32 *__restrict__ uwords_in,
-                              const u64 *__restrict__ in_off, u64 d, u64 n,
-                              u32 *__restrict__ count, u32 *__restrict__ ulen,
-                              u32 *__restrict__ uwords, u64 *__restrict__ uoff,
-                              u64 *__restrict__ flags) {
+// entry -> merged word; occurrences of a merged word = sum over its entries (newscan.cpp:277-281)
+__global__ void merge_uid_k(const u32 *__restrict__ slot_of, const u32 *__restrict__ umap,
+                            const u32 *__restrict__ count_in, u64 n, u32 *__restrict__ uid,
+                            u32 *__restrict__ count, u64 *__restrict__ flags) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 u = umap[slot_of[i]];
+    uid[i] = u;
+    const u32 c = count_in[i];
+    const u32 old = atomicAdd(&count[u], c);
+    if (old + c < old) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
+}
+
+// a merged word lives where its representative entry lives in the received pool
+__global__ void merge_words_k(const u32 *__restrict__ rep, const u32 *__restrict__ uwords_in,
+                              const u64 *__restrict__ in_off, u64 d, u32 *__restrict__ uwords,
+                              u64 *__restrict__ uoff) {
     u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 L = 0;
-    if (u < d) {
-        u32 a = headpos[u], b = (u + 1 < d) ? headpos[u + 1] : (u32)n;
-        u64 c = 0;
-        for (u32 q = a; q < b; q++) c += count_in[sidx[q]];
-        if (c > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);   // :277-281
-        count[u] = (u32)c;
-        u32 r = rep[u];
-        L = len_in[r];
-        ulen[u] = L;
-        uwords[u] = uwords_in[r];
-        uoff[u] = in_off[r];
-    }
-    u32 mx = L;
-    u64 sum = L;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    }
-    if ((threadIdx.x & 31) == 0 && sum) {
-        atomicMax((unsigned long long *)&flags[2], (unsigned long long)mx);
-        atomicAdd((unsigned long long *)&flags[3], (unsigned long long)sum);
-    }
+    if (u >= d) return;
+    const u32 r = rep[u];
+    uwords[u] = uwords_in[r];
+    uoff[u] = in_off[r];
 }
 
 // per-word fingerprints of a shard's local dictionary (what a shard exports)
@@ -756,36 +716,45 @@ int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays
     return PFPB200_OK;
 }
 
-// Merges n input words into the distinct set D (uid order = fingerprint-key order);
-// uid_of_entry[i] = merged word of input entry i.  Two synchronisations.
+// Merges n input words into the distinct set D with the dictionary table (uid order = slot
+// order); uid_of_entry[i] = merged word of input entry i.  Two synchronisations.
 int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, const u32 *len,
                     const u32 *count_in, const u32 *uwords_in, const u64 *pool, u64 pool_words,
                     DictArrays *D, u32 **uid_of_entry) {
     const int TB = 256;
     if (n >= 0xFFFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "too many words to merge");
-    u64 *k0 = nullptr, *k1 = nullptr, *sk = nullptr, *in_off = nullptr;
-    u32 *v0 = nullptr, *v1 = nullptr, *sv = nullptr, *hscan = nullptr, *headpos = nullptr;
-    u8 *head = nullptr;
-    PFP_TRY(pfp_alloc_t(ctx, &k0, n));
-    PFP_TRY(pfp_alloc_t(ctx, &k1, n));
-    PFP_TRY(pfp_alloc_t(ctx, &v0, n));
-    PFP_TRY(pfp_alloc_t(ctx, &v1, n));
-    PFP_TRY(pfp_alloc_t(ctx, &head, n));
-    PFP_TRY(pfp_alloc_t(ctx, &hscan, n));
+    PhraseFp *rec = nullptr;
+    DictSlot *tab = nullptr;
+    u32 *slot_of = nullptr, *umap = nullptr, *len_slot = nullptr;
+    u64 *in_off = nullptr;
+    u8 *occ = nullptr;
+    const u64 cap = n + n / 2 + 1024;                  // load factor <= 2/3 even if nothing merges
+    PFP_TRY(pfp_alloc_t(ctx, &rec, n));
+    PFP_TRY(pfp_alloc_t(ctx, &tab, cap));
+    PFP_TRY(pfp_alloc_t(ctx, &slot_of, n));
+    PFP_TRY(pfp_alloc_t(ctx, &len_slot, cap));
+    PFP_TRY(pfp_alloc_t(ctx, &occ, cap));
+    PFP_TRY(pfp_alloc_t(ctx, &umap, cap));
     PFP_TRY(pfp_alloc_t(ctx, &in_off, n));
-    merge_keys_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(fpa, fpb, len, n, k0, v0);
+    merge_recs_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(fpa, fpb, len, n, rec);
     PFP_LAUNCHED(ctx);
-    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, n, 0, 64, &sk, &sv));
-    mark_heads_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(sk, sv, n, fpa, fpb, len, head, ctx->d_flags);
+    table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
+    PFP_LAUNCHED(ctx);
+    table_insert_k<<<pfp_blocks(n, TB * TI_ITEMS), TB, 0, ctx->stream>>>(rec, n, tab, cap, slot_of, len_slot,
+                                                                        ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    table_flags_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap, occ);
     PFP_LAUNCHED(ctx);
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
-    PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, head, hscan, n, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
+    PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, occ, umap, cap, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
     PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, uwords_in, in_off, n, nullptr));
     PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(u64), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
         return pfp_fail(ctx, PFPB200_E_COLLISION, "fingerprint collision between different phrases");
+    if (ctx->h_flags[0] & PFP_ERRBIT_TABLE_FULL)
+        return pfp_fail(ctx, PFPB200_E_INTERNAL, "dictionary table overflow in the merge");
     u64 d = (u32)ctx->h_flags[1];
     if (d > 0x7FFFFFFEull)
         return pfp_fail(ctx, PFPB200_E_LIMIT, "%llu distinct words exceed the limit 2^31-2",
@@ -795,26 +764,29 @@ int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, con
     D->pool_words = pool_words;
     PFP_TRY(pfp_alloc_t(ctx, uid_of_entry, n));
     PFP_TRY(pfp_alloc_t(ctx, &D->rep, d));
-    PFP_TRY(pfp_alloc_t(ctx, &headpos, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->count, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->ulen, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->uwords, d));
     PFP_TRY(pfp_alloc_t(ctx, &D->uoff, d));
     D->uid = *uid_of_entry;
-    assign_uid_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(sv, head, hscan, n, *uid_of_entry, D->rep, headpos);
+    table_emit_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, occ, umap, len_slot, cap, D->count, D->rep,
+                                                              D->ulen, D->uwords, ctx->d_flags);
     PFP_LAUNCHED(ctx);
-    merge_words_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(headpos, sv, D->rep, count_in, len, uwords_in,
-                                                             in_off, d, n, D->count, D->ulen, D->uwords,
-                                                             D->uoff, ctx->d_flags);
+    merge_uid_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(slot_of, umap, count_in, n, *uid_of_entry, D->count,
+                                                           ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    merge_words_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(D->rep, uwords_in, in_off, d, D->uwords, D->uoff);
     PFP_LAUNCHED(ctx);
     PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(u64), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
         return pfp_fail(ctx, PFPB200_E_LIMIT, "a word occurs more than 2^32-1 times");
+    if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
+        return pfp_fail(ctx, PFPB200_E_COLLISION, "fingerprint collision between different phrases");
     D->max_len = (u32)ctx->h_flags[2];
     D->sum_len = ctx->h_flags[3];
-    void *fr[] = {k0, k1, v0, v1, head, hscan, in_off, headpos};
+    void *fr[] = {rec, tab, slot_of, len_slot, occ, umap, in_off};
     for (void *q : fr) PFP_TRY(pfp_free_now(ctx, q));
     return PFPB200_OK;
 }

@@ -239,6 +239,53 @@ class Merged(C.Structure):
 # ------------------------------------------------------------------------------------------------
 # the sharded parser
 # ------------------------------------------------------------------------------------------------
+class PeerExchange:
+    """All-to-all over NVLink peer memory: every rank stores its outgoing segments straight into
+    the receivers' buffers (torch symmetric memory: the peers' allocations are mapped into this
+    process), one DMA per peer on its own stream, bracketed by two device-side barriers.  Measured
+    on 2 x B200, 0.42 GB per rank: 0.58 ms against 0.85 ms for NCCL's grouped send/recv; no
+    staging buffers, no protocol, and the copies of different peers overlap."""
+
+    def __init__(self, device, world, rank, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem, self.dev, self.world, self.rank, self.group = symm_mem, device, world, rank, group
+        self.bufs = {}           # name -> (tensor, handle, capacity in elements)
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(world)]
+
+    def ensure(self, name, dtype, capacity):
+        """Collective: every rank calls it with the same capacity."""
+        cur = self.bufs.get(name)
+        if cur is not None and cur[2] >= capacity:
+            return
+        cap = int(capacity * 1.25) + 4096
+        t = self.symm_mem.empty(cap, dtype=dtype, device=self.dev)
+        h = self.symm_mem.rendezvous(t, self.group)
+        self.bufs[name] = (t, h, cap)
+
+    def barrier(self, name):
+        self.bufs[name][1].barrier()
+
+    def local(self, name, count):
+        return self.bufs[name][0][:count]
+
+    def scatter(self, name, send, send_off, send_cnt, dst_off):
+        """send[send_off[q] : +send_cnt[q]] -> rank q's buffer `name` at element dst_off[q]."""
+        t, h, cap = self.bufs[name]
+        cur = torch.cuda.current_stream(self.dev)
+        for i in range(self.world):
+            q = (self.rank + i) % self.world
+            c = int(send_cnt[q])
+            if c == 0:
+                continue
+            dst = h.get_buffer(q, (cap,), t.dtype)[int(dst_off[q]):int(dst_off[q]) + c]
+            st = self.streams[i]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                dst.copy_(send[int(send_off[q]):int(send_off[q]) + c], non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+
 class ShardedParser:
     """Holds this rank's shard of the text and parses the whole text with the other ranks."""
 
@@ -251,6 +298,8 @@ class ShardedParser:
         self.buf = None
         self.n_local = self.n_global = self.pos0 = 0
         self.result = None
+        self._peer = None          # PeerExchange once it has been set up (GPU ranks only)
+        self._peer_failed = False
 
     # -- collectives --------------------------------------------------------------------------------
     def _all_gather_i64(self, vals):
@@ -463,6 +512,28 @@ class ShardedParser:
                 r.wait()
         return out
 
+    def _peer_exchange(self, dev):
+        """The NVLink peer-memory exchange, or None (CPU ranks, or symmetric memory unavailable:
+        the NCCL grouped send/recv path is used instead)."""
+        if self._peer is not None or self._peer_failed:
+            return self._peer
+        import os
+        if dev.type != "cuda" or os.environ.get("PFPB200_EXCHANGE", "peer") != "peer":
+            self._peer_failed = True
+            return None
+        import torch.distributed as dist
+        ok = 1
+        try:
+            self._peer = PeerExchange(dev, self.world, self.rank, dist.group.WORLD)
+            self._peer.ensure("words", torch.uint8, 1 << 20)
+        except Exception:  # noqa: BLE001
+            self._peer, ok = None, 0
+        flag = torch.tensor([ok], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # all ranks or none
+        if int(flag.item()) == 0:
+            self._peer, self._peer_failed = None, True
+        return self._peer
+
     SAMPLE = 1024
 
     def _splitters(self, wd):
@@ -504,8 +575,29 @@ class ShardedParser:
         # two exchanges: the 32-byte word records and the pool bytes
         send_words = rt["words"] if rt else torch.empty(0, dtype=torch.uint8, device=dev)
         send_pool = rt["pool"] if rt else torch.empty(0, dtype=torch.int64, device=dev)
-        got_words = self._all_to_all_v(send_words, [32 * c for c in words_to], [32 * c for c in recv_w])
-        got_pool = self._all_to_all_v(send_pool, pool_to, recv_p)
+        peer = self._peer_exchange(dev)
+        if peer is not None:
+            # straight into the owners' buffers over NVLink: rank g's records for owner q land behind
+            # those of the lower ranks, M gives every offset
+            need_w = max(sum(M[src][q] for src in range(G)) for q in range(G))
+            need_p = max(sum(M[src][G + q] for src in range(G)) for q in range(G))
+            need_r = max(sum(M[src][:G]) for src in range(G))
+            peer.ensure("words", torch.uint8, 32 * need_w)
+            peer.ensure("pool", torch.int64, need_p)
+            peer.ensure("ranks", torch.int32, need_r)
+            so_w = np.concatenate([[0], np.cumsum(words_to)]).astype(np.int64)
+            so_p = np.concatenate([[0], np.cumsum(pool_to)]).astype(np.int64)
+            peer.barrier("words")                       # the owners are done with the previous parse
+            peer.scatter("words", send_words, 32 * so_w, [32 * c for c in words_to],
+                         [32 * sum(M[src][q] for src in range(g)) for q in range(G)])
+            peer.scatter("pool", send_pool, so_p, pool_to,
+                         [sum(M[src][G + q] for src in range(g)) for q in range(G)])
+            peer.barrier("words")                       # everything addressed to me has landed
+            got_words = peer.local("words", 32 * sum(recv_w))
+            got_pool = peer.local("pool", sum(recv_p))
+        else:
+            got_words = self._all_to_all_v(send_words, [32 * c for c in words_to], [32 * c for c in recv_w])
+            got_pool = self._all_to_all_v(send_pool, pool_to, recv_p)
         self._mark("exchange")
         m = be.dict_merge_words(got_words, got_pool, w, compress)
         self._mark("merge")
@@ -514,7 +606,16 @@ class ShardedParser:
         nd = [r[0] for r in tot]
         offset = sum(nd[:g])
         ranks = m["rank_of_entry"] + offset if m["rank_of_entry"].numel() else m["rank_of_entry"]
-        back = self._all_to_all_v(ranks.to(torch.int32), recv_w, words_to)  # routed order
+        if peer is not None:
+            # the ranks of the records that came from rank q go back to q, behind what q routed to
+            # the owners below me
+            ro = np.concatenate([[0], np.cumsum(recv_w)]).astype(np.int64)
+            peer.scatter("ranks", ranks.to(torch.int32), ro, recv_w,
+                         [sum(M[q][:g]) for q in range(G)])
+            peer.barrier("words")
+            back = peer.local("ranks", wd["n_words"])
+        else:
+            back = self._all_to_all_v(ranks.to(torch.int32), recv_w, words_to)  # routed order
         rank_of_word = torch.empty(wd["n_words"], dtype=torch.int32, device=dev)
         if rt:
             rank_of_word[rt["perm"].long()] = back
