@@ -445,6 +445,8 @@ extern "C" int pfpb200_shard_scan(pfpb200_ctx *ctx, const pfpb200_shard *shard, 
     PFP_TRY(begin_call(ctx));
     ctx->sh.desc = *shard;
     ctx->sh.opts = *opts;
+    ctx->sh.route_perm = nullptr;
+    ctx->sh.route_ooff = nullptr;
     CallTimer tm(ctx->stream);
     u64 *ends = nullptr, k = 0;
     float a = 0;
@@ -455,11 +457,20 @@ extern "C" int pfpb200_shard_scan(pfpb200_ctx *ctx, const pfpb200_shard *shard, 
         k = sb.total;
         rc = pfp_alloc_t(ctx, &ends, k + 1, true);
     }
-    if (rc == PFPB200_OK) rc = pfp_scan_emit(ctx, sb, ends);
+    // the streaming K2 pass of shard_words writes the positions itself; the seams only need the
+    // first and the last trigger now
+    const bool stream_k2 = rc == PFPB200_OK && pfp_stream_ok(sb, opts->w) && !ctx->legacy_k2;
+    ctx->sh.ends_emitted = !stream_k2;
+    if (rc == PFPB200_OK && !stream_k2) rc = pfp_scan_emit(ctx, sb, ends);
     ctx->sh.bits = sb;
     if (rc == PFPB200_OK && k > 0) {
-        cudaMemcpyAsync(&ctx->h_flags[8], ends, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(&ctx->h_flags[9], ends + (k - 1), sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        if (stream_k2) {
+            rc = pfp_scan_first_last(ctx, sb, &ctx->d_flags[8]);
+            cudaMemcpyAsync(&ctx->h_flags[8], &ctx->d_flags[8], 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        } else {
+            cudaMemcpyAsync(&ctx->h_flags[8], ends, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(&ctx->h_flags[9], ends + (k - 1), sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        }
     }
     float t = tm.stop();
     pfp_release_scratch(ctx);
@@ -502,7 +513,8 @@ extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb20
         PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
         if (o.flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
         TextView tv{sh.d_buf, sh.n_buf, (i64)sh.buf_pos0, (i64)sh.n_global};
-        if (pfp_stream_ok(ctx->sh.bits, w) && !ctx->legacy_k2) PFP_TRY(pfp_stream_stage(ctx, ctx->sh.bits, tv, ph, P, first_start, w, false));
+        if (pfp_stream_ok(ctx->sh.bits, w) && !ctx->legacy_k2)
+            PFP_TRY(pfp_stream_stage(ctx, ctx->sh.bits, tv, ph, P, first_start, w, !ctx->sh.ends_emitted));
         else PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, first_start, w));
         DictArrays D;
         PFP_TRY(pfp_dedup_stage(ctx, ph, P, &D));
@@ -668,4 +680,49 @@ extern "C" int pfpb200_shard_route(pfpb200_ctx *ctx, const uint64_t *splitters, 
     promote_scratch(ctx);
     if (ms) *ms = t;
     return PFPB200_OK;
+}
+
+// ---- routing fused with the exchange (peer memory) -------------------------------------------------
+extern "C" int pfp_route_plan_impl(pfpb200_ctx *ctx, const Splitters &sp, u32 n_ranks, u64 *words_to, u64 *pool_to,
+                                   const u32 **perm_out);
+extern "C" int pfp_route_push_impl(pfpb200_ctx *ctx, u32 n_ranks, const u64 *word_dst, const u64 *pool_dst);
+
+extern "C" int pfpb200_shard_route_plan(pfpb200_ctx *ctx, const uint64_t *splitters, uint32_t n_ranks,
+                                        uint64_t *words_to, uint64_t *pool_to, const uint32_t **d_perm,
+                                        float *ms) {
+    if (!ctx || !words_to || !pool_to || !d_perm || n_ranks < 1 || n_ranks > PFPB200_MAX_RANKS ||
+        (n_ranks > 1 && !splitters))
+        return PFPB200_E_ARG;
+    for (u32 q = 0; q < PFPB200_MAX_RANKS; q++) words_to[q] = pool_to[q] = 0;
+    *d_perm = nullptr;
+    if (ms) *ms = 0;
+    if (ctx->sh.d == 0) return PFPB200_OK;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Splitters sp;
+    sp.n = n_ranks - 1;
+    for (u32 i = 0; i < sp.n; i++) {
+        sp.s[i] = splitters[i];
+        if (i && sp.s[i] < sp.s[i - 1]) return pfp_fail(ctx, PFPB200_E_ARG, "splitters not ascending");
+    }
+    CallTimer tm(ctx->stream);
+    int rc = pfp_route_plan_impl(ctx, sp, n_ranks, words_to, pool_to, d_perm);
+    float t = tm.stop();
+    if (rc != PFPB200_OK) { pfp_release_scratch(ctx); return rc; }
+    promote_scratch(ctx);
+    if (ms) *ms = t;
+    return PFPB200_OK;
+}
+
+extern "C" int pfpb200_shard_route_push(pfpb200_ctx *ctx, uint32_t n_ranks, const uint64_t *word_dst,
+                                        const uint64_t *pool_dst, float *ms) {
+    if (!ctx || !word_dst || !pool_dst || n_ranks < 1 || n_ranks > PFPB200_MAX_RANKS) return PFPB200_E_ARG;
+    if (ms) *ms = 0;
+    if (ctx->sh.d == 0) return PFPB200_OK;
+    if (!ctx->sh.route_perm) return pfp_fail(ctx, PFPB200_E_ARG, "shard_route_push before shard_route_plan");
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    CallTimer tm(ctx->stream);
+    int rc = pfp_route_push_impl(ctx, n_ranks, word_dst, pool_dst);
+    float t = tm.stop();
+    if (ms) *ms = t;
+    return rc;
 }

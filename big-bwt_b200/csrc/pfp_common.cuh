@@ -70,12 +70,17 @@ struct pfpb200_ctx {
         pfpb200_shard desc;
         pfpb200_opts opts;
         u64 *ends = nullptr;
+        bool ends_emitted = true;      // false: shard_words' streaming pass still has to write ends[]
         ScanBits bits;                 // trigger bits of the shard, kept from shard_scan to shard_words
         u64 n_trig = 0, P = 0, d = 0;
         u32 *uid = nullptr;
         // local dictionary of the shard (held until the next parse)
         u64 *wfpa = nullptr, *wfpb = nullptr, *pool = nullptr, *uoff = nullptr, pool_words = 0;
         u32 *ulen = nullptr, *count = nullptr, *uwords = nullptr;
+        // routing plan kept between pfpb200_shard_route_plan and pfpb200_shard_route_push
+        u32 *route_perm = nullptr;
+        u64 *route_ooff = nullptr;
+        u64 route_words_to[PFPB200_MAX_RANKS] = {0}, route_pool_to[PFPB200_MAX_RANKS] = {0};
     } sh;
 };
 

@@ -511,6 +511,38 @@ int pfp_scan_bits_free(pfpb200_ctx *ctx, ScanBits *sb) {
     return PFPB200_OK;
 }
 
+// first and last trigger of the buffer straight from the bits (global positions; total > 0)
+__global__ void __launch_bounds__(1024) first_last_trigger_k(const u32 *__restrict__ mask32,
+                                                             const u32 *__restrict__ tile_cnt, u32 ntiles,
+                                                             u64 pos_bias, u64 *__restrict__ out2) {
+    __shared__ u32 s_first, s_last;
+    __shared__ u32 s_wf, s_wl;
+    const u32 t = threadIdx.x;
+    if (t == 0) { s_first = 0xFFFFFFFFu; s_last = 0; s_wf = 0xFFFFFFFFu; s_wl = 0; }
+    __syncthreads();
+    u32 lo = 0xFFFFFFFFu, hi = 0;
+    for (u32 i = t; i < ntiles; i += 1024)
+        if (tile_cnt[i]) { lo = min(lo, i); hi = max(hi, i + 1); }
+    if (lo != 0xFFFFFFFFu) { atomicMin(&s_first, lo); atomicMax(&s_last, hi); }
+    __syncthreads();
+    if (s_first == 0xFFFFFFFFu) return;
+    const u32 tf = s_first, tl = s_last - 1;
+    const u32 wf = mask32[(u64)tf * 1024 + t], wl = mask32[(u64)tl * 1024 + t];    // 1024 words per tile
+    if (wf) atomicMin(&s_wf, t);
+    if (wl) atomicMax(&s_wl, t + 1);
+    __syncthreads();
+    if (t == s_wf) out2[0] = ((u64)tf * 1024 + t) * 32 + (u64)(__ffs(wf) - 1) + pos_bias;
+    if (t + 1 == s_wl) out2[1] = ((u64)tl * 1024 + t) * 32 + (u64)(31 - __clz(wl)) + pos_bias;
+}
+
+int pfp_scan_first_last(pfpb200_ctx *ctx, const ScanBits &sb, u64 *d_out2) {
+    if (sb.ntiles == 0 || sb.total == 0) return PFPB200_OK;
+    first_last_trigger_k<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const u32 *>(sb.mask), sb.tile_cnt, sb.ntiles,
+                                                      sb.pos_bias, d_out2);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
 // K1c alone: bits -> ascending positions in out[0..total)
 int pfp_scan_emit(pfpb200_ctx *ctx, const ScanBits &sb, u64 *out) {
     if (sb.ntiles == 0 || sb.total == 0) return PFPB200_OK;

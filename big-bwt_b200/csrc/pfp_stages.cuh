@@ -61,6 +61,7 @@ int pfp_scan_stage(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u
 int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u64 own_lo, u64 own_hi,
                   u32 w, u32 p, bool held, ScanBits *sb, float *ms_scan);
 int pfp_scan_emit(pfpb200_ctx *ctx, const ScanBits &sb, u64 *out);
+int pfp_scan_first_last(pfpb200_ctx *ctx, const ScanBits &sb, u64 *d_out2);   // global positions of the first / last trigger
 int pfp_scan_bits_free(pfpb200_ctx *ctx, ScanBits *sb);
 int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 P,
                    i64 first_start, u32 w);

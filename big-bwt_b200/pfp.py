@@ -78,7 +78,8 @@ SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_p
            "pfpb200_parse_host", "pfpb200_parse_file", "pfpb200_fasta_extract",
            "pfpb200_scan_triggers", "pfpb200_memcpy_d2h", "pfpb200_strerror",
            "pfpb200_shard_scan", "pfpb200_shard_words", "pfpb200_dict_merge", "pfpb200_shard_remap",
-           "pfpb200_shard_first_keys", "pfpb200_shard_route", "pfpb200_dict_merge_words",
+           "pfpb200_shard_first_keys", "pfpb200_shard_route", "pfpb200_shard_route_plan",
+           "pfpb200_shard_route_push", "pfpb200_dict_merge_words",
            "pfpb200_launch_count", "pfpb200_last_error", "pfpb200_abi_version"]
 
 

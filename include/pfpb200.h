@@ -205,6 +205,18 @@ typedef struct pfpb200_routed {     /* the local dictionary regrouped by destina
 int pfpb200_shard_route(pfpb200_ctx *ctx, const uint64_t *splitters, uint32_t n_ranks,
                         pfpb200_routed *out, float *ms);
 
+/* The same routing fused with the exchange, for ranks that can store into each other's memory
+ * (NVLink peer mappings, e.g. torch symmetric memory).  _plan decides the owner of every word and
+ * returns how many words / pool words go to each owner (arrays of PFPB200_MAX_RANKS) and the
+ * routed order d_perm; after the ranks have exchanged those counts, _push writes this rank's
+ * pfpb200_word records for owner q to word_dst[q] and their pool words to pool_dst[q] -- device
+ * addresses inside the owners' receive buffers, as mapped into THIS process -- in routed order.
+ * The caller brackets the push with barriers among the ranks. */
+int pfpb200_shard_route_plan(pfpb200_ctx *ctx, const uint64_t *splitters, uint32_t n_ranks,
+                             uint64_t *words_to, uint64_t *pool_to, const uint32_t **d_perm, float *ms);
+int pfpb200_shard_route_push(pfpb200_ctx *ctx, uint32_t n_ranks, const uint64_t *word_dst,
+                             const uint64_t *pool_dst, float *ms);
+
 /* pfpb200_dict_merge for words received as pfpb200_word records (the all-to-all payload). */
 int pfpb200_dict_merge_words(pfpb200_ctx *ctx, uint64_t n_in, const pfpb200_word *words,
                              const uint64_t *pool, uint64_t pool_words, uint32_t w, uint32_t flags,
