@@ -26,11 +26,10 @@ __device__ __forceinline__ u64 sort_key_of(u64 fa, u64 fb, u32 len) {
     return k ? k : 0x9E3779B97F4A7C15ULL;
 }
 
+__device__ __forceinline__ u32 fold_fb(u64 fb) { return (u32)fb ^ (u32)(fb >> 32); }
+
 __device__ __forceinline__ void store_rec(PhraseFp *rec, u64 j, u64 fa, u64 fb, u32 len) {
-    uint4 *q = reinterpret_cast<uint4 *>(rec + j);
-    u64 key = sort_key_of(fa, fb, len);
-    q[0] = make_uint4((u32)fa, (u32)(fa >> 32), (u32)fb, (u32)(fb >> 32));
-    q[1] = make_uint4(len, 0u, (u32)key, (u32)(key >> 32));
+    *reinterpret_cast<uint4 *>(rec + j) = make_uint4((u32)fa, (u32)(fa >> 32), fold_fb(fb), len);
 }
 
 // base^e mod 2^64 (long phrases only)

@@ -318,7 +318,7 @@ constexpr u32 TABLE_MAX_PROBES = 2048;
 
 __device__ __forceinline__ u32 check_of(const PhraseFp &r) {
     u64 x = (r.fpa + 0x632BE59BD9B4E019ULL) * 0xD1342543DE82EF95ULL;
-    x ^= rotl64(r.fpb, 23) * 0xAF251AF3B0F025B5ULL;
+    x ^= rotl64((u64)r.fpb, 23) * 0xAF251AF3B0F025B5ULL;
     x ^= (u64)r.len << 32;
     x ^= x >> 29;
     u32 c = (u32)(x ^ (x >> 32));
@@ -371,14 +371,14 @@ __global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict
     for (int it = 0; it < TI_ITEMS; it++) {
         const u64 j = base + (u64)it * 256;
         PhraseFp r;
-        r.key = 0; r.len = 0; r.fpa = r.fpb = 0;
+        r.len = 0; r.fpa = 0; r.fpb = 0;
+        u64 key = 0;
         if (j < P) {                                  // streamed once: keep it out of the table's way in L2
-            const uint4 *q = reinterpret_cast<const uint4 *>(rec + j);
-            uint4 a = __ldcs(q), b = __ldcs(q + 1);
-            r.fpa = ((u64)a.y << 32) | a.x; r.fpb = ((u64)a.w << 32) | a.z;
-            r.len = b.x; r.key = ((u64)b.w << 32) | b.z;
+            const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(rec + j));
+            r.fpa = ((u64)a.y << 32) | a.x; r.fpb = a.z; r.len = a.w;
+            key = sort_key_of(r.fpa, (u64)r.fpb, r.len);
         }
-        k[it] = r.key;
+        k[it] = key;
         len[it] = r.len;
         chk[it] = j < P ? check_of(r) : 0u;
         peers[it] = __match_any_sync(0xffffffffu, k[it]);
@@ -706,7 +706,7 @@ __global__ void gather_word_fp_k(const u32 *__restrict__ rep, const PhraseFp *__
     if (u >= d) return;
     u32 j = rep[u];
     wfpa[u] = rec[j].fpa;
-    wfpb[u] = rec[j].fpb;
+    wfpb[u] = (u64)rec[j].fpb;
 }
 
 int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays &ph, u64 *wfpa,

@@ -18,12 +18,13 @@ __device__ __forceinline__ u8 tv_byte(const TextView &tv, i64 g) {
 }
 
 // ---- per-phrase arrays (P entries, text order) ----------------------------------------------------
-// 32-byte fingerprint record of a phrase: one sector, written once by K2, read by K3
-struct __align__(32) PhraseFp {
-    u64 fpa, fpb;   // 128-bit NH fingerprint
+// 16-byte fingerprint record of a phrase, written once by K2, read once by K3: the first NH sum,
+// the second folded to 32 bits, the length.  (The table key and the check digest are recomputed
+// from these by K3: 16 bytes less to write and to read per phrase than carrying the key along.)
+struct __align__(16) PhraseFp {
+    u64 fpa;        // first NH sum
+    u32 fpb;        // second NH sum (Toeplitz-shifted keys), high and low half xor-ed
     u32 len;        // phrase length in bytes, including the w-byte overlap and virtual borders
-    u32 pad;
-    u64 key;        // table key derived from (fpa, fpb, len); never 0
 };
 
 struct PhraseArrays {
