@@ -1,0 +1,76 @@
+"""pfp_arith.h (shared by the device kernels and the host): the division-free forms against plain
+`%` arithmetic -- newscan.cpp:194-202 (window hash mod 1999999973) and :344,367 (hash % p == 0)."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PW = 1999999973
+
+SRC = r"""
+#include "pfp_arith.h"
+uint32_t t_reduce(uint64_t t) { return pfp_reduce_pw(t); }
+uint32_t t_roll(uint32_t h, uint32_t cin, uint32_t cout, uint32_t negw) { return pfp_roll(h, cin, cout, negw); }
+uint32_t t_push(uint32_t h, uint32_t c) { return pfp_push(h, c); }
+int t_trig(uint32_t r, uint32_t w, uint32_t p) { pfp_scan_consts c = pfp_make_scan_consts(w, p);
+    return pfp_is_trigger(r, c.pinv, c.pshift, c.plimit); }
+uint32_t t_negw(uint32_t w) { return pfp_make_scan_consts(w, 100).negw; }
+"""
+
+
+@pytest.fixture(scope="module")
+def lib():
+    tmp = tempfile.mkdtemp(prefix="pfparith_")
+    src, so = os.path.join(tmp, "a.c"), os.path.join(tmp, "a.so")
+    with open(src, "w") as f:
+        f.write(SRC)
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "big-bwt_b200", "csrc"),
+                           "-o", so, src])
+    L = C.CDLL(so)
+    L.t_reduce.argtypes = [C.c_uint64]; L.t_reduce.restype = C.c_uint32
+    L.t_roll.argtypes = [C.c_uint32] * 4; L.t_roll.restype = C.c_uint32
+    L.t_push.argtypes = [C.c_uint32] * 2; L.t_push.restype = C.c_uint32
+    L.t_trig.argtypes = [C.c_uint32] * 3; L.t_trig.restype = C.c_int
+    L.t_negw.argtypes = [C.c_uint32]; L.t_negw.restype = C.c_uint32
+    return L
+
+
+def test_reduce_below_2_41(lib):
+    rng = np.random.default_rng(1)
+    vals = [0, 1, PW - 1, PW, PW + 1, 2 * PW - 1, 2 * PW, (1 << 41) - 1, (1 << 40), 255 * PW + 7]
+    vals += [int(x) for x in rng.integers(0, 1 << 41, 20000, dtype=np.uint64)]
+    vals += [k * PW + d for k in (1, 2, 1000, 1099) for d in (-1, 0, 1)]
+    for t in vals:
+        if 0 <= t < (1 << 41):
+            assert lib.t_reduce(t) == t % PW, t
+
+
+@pytest.mark.parametrize("w", [4, 6, 10, 16, 32])
+def test_roll_is_the_reference_update(lib, w):
+    """h' = (256 h + c_in - c_out 256^w) mod PW, as KR_window::addchar computes it."""
+    rng = np.random.default_rng(w)
+    negw = lib.t_negw(w)
+    assert negw == (PW - pow(256, w, PW)) % PW
+    for _ in range(20000):
+        h, cin, cout = int(rng.integers(0, PW)), int(rng.integers(0, 256)), int(rng.integers(0, 256))
+        want = (256 * h + cin - cout * pow(256, w, PW)) % PW
+        assert lib.t_roll(h, cin, cout, negw) == want
+    for h in (0, PW - 1):
+        for cin in (0, 255):
+            for cout in (0, 255):
+                assert lib.t_roll(h, cin, cout, negw) == (256 * h + cin - cout * pow(256, w, PW)) % PW
+                assert lib.t_push(h, cin) == (256 * h + cin) % PW
+
+
+@pytest.mark.parametrize("p", [10, 11, 16, 50, 64, 100, 500, 1000, 1024, 99991, 1 << 20])
+def test_divisibility_test(lib, p):
+    rng = np.random.default_rng(p)
+    vals = [0, 1, p - 1, p, p + 1, PW - 1, (PW // p) * p, (PW // p) * p - 1, 0xFFFFFFFF // p * p]
+    vals += [int(x) for x in rng.integers(0, PW, 20000)]
+    vals += [int(x) * p for x in rng.integers(0, PW // p, 5000)]
+    for r in vals:
+        assert bool(lib.t_trig(r, 10, p)) == (r % p == 0), (r, p)
