@@ -313,8 +313,9 @@ __global__ void iota_u32_k(u32 *v, u64 n) {
 // atomic per warp instead of 32.  `chk` is a 32-bit digest of the full 128-bit fingerprint and
 // the length, independent of the key: every phrase that lands in a slot must agree with it, or
 // the parse stops with PFPB200_E_COLLISION (the reference compares strings, newscan.cpp:282-286).
-struct __align__(16) DictSlot { u64 key; u32 rep; u32 chk; };
+struct __align__(16) DictSlot { u64 key; u32 uid1; u32 chk; };   // uid1 = word id + 1; 0 until its creator stored it
 constexpr u32 TABLE_MAX_PROBES = 2048;
+constexpr u32 UID_PENDING = 0x80000000u;       // uid[j] = UID_PENDING | slot: resolved by table_pending_k
 
 __device__ __forceinline__ u32 check_of(const PhraseFp &r) {
     u64 x = (r.fpa + 0x632BE59BD9B4E019ULL) * 0xD1342543DE82EF95ULL;
@@ -331,17 +332,19 @@ __global__ void table_init_k(DictSlot *__restrict__ tab, u64 cap) {
 }
 
 // One probe sequence: a plain 16-byte load of the slot first -- on repetitive inputs nine phrases
-// in ten find their word already there and finish with one fire-and-forget add -- and a CAS only
-// on an empty slot.  The thread that wins the CAS (the word's creator) records itself as the
-// word's representative occurrence and the word's length next to the table.
-struct Probe { u64 slot; bool placed; bool creator; u32 seen_chk; };
+// in ten find their word already there, read its id from the slot and finish with one
+// fire-and-forget add to its count -- and a CAS only on an empty slot.  The thread that wins the
+// CAS is the word's creator: it draws the next word id from a counter (ids are dense, in creation
+// order: no flag / scan / compaction passes over the table afterwards), stores it in the slot and
+// records itself as the word's representative occurrence.
+struct Probe { u64 slot; bool placed; bool creator; u32 seen_chk; u32 seen_uid1; };
 
 __device__ __forceinline__ Probe table_probe(DictSlot *__restrict__ tab, u64 cap, u64 slot, uint4 sv, u64 k) {
-    Probe r{slot, false, false, 0u};
+    Probe r{slot, false, false, 0u, 0u};
     u32 probes = 0;
     for (;;) {
         const u64 key = ((u64)sv.y << 32) | sv.x;
-        if (key == k) { r.placed = true; r.seen_chk = sv.w; break; }
+        if (key == k) { r.placed = true; r.seen_uid1 = sv.z; r.seen_chk = sv.w; break; }
         if (key == 0ull) {
             const u64 prev = atomicCAS((unsigned long long *)&tab[r.slot].key, 0ull, (unsigned long long)k);
             if (prev == 0ull) { r.placed = true; r.creator = true; break; }
@@ -356,11 +359,15 @@ __device__ __forceinline__ Probe table_probe(DictSlot *__restrict__ tab, u64 cap
 
 constexpr int TI_ITEMS = 2;      // phrases per thread: their first probes are in flight together
 
+// weight == nullptr: every record counts once (phrases); else record i counts weight[i] times
+// (words of several shards being merged, newscan.cpp:277-281)
 __global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict__ rec, u64 P,
                                                       DictSlot *__restrict__ tab, u64 cap,
-                                                      u32 *__restrict__ slot_of,
-                                                      u32 *__restrict__ len_slot,
-                                                      u64 *__restrict__ flags) {
+                                                      const u32 *__restrict__ weight,
+                                                      u32 *__restrict__ uid, u32 *__restrict__ rep,
+                                                      u32 *__restrict__ ulen, u32 *__restrict__ uwords,
+                                                      u32 *__restrict__ count,
+                                                      u64 *__restrict__ flags /* [0] errors, [1] words, [2] max len, [3] sum len, [6] pending */) {
     const u32 lane = threadIdx.x & 31;
     const u64 base = (u64)blockIdx.x * (256 * TI_ITEMS) + threadIdx.x;
     u64 k[TI_ITEMS];
@@ -385,83 +392,90 @@ __global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict
         lead[it] = j < P && (int)lane == __ffs(peers[it]) - 1;
         if (lead[it]) sv[it] = __ldcg(reinterpret_cast<const uint4 *>(tab + __umul64hi(k[it], cap)));
     }
+    // ---- probes: slot of every leader's word; creators only note that they are creators ------------
+    __shared__ u32 s_new;                            // words created by this CTA
+    __shared__ u32 s_max;
+    __shared__ unsigned long long s_sum, s_base;
+    if (threadIdx.x == 0) { s_new = 0; s_max = 0; s_sum = 0; }
+    __syncthreads();
+    u32 res[TI_ITEMS];                               // word id + 1, or UID_PENDING | slot
+    u32 mine[TI_ITEMS];                              // creator: index among the CTA's new words
+    u64 slot[TI_ITEMS];
 #pragma unroll
     for (int it = 0; it < TI_ITEMS; it++) {
-        const u64 j = base + (u64)it * 256;
-        u64 slot = 0;
+        res[it] = 0; mine[it] = 0xFFFFFFFFu; slot[it] = 0;
         if (lead[it]) {
             const Probe pr = table_probe(tab, cap, __umul64hi(k[it], cap), sv[it], k[it]);
             if (pr.placed) {
-                slot = pr.slot;
+                slot[it] = pr.slot;
                 u32 seen = pr.seen_chk;
-                if (pr.creator) { tab[slot].rep = (u32)j; len_slot[slot] = len[it]; }
-                if (seen == 0u) seen = atomicCAS(&tab[slot].chk, 0u, chk[it]);   // creator, or racing with it
+                if (pr.creator) {
+                    mine[it] = atomicAdd(&s_new, 1u);
+                    atomicMax(&s_max, len[it]);
+                    atomicAdd(&s_sum, (unsigned long long)len[it]);
+                } else {
+                    res[it] = pr.seen_uid1 ? pr.seen_uid1 : (UID_PENDING | (u32)pr.slot);
+                }
+                if (seen == 0u) seen = atomicCAS(&tab[pr.slot].chk, 0u, chk[it]);   // creator, or racing with it
                 if (seen != 0u && seen != chk[it]) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
             } else {
                 atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_TABLE_FULL);
+                res[it] = 1;                         // any valid id: the stage is rerun
             }
         }
-        const int leader = __ffs(peers[it]) - 1;
-        slot = __shfl_sync(0xffffffffu, slot, leader);
-        const u32 lchk = __shfl_sync(0xffffffffu, chk[it], leader);
-        if (j < P) {
-            __stcs(slot_of + j, (u32)slot);
-            if (chk[it] != lchk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
-        }
     }
-}
-
-__global__ void table_flags_k(const DictSlot *__restrict__ tab, u64 cap, u8 *__restrict__ occ) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap) occ[i] = tab[i].key != 0ull ? 1 : 0;
-}
-
-// per distinct word (= occupied slot): occurrences, representative phrase, length; max / total length
-__global__ void __launch_bounds__(256) table_emit_k(const DictSlot *__restrict__ tab, const u8 *__restrict__ occ,
-                                                    const u32 *__restrict__ umap,
-                                                    const u32 *__restrict__ len_slot, u64 cap,
-                                                    u32 *__restrict__ count, u32 *__restrict__ rep,
-                                                    u32 *__restrict__ ulen, u32 *__restrict__ uwords,
-                                                    u64 *__restrict__ flags /* [2]=max len, [3]=sum len */) {
-    __shared__ unsigned long long s_sum;
-    __shared__ u32 s_max;
-    if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }
+    // ---- one global add per CTA hands out the ids of its new words (a single counter bumped by
+    //      every creator cost 4 ms of same-address atomics) ---------------------------------------------
     __syncthreads();
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 L = 0;
-    if (i < cap && occ[i]) {
-        u32 u = umap[i];
-        count[u] = 0;                                 // occurrences are counted by table_uid_k
-        rep[u] = tab[i].rep;
-        L = len_slot[i];
-        ulen[u] = L;
-        uwords[u] = (L + 7) >> 3;
-    }
-    u32 mx = L;
-    u64 sum = L;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    }
-    if ((threadIdx.x & 31) == 0 && sum) { atomicAdd(&s_sum, (unsigned long long)sum); atomicMax(&s_max, mx); }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_sum) {
+    if (threadIdx.x == 0 && s_new) {
+        s_base = atomicAdd((unsigned long long *)&flags[1], (unsigned long long)s_new);
         atomicMax((unsigned long long *)&flags[2], (unsigned long long)s_max);
         atomicAdd((unsigned long long *)&flags[3], s_sum);
     }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < TI_ITEMS; it++) {
+        const u64 j = base + (u64)it * 256;
+        if (mine[it] != 0xFFFFFFFFu) {
+            const u32 u = (u32)s_base + mine[it];
+            rep[u] = (u32)j; ulen[u] = len[it]; uwords[u] = (len[it] + 7) >> 3;
+            tab[slot[it]].uid1 = u + 1;
+            res[it] = u + 1;
+        }
+        const int leader = __ffs(peers[it]) - 1;
+        const u32 r = __shfl_sync(0xffffffffu, res[it], leader);
+        const u32 lchk = __shfl_sync(0xffffffffu, chk[it], leader);
+        if (j < P) {
+            if (chk[it] != lchk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+            if (r & UID_PENDING) {                   // the creator had not stored the id yet: table_pending_k
+                __stcs(uid + j, r);
+                if (lead[it]) atomicOr((unsigned long long *)&flags[6], 1ull);
+            } else {
+                __stcs(uid + j, r - 1);
+                if (weight) {
+                    const u32 c = weight[j];
+                    const u32 old = atomicAdd(&count[r - 1], c);
+                    if (old + c < old) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
+                } else if (lead[it]) {
+                    atomicAdd(&count[r - 1], (u32)__popc(peers[it]));
+                }
+            }
+        }
+    }
 }
 
-// phrase -> word id, and the occurrence counts: the adds go to the d-entry count array, which
-// stays in L2, instead of dirtying the (much larger) table
-__global__ void table_uid_k(const u32 *__restrict__ slot_of, const u32 *__restrict__ umap, u64 P,
-                            u32 *__restrict__ uid, u32 *__restrict__ count) {
+// the few records that met a slot whose creator had not stored the word id yet
+__global__ void table_pending_k(const DictSlot *__restrict__ tab, u64 P, const u32 *__restrict__ weight,
+                                u32 *__restrict__ uid, u32 *__restrict__ count, u64 *__restrict__ flags) {
     u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = j < P;
-    u32 u = active ? umap[__ldcs(slot_of + j)] : 0xFFFFFFFFu;
-    if (active) uid[j] = u;
-    const u32 peers = __match_any_sync(0xffffffffu, u);
-    if (active && (peers & lanemask_lt()) == 0) atomicAdd(&count[u], (u32)__popc(peers));
+    if (j >= P) return;
+    const u32 v = uid[j];
+    if (!(v & UID_PENDING)) return;
+    const u32 u = tab[v & ~UID_PENDING].uid1 - 1;
+    uid[j] = u;
+    const u32 c = weight ? weight[j] : 1u;
+    const u32 old = atomicAdd(&count[u], c);
+    if (old + c < old) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
 }
 
 // phrase pool: every distinct word once, zero padded to 8 bytes, 8-byte aligned
@@ -563,21 +577,21 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     return PFPB200_OK;
 }
 
-// Inserts every phrase into the dictionary table and derives the dictionary arrays.
+// Inserts every phrase into the dictionary table; the table hands out the word ids, so when the
+// kernel is done uid[], rep[], ulen[], uwords[] and count[] are complete.
 // Reads d (and length stats) back to the host: one synchronisation.
 int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D) {
     const int TB = 256;
     // Capacity: without a hint 1.5 P (load factor <= 2/3 even if every phrase is distinct).  The
     // distinct/phrase ratio of the previous parse on this context sizes the table 2x the expected
-    // dictionary instead, which keeps it (and the passes over it) several times smaller on
-    // repetitive inputs -- small enough to live in L2; if that guess turns out too small the
-    // insert kernel says so and the stage reruns with the safe size.  Slots are addressed by
-    // fastrange (mulhi(key, cap)), so the capacity need not be a power of two.
+    // dictionary instead, which keeps it several times smaller on repetitive inputs -- small
+    // enough to live in L2; if that guess turns out too small the insert kernel says so and the
+    // stage reruns with the safe size.  Slots are addressed by fastrange (mulhi(key, cap)), so the
+    // capacity need not be a power of two.  The per-word arrays are sized by the capacity.
+    if (P >= 0x7FFFFFFEull) return pfp_fail(ctx, PFPB200_E_LIMIT, "more than 2^31-2 phrases in one shard");
     DictSlot *tab = nullptr;
-    u32 *slot_of = nullptr, *umap = nullptr, *len_slot = nullptr;
-    u8 *occ = nullptr;
     u64 cap = 0, d = 0;
-    PFP_TRY(pfp_alloc_t(ctx, &slot_of, P));
+    PFP_TRY(pfp_alloc_t(ctx, &D->uid, P));
     for (int attempt = 0;; attempt++) {
         double want = (double)P * 1.5;
         if (attempt == 0 && ctx->dedup_ratio > 0.0) {
@@ -585,58 +599,50 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays 
             if (guess < want) want = guess;
         }
         cap = (u64)want + 1024;
+        if (cap >= 0x7FFFFFFFull) cap = 0x7FFFFFFEull;
+        const u64 wcap = cap < P ? cap : P;            // there are at most min(cap, P) words
         PFP_TRY(pfp_alloc_t(ctx, &tab, cap));
-        PFP_TRY(pfp_alloc_t(ctx, &len_slot, cap));
+        PFP_TRY(pfp_alloc_t(ctx, &D->rep, wcap));
+        PFP_TRY(pfp_alloc_t(ctx, &D->count, wcap));
+        PFP_TRY(pfp_alloc_t(ctx, &D->ulen, wcap));
+        PFP_TRY(pfp_alloc_t(ctx, &D->uwords, wcap));
         table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
         PFP_LAUNCHED(ctx);
-        table_insert_k<<<pfp_blocks(P, TB * TI_ITEMS), TB, 0, ctx->stream>>>(ph.rec, P, tab, cap, slot_of, len_slot,
-                                                                            ctx->d_flags);
-        PFP_LAUNCHED(ctx);
-        PFP_TRY(pfp_alloc_t(ctx, &occ, cap));
-        PFP_TRY(pfp_alloc_t(ctx, &umap, cap));
-        table_flags_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap, occ);
-        PFP_LAUNCHED(ctx);
+        PFP_CUDA(ctx, cudaMemsetAsync(D->count, 0, wcap * sizeof(u32), ctx->stream));
         PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
-        PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, occ, umap, cap, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
-        PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(u64), cudaMemcpyDeviceToHost,
+        PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[6], 0, sizeof(u64), ctx->stream));
+        table_insert_k<<<pfp_blocks(P, TB * TI_ITEMS), TB, 0, ctx->stream>>>(
+            ph.rec, P, tab, cap, nullptr, D->uid, D->rep, D->ulen, D->uwords, D->count, ctx->d_flags);
+        PFP_LAUNCHED(ctx);
+        PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 7 * sizeof(u64), cudaMemcpyDeviceToHost,
                                       ctx->stream));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
             return pfp_fail(ctx, PFPB200_E_LIMIT, "a phrase is longer than 2^32-1 bytes");
-        d = (u32)ctx->h_flags[1];
+        d = ctx->h_flags[1];
         const bool full = (ctx->h_flags[0] & PFP_ERRBIT_TABLE_FULL) != 0 || (double)d > 0.85 * (double)cap;
         if (!full) break;
         if (attempt > 0) return pfp_fail(ctx, PFPB200_E_INTERNAL, "dictionary table overflow");
         // undo and retry with the safe capacity
-        PFP_TRY(pfp_free_now(ctx, tab));
-        PFP_TRY(pfp_free_now(ctx, len_slot));
-        PFP_TRY(pfp_free_now(ctx, occ));
-        PFP_TRY(pfp_free_now(ctx, umap));
+        void *fr[] = {tab, D->rep, D->count, D->ulen, D->uwords};
+        for (void *q : fr) PFP_TRY(pfp_free_now(ctx, q));
         ctx->dedup_ratio = 0.0;
-        const u64 keep = ctx->h_flags[0] & ~PFP_ERRBIT_TABLE_FULL;
+        const u64 keep = ctx->h_flags[0] & ~(PFP_ERRBIT_TABLE_FULL | PFP_ERRBIT_COLLISION);
         PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->d_flags[0], &keep, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (ctx->h_flags[6]) {                             // records that raced with the creation of their word
+        table_pending_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(tab, P, nullptr, D->uid, D->count, ctx->d_flags);
+        PFP_LAUNCHED(ctx);
     }
     ctx->dedup_ratio = (double)d / (double)P;
     if (d > 0x7FFFFFFEull)
         return pfp_fail(ctx, PFPB200_E_LIMIT, "%llu distinct words exceed the limit 2^31-2",
                         (unsigned long long)d);
     D->d = d;
-    PFP_TRY(pfp_alloc_t(ctx, &D->uid, P));
-    PFP_TRY(pfp_alloc_t(ctx, &D->rep, d));
-    PFP_TRY(pfp_alloc_t(ctx, &D->count, d));
-    PFP_TRY(pfp_alloc_t(ctx, &D->ulen, d));
-    PFP_TRY(pfp_alloc_t(ctx, &D->uwords, d));
-    table_emit_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, occ, umap, len_slot, cap, D->count, D->rep,
-                                                              D->ulen, D->uwords, ctx->d_flags);
-    PFP_LAUNCHED(ctx);
-    table_uid_k<<<pfp_blocks(P, TB), TB, 0, ctx->stream>>>(slot_of, umap, P, D->uid, D->count);
-    PFP_LAUNCHED(ctx);
+    D->max_len = (u32)ctx->h_flags[2];
+    D->sum_len = ctx->h_flags[3];
     PFP_TRY(pfp_free_now(ctx, tab));
-    PFP_TRY(pfp_free_now(ctx, len_slot));
-    PFP_TRY(pfp_free_now(ctx, slot_of));
-    PFP_TRY(pfp_free_now(ctx, occ));
-    PFP_TRY(pfp_free_now(ctx, umap));
     return PFPB200_OK;
 }
 
@@ -675,25 +681,12 @@ __global__ void merge_recs_k(const u64 *__restrict__ fpa, const u64 *__restrict_
     if (i < n) store_rec(rec, i, fpa[i], fpb[i], len[i]);
 }
 
-// entry -> merged word; occurrences of a merged word = sum over its entries (newscan.cpp:277-281)
-__global__ void merge_uid_k(const u32 *__restrict__ slot_of, const u32 *__restrict__ umap,
-                            const u32 *__restrict__ count_in, u64 n, u32 *__restrict__ uid,
-                            u32 *__restrict__ count, u64 *__restrict__ flags) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u32 u = umap[slot_of[i]];
-    uid[i] = u;
-    const u32 c = count_in[i];
-    const u32 old = atomicAdd(&count[u], c);
-    if (old + c < old) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
-}
-
 // a merged word lives where its representative entry lives in the received pool
 __global__ void merge_words_k(const u32 *__restrict__ rep, const u32 *__restrict__ uwords_in,
-                              const u64 *__restrict__ in_off, u64 d, u32 *__restrict__ uwords,
-                              u64 *__restrict__ uoff) {
+                              const u64 *__restrict__ in_off, const u64 *__restrict__ d_ptr,
+                              u32 *__restrict__ uwords, u64 *__restrict__ uoff) {
     u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= d) return;
+    if (u >= *d_ptr) return;
     const u32 r = rep[u];
     uwords[u] = uwords_in[r];
     uoff[u] = in_off[r];
@@ -716,77 +709,66 @@ int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays
     return PFPB200_OK;
 }
 
-// Merges n input words into the distinct set D with the dictionary table (uid order = slot
-// order); uid_of_entry[i] = merged word of input entry i.  Two synchronisations.
+// Merges n input words into the distinct set D with the dictionary table (word ids in creation
+// order); uid_of_entry[i] = merged word of input entry i, occurrences summed per word.
+// One synchronisation.
 int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, const u32 *len,
                     const u32 *count_in, const u32 *uwords_in, const u64 *pool, u64 pool_words,
                     DictArrays *D, u32 **uid_of_entry) {
     const int TB = 256;
-    if (n >= 0xFFFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "too many words to merge");
+    if (n >= 0x7FFFFFFEull / 2) return pfp_fail(ctx, PFPB200_E_LIMIT, "too many words to merge");
     PhraseFp *rec = nullptr;
     DictSlot *tab = nullptr;
-    u32 *slot_of = nullptr, *umap = nullptr, *len_slot = nullptr;
     u64 *in_off = nullptr;
-    u8 *occ = nullptr;
     const u64 cap = n + n / 2 + 1024;                  // load factor <= 2/3 even if nothing merges
     PFP_TRY(pfp_alloc_t(ctx, &rec, n));
     PFP_TRY(pfp_alloc_t(ctx, &tab, cap));
-    PFP_TRY(pfp_alloc_t(ctx, &slot_of, n));
-    PFP_TRY(pfp_alloc_t(ctx, &len_slot, cap));
-    PFP_TRY(pfp_alloc_t(ctx, &occ, cap));
-    PFP_TRY(pfp_alloc_t(ctx, &umap, cap));
     PFP_TRY(pfp_alloc_t(ctx, &in_off, n));
+    PFP_TRY(pfp_alloc_t(ctx, uid_of_entry, n));
+    PFP_TRY(pfp_alloc_t(ctx, &D->rep, n));
+    PFP_TRY(pfp_alloc_t(ctx, &D->count, n));
+    PFP_TRY(pfp_alloc_t(ctx, &D->ulen, n));
+    PFP_TRY(pfp_alloc_t(ctx, &D->uwords, n));
+    PFP_TRY(pfp_alloc_t(ctx, &D->uoff, n));
+    D->uid = *uid_of_entry;
     merge_recs_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(fpa, fpb, len, n, rec);
     PFP_LAUNCHED(ctx);
     table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
     PFP_LAUNCHED(ctx);
-    table_insert_k<<<pfp_blocks(n, TB * TI_ITEMS), TB, 0, ctx->stream>>>(rec, n, tab, cap, slot_of, len_slot,
-                                                                        ctx->d_flags);
-    PFP_LAUNCHED(ctx);
-    table_flags_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap, occ);
-    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemsetAsync(D->count, 0, n * sizeof(u32), ctx->stream));
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
-    PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, occ, umap, cap, reinterpret_cast<u32 *>(&ctx->d_flags[1])));
+    PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[6], 0, sizeof(u64), ctx->stream));
+    table_insert_k<<<pfp_blocks(n, TB * TI_ITEMS), TB, 0, ctx->stream>>>(
+        rec, n, tab, cap, count_in, *uid_of_entry, D->rep, D->ulen, D->uwords, D->count, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    // stragglers (ids not stored yet when they looked) -- cheap, and saves a synchronisation to ask
+    table_pending_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(tab, n, count_in, *uid_of_entry, D->count,
+                                                               ctx->d_flags);
+    PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, uwords_in, in_off, n, nullptr));
-    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(u64), cudaMemcpyDeviceToHost,
+    merge_words_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(D->rep, uwords_in, in_off,
+                                                             reinterpret_cast<const u64 *>(&ctx->d_flags[1]),
+                                                             D->uwords, D->uoff);
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(u64), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
         return pfp_fail(ctx, PFPB200_E_COLLISION, "fingerprint collision between different phrases");
     if (ctx->h_flags[0] & PFP_ERRBIT_TABLE_FULL)
         return pfp_fail(ctx, PFPB200_E_INTERNAL, "dictionary table overflow in the merge");
-    u64 d = (u32)ctx->h_flags[1];
+    if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
+        return pfp_fail(ctx, PFPB200_E_LIMIT, "a word occurs more than 2^32-1 times");
+    const u64 d = ctx->h_flags[1];
     if (d > 0x7FFFFFFEull)
         return pfp_fail(ctx, PFPB200_E_LIMIT, "%llu distinct words exceed the limit 2^31-2",
                         (unsigned long long)d);
     D->d = d;
     D->pool = const_cast<u64 *>(pool);
     D->pool_words = pool_words;
-    PFP_TRY(pfp_alloc_t(ctx, uid_of_entry, n));
-    PFP_TRY(pfp_alloc_t(ctx, &D->rep, d));
-    PFP_TRY(pfp_alloc_t(ctx, &D->count, d));
-    PFP_TRY(pfp_alloc_t(ctx, &D->ulen, d));
-    PFP_TRY(pfp_alloc_t(ctx, &D->uwords, d));
-    PFP_TRY(pfp_alloc_t(ctx, &D->uoff, d));
-    D->uid = *uid_of_entry;
-    table_emit_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, occ, umap, len_slot, cap, D->count, D->rep,
-                                                              D->ulen, D->uwords, ctx->d_flags);
-    PFP_LAUNCHED(ctx);
-    merge_uid_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(slot_of, umap, count_in, n, *uid_of_entry, D->count,
-                                                           ctx->d_flags);
-    PFP_LAUNCHED(ctx);
-    merge_words_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(D->rep, uwords_in, in_off, d, D->uwords, D->uoff);
-    PFP_LAUNCHED(ctx);
-    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(u64), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_flags[0] & PFP_ERRBIT_LIMIT)
-        return pfp_fail(ctx, PFPB200_E_LIMIT, "a word occurs more than 2^32-1 times");
-    if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
-        return pfp_fail(ctx, PFPB200_E_COLLISION, "fingerprint collision between different phrases");
     D->max_len = (u32)ctx->h_flags[2];
     D->sum_len = ctx->h_flags[3];
-    void *fr[] = {rec, tab, slot_of, len_slot, occ, umap, in_off};
+    void *fr[] = {rec, tab, in_off};
     for (void *q : fr) PFP_TRY(pfp_free_now(ctx, q));
     return PFPB200_OK;
 }
