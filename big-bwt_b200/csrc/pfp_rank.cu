@@ -312,7 +312,7 @@ struct TieSort {
     u32 wn[2][CAP];               // its length in 8-byte words
     u16 lo[2][CAP];
     u16 hi[2][CAP];
-    u16 dep[2][CAP];
+    u32 dep[2][CAP];              // chunks the words of the range are known to share
 };
 
 template <int NT>
@@ -368,7 +368,7 @@ __device__ __noinline__ void tie_refine_e(TieSort<CAP> &S, u64 *sm_v, u32 *sm_f,
     for (u32 i = t; i < m; i += NT) {
         const u32 u = ord[s + i];
         S.uid[0][i] = u; S.off[0][i] = (u32)uoff[u]; S.wn[0][i] = uwords[u];
-        S.lo[0][i] = 0; S.hi[0][i] = (u16)m; S.dep[0][i] = (u16)(r0 < 0xFFFFu ? r0 : 0xFFFFu);
+        S.lo[0][i] = 0; S.hi[0][i] = (u16)m; S.dep[0][i] = r0;
     }
     tie_sync<NT>();
     const u32 E = (m + NT - 1) / NT;                     // positions per thread for this group (<= TIE_E)
@@ -397,6 +397,7 @@ __device__ __noinline__ void tie_refine_e(TieSort<CAP> &S, u64 *sm_v, u32 *sm_f,
         u32 cls[TIE_E];
         u64 run = 0;
         bool started = false;                            // a range starts inside my block
+        int differs = 0;
 #pragma unroll
         for (u32 e = 0; e < TIE_E; e++) {
             const u32 p = p0 + e;
@@ -407,9 +408,18 @@ __device__ __noinline__ void tie_refine_e(TieSort<CAP> &S, u64 *sm_v, u32 *sm_f,
                 const bool act = (u32)(S.hi[cur][p] - l) > 1;
                 const u64 k = S.key[p], hk = S.key[l];
                 cls[e] = !act ? 1u : (k < hk ? 0u : (k == hk ? 1u : 2u));
+                differs |= cls[e] != 1u ? 1 : 0;
                 run += 1ull << (16 * cls[e]);
                 incl[e] = run;
             }
+        }
+        if (!tie_any<NT>(differs)) {                     // a chunk every range shares: nothing moves
+#pragma unroll
+            for (u32 e = 0; e < TIE_E; e++) {
+                const u32 p = p0 + e;
+                if (e < E && p < m && (u32)(S.hi[cur][p] - S.lo[cur][p]) > 1) S.dep[cur][p]++;
+            }
+            continue;
         }
         // run = my block behind its last range start (or all of it): what the next threads continue
         const u64 carry = tie_carry<NT>(run, started, sm_v, sm_f);
@@ -447,7 +457,7 @@ __device__ __noinline__ void tie_refine_e(TieSort<CAP> &S, u64 *sm_v, u32 *sm_f,
                 S.wn[cur ^ 1][np] = S.wn[cur][p];
                 S.lo[cur ^ 1][np] = (u16)nlo;
                 S.hi[cur ^ 1][np] = (u16)nhi;
-                S.dep[cur ^ 1][np] = (u16)nr;
+                S.dep[cur ^ 1][np] = nr;
             }
         }
         tie_sync<NT>();
