@@ -6,7 +6,7 @@
 #include <time.h>
 
 extern "C" {
-int pfp_io_read_file(const char *path, uint8_t **buf, uint64_t *n, char *err, size_t errlen);
+int pfp_io_read_file(const char *path, int gz_ok, uint8_t **buf, uint64_t *n, char *err, size_t errlen);
 int pfp_io_write_outputs(const char *path, const pfpb200_opts *opts, const pfpb200_outputs *o,
                          char *err, size_t errlen);
 }
@@ -363,7 +363,8 @@ extern "C" int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb
     double t0 = wall_sec();
     uint8_t *file = nullptr;
     uint64_t fn = 0;
-    if (pfp_io_read_file(path, &file, &fn, ctx->err, sizeof(ctx->err)) != 0) return PFPB200_E_IO;
+    if (pfp_io_read_file(path, (opts->flags & PFPB200_F_FASTA) != 0, &file, &fn, ctx->err, sizeof(ctx->err)) != 0)
+        return PFPB200_E_IO;
     const uint8_t *text = file;
     uint64_t n = fn;
     uint8_t *seq = nullptr;

@@ -8,13 +8,56 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <zlib.h>
 #include "../../include/pfpb200.h"
 
-int pfp_io_read_file(const char *path, uint8_t **buf, uint64_t *n, char *err, size_t errlen) {
+/* gzip-compressed input, as the reference's kseq reader takes it through gzopen()/gzread()
+ * (newscan.cpp:332-336): inflate the whole file into memory */
+static int read_gz(const char *path, uint8_t **buf, uint64_t *n, char *err, size_t errlen) {
+    gzFile g = gzopen(path, "rb");
+    if (!g) { snprintf(err, errlen, "%s: %s", path, strerror(errno)); return -1; }
+    gzbuffer(g, 1u << 20);
+    uint64_t cap = (uint64_t)1 << 24, got = 0;
+    uint8_t *b = (uint8_t *)malloc(cap);
+    if (!b) { snprintf(err, errlen, "%s: out of memory", path); gzclose(g); return -1; }
+    for (;;) {
+        if (got == cap) {
+            uint8_t *nb = (uint8_t *)realloc(b, cap * 2);
+            if (!nb) { snprintf(err, errlen, "%s: out of memory inflating", path); free(b); gzclose(g); return -1; }
+            b = nb;
+            cap *= 2;
+        }
+        uint64_t want = cap - got;
+        if (want > ((uint64_t)1 << 30)) want = (uint64_t)1 << 30;
+        int r = gzread(g, b + got, (unsigned)want);
+        if (r < 0) {
+            int ec = 0;
+            snprintf(err, errlen, "%s: %s", path, gzerror(g, &ec));
+            free(b);
+            gzclose(g);
+            return -1;
+        }
+        if (r == 0) break;
+        got += (uint64_t)r;
+    }
+    gzclose(g);
+    *buf = b;
+    *n = got;
+    return 0;
+}
+
+/* gz_ok: a file starting with the gzip magic is inflated (FASTA mode; the reference reads plain
+ * text through ifstream, newscan.cpp:354-358, so a .gz given without -f is parsed as bytes) */
+int pfp_io_read_file(const char *path, int gz_ok, uint8_t **buf, uint64_t *n, char *err, size_t errlen) {
     *buf = NULL;
     *n = 0;
     FILE *f = fopen(path, "rb");
     if (!f) { snprintf(err, errlen, "%s: %s", path, strerror(errno)); return -1; }
+    if (gz_ok) {
+        int c0 = fgetc(f), c1 = fgetc(f);
+        if (c0 == 0x1f && c1 == 0x8b) { fclose(f); return read_gz(path, buf, n, err, errlen); }
+        rewind(f);
+    }
     struct stat st;
     if (fstat(fileno(f), &st) != 0) { snprintf(err, errlen, "%s: %s", path, strerror(errno)); fclose(f); return -1; }
     uint64_t size = (uint64_t)st.st_size;
@@ -166,3 +209,27 @@ int pfp_io_write_outputs(const char *path, const pfpb200_opts *opts, const pfpb2
     }
     return 0;
 }
+
+/* The text T the parser sees for `path` (host memory): file bytes, or -- with PFPB200_F_FASTA --
+ * the kseq-equivalent extraction of a plain or gzip-compressed FASTA/FASTQ file.  No GPU needed. */
+int pfpb200_read_input(const char *path, uint32_t flags, uint8_t **text, uint64_t *n_text, int *truncated) {
+    char err[256];
+    if (!path || !text || !n_text) return PFPB200_E_ARG;
+    *text = NULL;
+    *n_text = 0;
+    if (truncated) *truncated = 0;
+    uint8_t *file = NULL;
+    uint64_t fn = 0;
+    if (pfp_io_read_file(path, (flags & PFPB200_F_FASTA) != 0, &file, &fn, err, sizeof(err)) != 0) return PFPB200_E_IO;
+    if (!(flags & PFPB200_F_FASTA)) { *text = file; *n_text = fn; return PFPB200_OK; }
+    uint8_t *seq = (uint8_t *)malloc(fn ? fn : 1);
+    if (!seq) { free(file); return PFPB200_E_NOMEM; }
+    int tr = 0;
+    *n_text = pfpb200_fasta_extract(file, fn, seq, &tr);
+    if (truncated) *truncated = tr;
+    free(file);
+    *text = seq;
+    return PFPB200_OK;
+}
+
+void pfpb200_free_host(void *p) { free(p); }

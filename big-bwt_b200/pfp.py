@@ -75,7 +75,8 @@ class PfpFiles:
 _lib = None
 
 SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_parse_device",
-           "pfpb200_parse_host", "pfpb200_parse_file", "pfpb200_fasta_extract",
+           "pfpb200_parse_host", "pfpb200_parse_file", "pfpb200_fasta_extract", "pfpb200_read_input",
+           "pfpb200_free_host",
            "pfpb200_scan_triggers", "pfpb200_memcpy_d2h", "pfpb200_strerror",
            "pfpb200_shard_scan", "pfpb200_shard_words", "pfpb200_dict_merge", "pfpb200_shard_remap",
            "pfpb200_shard_first_keys", "pfpb200_shard_route", "pfpb200_shard_route_plan",
@@ -130,6 +131,24 @@ def fasta_extract(file_bytes) -> tuple[bytes, bool]:
     tr = C.c_int(0)
     n = L.pfpb200_fasta_extract(a.ctypes.data if a.size else None, a.size, out.ctypes.data, C.byref(tr))
     return out[:n].tobytes(), bool(tr.value)
+
+
+def read_input(path, fasta=False) -> tuple[bytes, bool]:
+    """The text the parser sees for `path` (plain, FASTA/FASTQ, gzip-compressed FASTA); no GPU."""
+    L = load_library()
+    L.pfpb200_read_input.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_int)]
+    L.pfpb200_read_input.restype = C.c_int
+    L.pfpb200_free_host.argtypes = [C.c_void_p]
+    L.pfpb200_free_host.restype = None
+    ptr, n, tr = C.c_void_p(), C.c_uint64(), C.c_int()
+    rc = L.pfpb200_read_input(os.fsencode(path), F_FASTA if fasta else 0, C.byref(ptr), C.byref(n), C.byref(tr))
+    if rc != 0:
+        raise PfpError(rc, f"cannot read {path}")
+    try:
+        return C.string_at(ptr, n.value), bool(tr.value)
+    finally:
+        L.pfpb200_free_host(ptr)
 
 
 def _flags(sai, fasta, compress, verbose=False):

@@ -117,6 +117,13 @@ int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *o
  * *truncated when an invalid byte ended the input. */
 uint64_t pfpb200_fasta_extract(const uint8_t *file, uint64_t n, uint8_t *out, int *truncated);
 
+/* The text T that pfpb200_parse_file() parses for `path`, in host memory (release it with
+ * pfpb200_free_host): the file bytes, or with PFPB200_F_FASTA the extraction above of a plain or
+ * gzip-compressed FASTA/FASTQ file (the reference reads -f input through zlib's gzread,
+ * newscan.cpp:332-336, kseq.h).  Host only, no GPU needed. */
+int pfpb200_read_input(const char *path, uint32_t flags, uint8_t **text, uint64_t *n_text, int *truncated);
+void pfpb200_free_host(void *p);
+
 /* ---- stage-level entry points (device pointers) ------------------------------------------ *
  * The scan stage alone: KR_window::addchar + `hash % p == 0` over a shard of the text
  * (newscan.cpp:194-202,344,367; sharding as pscan.hpp:44-108).  d_buf holds n_buf text bytes

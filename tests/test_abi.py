@@ -65,3 +65,47 @@ def test_host_fasta_reader_matches_oracle(pkg, name):
     want, want_tr = orc.fasta_extract(c["input"])
     got, got_tr = pkg.pfp.fasta_extract(c["input"])
     assert got == want and got_tr == want_tr
+
+
+def test_read_input_plain_fasta_and_gzip(pkg, tmp_path):
+    """pfpb200_read_input: the text the parser sees for a file -- bytes as they are, the kseq
+    extraction of a FASTA file, and the same through gzip (the reference reads -f input with
+    gzread, newscan.cpp:332-336).  Host only."""
+    import gzip
+    recs = [r.numpy() for r in pkg.synth.pangenome_records(5_000, 3, 17)]
+    fa = pkg.synth.to_fasta(recs, width=60)
+    want, _ = orc.fasta_extract(fa)
+    plain, gz = tmp_path / "x.fa", tmp_path / "x.fa.gz"
+    plain.write_bytes(fa)
+    with gzip.open(gz, "wb") as f:
+        f.write(fa)
+    assert pkg.pfp.read_input(str(plain), fasta=True) == (want, False)
+    assert pkg.pfp.read_input(str(gz), fasta=True) == (want, False)
+    assert pkg.pfp.read_input(str(plain), fasta=False) == (fa, False)
+    assert pkg.pfp.read_input(str(gz), fasta=False)[0] == gz.read_bytes()      # no -f: bytes, as ifstream reads them
+    with pytest.raises(pkg.pfp.PfpError):
+        pkg.pfp.read_input(str(tmp_path / "missing.fa"), fasta=True)
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+def test_gzip_fasta_text_equals_what_the_reference_parses(pkg, tmp_path):
+    """newscanNT.x -f on x.fa.gz and on x.fa write identical files, i.e. the reference's text for
+    the gzip file is the extraction read_input returns."""
+    import gzip
+    import subprocess
+    recs = [r.numpy() for r in pkg.synth.pangenome_records(20_000, 4, 19)]
+    fa = pkg.synth.to_fasta(recs)
+    a, b = tmp_path / "a.fa", tmp_path / "b.fa.gz"
+    a.write_bytes(fa)
+    with gzip.open(b, "wb") as f:
+        f.write(fa)
+    for pth in (a, b):
+        subprocess.run([orc.ref_exe("newscanNT.x"), str(pth), "-w", "10", "-p", "100", "-s", "-f"], check=True,
+                       stdout=subprocess.PIPE)
+    fa_files, gz_files = orc.collect_files(str(a)), orc.collect_files(str(b))
+    for ext in ("dict", "occ", "parse", "last", "sai"):
+        assert getattr(fa_files, ext) == getattr(gz_files, ext), ext
+    text, _ = pkg.pfp.read_input(str(b), fasta=True)
+    want = orc.parse(text, 10, 100)
+    for ext in ("dict", "occ", "parse", "last", "sai"):
+        assert getattr(gz_files, ext) == getattr(want, ext), ext

@@ -242,5 +242,16 @@ def test_cli_files_and_bwt_match_reference(pkg):
         subprocess.run([pkg.pfp.CLI_PATH, seg, "-w", "10", "-p", "100", "-s", "-f", "-t", "3"], check=True,
                        stdout=subprocess.PIPE)
         assert_same_files(orc.collect_files(seg, nseg=3), orc.collect_files(ref), "cli -t 3")
+        # gzip-compressed FASTA, as the reference's kseq/gzread takes it
+        import gzip
+        for base in ("ours", "ref"):
+            with gzip.open(os.path.join(tmp, base + ".gz"), "wb") as f:
+                f.write(fa)
+        subprocess.run([pkg.pfp.CLI_PATH, os.path.join(tmp, "ours.gz"), "-w", "10", "-p", "100", "-s", "-f"],
+                       check=True, stdout=subprocess.PIPE)
+        subprocess.run([orc.ref_exe("newscanNT.x"), os.path.join(tmp, "ref.gz"), "-w", "10", "-p", "100", "-s", "-f"],
+                       check=True, stdout=subprocess.PIPE)
+        assert_same_files(orc.collect_files(os.path.join(tmp, "ours.gz")), orc.collect_files(os.path.join(tmp, "ref.gz")),
+                          "cli gzip")
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
