@@ -1,17 +1,19 @@
-// pfp_phrase.cu -- K2 phrase records + fingerprints, K3 dictionary build, phrase pool.
+// pfp_phrase.cu -- K2 in its per-phrase form, K3 dictionary table, phrase pool, dictionary merge.
 //
 // K2 replaces save_update_word() (newscan.cpp:245-304): from consecutive trigger positions it
 // derives every phrase (start, length), its `.last` byte (:296) and `.sai` value (:299-301), and
-// a 128-bit fingerprint standing in for kr_hash() (:229-239).  The reference's 64-bit hash only
-// ever reaches the private .parse_old file, so its VALUE is not part of the contract; what
-// matters is that equal phrases get equal ids and different phrases different ones.  We use two
-// NH sums (UMAC's universal family: sum of (x_2i + k_2i)(x_2i+1 + k_2i+1) mod 2^64 over 32-bit
-// words, Toeplitz-shifted keys) folded over 8 KB segments, plus the length; any disagreement
-// inside a run of equal sort keys is reported as a collision, as the reference does (:282-286).
+// a fingerprint standing in for kr_hash() (:229-239).  The reference's 64-bit hash only ever
+// reaches the private .parse_old file, so its VALUE is not part of the contract; what matters is
+// that equal phrases get equal ids and different phrases different ones.  The fingerprint is
+// two NH sums (UMAC's universal family: sum of (x_2i + k_2i)(x_2i+1 + k_2i+1) mod 2^64 over
+// 32-bit words, Toeplitz-shifted keys), segments of 8 KB weighted by powers of an odd constant,
+// plus the length (pfp_fp.cuh).  The streaming form of K2 (pfp_stream.cu) is what normally runs;
+// the kernels here take over for w > 32, for tiles denser than it handles, and for the listed
+// phrases (borders, very long ones).
 //
-// K3 replaces the std::map<uint64_t,word_stats> updates (:256-288): radix sort of
-// (key, phrase index), run heads = distinct words, run lengths = occurrences, first index of
-// the run = representative occurrence.
+// K3 replaces the std::map<uint64_t,word_stats> updates (:256-288) with an open-addressing table
+// in HBM whose creators hand out the word ids (see table_insert_k); a collision of the 64-bit
+// key is detected through an independent check digest, as the reference detects its own (:282-286).
 #include "pfp_common.cuh"
 #include "pfp_stages.cuh"
 #include "pfp_fp.cuh"
@@ -300,11 +302,6 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
             store_rec(ph.rec, j, fa, fb, (u32)len);
         }
     }
-}
-
-__global__ void iota_u32_k(u32 *v, u64 n) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = (u32)i;
 }
 
 // ---- K3: dictionary table ----------------------------------------------------------------------------

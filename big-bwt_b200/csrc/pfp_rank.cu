@@ -3,11 +3,14 @@
 // Replaces std::sort with pstringCompare (newscan.cpp:387-390,636), writeDictOcc (:394-441)
 // and remapParse (:443-466).  Order = unsigned-byte lexicographic, as std::string compares.
 //
-// The distinct words sit in a pool, each zero-padded to 8-byte words.  Ranking is an MSD
-// refinement on 8-byte big-endian chunks: round r sorts the still-tied words by
-// (tie-group, chunk r) with the LSD radix sort (chunk bits first, then the group id, stable),
-// writes them back into their group's slots and splits groups where the chunk changes.  A
-// word's padding is 0x00, below every text byte (> 0x02), so shorter-is-smaller falls out.
+// The distinct words sit in a pool, each zero-padded to 8-byte words.  Ranking: one global LSD
+// radix sort on an alphabet-compacted first key (21 symbols for DNA), then MSD refinement of the
+// tie groups on 8-byte big-endian chunks -- inside a warp for groups of up to 32 words
+// (rank_window_k / rank_warp_k), in shared memory up to 2048 (rank_mid_k / rank_cta_k:
+// multikey-quicksort passes, one segmented scan per pass), and by further global radix-sort
+// rounds on (tie group, chunk) only for larger groups.  A word's padding is 0x00, below every
+// text byte (> 0x02), so shorter-is-smaller falls out.  Also here: routing of a shard's words to
+// the owners of their lexicographic range (multi-GPU).
 #include "pfp_common.cuh"
 #include "pfp_stages.cuh"
 
