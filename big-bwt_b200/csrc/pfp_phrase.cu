@@ -358,7 +358,7 @@ constexpr int TI_ITEMS = 2;      // phrases per thread: their first probes are i
 
 // weight == nullptr: every record counts once (phrases); else record i counts weight[i] times
 // (words of several shards being merged, newscan.cpp:277-281)
-__global__ void __launch_bounds__(256) table_insert_k(const PhraseFp *__restrict__ rec, u64 P,
+__global__ void __launch_bounds__(256, 8) table_insert_k(const PhraseFp *__restrict__ rec, u64 P,
                                                       DictSlot *__restrict__ tab, u64 cap,
                                                       const u32 *__restrict__ weight,
                                                       u32 *__restrict__ uid, u32 *__restrict__ rep,
