@@ -120,6 +120,9 @@ extern "C" void pfpb200_destroy(pfpb200_ctx *ctx) {
     if (ctx->dna_table) cudaFree(ctx->dna_table);
     for (int i = 0; i < 5; i++)
         if (ctx->pin_buf[i]) cudaFreeHost(ctx->pin_buf[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_k2) cudaEventDestroy(ctx->ev_k2);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     delete ctx;
 }
 
@@ -166,6 +169,23 @@ struct StageTimer {
     void destroy() { for (int i = 0; i < 10; i++) cudaEventDestroy(ev[i]); }
 };
 
+// pinned host buffer `slot` of the context, grown on demand
+static int pfp_pin(pfpb200_ctx *ctx, int slot, void **h, size_t bytes) {
+    if (bytes > ctx->pin_cap[slot]) {
+        if (ctx->pin_buf[slot]) cudaFreeHost(ctx->pin_buf[slot]);
+        ctx->pin_buf[slot] = nullptr;
+        ctx->pin_cap[slot] = 0;
+        size_t cap = bytes + bytes / 8 + 4096;
+        if (cudaMallocHost(&ctx->pin_buf[slot], cap) != cudaSuccess) {
+            cudaGetLastError();
+            return pfp_fail(ctx, PFPB200_E_NOMEM, "pinned host allocation of %zu bytes failed", cap);
+        }
+        ctx->pin_cap[slot] = cap;
+    }
+    *h = ctx->pin_buf[slot];
+    return PFPB200_OK;
+}
+
 // text resident on the device -> all outputs on the device
 static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pfpb200_opts *o,
                              pfpb200_outputs *out, pfpb200_stats *st) {
@@ -204,6 +224,23 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
         }
         PFP_TRY(pfp_scan_bits_free(ctx, &sb));
         tm.mark(ctx->stream);                                           // 2
+        if (ctx->early_copy) {          // .last/.sai are final: to the host while K3/K4 run
+            void *h_last = nullptr, *h_sai = nullptr;
+            PFP_TRY(pfp_pin(ctx, 3, &h_last, P));
+            if (ph.sai) PFP_TRY(pfp_pin(ctx, 4, &h_sai, P * PFP_IBYTES));
+            if (!ctx->copy_stream) {
+                PFP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+                PFP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_k2, cudaEventDisableTiming));
+                PFP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+            }
+            PFP_CUDA(ctx, cudaEventRecord(ctx->ev_k2, ctx->stream));
+            PFP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k2, 0));
+            PFP_CUDA(ctx, cudaMemcpyAsync(h_last, ph.last, P, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (ph.sai)
+                PFP_CUDA(ctx, cudaMemcpyAsync(h_sai, ph.sai, P * PFP_IBYTES, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            PFP_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+            ctx->early_done = true;
+        }
         // K3
         DictArrays D;
         PFP_TRY(pfp_dedup_stage(ctx, ph, P, &D));
@@ -307,38 +344,33 @@ extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_
         fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
     pfpb200_outputs dv;
     memset(&dv, 0, sizeof(dv));
+    ctx->early_copy = true;
+    ctx->early_done = false;
     int rc = parse_device_impl(ctx, d_text, n, opts, &dv, stats);
-    if (rc != PFPB200_OK) return rc;
+    ctx->early_copy = false;
+    if (rc != PFPB200_OK) {
+        if (ctx->early_done) cudaEventSynchronize(ctx->ev_copy);
+        return rc;
+    }
     // device -> pinned host
     const u64 P = dv.n_phrases, d = dv.n_distinct;
     void *h_dict = nullptr, *h_occ = nullptr, *h_parse = nullptr, *h_last = nullptr, *h_sai = nullptr;
-    auto pin = [&](int slot, void **h, size_t bytes) -> int {
-        if (bytes > ctx->pin_cap[slot]) {
-            if (ctx->pin_buf[slot]) cudaFreeHost(ctx->pin_buf[slot]);
-            ctx->pin_buf[slot] = nullptr;
-            ctx->pin_cap[slot] = 0;
-            size_t cap = bytes + bytes / 8 + 4096;
-            if (cudaMallocHost(&ctx->pin_buf[slot], cap) != cudaSuccess) {
-                cudaGetLastError();
-                return pfp_fail(ctx, PFPB200_E_NOMEM, "pinned host allocation of %zu bytes failed", cap);
-            }
-            ctx->pin_cap[slot] = cap;
-        }
-        *h = ctx->pin_buf[slot];
-        return PFPB200_OK;
-    };
-    PFP_TRY(pin(0, &h_dict, dv.dict_bytes));
-    PFP_TRY(pin(1, &h_occ, d * 4));
-    PFP_TRY(pin(2, &h_parse, P * 4));
-    PFP_TRY(pin(3, &h_last, P));
-    if (dv.sai) PFP_TRY(pin(4, &h_sai, P * PFP_IBYTES));
+    PFP_TRY(pfp_pin(ctx, 0, &h_dict, dv.dict_bytes));
+    PFP_TRY(pfp_pin(ctx, 1, &h_occ, d * 4));
+    PFP_TRY(pfp_pin(ctx, 2, &h_parse, P * 4));
+    PFP_TRY(pfp_pin(ctx, 3, &h_last, P));
+    if (dv.sai) PFP_TRY(pfp_pin(ctx, 4, &h_sai, P * PFP_IBYTES));
     cudaEventRecord(e2, ctx->stream);
     PFP_CUDA(ctx, cudaMemcpyAsync(h_dict, dv.dict, dv.dict_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PFP_CUDA(ctx, cudaMemcpyAsync(h_occ, dv.occ, d * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PFP_CUDA(ctx, cudaMemcpyAsync(h_parse, dv.parse, P * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PFP_CUDA(ctx, cudaMemcpyAsync(h_last, dv.last, P, cudaMemcpyDeviceToHost, ctx->stream));
-    if (dv.sai)
-        PFP_CUDA(ctx, cudaMemcpyAsync(h_sai, dv.sai, P * PFP_IBYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->early_done) {              // .last/.sai left on the copy stream right after K2
+        PFP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    } else {
+        PFP_CUDA(ctx, cudaMemcpyAsync(h_last, dv.last, P, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dv.sai)
+            PFP_CUDA(ctx, cudaMemcpyAsync(h_sai, dv.sai, P * PFP_IBYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     cudaEventRecord(e3, ctx->stream);
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (stats) {

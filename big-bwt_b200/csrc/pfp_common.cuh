@@ -61,6 +61,12 @@ struct pfpb200_ctx {
     std::vector<void *> held;      // outputs: freed at the start of the next call / destroy
     void *pin_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // host outputs of parse_host,
     size_t pin_cap[5] = {0, 0, 0, 0, 0};                                 // kept and grown across calls
+    // parse_host: .last/.sai are final after K2 and travel to the host on a second stream while
+    // the dictionary stages run
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_k2 = nullptr, ev_copy = nullptr;
+    bool early_copy = false;       // set by parse_host for the duration of the call
+    bool early_done = false;       // the copies were issued (ev_copy marks their end)
     // persistent small device state
     u32 *d_keys = nullptr;         // NH key table (phrase fingerprints)
     u64 *d_flags = nullptr;        // [0] error bits, [1..] counters read back by the host
