@@ -136,6 +136,16 @@ static inline int pfp_alloc_t(pfpb200_ctx *ctx, T **p, size_t count, bool held =
     return pfp_alloc(ctx, (void **)p, (count ? count : 1) * sizeof(T), held);
 }
 
+// Function attributes (dynamic shared memory limits) and constant memory are per DEVICE: a process
+// that opens contexts on several GPUs has to set them once on each.  True the first time it is
+// called for (mask, device).
+static inline bool pfp_first_on_device(unsigned long long &mask, int device) {
+    const unsigned long long b = 1ull << (device & 63);
+    if (mask & b) return false;
+    mask |= b;
+    return true;
+}
+
 static inline u32 pfp_blocks(u64 n, u32 per_block) { return (u32)((n + per_block - 1) / per_block); }
 
 // ---- primitives (pfp_prims.cu) -----------------------------------------------------------

@@ -554,11 +554,10 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     u64 maxb = (u64)ctx->sm_count * 32;
     u32 nb = (u32)(want < maxb ? want : maxb);
     if (nb == 0) nb = 1;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pfp_first_on_device(attr, ctx->device)) {
         PFP_CUDA(ctx, cudaFuncSetAttribute(phrase_hash_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            PH_WARPS * PH_WIN));
-        attr = true;
     }
     static int use_window = -1;
     if (use_window < 0) {

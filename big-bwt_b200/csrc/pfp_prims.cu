@@ -373,11 +373,10 @@ int pfp_radix_sort_pairs(pfpb200_ctx *ctx, u64 *k0, u32 *v0, u64 *k1, u32 *v1, u
     *res_v = v0;
     if (n <= 1 || end_bit <= begin_bit) return PFPB200_OK;
     if (n >= 0xFFFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "radix sort: too many items");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (pfp_first_on_device(attr_set, ctx->device)) {
         PFP_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(RsSmem)));
-        attr_set = true;
     }
     u32 nb = pfp_blocks(n, RS_TILE);
     u32 *hist = nullptr;

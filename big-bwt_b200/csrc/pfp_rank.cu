@@ -627,13 +627,12 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
     }
     // finish every remaining tie group on chip
     if (d >= 2) {
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (pfp_first_on_device(attr, ctx->device)) {
             PFP_CUDA(ctx, cudaFuncSetAttribute(rank_cta_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)sizeof(TieSort<LOCAL_MAX>)));
             PFP_CUDA(ctx, cudaFuncSetAttribute(rank_mid_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)(8 * sizeof(TieSort<MID_MAX>))));
-            attr = true;
         }
         u32 *mid_list = v1, *big_list = v0;      // sort buffers are free again
         u32 *counts = reinterpret_cast<u32 *>(&ctx->d_flags[5]);

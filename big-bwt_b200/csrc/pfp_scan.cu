@@ -368,10 +368,9 @@ __global__ void __launch_bounds__(256) tile_max_k(const u32 *__restrict__ tile_c
 template <int W>
 static void launch_scan(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
                         const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pfp_first_on_device(attr, ctx->device)) {
         cudaFuncSetAttribute(kr_scan_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
-        attr = true;
     }
     kr_scan_k<W><<<ntiles, K1_T, K1_SMEM, ctx->stream>>>(A, q_end, q_lo, q_hi, C, mask, tile_cnt);
 }
@@ -382,11 +381,10 @@ template <int W>
 static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
                                    const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
     const size_t smem = (((size_t)1 << (2 * W)) + 31) / 32 * 4;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pfp_first_on_device(attr, ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(kr_scan_dna_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     const u64 nwords = (u64)ntiles * (K1_TILE / 32);      // every word of every tile gets written
     static int mix = -1;
@@ -403,14 +401,13 @@ static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A,
 
 // the 4^w-bit trigger table of (w, p), cached in the context
 static int ensure_dna_table(pfpb200_ctx *ctx, const pfp_scan_consts &C) {
-    static int pow_dev = -1;                 // constant memory is per device
-    if (pow_dev != ctx->device) {
+    static unsigned long long pow_dev = 0;   // constant memory is per device
+    if (pfp_first_on_device(pow_dev, ctx->device)) {
         u32 h[33];
         for (int i = 0; i < 32; i++) h[i] = 1u << i;
         h[32] = 0;
         PFP_CUDA(ctx, cudaMemcpyToSymbolAsync(kd_pow2, h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        pow_dev = ctx->device;
     }
     if (ctx->dna_table && ctx->dna_w == C.w && ctx->dna_p == C.p) return PFPB200_OK;
     if (!ctx->dna_table) PFP_CUDA(ctx, cudaMalloc(&ctx->dna_table, ((size_t)1 << (2 * KD_MAXW)) / 8));

@@ -318,10 +318,9 @@ int pfp_stream_stage(pfpb200_ctx *ctx, const ScanBits &sb, const TextView &tv, c
         a.keytab = ctx->d_keys; a.flags = ctx->d_flags;
         a.long_list = list; a.long_count = count;
         a.n_regular = sb.total;
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (pfp_first_on_device(attr, ctx->device)) {
             PFP_CUDA(ctx, cudaFuncSetAttribute(phrase_stream_k, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
-            attr = true;
         }
         phrase_stream_k<<<sb.ntiles, K2_T, K2_SMEM, ctx->stream>>>(a);
         PFP_LAUNCHED(ctx);
