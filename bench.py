@@ -40,17 +40,33 @@ def parse_args():
     ap.add_argument("--workload", default="pangenome", choices=["pangenome", "random"])
     ap.add_argument("--cpu-haplotypes", type=int, default=4, help="prefix timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-full", action="store_true",
+                    help="reference arm: skip the single run on the whole workload (N=1 only, about a minute)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the byte-exact output check after the timed region")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--merge", default="partition", choices=["partition", "replicate"],
                     help="multi-GPU dictionary merge: range-partitioned all-to-all or replicated all-gather")
     return ap.parse_args()
 
 
-def workload_name(a):
+def workload_name(a, world=None):
+    world = world or a.gpus
     if a.workload == "random":
-        return f"uniform random ACGT, {a.base_len * a.haplotypes / 1e9:.2f} GB, w={W} p={P}"
-    return (f"{a.haplotypes} haplotypes x {a.base_len / 1e6:g} Mbp, 0.1% SNP/indel "
-            f"({a.base_len * a.haplotypes / 1e9:.2f} GB text), w={W} p={P}, -s")
+        return f"uniform random ACGT, {a.base_len * a.haplotypes * world / 1e9:.2f} GB, w={W} p={P}, -s"
+    return (f"{a.haplotypes * world} haplotypes x {a.base_len / 1e6:g} Mbp, 0.1% SNP/indel "
+            f"({a.base_len * a.haplotypes * world / 1e9:.2f} GB text), w={W} p={P}, -s")
+
+
+def workload_config(a, world=None):
+    """`config` of the JSON line: the same dict from both arms (the reference arm measures the
+    same workload; how much of it one of its steps covers is in its cpu_baseline.sample)."""
+    world = world or a.gpus
+    per_gpu = a.base_len * a.haplotypes
+    return {"workload": workload_name(a, world),
+            "l2": "inputs larger than L2 (no flush needed)" if per_gpu > 256e6 else "input smaller than L2",
+            "parallelism": f"{world} shard(s) of {per_gpu / 1e9:.2f} GB, one process per GPU" +
+                           (f", {a.merge} dictionary merge" if world > 1 else "")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -154,15 +170,48 @@ def run_reference_scanner(text_np, threads, tmpdir, reps):
     return secs, "port", "oracle/pfp_oracle.c (single thread)", 1
 
 
+def run_newscan_fasta(text_np, threads, tmpdir):
+    """`newscan.x <fasta> -f -t T` -- the command `bigbwt -f -t T` issues and BASELINE.json names --
+    once, on the sample wrapped as one 60-column FASTA record.  Its threads are serialised by a
+    global mutex and a serial prescan, which is why pscan is the headline baseline."""
+    from oracle import pfp_oracle as orc
+    from __graft_entry__ import load_package
+    exe = next((orc.ref_exe(c) for c in ("newscan_fast.x", "newscan.x") if orc.have_ref(c)), None)
+    if exe is None:
+        return None
+    path = os.path.join(tmpdir, "sample.fa")
+    load_package().synth.to_fasta_np(text_np, "sample").tofile(path)
+    cmd = [exe, path, "-w", str(W), "-p", str(P), "-s", "-f", "-t", str(threads)]
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        return {"cmd": f"{os.path.basename(exe)} -f -t {threads}", "failed": r.returncode}
+    return {"cmd": f"{os.path.basename(exe)} -f -t {threads}", "value": text_np.size / dt / 1e9, "unit": UNIT,
+            "seconds": dt, "text_bytes": int(text_np.size)}
+
+
 def reference_arm(a, synth):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
     threads = os.cpu_count() or 1
     text, sample = cpu_sample_text(a, synth)
     tmp = tempfile.mkdtemp(prefix="pfpbench_")
+    full = newscan = None
     try:
         secs, kind, how, cores = run_reference_scanner(text, threads, tmp, a.warmup + a.steps)
+        if kind == "reference":
+            newscan = run_newscan_fasta(text, threads, tmp)
+        # one run on the WHOLE workload (the same 4 GB the GPU arm parses) when it is one GPU's
+        if kind == "reference" and a.gpus == 1 and not a.no_ref_full and a.workload == "pangenome":
+            dev = "cuda" if torch.cuda.is_available() else "cpu"
+            whole = synth.pangenome_text(a.base_len, a.haplotypes, SEED, device=dev).cpu().numpy()
+            fs, _, fhow, _ = run_reference_scanner(whole, threads, tmp, 1)
+            full = {"value": whole.size / fs[0] / 1e9, "unit": UNIT, "seconds": fs[0],
+                    "text_bytes": int(whole.size), "cmd": fhow, "steps": 1}
+            del whole
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     timed = secs[a.warmup:]
@@ -173,10 +222,12 @@ def reference_arm(a, synth):
         "warmup": a.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": workload_name(a), "sample": sample, "timing": "wall clock of the scanner process"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{how}; {sample}"},
+        "config": workload_config(a),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{how}; every step = {sample}; wall clock of the scanner process"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "whole_workload_once": full, "newscan_fasta_once": newscan,
     }
     print(json.dumps(line))
 
@@ -206,6 +257,63 @@ def load_traffic(n_text):
         return per_byte * n_text
     except Exception:
         return None
+
+
+# ------------------------------------------------------------------------------------------------
+# byte-exact check of the code path that was just timed (outside the timed region)
+# ------------------------------------------------------------------------------------------------
+PARITY_BASE, PARITY_HAP, PARITY_NRUN = 4_000_000, 100, 3 << 20
+
+
+def parity_text_and_cuts(synth, world, dev):
+    """400 MB pan-genome (100 haplotypes x 4 Mbp, own seed) with a 3 MB run of N, cut into `world`
+    uneven shards.  With 3 or more shards, shard 1 is 1 MB long and lies INSIDE the run: it owns no
+    phrase at all, and the phrase straddling into shard 2 crosses two seams and starts 2 MB before
+    it -- more than the megabyte a rank reserves in front of its shard."""
+    import torch
+    t = synth.pangenome_text(PARITY_BASE, PARITY_HAP, SEED + 7, device=dev)
+    n = t.numel()
+    cuts = [0] + [n * k // world + 1237 * k for k in range(1, world)] + [n]
+    if world >= 3:
+        cuts[2] = cuts[1] + (1 << 20)
+    c1 = cuts[1] if world > 1 else n // 2
+    t[c1 - (1 << 20): c1 - (1 << 20) + PARITY_NRUN] = ord("N")
+    return t, cuts
+
+
+def parity_check(job, pkg, synth, world, rank, local, dev, merge):
+    """Parse the parity text through the SAME ShardedParser object (same merge mode, same peer
+    exchange) that was timed and compare all five streams byte for byte: at N > 1 with a 1-GPU
+    pfpb200_parse_device of the whole text on rank 0, at N = 1 with the CPU oracle (the checker,
+    pinned to the reference's newscanNT.x by tests/test_oracle_golden.py)."""
+    import hashlib
+    import torch
+    text, cuts = parity_text_and_cuts(synth, world, dev)
+    job.set_text(text[cuts[rank]:cuts[rank + 1]].clone() if world > 1 else text)
+    job.parse_device(W, P, sai=True)
+    if world > 1:
+        got = job.gather_files()
+    else:
+        f = job.scanner.fetch(job.out)
+        got = {k: getattr(f, k) for k in ("dict", "occ", "parse", "last", "sai")}
+    if rank != 0:
+        return None
+    if world > 1:
+        sc = pkg.pfp.Scanner(local)
+        f = sc.fetch(sc.parse_device(text, W, P, sai=True))
+        want = {k: getattr(f, k) for k in got}
+        sc.close()
+        against = "pfpb200_parse_device of the whole text on one GPU (rank 0)"
+    else:
+        from oracle import pfp_oracle as orc
+        f = orc.parse(text.cpu().numpy(), W, P)
+        want = {k: getattr(f, k) for k in got}
+        against = "oracle/pfp_oracle.c on the host (CPU restatement of newscan.cpp, the checker)"
+    bad = [k for k in got if got[k] != want[k]]
+    return {"ok": not bad, "bytes": sum(len(v) for v in got.values()), "text_bytes": int(text.numel()),
+            "shard_cuts": cuts, "n_run_bytes": PARITY_NRUN, "mismatch": bad, "against": against,
+            "phrases": len(got["parse"]) // 4, "distinct": len(got["occ"]) // 4,
+            "sha256": {k: hashlib.sha256(v).hexdigest()[:16] for k, v in got.items()}}
 
 
 def main():
@@ -289,6 +397,7 @@ def main():
 
     # ---- e2e: host buffers in, host buffers out ------------------------------------------------
     e2e = None
+    host = None
     if not a.no_e2e:
         host = torch.empty(n_local, dtype=torch.uint8, pin_memory=True)
         host.copy_(text)
@@ -297,14 +406,17 @@ def main():
         del text
         torch.cuda.empty_cache()
         h2d = d2h = 0
-        es = max(1, min(a.steps, 3))
-        for _ in range(1):
+        es = max(1, a.e2e_steps)
+        ms_h2d, ms_d2h = [], []
+        for _ in range(2):
             job.parse_host(host, W, P, sai=True)
         barrier()
         t0 = time.perf_counter()
         for _ in range(es):
             st2 = job.parse_host(host, W, P, sai=True)
             h2d, d2h = st2["h2d_bytes"], st2["d2h_bytes"]
+            ms_h2d.append(st2.get("ms_h2d", 0.0))
+            ms_d2h.append(st2.get("ms_d2h", 0.0))
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -312,8 +424,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": n_total * es / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": es, "ms_per_step": 1e3 * dt / es,
+               "d2h_bytes_per_step": d2h, "steps": es, "warmup": 2, "ms_per_step": 1e3 * dt / es,
+               "ms_h2d": sum(ms_h2d) / es, "ms_d2h": sum(ms_d2h) / es,
+               "h2d_gbs": (h2d / (sum(ms_h2d) / es) / 1e6) if sum(ms_h2d) > 0 else None,
                "how": "pfpb200_parse_host: pinned host text -> H2D -> parse -> D2H of all five outputs"}
+        job.release_text()
+        torch.cuda.empty_cache()
+
+    # ---- parity of the timed code path (outside every timed region) -------------------------------
+    parity = None
+    if not a.no_parity:
+        parity = parity_check(job, pkg, synth, world, rank, local, dev, a.merge)
 
     if rank != 0:
         if world > 1:
@@ -351,19 +472,22 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32/u64 integer", "data": "synthetic",
-        "config": {"workload": workload_name(a), "text_bytes_total": n_total, "text_bytes_per_gpu": n_local,
-                   "phrases": last_stats["n_phrases"], "distinct": last_stats["n_distinct"],
-                   "dict_bytes": last_stats["dict_bytes"], "rank_rounds": last_stats["rank_rounds"],
-                   "l2": "inputs larger than L2 (no flush needed)" if n_local > 256e6 else "input smaller than L2",
-                   "parallelism": f"{world} shard(s), one process per GPU" + (f", {a.merge} dictionary merge" if world > 1 else "")},
+        "config": workload_config(a, world),
+        "workload_stats": {"text_bytes_total": n_total, "text_bytes_per_gpu": n_local,
+                           "phrases": last_stats["n_phrases"], "distinct": last_stats["n_distinct"],
+                           "dict_bytes": last_stats["dict_bytes"], "rank_rounds": last_stats["rank_rounds"]},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         "stages_ms": stage_ms,
     }
     if per_rank:
         line["per_rank_phase_ms"] = per_rank
+    if parity is not None:
+        line["parity_check"] = parity
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(f"bench.py: parity check FAILED: {parity['mismatch']} differ")
 
 
 if __name__ == "__main__":

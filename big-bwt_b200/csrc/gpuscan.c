@@ -21,25 +21,37 @@ static void usage(const char *exe, const pfpb200_opts *o) {
     printf("\t-s  \tcompute suffix array info\n");
     printf("\t-f  \tread a FASTA/FASTQ file\n");
     printf("\t-P  \taccepted for compatibility (collisions are always detected)\n");
+    printf("\t-V  \tverify: compare every phrase with its dictionary word byte for byte\n");
     printf("\t-c  \tcompress the output dictionary\n");
     exit(1);
+}
+
+/* the reference reads -w/-p/-t with atoi into ints and rejects what is out of range
+ * (newscan.cpp:537-548): parse signed, check, then cast */
+static long int_arg(const char *s) {
+    char *end = NULL;
+    long v = strtol(s, &end, 10);
+    if (end == s) return 0;            /* atoi semantics: no digits -> 0, rejected by the range checks */
+    return v;
 }
 
 int main(int argc, char **argv) {
     pfpb200_opts o = {10, 100, 0, 0};
     int device = 0, verbose = 0, c;
+    long w = 10, p = 100, nseg = 0;
     puts("==== Command line:");
     for (int i = 0; i < argc; i++) printf(" %s", argv[i]);
     puts("");
-    while ((c = getopt(argc, argv, "p:w:fsPcht:vg:")) != -1) {
+    while ((c = getopt(argc, argv, "p:w:fsPcht:vg:V")) != -1) {
         switch (c) {
             case 's': o.flags |= PFPB200_F_SAI; break;
             case 'P': break;
             case 'c': o.flags |= PFPB200_F_COMPRESS; break;
-            case 'w': o.w = (uint32_t)atoi(optarg); break;
-            case 'p': o.p = (uint32_t)atoi(optarg); break;
+            case 'w': w = int_arg(optarg); break;
+            case 'p': p = int_arg(optarg); break;
+            case 'V': o.flags |= PFPB200_F_VERIFY; break;
             case 'f': o.flags |= PFPB200_F_FASTA; break;
-            case 't': o.nseg = atoi(optarg); break;
+            case 't': nseg = int_arg(optarg); break;
             case 'g': device = atoi(optarg); break;
             case 'v': verbose++; o.flags |= PFPB200_F_VERBOSE; break;
             case 'h': usage(argv[0], &o); break;
@@ -48,9 +60,11 @@ int main(int argc, char **argv) {
     }
     if (argc != optind + 1) { puts("Invalid number of arguments"); usage(argv[0], &o); }
     const char *path = argv[optind];
-    if (o.w < 4) { puts("Windows size must be at least 4"); exit(1); }
-    if (o.p < 10) { puts("Modulus must be at least 10"); exit(1); }
-    if (o.nseg < 0) { puts("Number of threads cannot be negative"); exit(1); }
+    if (w < 4) { puts("Windows size must be at least 4"); exit(1); }
+    if (p < 10) { puts("Modulus must be at least 10"); exit(1); }
+    if (nseg < 0) { puts("Number of threads cannot be negative"); exit(1); }
+    if (w > 65536 || p > 0x7FFFFFFFL || nseg > 4096) { puts("Option value too large"); exit(1); }
+    o.w = (uint32_t)w; o.p = (uint32_t)p; o.nseg = (int32_t)nseg;
     printf("Windows size: %u\n", o.w);
     printf("Stop word modulus: %u\n", o.p);
     time_t start = time(NULL);

@@ -80,6 +80,9 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     ctx->device = device;
     { const char *ev = getenv("PFPB200_LEGACY_K2"); ctx->legacy_k2 = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_K1"); ctx->k1_mode = (ev && strcmp(ev, "rolling") == 0) ? 1 : 0; }
+    { const char *ev = getenv("PFPB200_TEST_WEAK_FP"); ctx->weak_fp = (ev && atoi(ev) != 0) ? 1u : 0u; }
+    { const char *ev = getenv("PFPB200_K1_MIX"); ctx->k1_mix = ev ? atoi(ev) : 0; }
+    { const char *ev = getenv("PFPB200_K2_WINDOW"); ctx->k2_window = ev ? atoi(ev) : 0; }
     auto bail = [&](int code) { pfpb200_destroy(ctx); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(PFPB200_E_CUDA);
     cudaDeviceProp prop;
@@ -101,6 +104,10 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     // fail here, loudly, if the library carries no kernel image for this GPU
     set_u64_k<<<1, 1, 0, ctx->stream>>>(&ctx->d_flags[15], 1);
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return bail(PFPB200_E_CUDA);
+    // per-device kernel attributes and constants of every stage (see pfp_common.cuh)
+    if (pfp_scan_init(ctx) || pfp_stream_init(ctx) || pfp_phrase_init(ctx) || pfp_prims_init(ctx) ||
+        pfp_rank_init(ctx))
         return bail(PFPB200_E_CUDA);
     *out = ctx;
     return PFPB200_OK;
@@ -157,16 +164,19 @@ static int begin_call(pfpb200_ctx *ctx) {
 }
 
 struct StageTimer {
-    cudaEvent_t ev[10];
+    cudaEvent_t ev[10] = {nullptr};
     int n = 0;
     int init() {
         for (int i = 0; i < 10; i++)
-            if (cudaEventCreate(&ev[i]) != cudaSuccess) return -1;
+            if (cudaEventCreate(&ev[i]) != cudaSuccess) { ev[i] = nullptr; return -1; }
         return 0;
     }
     void mark(cudaStream_t s) { cudaEventRecord(ev[n++], s); }
     float ms(int a, int b) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b]); return t; }
-    void destroy() { for (int i = 0; i < 10; i++) cudaEventDestroy(ev[i]); }
+    ~StageTimer() {
+        for (int i = 0; i < 10; i++)
+            if (ev[i]) cudaEventDestroy(ev[i]);
+    }
 };
 
 // pinned host buffer `slot` of the context, grown on demand
@@ -243,9 +253,10 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
         }
         // K3
         DictArrays D;
-        PFP_TRY(pfp_dedup_stage(ctx, ph, P, &D));
+        PFP_TRY(pfp_dedup_stage(ctx, ph, P, -1, w, &D));
         PFP_TRY(pfp_free_now(ctx, ph.rec));
         PFP_TRY(pfp_pool_stage(ctx, tv, ends, -1, w, &D));
+        if (o->flags & PFPB200_F_VERIFY) PFP_TRY(pfp_verify_stage(ctx, tv, ends, -1, w, P, D));
         tm.mark(ctx->stream);                                           // 3
         // K4
         u32 *order = nullptr, rounds = 0;
@@ -262,8 +273,11 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
         PFP_TRY(pfp_alloc_t(ctx, &parse, P, true));
         PFP_TRY(pfp_remap_stage(ctx, D.uid, rank_of_uid, P, parse));
         tm.mark(ctx->stream);                                           // 6
+        PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         PFP_CUDA(ctx, cudaGetLastError());
+        if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
+            return pfp_fail(ctx, PFPB200_E_COLLISION, "two different phrases share a fingerprint (found by the verify pass)");
         out->dict = dict; out->dict_bytes = dict_bytes;
         out->occ = occ; out->n_distinct = D.d;
         out->parse = parse; out->n_phrases = P;
@@ -285,7 +299,6 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
     rc = run();
     if (rc != PFPB200_OK) cudaStreamSynchronize(ctx->stream);
     pfp_release_scratch(ctx);
-    tm.destroy();
     return rc;
 }
 
@@ -318,8 +331,9 @@ extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_
     if (stats) memset(stats, 0, sizeof(*stats));
     memset(host_out, 0, sizeof(*host_out));
     PFP_TRY(begin_call(ctx));
-    cudaEvent_t e0, e1, e2, e3;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    PfpEvents evs(4);
+    if (!evs.ok) return pfp_fail(ctx, PFPB200_E_CUDA, "cudaEventCreate failed");
+    const cudaEvent_t e0 = evs[0], e1 = evs[1], e2 = evs[2], e3 = evs[3];
     u8 *d_text = nullptr;
     PFP_TRY(pfp_alloc(ctx, (void **)&d_text, n_text, true));
     cudaEventRecord(e0, ctx->stream);
@@ -377,7 +391,6 @@ extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_
         cudaEventElapsedTime(&stats->ms_h2d, e0, e1);
         cudaEventElapsedTime(&stats->ms_d2h, e2, e3);
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     host_out->dict = (const u8 *)h_dict; host_out->dict_bytes = dv.dict_bytes;
     host_out->occ = (const u32 *)h_occ; host_out->n_distinct = d;
     host_out->parse = (const u32 *)h_parse; host_out->n_phrases = P;
@@ -449,15 +462,15 @@ extern "C" int pfpb200_scan_triggers(pfpb200_ctx *ctx, const uint8_t *d_buf, uin
 // sharded parsing (one process per GPU drives these between its collectives)
 // ------------------------------------------------------------------------------------------------
 struct CallTimer {
-    cudaEvent_t a, b;
+    PfpEvents ev;
     cudaStream_t s;
-    explicit CallTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    explicit CallTimer(cudaStream_t st) : ev(2), s(st) { if (ev.ok) cudaEventRecord(ev[0], s); }
     float stop() {
-        cudaEventRecord(b, s);
-        cudaEventSynchronize(b);
         float t = 0;
-        cudaEventElapsedTime(&t, a, b);
-        cudaEventDestroy(a); cudaEventDestroy(b);
+        if (!ev.ok) { cudaStreamSynchronize(s); return t; }
+        cudaEventRecord(ev[1], s);
+        cudaEventSynchronize(ev[1]);
+        cudaEventElapsedTime(&t, ev[0], ev[1]);
         return t;
     }
 };
@@ -550,7 +563,7 @@ extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb20
             PFP_TRY(pfp_stream_stage(ctx, ctx->sh.bits, tv, ph, P, first_start, w, !ctx->sh.ends_emitted));
         else PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, first_start, w));
         DictArrays D;
-        PFP_TRY(pfp_dedup_stage(ctx, ph, P, &D));
+        PFP_TRY(pfp_dedup_stage(ctx, ph, P, first_start, w, &D));
         u64 *wfpa = nullptr, *wfpb = nullptr;
         PFP_TRY(pfp_alloc_t(ctx, &wfpa, D.d));
         PFP_TRY(pfp_alloc_t(ctx, &wfpb, D.d));
@@ -558,8 +571,12 @@ extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb20
         PFP_TRY(pfp_free_now(ctx, ph.rec));
         PFP_TRY(pfp_pool_stage(ctx, tv, ends, first_start, w, &D));
         PFP_TRY(pfp_free_now(ctx, D.rep));
+        if (o.flags & PFPB200_F_VERIFY) PFP_TRY(pfp_verify_stage(ctx, tv, ends, first_start, w, P, D));
+        PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         PFP_CUDA(ctx, cudaGetLastError());
+        if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
+            return pfp_fail(ctx, PFPB200_E_COLLISION, "two different phrases share a fingerprint (found by the verify pass)");
         ctx->sh.d = D.d;
         ctx->sh.uid = D.uid;
         ctx->sh.wfpa = wfpa; ctx->sh.wfpb = wfpb; ctx->sh.pool = D.pool; ctx->sh.uoff = D.uoff;
@@ -600,7 +617,8 @@ extern "C" int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_
         StageTimer tm;
         const bool trace = getenv("PFPB200_TRACE") != nullptr && tm.init() == 0;
         if (trace) tm.mark(ctx->stream);
-        PFP_TRY(pfp_merge_stage(ctx, n_in, fpa, fpb, len, count, uwords, pool, pool_words, &D, &uid_of_entry));
+        PFP_TRY(pfp_merge_stage(ctx, n_in, fpa, fpb, len, count, uwords, pool, pool_words,
+                                (flags & PFPB200_F_VERIFY) != 0, &D, &uid_of_entry));
         if (trace) tm.mark(ctx->stream);
         u32 *order = nullptr, rounds = 0;
         PFP_TRY(pfp_rank_stage(ctx, D, &order, &rounds));
@@ -618,7 +636,6 @@ extern "C" int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_
         if (trace) {
             fprintf(stderr, "[pfpb200 merge] n_in %llu -> d %llu: dedup %.3f ms, rank %.3f ms (%u rounds), dict+remap %.3f ms\n",
                     (unsigned long long)n_in, (unsigned long long)D.d, tm.ms(0, 1), tm.ms(1, 2), rounds, tm.ms(2, 3));
-            tm.destroy();
         }
         out->n_distinct = D.d; out->dict_bytes = dict_bytes; out->sum_word_len = D.sum_len;
         out->dict = dict; out->occ = occ; out->rank_of_entry = rank_of_entry;

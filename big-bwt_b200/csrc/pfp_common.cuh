@@ -55,6 +55,9 @@ struct pfpb200_ctx {
     u32 *dna_table = nullptr;      // 4^w-bit trigger table of (dna_w, dna_p) for the DNA scan (w <= 10)
     u32 dna_w = 0, dna_p = 0;
     bool legacy_k2 = false;        // PFPB200_LEGACY_K2=1: per-phrase K2 kernels (A/B measurements)
+    u32 weak_fp = 0;               // PFPB200_TEST_WEAK_FP=1 (tests): 2-bit fingerprints, so that PFPB200_F_VERIFY has collisions to catch
+    int k1_mix = 0;                // PFPB200_K1_MIX: every k-th row of the table scan by arithmetic (A/B)
+    int k2_window = 0;             // PFPB200_K2_WINDOW: shared-memory text window in phrase_hash_k (A/B)
     double dedup_ratio = 0.0;      // distinct words / phrases of the previous parse (table sizing hint)
     char err[512] = {0};
     std::vector<void *> scratch;   // freed at the end of every call
@@ -136,15 +139,31 @@ static inline int pfp_alloc_t(pfpb200_ctx *ctx, T **p, size_t count, bool held =
     return pfp_alloc(ctx, (void **)p, (count ? count : 1) * sizeof(T), held);
 }
 
-// Function attributes (dynamic shared memory limits) and constant memory are per DEVICE: a process
-// that opens contexts on several GPUs has to set them once on each.  True the first time it is
-// called for (mask, device).
-static inline bool pfp_first_on_device(unsigned long long &mask, int device) {
-    const unsigned long long b = 1ull << (device & 63);
-    if (mask & b) return false;
-    mask |= b;
-    return true;
-}
+// Function attributes (dynamic shared memory limits) and constant memory are per DEVICE.  Every
+// translation unit sets its own in pfpb200_create() -- unconditionally, once per context, on the
+// context's device -- so there is no process-wide "already done" state for host threads to race on.
+int pfp_scan_init(pfpb200_ctx *ctx);
+int pfp_stream_init(pfpb200_ctx *ctx);
+int pfp_phrase_init(pfpb200_ctx *ctx);
+int pfp_prims_init(pfpb200_ctx *ctx);
+int pfp_rank_init(pfpb200_ctx *ctx);
+
+// a handful of CUDA events that are destroyed on every exit path of the scope that made them
+struct PfpEvents {
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ok = true;
+    explicit PfpEvents(int n) {
+        for (int i = 0; i < n && i < 4; i++)
+            if (cudaEventCreate(&ev[i]) != cudaSuccess) { ev[i] = nullptr; ok = false; }
+    }
+    ~PfpEvents() {
+        for (int i = 0; i < 4; i++)
+            if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    PfpEvents(const PfpEvents &) = delete;
+    PfpEvents &operator=(const PfpEvents &) = delete;
+    cudaEvent_t operator[](int i) const { return ev[i]; }
+};
 
 static inline u32 pfp_blocks(u64 n, u32 per_block) { return (u32)((n + per_block - 1) / per_block); }
 

@@ -21,15 +21,13 @@ __device__ __forceinline__ u64 fmix64(u64 k) {
 }
 
 // never 0: 0 marks an empty slot of the dictionary table
-__device__ __forceinline__ u64 sort_key_of(u64 fa, u64 fb, u32 len) {
-    u64 k = fmix64(fa ^ rotl64(fb, 32) ^ ((u64)len * 0x9E3779B97F4A7C15ULL));
+__device__ __forceinline__ u64 sort_key_of(u64 fa, u64 fb) {
+    u64 k = fmix64(fa ^ rotl64(fb, 29) ^ 0x9E3779B97F4A7C15ULL);
     return k ? k : 0x9E3779B97F4A7C15ULL;
 }
 
-__device__ __forceinline__ u32 fold_fb(u64 fb) { return (u32)fb ^ (u32)(fb >> 32); }
-
-__device__ __forceinline__ void store_rec(PhraseFp *rec, u64 j, u64 fa, u64 fb, u32 len) {
-    *reinterpret_cast<uint4 *>(rec + j) = make_uint4((u32)fa, (u32)(fa >> 32), fold_fb(fb), len);
+__device__ __forceinline__ void store_rec(PhraseFp *rec, u64 j, u64 fa, u64 fb) {
+    *reinterpret_cast<uint4 *>(rec + j) = make_uint4((u32)fa, (u32)(fa >> 32), (u32)fb, (u32)(fb >> 32));
 }
 
 // base^e mod 2^64 (long phrases only)

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
                                                       i64 first_start, u32 w,
                                                       const u32 *__restrict__ keytab,
                                                       u32 *__restrict__ long_list,
-                                                      u32 *__restrict__ long_count,
+                                                      u32 *__restrict__ long_count, u32 long_cap,
                                                       u64 *__restrict__ flags, int use_window) {
     __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
     __shared__ const u8 *s_ptr[PH_WARPS][32];
@@ -150,7 +150,11 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
                                     (u64)(e - tv.pos0) + 24 > tv.n_buf);
         if (slow) {
             if (len > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
-            else long_list[atomicAdd(long_count, 1u)] = (u32)j;
+            else {
+                const u32 li = atomicAdd(long_count, 1u);
+                if (li < long_cap) long_list[li] = (u32)j;
+                else atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);   // cannot happen: cap = P
+            }
         }
         const u32 mylen = slow ? 0u : (u32)len;
         const u32 nch = (mylen + 15) >> 4;
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_k(TextView tv, PhraseArrays 
             s_acc[wp][head_q][1] = head_b + (lane ? cb : 0ull);
         }
         __syncwarp();
-        if (valid && !slow) store_rec(ph.rec, j, s_acc[wp][lane][0], s_acc[wp][lane][1], (u32)len);
+        if (valid && !slow) store_rec(ph.rec, j, s_acc[wp][lane][0], s_acc[wp][lane][1]);
         __syncwarp();
     }
 }
@@ -264,13 +268,13 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
                                                            i64 first_start, u32 w,
                                                            const u32 *__restrict__ keytab,
                                                            const u32 *__restrict__ long_list,
-                                                           const u32 *__restrict__ long_count,
+                                                           const u32 *__restrict__ long_count, u32 long_cap,
                                                            u64 *__restrict__ flags) {
     __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
     for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
     __syncthreads();
     const u32 lane = threadIdx.x & 31;
-    const u32 nlong = *long_count;
+    const u32 nlong = min(*long_count, long_cap);
     for (u32 q = blockIdx.x * PH_WARPS + (threadIdx.x >> 5); q < nlong; q += gridDim.x * PH_WARPS) {
         const u64 j = long_list[q];
         const i64 e = (i64)ph.ends[j];
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
         }
         if (lane == 0) {
             if (len > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
-            store_rec(ph.rec, j, fa, fb, (u32)len);
+            store_rec(ph.rec, j, fa, fb);
         }
     }
 }
@@ -316,8 +320,7 @@ constexpr u32 UID_PENDING = 0x80000000u;       // uid[j] = UID_PENDING | slot: r
 
 __device__ __forceinline__ u32 check_of(const PhraseFp &r) {
     u64 x = (r.fpa + 0x632BE59BD9B4E019ULL) * 0xD1342543DE82EF95ULL;
-    x ^= rotl64((u64)r.fpb, 23) * 0xAF251AF3B0F025B5ULL;
-    x ^= (u64)r.len << 32;
+    x ^= (rotl64(r.fpb, 23) + 0x2545F4914F6CDD1DULL) * 0xAF251AF3B0F025B5ULL;
     x ^= x >> 29;
     u32 c = (u32)(x ^ (x >> 32));
     return c ? c : 1u;
@@ -356,11 +359,16 @@ __device__ __forceinline__ Probe table_probe(DictSlot *__restrict__ tab, u64 cap
 
 constexpr int TI_ITEMS = 2;      // phrases per thread: their first probes are in flight together
 
-// weight == nullptr: every record counts once (phrases); else record i counts weight[i] times
-// (words of several shards being merged, newscan.cpp:277-281)
+// weight == nullptr: every record counts once (phrases) and the creator of a word takes its length
+// from ends[] (phrase j = text from ends[j-1]-w+1, or first_start for j = 0, to ends[j]); else
+// record i counts weight[i] times and is len_in[i] bytes long (words of several shards being
+// merged, newscan.cpp:277-281)
 __global__ void __launch_bounds__(256, 8) table_insert_k(const PhraseFp *__restrict__ rec, u64 P,
                                                       DictSlot *__restrict__ tab, u64 cap,
                                                       const u32 *__restrict__ weight,
+                                                      const u32 *__restrict__ len_in,
+                                                      const u64 *__restrict__ ends, i64 first_start, u32 w,
+                                                      u32 weak /* test hook: keep 2 fingerprint bits */,
                                                       u32 *__restrict__ uid, u32 *__restrict__ rep,
                                                       u32 *__restrict__ ulen, u32 *__restrict__ uwords,
                                                       u32 *__restrict__ count,
@@ -368,22 +376,22 @@ __global__ void __launch_bounds__(256, 8) table_insert_k(const PhraseFp *__restr
     const u32 lane = threadIdx.x & 31;
     const u64 base = (u64)blockIdx.x * (256 * TI_ITEMS) + threadIdx.x;
     u64 k[TI_ITEMS];
-    u32 chk[TI_ITEMS], len[TI_ITEMS], peers[TI_ITEMS];
+    u32 chk[TI_ITEMS], peers[TI_ITEMS];
     uint4 sv[TI_ITEMS];
     bool lead[TI_ITEMS];
 #pragma unroll
     for (int it = 0; it < TI_ITEMS; it++) {
         const u64 j = base + (u64)it * 256;
         PhraseFp r;
-        r.len = 0; r.fpa = 0; r.fpb = 0;
+        r.fpa = 0; r.fpb = 0;
         u64 key = 0;
         if (j < P) {                                  // streamed once: keep it out of the table's way in L2
             const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(rec + j));
-            r.fpa = ((u64)a.y << 32) | a.x; r.fpb = a.z; r.len = a.w;
-            key = sort_key_of(r.fpa, (u64)r.fpb, r.len);
+            r.fpa = ((u64)a.y << 32) | a.x; r.fpb = ((u64)a.w << 32) | a.z;
+            if (weak) { r.fpa &= 3ull; r.fpb = 0; }
+            key = sort_key_of(r.fpa, r.fpb);
         }
         k[it] = key;
-        len[it] = r.len;
         chk[it] = j < P ? check_of(r) : 0u;
         peers[it] = __match_any_sync(0xffffffffu, k[it]);
         lead[it] = j < P && (int)lane == __ffs(peers[it]) - 1;
@@ -397,16 +405,23 @@ __global__ void __launch_bounds__(256, 8) table_insert_k(const PhraseFp *__restr
     __syncthreads();
     u32 res[TI_ITEMS];                               // word id + 1, or UID_PENDING | slot
     u32 mine[TI_ITEMS];                              // creator: index among the CTA's new words
+    u32 len[TI_ITEMS];                               // creator: length of the new word
     u64 slot[TI_ITEMS];
 #pragma unroll
     for (int it = 0; it < TI_ITEMS; it++) {
-        res[it] = 0; mine[it] = 0xFFFFFFFFu; slot[it] = 0;
+        res[it] = 0; mine[it] = 0xFFFFFFFFu; slot[it] = 0; len[it] = 0;
         if (lead[it]) {
             const Probe pr = table_probe(tab, cap, __umul64hi(k[it], cap), sv[it], k[it]);
             if (pr.placed) {
                 slot[it] = pr.slot;
                 u32 seen = pr.seen_chk;
                 if (pr.creator) {
+                    const u64 j = base + (u64)it * 256;
+                    if (len_in) len[it] = len_in[j];
+                    else {
+                        const i64 s0 = j ? (i64)ends[j - 1] - (i64)w + 1 : first_start;
+                        len[it] = (u32)((i64)ends[j] - s0 + 1);     // > 2^32-1 was flagged by K2
+                    }
                     mine[it] = atomicAdd(&s_new, 1u);
                     atomicMax(&s_max, len[it]);
                     atomicAdd(&s_sum, (unsigned long long)len[it]);
@@ -479,6 +494,28 @@ __global__ void table_pending_k(const DictSlot *__restrict__ tab, u64 P, const u
 constexpr int PC_GROUP = 8;                          // lanes per word
 constexpr int PC_PER_BLOCK = PH_T / PC_GROUP;
 
+// 8-byte word k of the phrase that starts at global position s0 and is len bytes long (zero
+// behind its end); special: the phrase touches a virtual border of the text
+__device__ __forceinline__ u64 phrase_word8(const TextView &tv, i64 s0, u64 len, u64 k, bool special) {
+    const u64 o = 8 * k;
+    const u32 nbv = (u32)((len - o) < 8 ? (len - o) : 8);
+    u64 v = 0;
+    if (!special) {
+        const u8 *p = tv.T + (s0 + (i64)o - tv.pos0);
+        const u32 bs = (u32)((uintptr_t)p & 7);
+        const u64 *p8 = reinterpret_cast<const u64 *>(p - bs);
+        const u64 lo = __ldg(p8);
+        if (bs) {
+            const u64 hi = (bs + nbv > 8) ? __ldg(p8 + 1) : 0ull;
+            v = (lo >> (8 * bs)) | (hi << (64 - 8 * bs));
+        } else v = lo;
+    } else {
+        for (u32 b = 0; b < nbv; b++) v |= (u64)tv_byte(tv, s0 + (i64)o + b) << (8 * b);
+    }
+    if (nbv < 8) v &= (1ull << (8 * nbv)) - 1ull;
+    return v;
+}
+
 __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__restrict__ ends,
                                                     i64 first_start, u32 w,
                                                     const u32 *__restrict__ rep,
@@ -495,25 +532,59 @@ __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__re
         bool special = (s0 < 0) || (e >= tv.n_global);
         u64 nw = (len + 7) >> 3;
         u64 *dst = pool + uoff[u];
-        for (u64 k = li; k < nw; k += PC_GROUP) {
-            u64 o = 8 * k;
-            u32 nbv = (u32)((len - o) < 8 ? (len - o) : 8);
-            u64 v = 0;
-            if (!special) {
-                const u8 *p = tv.T + (s0 + (i64)o - tv.pos0);
-                u32 bs = (u32)((uintptr_t)p & 7);
-                const u64 *p8 = reinterpret_cast<const u64 *>(p - bs);
-                u64 lo = __ldg(p8);
-                if (bs) {
-                    u64 hi = (bs + nbv > 8) ? __ldg(p8 + 1) : 0ull;
-                    v = (lo >> (8 * bs)) | (hi << (64 - 8 * bs));
-                } else v = lo;
-            } else {
-                for (u32 b = 0; b < nbv; b++) v |= (u64)tv_byte(tv, s0 + (i64)o + b) << (8 * b);
-            }
-            if (nbv < 8) v &= (1ull << (8 * nbv)) - 1ull;
-            dst[k] = v;
+        for (u64 k = li; k < nw; k += PC_GROUP) dst[k] = phrase_word8(tv, s0, len, k, special);
+    }
+}
+
+// PFPB200_F_VERIFY: every phrase is compared byte for byte with the pool copy of the word it was
+// given -- what the reference does on every map hit (newscan.cpp:282-286).  With it a wrong merge
+// of two different phrases is impossible, whatever the fingerprints say: the parse either is
+// exact or stops with PFPB200_E_COLLISION.  One warp per phrase.
+__global__ void __launch_bounds__(PH_T) verify_phrases_k(TextView tv, const u64 *__restrict__ ends,
+                                                         i64 first_start, u32 w, u64 P,
+                                                         const u32 *__restrict__ uid,
+                                                         const u32 *__restrict__ ulen,
+                                                         const u64 *__restrict__ uoff,
+                                                         const u64 *__restrict__ pool,
+                                                         u64 *__restrict__ flags) {
+    const u32 lane = threadIdx.x & 31;
+    for (u64 j = (u64)blockIdx.x * PH_WARPS + (threadIdx.x >> 5); j < P; j += (u64)gridDim.x * PH_WARPS) {
+        const i64 e = (i64)ends[j];
+        const i64 s0 = (j == 0) ? first_start : (i64)ends[j - 1] - (i64)w + 1;
+        const u64 len = (u64)(e - s0 + 1);
+        const u32 u = uid[j];
+        bool bad = len != (u64)ulen[u];
+        if (!bad) {
+            const bool special = (s0 < 0) || (e >= tv.n_global);
+            const u64 *src = pool + uoff[u];
+            const u64 nw = (len + 7) >> 3;
+            for (u64 k = lane; k < nw; k += 32) bad |= phrase_word8(tv, s0, len, k, special) != src[k];
         }
+        if (__any_sync(0xffffffffu, bad) && lane == 0)
+            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+    }
+}
+
+// the same for the entries of a dictionary merge: entry i against the representative entry of
+// the word it was merged into (both in the received pool)
+__global__ void __launch_bounds__(PH_T) verify_entries_k(u64 n, const u32 *__restrict__ uid_of_entry,
+                                                         const u32 *__restrict__ rep,
+                                                         const u32 *__restrict__ len_in,
+                                                         const u64 *__restrict__ in_off,
+                                                         const u64 *__restrict__ pool,
+                                                         u64 *__restrict__ flags) {
+    const u32 lane = threadIdx.x & 31;
+    for (u64 i = (u64)blockIdx.x * PH_WARPS + (threadIdx.x >> 5); i < n; i += (u64)gridDim.x * PH_WARPS) {
+        const u32 r = rep[uid_of_entry[i]];
+        if (r == (u32)i) continue;
+        bool bad = len_in[i] != len_in[r];
+        if (!bad) {
+            const u64 *a = pool + in_off[i], *b = pool + in_off[r];
+            const u64 nw = ((u64)len_in[i] + 7) >> 3;
+            for (u64 k = lane; k < nw; k += 32) bad |= a[k] != b[k];
+        }
+        if (__any_sync(0xffffffffu, bad) && lane == 0)
+            atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
     }
 }
 
@@ -528,7 +599,8 @@ int pfp_hash_list(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, 
     u32 nlb = (u32)(want < maxb ? want : maxb);
     if (nlb == 0) nlb = 1;
     phrase_hash_long_k<<<nlb, PH_T, 0, ctx->stream>>>(tv, ph, first_start, w, ctx->d_keys, long_list,
-                                                      long_count, ctx->d_flags);
+                                                      long_count, (u32)(max_count < 0xFFFFFFFFull ? max_count : 0xFFFFFFFFull),
+                                                      ctx->d_flags);
     PFP_LAUNCHED(ctx);
     return PFPB200_OK;
 }
@@ -541,10 +613,18 @@ int pfp_records_range(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &
     return PFPB200_OK;
 }
 
+int pfp_phrase_init(pfpb200_ctx *ctx) {
+    PFP_CUDA(ctx, cudaFuncSetAttribute(phrase_hash_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       PH_WARPS * PH_WIN));
+    return PFPB200_OK;
+}
+
 int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, u64 P,
                    i64 first_start, u32 w) {
     u32 *long_list = nullptr, *long_count = nullptr;
-    u64 cap = tv.n_buf / NH_SEG_BYTES + 8;   // phrases beyond one NH segment + the few at the borders
+    // every phrase may be listed: all of them are longer than one NH segment when w >= 8192, and up
+    // to 24 short ones can end within the last 24 bytes of the buffer (4 bytes per phrase)
+    const u64 cap = P + 8;
     PFP_TRY(pfp_alloc_t(ctx, &long_list, (size_t)cap));
     PFP_TRY(pfp_alloc_t(ctx, &long_count, 1));
     PFP_CUDA(ctx, cudaMemsetAsync(long_count, 0, sizeof(u32), ctx->stream));
@@ -554,18 +634,9 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     u64 maxb = (u64)ctx->sm_count * 32;
     u32 nb = (u32)(want < maxb ? want : maxb);
     if (nb == 0) nb = 1;
-    static unsigned long long attr = 0;
-    if (pfp_first_on_device(attr, ctx->device)) {
-        PFP_CUDA(ctx, cudaFuncSetAttribute(phrase_hash_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           PH_WARPS * PH_WIN));
-    }
-    static int use_window = -1;
-    if (use_window < 0) {
-        const char *ev = getenv("PFPB200_K2_WINDOW");
-        use_window = ev ? atoi(ev) : 0;      // measured: no gain on B200 once the atomics were gone
-    }
+    const int use_window = ctx->k2_window;   // measured: no gain on B200 once the atomics were gone
     phrase_hash_k<<<nb, PH_T, use_window ? PH_WARPS * PH_WIN : 0, ctx->stream>>>(
-        tv, ph, P, first_start, w, ctx->d_keys, long_list, long_count, ctx->d_flags, use_window);
+        tv, ph, P, first_start, w, ctx->d_keys, long_list, long_count, (u32)cap, ctx->d_flags, use_window);
     PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_hash_list(ctx, tv, ph, first_start, w, long_list, long_count, cap));
     PFP_TRY(pfp_free_now(ctx, long_list));
@@ -576,7 +647,7 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
 // Inserts every phrase into the dictionary table; the table hands out the word ids, so when the
 // kernel is done uid[], rep[], ulen[], uwords[] and count[] are complete.
 // Reads d (and length stats) back to the host: one synchronisation.
-int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D) {
+int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, i64 first_start, u32 w, DictArrays *D) {
     const int TB = 256;
     // Capacity: without a hint 1.5 P (load factor <= 2/3 even if every phrase is distinct).  The
     // distinct/phrase ratio of the previous parse on this context sizes the table 2x the expected
@@ -608,7 +679,8 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays 
         PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
         PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[6], 0, sizeof(u64), ctx->stream));
         table_insert_k<<<pfp_blocks(P, TB * TI_ITEMS), TB, 0, ctx->stream>>>(
-            ph.rec, P, tab, cap, nullptr, D->uid, D->rep, D->ulen, D->uwords, D->count, ctx->d_flags);
+            ph.rec, P, tab, cap, nullptr, nullptr, ph.ends, first_start, w, ctx->weak_fp, D->uid, D->rep, D->ulen, D->uwords,
+            D->count, ctx->d_flags);
         PFP_LAUNCHED(ctx);
         PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 7 * sizeof(u64), cudaMemcpyDeviceToHost,
                                       ctx->stream));
@@ -667,14 +739,26 @@ int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 fi
     return PFPB200_OK;
 }
 
+// PFPB200_F_VERIFY for a parse: after the pool exists.  The caller reads flags[0] back.
+int pfp_verify_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w, u64 P,
+                     const DictArrays &D) {
+    if (P == 0) return PFPB200_OK;
+    u64 want = (P + PH_WARPS - 1) / PH_WARPS;
+    u64 maxb = (u64)ctx->sm_count * 32;
+    verify_phrases_k<<<(u32)(want < maxb ? want : maxb), PH_T, 0, ctx->stream>>>(
+        tv, ends, first_start, w, P, D.uid, D.ulen, D.uoff, D.pool, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // dictionary merge: words (fingerprint, length, count, pool bytes) coming from several shards
 // ------------------------------------------------------------------------------------------
 // the incoming words as fingerprint records, so that the dictionary-table kernels above dedup them
-__global__ void merge_recs_k(const u64 *__restrict__ fpa, const u64 *__restrict__ fpb,
-                             const u32 *__restrict__ len, u64 n, PhraseFp *__restrict__ rec) {
+__global__ void merge_recs_k(const u64 *__restrict__ fpa, const u64 *__restrict__ fpb, u64 n,
+                             PhraseFp *__restrict__ rec) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) store_rec(rec, i, fpa[i], fpb[i], len[i]);
+    if (i < n) store_rec(rec, i, fpa[i], fpb[i]);
 }
 
 // a merged word lives where its representative entry lives in the received pool
@@ -695,7 +779,7 @@ __global__ void gather_word_fp_k(const u32 *__restrict__ rep, const PhraseFp *__
     if (u >= d) return;
     u32 j = rep[u];
     wfpa[u] = rec[j].fpa;
-    wfpb[u] = (u64)rec[j].fpb;
+    wfpb[u] = rec[j].fpb;
 }
 
 int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays &ph, u64 *wfpa,
@@ -710,7 +794,7 @@ int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays
 // One synchronisation.
 int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, const u32 *len,
                     const u32 *count_in, const u32 *uwords_in, const u64 *pool, u64 pool_words,
-                    DictArrays *D, u32 **uid_of_entry) {
+                    bool verify, DictArrays *D, u32 **uid_of_entry) {
     const int TB = 256;
     if (n >= 0x7FFFFFFEull / 2) return pfp_fail(ctx, PFPB200_E_LIMIT, "too many words to merge");
     PhraseFp *rec = nullptr;
@@ -727,7 +811,7 @@ int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, con
     PFP_TRY(pfp_alloc_t(ctx, &D->uwords, n));
     PFP_TRY(pfp_alloc_t(ctx, &D->uoff, n));
     D->uid = *uid_of_entry;
-    merge_recs_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(fpa, fpb, len, n, rec);
+    merge_recs_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(fpa, fpb, n, rec);
     PFP_LAUNCHED(ctx);
     table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
     PFP_LAUNCHED(ctx);
@@ -735,7 +819,8 @@ int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, con
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 3 * sizeof(u64), ctx->stream));
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[6], 0, sizeof(u64), ctx->stream));
     table_insert_k<<<pfp_blocks(n, TB * TI_ITEMS), TB, 0, ctx->stream>>>(
-        rec, n, tab, cap, count_in, *uid_of_entry, D->rep, D->ulen, D->uwords, D->count, ctx->d_flags);
+        rec, n, tab, cap, count_in, len, nullptr, 0, 0, ctx->weak_fp, *uid_of_entry, D->rep, D->ulen, D->uwords, D->count,
+        ctx->d_flags);
     PFP_LAUNCHED(ctx);
     // stragglers (ids not stored yet when they looked) -- cheap, and saves a synchronisation to ask
     table_pending_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(tab, n, count_in, *uid_of_entry, D->count,
@@ -746,6 +831,13 @@ int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, con
                                                              reinterpret_cast<const u64 *>(&ctx->d_flags[1]),
                                                              D->uwords, D->uoff);
     PFP_LAUNCHED(ctx);
+    if (verify) {
+        u64 want = (n + PH_WARPS - 1) / PH_WARPS;
+        u64 maxb = (u64)ctx->sm_count * 32;
+        verify_entries_k<<<(u32)(want < maxb ? want : maxb), PH_T, 0, ctx->stream>>>(
+            n, *uid_of_entry, D->rep, len, in_off, pool, ctx->d_flags);
+        PFP_LAUNCHED(ctx);
+    }
     PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(u64), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

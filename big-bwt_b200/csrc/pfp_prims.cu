@@ -367,17 +367,18 @@ __global__ void __launch_bounds__(RS_T) rs_scatter_k(const u64 *__restrict__ kin
     }
 }
 
+int pfp_prims_init(pfpb200_ctx *ctx) {
+    PFP_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(RsSmem)));
+    return PFPB200_OK;
+}
+
 int pfp_radix_sort_pairs(pfpb200_ctx *ctx, u64 *k0, u32 *v0, u64 *k1, u32 *v1, u64 n,
                          int begin_bit, int end_bit, u64 **res_k, u32 **res_v) {
     *res_k = k0;
     *res_v = v0;
     if (n <= 1 || end_bit <= begin_bit) return PFPB200_OK;
     if (n >= 0xFFFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "radix sort: too many items");
-    static unsigned long long attr_set = 0;
-    if (pfp_first_on_device(attr_set, ctx->device)) {
-        PFP_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(RsSmem)));
-    }
     u32 nb = pfp_blocks(n, RS_TILE);
     u32 *hist = nullptr;
     PFP_TRY(pfp_alloc_t(ctx, &hist, (size_t)256 * nb));

@@ -531,6 +531,14 @@ __global__ void __launch_bounds__(256) rank_cta_k(const u32 *__restrict__ hp,
     }
 }
 
+int pfp_rank_init(pfpb200_ctx *ctx) {
+    PFP_CUDA(ctx, cudaFuncSetAttribute(rank_cta_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(TieSort<LOCAL_MAX>)));
+    PFP_CUDA(ctx, cudaFuncSetAttribute(rank_mid_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(8 * sizeof(TieSort<MID_MAX>))));
+    return PFPB200_OK;
+}
+
 int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *rounds) {
     const int TB = 256;
     const u64 d = D.d;
@@ -627,13 +635,6 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
     }
     // finish every remaining tie group on chip
     if (d >= 2) {
-        static unsigned long long attr = 0;
-        if (pfp_first_on_device(attr, ctx->device)) {
-            PFP_CUDA(ctx, cudaFuncSetAttribute(rank_cta_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)sizeof(TieSort<LOCAL_MAX>)));
-            PFP_CUDA(ctx, cudaFuncSetAttribute(rank_mid_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(8 * sizeof(TieSort<MID_MAX>))));
-        }
         u32 *mid_list = v1, *big_list = v0;      // sort buffers are free again
         u32 *counts = reinterpret_cast<u32 *>(&ctx->d_flags[5]);
         PFP_CUDA(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(u32), ctx->stream));

@@ -368,10 +368,6 @@ __global__ void __launch_bounds__(256) tile_max_k(const u32 *__restrict__ tile_c
 template <int W>
 static void launch_scan(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
                         const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
-    static unsigned long long attr = 0;
-    if (pfp_first_on_device(attr, ctx->device)) {
-        cudaFuncSetAttribute(kr_scan_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
-    }
     kr_scan_k<W><<<ntiles, K1_T, K1_SMEM, ctx->stream>>>(A, q_end, q_lo, q_hi, C, mask, tile_cnt);
 }
 
@@ -381,17 +377,8 @@ template <int W>
 static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
                                    const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
     const size_t smem = (((size_t)1 << (2 * W)) + 31) / 32 * 4;
-    static unsigned long long attr = 0;
-    if (pfp_first_on_device(attr, ctx->device)) {
-        cudaError_t e = cudaFuncSetAttribute(kr_scan_dna_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
     const u64 nwords = (u64)ntiles * (K1_TILE / 32);      // every word of every tile gets written
-    static int mix = -1;
-    if (mix < 0) {
-        const char *ev = getenv("PFPB200_K1_MIX");
-        mix = ev ? atoi(ev) : 0;
-    }
+    const int mix = ctx->k1_mix;
     kr_scan_dna_k<W><<<ctx->sm_count, KD_T, smem, ctx->stream>>>(A, q_end, q_lo, q_hi, C, ctx->dna_table,
                                                                 reinterpret_cast<u32 *>(mask), tile_cnt, nwords,
                                                                 (u32)mix);
@@ -399,16 +386,31 @@ static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A,
 }
 #define KD_CASE(W) case W: le = launch_scan_dna<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
 
+template <int W> static cudaError_t scan_attr() {
+    cudaError_t e = cudaFuncSetAttribute(kr_scan_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
+    if (e == cudaSuccess && W <= KD_MAXW)
+        e = cudaFuncSetAttribute(kr_scan_dna_k<(W <= KD_MAXW ? W : KD_MAXW)>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((((size_t)1 << (2 * (W <= KD_MAXW ? W : KD_MAXW))) + 31) / 32 * 4));
+    return e;
+}
+
+// dynamic shared memory limits of every scan kernel and the constant powers of two, on ctx's device
+int pfp_scan_init(pfpb200_ctx *ctx) {
+#define K1_ATTR(W) PFP_CUDA(ctx, scan_attr<W>());
+    K1_ATTR(4) K1_ATTR(5) K1_ATTR(6) K1_ATTR(7) K1_ATTR(8) K1_ATTR(9) K1_ATTR(10)
+    K1_ATTR(11) K1_ATTR(12) K1_ATTR(13) K1_ATTR(14) K1_ATTR(15) K1_ATTR(16)
+    K1_ATTR(20) K1_ATTR(24) K1_ATTR(28) K1_ATTR(31) K1_ATTR(32)
+#undef K1_ATTR
+    u32 h[33];
+    for (int i = 0; i < 32; i++) h[i] = 1u << i;
+    h[32] = 0;
+    PFP_CUDA(ctx, cudaMemcpyToSymbol(kd_pow2, h, sizeof(h), 0, cudaMemcpyHostToDevice));
+    return PFPB200_OK;
+}
+
 // the 4^w-bit trigger table of (w, p), cached in the context
 static int ensure_dna_table(pfpb200_ctx *ctx, const pfp_scan_consts &C) {
-    static unsigned long long pow_dev = 0;   // constant memory is per device
-    if (pfp_first_on_device(pow_dev, ctx->device)) {
-        u32 h[33];
-        for (int i = 0; i < 32; i++) h[i] = 1u << i;
-        h[32] = 0;
-        PFP_CUDA(ctx, cudaMemcpyToSymbolAsync(kd_pow2, h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
-        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
     if (ctx->dna_table && ctx->dna_w == C.w && ctx->dna_p == C.p) return PFPB200_OK;
     if (!ctx->dna_table) PFP_CUDA(ctx, cudaMalloc(&ctx->dna_table, ((size_t)1 << (2 * KD_MAXW)) / 8));
     const u32 nwords = (u32)((((size_t)1 << (2 * C.w)) + 31) / 32);
@@ -451,9 +453,9 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
     PFP_TRY(pfp_alloc_t(ctx, &mask, (size_t)ntiles * K1_T, held));
     PFP_TRY(pfp_alloc_t(ctx, &tile_cnt, ntiles, held));
     PFP_TRY(pfp_alloc_t(ctx, &tile_off, ntiles, held));
-    cudaEvent_t e0, e1;
-    PFP_CUDA(ctx, cudaEventCreate(&e0));
-    PFP_CUDA(ctx, cudaEventCreate(&e1));
+    PfpEvents evs(2);
+    if (!evs.ok) return pfp_fail(ctx, PFPB200_E_CUDA, "cudaEventCreate failed");
+    const cudaEvent_t e0 = evs[0], e1 = evs[1];
     const bool dna = w <= (u32)KD_MAXW && ctx->k1_mode != 1;
     if (dna) PFP_TRY(ensure_dna_table(ctx, C));
     PFP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
@@ -490,8 +492,6 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float a = 0;
     cudaEventElapsedTime(&a, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (ms_scan) *ms_scan = a;
     sb->ntiles = ntiles;
     sb->mask = mask; sb->tile_cnt = tile_cnt; sb->tile_off = tile_off;
@@ -559,9 +559,9 @@ int pfp_scan_stage(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u
     PFP_TRY(pfp_scan_bits(ctx, d_buf, n_buf, buf_pos0, own_lo, own_hi, w, p, false, &sb, ms_scan));
     u64 *out = nullptr;
     PFP_TRY(pfp_alloc_t(ctx, &out, (size_t)(sb.total + extra_slots), held));
-    cudaEvent_t e1, e2;
-    PFP_CUDA(ctx, cudaEventCreate(&e1));
-    PFP_CUDA(ctx, cudaEventCreate(&e2));
+    PfpEvents evs(2);
+    if (!evs.ok) return pfp_fail(ctx, PFPB200_E_CUDA, "cudaEventCreate failed");
+    const cudaEvent_t e1 = evs[0], e2 = evs[1];
     PFP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     PFP_TRY(pfp_scan_emit(ctx, sb, out));
     PFP_CUDA(ctx, cudaEventRecord(e2, ctx->stream));
@@ -570,8 +570,6 @@ int pfp_scan_stage(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u
     float b = 0;
     cudaEventElapsedTime(&b, e1, e2);
     if (ms_emit) *ms_emit = b;
-    cudaEventDestroy(e1);
-    cudaEventDestroy(e2);
     *d_out = out;
     *n_out = sb.total;
     return PFPB200_OK;

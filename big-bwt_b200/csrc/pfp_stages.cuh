@@ -18,13 +18,14 @@ __device__ __forceinline__ u8 tv_byte(const TextView &tv, i64 g) {
 }
 
 // ---- per-phrase arrays (P entries, text order) ----------------------------------------------------
-// 16-byte fingerprint record of a phrase, written once by K2, read once by K3: the first NH sum,
-// the second folded to 32 bits, the length.  (The table key and the check digest are recomputed
-// from these by K3: 16 bytes less to write and to read per phrase than carrying the key along.)
+// 16-byte fingerprint record of a phrase, written once by K2, read once by K3: both 64-bit NH
+// sums in full (128 bits).  The length is NOT carried: text bytes are never zero, so the zero
+// padded chunks determine it, and the one thread per word that needs it (the word's creator in
+// K3) recomputes it from ends[].  The table key and the check digest are derived from the 128
+// bits by K3.
 struct __align__(16) PhraseFp {
     u64 fpa;        // first NH sum
-    u32 fpb;        // second NH sum (Toeplitz-shifted keys), high and low half xor-ed
-    u32 len;        // phrase length in bytes, including the w-byte overlap and virtual borders
+    u64 fpb;        // second NH sum (Toeplitz-shifted keys)
 };
 
 struct PhraseArrays {
@@ -74,7 +75,7 @@ int pfp_records_range(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &
 bool pfp_stream_ok(const ScanBits &sb, u32 w);   // false: w > 32 or a tile too dense -> per-phrase kernels
 int pfp_stream_stage(pfpb200_ctx *ctx, const ScanBits &sb, const TextView &tv, const PhraseArrays &ph,
                      u64 P, i64 first_start, u32 w, bool emit_ends);
-int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, DictArrays *D);
+int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, i64 first_start, u32 w, DictArrays *D);
 int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w,
                    DictArrays *D);
 // Lexicographic order of the d pool words: order[i] = uid of the word of rank i+1.
@@ -89,4 +90,6 @@ int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays
                        u64 *wfpb);
 int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, const u32 *len,
                     const u32 *count_in, const u32 *uwords_in, const u64 *pool, u64 pool_words,
-                    DictArrays *D, u32 **uid_of_entry);
+                    bool verify, DictArrays *D, u32 **uid_of_entry);
+int pfp_verify_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w, u64 P,
+                     const DictArrays &D);

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(K2_T, 4) phrase_stream_k(const StreamArgs a) {
             pa += __shfl_xor_sync(0xffffffffu, pa, o);
             pb += __shfl_xor_sync(0xffffffffu, pb, o);
         }
-        if (lane == 0) store_rec(a.rec, tile_first + q, pa, pb, len);
+        if (lane == 0) store_rec(a.rec, tile_first + q, pa, pb);
     }
 
     // ---- all other phrases: one lane each, warps hold phrases of (almost) equal length ---------------
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(K2_T, 4) phrase_stream_k(const StreamArgs a) {
             mask_tail(x0, x1, x2, x3, (int)(len - 16 * (nch - 1)));
             nh_add(pa, pb, x0, x1, x2, x3, k0, k1);
         }
-        store_rec(a.rec, tile_first + q, pa, pb, len);
+        store_rec(a.rec, tile_first + q, pa, pb);
     }
 }
 
@@ -318,10 +318,6 @@ int pfp_stream_stage(pfpb200_ctx *ctx, const ScanBits &sb, const TextView &tv, c
         a.keytab = ctx->d_keys; a.flags = ctx->d_flags;
         a.long_list = list; a.long_count = count;
         a.n_regular = sb.total;
-        static unsigned long long attr = 0;
-        if (pfp_first_on_device(attr, ctx->device)) {
-            PFP_CUDA(ctx, cudaFuncSetAttribute(phrase_stream_k, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
-        }
         phrase_stream_k<<<sb.ntiles, K2_T, K2_SMEM, ctx->stream>>>(a);
         PFP_LAUNCHED(ctx);
     }
@@ -330,6 +326,11 @@ int pfp_stream_stage(pfpb200_ctx *ctx, const ScanBits &sb, const TextView &tv, c
     PFP_TRY(pfp_hash_list(ctx, tv, ph, first_start, w, list, count, cap));
     PFP_TRY(pfp_records_range(ctx, tv, ph, sb.total, P, w));
     PFP_TRY(pfp_free_now(ctx, list));
+    return PFPB200_OK;
+}
+
+int pfp_stream_init(pfpb200_ctx *ctx) {
+    PFP_CUDA(ctx, cudaFuncSetAttribute(phrase_stream_k, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
     return PFPB200_OK;
 }
 

@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libpfpb200.so")
 CLI_PATH = os.path.join(PKG_DIR, "gpuscan.x")
 
-F_SAI, F_FASTA, F_COMPRESS, F_VERBOSE = 1, 2, 4, 8
+F_SAI, F_FASTA, F_COMPRESS, F_VERBOSE, F_VERIFY = 1, 2, 4, 8, 16
 
 ERRORS = {0: "OK", -1: "E_ARG", -2: "E_IO", -3: "E_CUDA", -4: "E_NOMEM", -5: "E_LIMIT",
           -6: "E_COLLISION", -7: "E_INTERNAL"}
@@ -151,9 +151,9 @@ def read_input(path, fasta=False) -> tuple[bytes, bool]:
         L.pfpb200_free_host(ptr)
 
 
-def _flags(sai, fasta, compress, verbose=False):
+def _flags(sai, fasta, compress, verbose=False, verify=False):
     return (F_SAI if sai else 0) | (F_FASTA if fasta else 0) | (F_COMPRESS if compress else 0) | \
-        (F_VERBOSE if verbose else 0)
+        (F_VERBOSE if verbose else 0) | (F_VERIFY if verify else 0)
 
 
 class Scanner:
@@ -189,9 +189,9 @@ class Scanner:
         self._check(self.L.pfpb200_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
 
     # -- text already in HBM (torch uint8 CUDA tensor); returns device pointers + sizes ---------
-    def parse_device(self, text, w=10, p=100, sai=True, compress=False) -> Outputs:
+    def parse_device(self, text, w=10, p=100, sai=True, compress=False, verify=False) -> Outputs:
         assert text.is_cuda and text.dtype.itemsize == 1 and text.is_contiguous()
-        o = Opts(w, p, _flags(sai, False, compress), 0)
+        o = Opts(w, p, _flags(sai, False, compress, verify=verify), 0)
         out = Outputs()
         self._check(self.L.pfpb200_parse_device(self.h, C.c_void_p(text.data_ptr()), text.numel(),
                                                 C.byref(o), C.byref(out), C.byref(self.stats)))
@@ -214,10 +214,10 @@ class Scanner:
                         sai=g(out.sai, 5 * P), stats=self.stats.as_dict())
 
     # -- text in host memory -----------------------------------------------------------------------
-    def parse_host(self, text, w=10, p=100, sai=True, compress=False, copy=True) -> PfpFiles:
+    def parse_host(self, text, w=10, p=100, sai=True, compress=False, copy=True, verify=False) -> PfpFiles:
         a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) \
             else np.ascontiguousarray(text, dtype=np.uint8)
-        o = Opts(w, p, _flags(sai, False, compress), 0)
+        o = Opts(w, p, _flags(sai, False, compress, verify=verify), 0)
         out = Outputs()
         self._check(self.L.pfpb200_parse_host(self.h, C.c_void_p(a.ctypes.data if a.size else 0), a.size,
                                               C.byref(o), C.byref(out), C.byref(self.stats)))

@@ -10,7 +10,9 @@ the shared dictionary of pscan.cpp:137-205.  Protocol of one parse (rank g, G ra
                 the sequential scanner's trigger set
   3. seams    : all-gather of (trigger count, last trigger).  The first phrase ending in shard g
                 starts at (last trigger of any lower rank) - w + 1; if that lies before the halo,
-                the missing head bytes are fetched peer to peer from the ranks that own them
+                the missing head bytes are fetched peer to peer from the ranks that own them --
+                however far back that is (a multi-megabyte run of N is ONE phrase that may cover
+                several whole shards): the rank's buffer grows in front as needed
   4. words    : K2 + K3 on the shard -> local dictionary (fingerprint, length, count, pool bytes),
                 `.last`/`.sai` of the shard
   5. merge    : mode "replicate": all-gather of the local dictionaries, every rank runs the global
@@ -147,9 +149,9 @@ class CudaBackend:
                   L.pfpb200_shard_first_keys, L.pfpb200_shard_route):
             f.restype = C.c_int
 
-    def shard_scan(self, buf, buf_pos0, own_lo, own_hi, n_global, is_last, w, p, sai):
+    def shard_scan(self, buf, buf_pos0, own_lo, own_hi, n_global, is_last, w, p, sai, verify=False):
         sh = Shard(buf.data_ptr(), buf.numel(), buf_pos0, own_lo, own_hi, n_global, 1 if is_last else 0, 0)
-        o = pfp.Opts(w, p, pfp.F_SAI if sai else 0, 0)
+        o = pfp.Opts(w, p, (pfp.F_SAI if sai else 0) | (pfp.F_VERIFY if verify else 0), 0)
         n, first, last, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_float()
         self.scanner._check(self.L.pfpb200_shard_scan(self.h, C.byref(sh), C.byref(o), C.byref(n),
                                                       C.byref(first), C.byref(last), C.byref(ms)))
@@ -169,11 +171,12 @@ class CudaBackend:
                 "last": dev_tensor(wd.last, wd.n_phrases, torch.uint8, dev),
                 "sai": dev_tensor(wd.sai, 5 * wd.n_phrases if wd.sai else 0, torch.uint8, dev)}
 
-    def dict_merge(self, fpa, fpb, ln, count, uwords, pool, w, compress=False):
+    def dict_merge(self, fpa, fpb, ln, count, uwords, pool, w, compress=False, verify=False):
         m, ms = Merged(), C.c_float()
         self.scanner._check(self.L.pfpb200_dict_merge(
             self.h, fpa.numel(), fpa.data_ptr(), fpb.data_ptr(), ln.data_ptr(), count.data_ptr(),
-            uwords.data_ptr(), pool.data_ptr(), pool.numel(), w, pfp.F_COMPRESS if compress else 0,
+            uwords.data_ptr(), pool.data_ptr(), pool.numel(), w,
+            (pfp.F_COMPRESS if compress else 0) | (pfp.F_VERIFY if verify else 0),
             C.byref(m), C.byref(ms)))
         self.ms["merge"] = ms.value
         dev = self.dev
@@ -218,12 +221,12 @@ class CudaBackend:
         self.scanner._check(self.L.pfpb200_shard_route_push(self.h, n_ranks, wd_, pd_, C.byref(ms)))
         self.ms["route"] = self.ms.get("route", 0.0) + ms.value
 
-    def dict_merge_words(self, words, pool, w, compress=False):
+    def dict_merge_words(self, words, pool, w, compress=False, verify=False):
         m, ms = Merged(), C.c_float()
         n_in = words.numel() // 32
         self.scanner._check(self.L.pfpb200_dict_merge_words(
             self.h, n_in, words.data_ptr(), pool.data_ptr(), pool.numel(), w,
-            pfp.F_COMPRESS if compress else 0, C.byref(m), C.byref(ms)))
+            (pfp.F_COMPRESS if compress else 0) | (pfp.F_VERIFY if verify else 0), C.byref(m), C.byref(ms)))
         self.ms["merge"] = ms.value
         dev = self.dev
         return {"n_distinct": m.n_distinct, "sum_word_len": m.sum_word_len,
@@ -364,10 +367,7 @@ class ShardedParser:
                 a = self.front + (lo - self.pos0)
                 todo.append(dist.P2POp(dist.isend, self.buf[a:a + (hi - lo)], dst))
             elif self.rank == dst:
-                a = self.front - (self.pos0 - lo)
-                if a < 0:
-                    raise RuntimeError(f"a phrase straddling into shard {dst} starts {self.pos0 - lo} bytes "
-                                       f"before it: more than the {self.front} bytes reserved")
+                a = self.front - (self.pos0 - lo)          # >= 0: the buffer was grown to hold the head
                 todo.append(dist.P2POp(dist.irecv, self.buf[a:a + (hi - lo)], src))
         if todo:
             for r in dist.batch_isend_irecv(todo):
@@ -399,12 +399,12 @@ class ShardedParser:
         self.buf = None
 
     # -- parse --------------------------------------------------------------------------------------------
-    def parse_device(self, w=10, p=100, sai=True, compress=False) -> dict:
+    def parse_device(self, w=10, p=100, sai=True, compress=False, verify=False) -> dict:
         if self.world == 1 and self.scanner is not None:
             self.backend.use_current_stream()
-            self.out = self.scanner.parse_device(self.buf, w, p, sai=sai, compress=compress)
+            self.out = self.scanner.parse_device(self.buf, w, p, sai=sai, compress=compress, verify=verify)
             return self.scanner.stats.as_dict()
-        return self._parse_sharded(w, p, sai, compress)
+        return self._parse_sharded(w, p, sai, compress, verify)
 
     def parse_host(self, host_text, w=10, p=100, sai=True) -> dict:
         """host_text: pinned CPU uint8 tensor holding this rank's shard."""
@@ -453,7 +453,16 @@ class ShardedParser:
             ev.record(torch.cuda.current_stream(self.buf.device))
             self._marks.append((name, ev))
 
-    def _parse_sharded(self, w, p, sai, compress) -> dict:
+    def _grow_front(self, need):
+        """More room in front of the shard (the head of a phrase that started `need` bytes before
+        it): new buffer, old content (halo included) at its end.  Local: no collective."""
+        need = (need + 4095) // 4096 * 4096
+        need = min(need, self.pos0)
+        new = torch.empty(need + self.n_local, dtype=torch.uint8, device=self.buf.device)
+        new[need - self.front:].copy_(self.buf)
+        self.buf, self.front = new, need
+
+    def _parse_sharded(self, w, p, sai, compress, verify=False) -> dict:
         be, G, g = self.backend, self.world, self.rank
         if hasattr(be, "use_current_stream"):
             be.use_current_stream()
@@ -468,14 +477,23 @@ class ShardedParser:
         self._p2p(transfers(halo_reqs, self.starts, self.sizes))
         self._mark("halo")
         # 2. scan
-        n_trig, first, last = be.shard_scan(self.buf, self.pos0 - self.front, self.pos0,
-                                            self.pos0 + self.n_local, self.n_global, g == G - 1, w, p, sai)
+        def scan():
+            return be.shard_scan(self.buf, self.pos0 - self.front, self.pos0, self.pos0 + self.n_local,
+                                 self.n_global, g == G - 1, w, p, sai, verify)
+        n_trig, first, last = scan()
         self._mark("scan")
-        # 3. seams
+        # 3. seams (every rank derives the same plan from the all-gathered triggers, so a rank
+        #    never waits for a transfer its peer did not post)
         info = self._all_gather_i64([n_trig, last])
         nts, lasts = [r[0] for r in info], [r[1] for r in info]
-        self._p2p(transfers(head_requests(self.starts, self.sizes, nts, lasts, w, self.halo),
-                            self.starts, self.sizes))
+        reqs = head_requests(self.starts, self.sizes, nts, lasts, w, self.halo)
+        a, b = reqs[g]
+        if a < b and self.pos0 - a > self.front:
+            # the phrase straddling into this shard starts before the reserved front: grow the
+            # buffer and scan it again (the library keeps pointers into the scanned buffer)
+            self._grow_front(self.pos0 - a)
+            n_trig, first, last = scan()
+        self._p2p(transfers(reqs, self.starts, self.sizes))
         fs = first_phrase_start(g, nts, lasts, w)
         self._mark("seams")
         # 4. words
@@ -483,9 +501,9 @@ class ShardedParser:
         self._mark("words")
         # 5. merge
         if self.mode == "replicate":
-            res = self._merge_replicated(wd, w, compress)
+            res = self._merge_replicated(wd, w, compress, verify)
         else:
-            res = self._merge_partitioned(wd, w, compress)
+            res = self._merge_partitioned(wd, w, compress, verify)
         # 6. remap
         parse = be.shard_remap(res["rank_of_word"], wd["n_phrases"])
         self._mark("remap")
@@ -506,13 +524,13 @@ class ShardedParser:
                 st["ms_phase_" + name] = st.get("ms_phase_" + name, 0.0) + a.elapsed_time(b)
         return st
 
-    def _merge_replicated(self, wd, w, compress):
+    def _merge_replicated(self, wd, w, compress, verify=False):
         be, G, g = self.backend, self.world, self.rank
         sizes = self._all_gather_i64([wd["n_words"], wd["pool"].numel()])
         nw, npool = [r[0] for r in sizes], [r[1] for r in sizes]
         cat = {k: self._all_gather_v(wd[k], nw) for k in ("fpa", "fpb", "len", "count", "uwords")}
         pool = self._all_gather_v(wd["pool"], npool)
-        m = be.dict_merge(cat["fpa"], cat["fpb"], cat["len"], cat["count"], cat["uwords"], pool, w, compress)
+        m = be.dict_merge(cat["fpa"], cat["fpb"], cat["len"], cat["count"], cat["uwords"], pool, w, compress, verify)
         base = sum(nw[:g])
         P = sum(r[0] for r in self._all_gather_i64([wd["n_phrases"]]))
         return {"dict": m["dict"], "occ": m["occ"], "n_distinct": m["n_distinct"],
@@ -588,7 +606,7 @@ class ShardedParser:
             return np.zeros(G - 1, dtype=np.uint64)
         return np.array([vals[min(vals.size - 1, (q + 1) * vals.size // G)] for q in range(G - 1)], dtype=np.uint64)
 
-    def _merge_partitioned(self, wd, w, compress):
+    def _merge_partitioned(self, wd, w, compress, verify=False):
         be, G, g = self.backend, self.world, self.rank
         dev = self.buf.device
         sp = self._splitters(wd)
@@ -643,7 +661,7 @@ class ShardedParser:
             got_words = self._all_to_all_v(send_words, [32 * c for c in words_to], [32 * c for c in recv_w])
             got_pool = self._all_to_all_v(send_pool, pool_to, recv_p)
         self._mark("exchange")
-        m = be.dict_merge_words(got_words, got_pool, w, compress)
+        m = be.dict_merge_words(got_words, got_pool, w, compress, verify)
         self._mark("merge")
         piece = m["dict"] if g == G - 1 else m["dict"][:-1]                 # only the last piece ends in 0x00
         tot = self._all_gather_i64([m["n_distinct"], int(piece.numel()), m["sum_word_len"], wd["n_phrases"]])

@@ -27,8 +27,11 @@ extern "C" {
 #define PFPB200_E_IO         -2  /* cannot open / read / write a file (utils.c:33-41)            */
 #define PFPB200_E_CUDA       -3  /* no usable GPU, kernel launch or runtime failure              */
 #define PFPB200_E_NOMEM      -4  /* host or device allocation failed (newscan.cpp:603-606)       */
-#define PFPB200_E_LIMIT      -5  /* > 2^31-2 distinct words, > 2^32-1 occurrences or phrases
-                                    (newscan.cpp:114-117,613-617; bigbwt:110-114)                */
+#define PFPB200_E_LIMIT      -5  /* > 2^31-2 distinct words, > 2^32-1 occurrences (newscan.cpp:114-117,
+                                    613-617), a phrase > 2^32-1 bytes, or >= 2^31-2 phrases on ONE
+                                    GPU (the reference allows 2^32-2 phrases, bigbwt:110-114; here
+                                    bit 31 of the per-phrase word id marks ids still being created,
+                                    so a text with more phrases needs two or more shards)        */
 #define PFPB200_E_COLLISION  -6  /* fingerprint collision detected (newscan.cpp:282-286)         */
 #define PFPB200_E_INTERNAL   -7  /* an invariant of the pipeline was violated                    */
 
@@ -37,6 +40,10 @@ extern "C" {
 #define PFPB200_F_FASTA     2u   /* -f : input is FASTA/FASTQ, kseq semantics (newscan.cpp:332)  */
 #define PFPB200_F_COMPRESS  4u   /* -c : write .dicz instead of .dict (newscan.cpp:410-413)      */
 #define PFPB200_F_VERBOSE   8u   /* -v                                                           */
+#define PFPB200_F_VERIFY   16u   /* compare every phrase byte for byte with the dictionary word it
+                                    was given, as the reference does on every map hit
+                                    (newscan.cpp:282-286): the parse is exact or fails with
+                                    PFPB200_E_COLLISION, whatever the 128-bit fingerprints say      */
 
 typedef struct pfpb200_opts {
     uint32_t w;       /* -w window size, >= 4, default 10 (newscan.cpp:155)                     */
@@ -69,7 +76,7 @@ typedef struct pfpb200_stats {
 } pfpb200_stats;
 
 /* The five output streams (utils.h:14-26).  Pointers are owned by the context and stay valid
- * until the next parse call on it or pfpb200_destroy().  `sai` is NULL without PFPB200_F_SAI. */
+ * until the next parse call on it, pfpb200_set_stream() or pfpb200_destroy().  `sai` is NULL without PFPB200_F_SAI. */
 typedef struct pfpb200_outputs {
     const uint8_t  *dict;   uint64_t dict_bytes;   /* words + 0x01 each, final 0x00             */
     const uint32_t *occ;    uint64_t n_distinct;   /* u32 LE occurrences in rank order          */
@@ -84,7 +91,9 @@ typedef struct pfpb200_ctx pfpb200_ctx;
  * device scratch and the output buffers.  Not thread-safe; one context per host thread. */
 int  pfpb200_create(int device, pfpb200_ctx **ctx);
 void pfpb200_destroy(pfpb200_ctx *ctx);
-/* Run on a caller-owned cudaStream_t (e.g. a torch stream); NULL restores the own stream. */
+/* Run on a caller-owned cudaStream_t (e.g. a torch stream); NULL restores the own stream.
+ * Synchronises the current stream and RELEASES the outputs of the previous parse: pointers
+ * obtained before the call are invalid afterwards. */
 int  pfpb200_set_stream(pfpb200_ctx *ctx, void *cuda_stream);
 
 /* Replaces process_file() + sort + writeDictOcc() + remapParse() (newscan.cpp:310-466,

@@ -129,6 +129,18 @@ def fasta_extract(file_bytes):
     return out[:n].tobytes(), bool(tr.value)
 
 
+def dicz_of(dict_bytes: bytes, w: int) -> bytes:
+    """The `.dicz` file newscan -c writes instead of `.dict` (newscan.cpp:410-413): every word
+    loses its last w bytes and, if it starts with Dollar (0x02), that byte too."""
+    assert dict_bytes[-1:] == b"\x00"
+    out = []
+    for wd in dict_bytes[:-1].split(b"\x01")[:-1]:
+        assert len(wd) > w
+        wd = wd[:-w]
+        out.append((wd[1:] if wd[:1] == b"\x02" else wd) + b"\x01")
+    return b"".join(out) + b"\x00"
+
+
 def kr_hash(s: bytes) -> int:
     a = _as_u8(s)
     return lib().pfp_oracle_kr_hash(a.ctypes.data if a.size else None, a.size)

@@ -56,6 +56,14 @@ def golden_names():
         return [c["name"] for c in json.load(f)["cases"]]
 
 
+def golden_dicz():
+    """name -> (case meta, .dicz bytes written by newscanNT.x -c); tools/make_golden_dicz.py"""
+    with open(os.path.join(GOLDEN_DIR, "cases_dicz.json")) as f:
+        meta = json.load(f)["cases"]
+    npz = np.load(os.path.join(GOLDEN_DIR, "golden_dicz.npz"))
+    return {c["name"]: (c, npz[c["name"] + "/dicz"].tobytes()) for c in meta}
+
+
 def assert_same_files(got, want, what=""):
     """Byte-compare the five outputs; `got`/`want` expose .dict .occ .parse .last .sai or keys."""
     for ext in FILES:

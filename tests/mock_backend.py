@@ -34,7 +34,7 @@ class MockBackend:
     def __init__(self):
         self.ms = {}
 
-    def shard_scan(self, buf, buf_pos0, own_lo, own_hi, n_global, is_last, w, p, sai):
+    def shard_scan(self, buf, buf_pos0, own_lo, own_hi, n_global, is_last, w, p, sai, verify=False):
         self.buf = buf.numpy()
         self.buf_pos0, self.own = buf_pos0, (own_lo, own_hi)
         self.n_global, self.is_last, self.w, self.sai = n_global, is_last, w, sai
@@ -107,14 +107,14 @@ class MockBackend:
                 "words_to": [int(np.sum(dest == q)) for q in range(n_ranks)],
                 "pool_to": [int(sum(uw[i] for i in range(len(uw)) if dest[perm[i]] == q)) for q in range(n_ranks)]}
 
-    def dict_merge_words(self, words, pool, w, compress=False):
+    def dict_merge_words(self, words, pool, w, compress=False, verify=False):
         rec = words.numpy().view([("fpa", "<i8"), ("fpb", "<i8"), ("len", "<u4"), ("count", "<u4"),
                                   ("uwords", "<u4"), ("pad", "<u4")])
         t = torch.from_numpy
         return self.dict_merge(t(rec["fpa"].copy()), t(rec["fpb"].copy()), t(rec["len"].astype(np.int32)),
                                t(rec["count"].astype(np.int32)), t(rec["uwords"].astype(np.int32)), pool, w, compress)
 
-    def dict_merge(self, fpa, fpb, ln, count, uwords, pool, w, compress=False):
+    def dict_merge(self, fpa, fpb, ln, count, uwords, pool, w, compress=False, verify=False):
         lens = ln.numpy().tolist()
         words = _unpack(pool.numpy(), uwords.numpy().tolist(), lens)
         keys = list(zip(fpa.numpy().tolist(), fpb.numpy().tolist(), lens))
@@ -134,3 +134,35 @@ class MockBackend:
     def shard_remap(self, rank_of_word, n_phrases):
         r = rank_of_word.numpy()
         return torch.from_numpy(r[self.uid].astype(np.int32)) if n_phrases else torch.zeros(0, dtype=torch.int32)
+
+
+class SharedMemExchange:
+    """CPU stand-in for shards.PeerExchange (NVLink peer memory): every rank's receive buffers are
+    torch tensors in POSIX shared memory, mapped into every process -- so the offset arithmetic
+    of the peer-memory exchange (my slot in owner q's buffer, the ranks travelling back) runs in
+    the gloo tests exactly as it does over symmetric memory on the GPUs."""
+
+    def __init__(self, bufs, rank, world):
+        self.bufs, self.rank, self.world = bufs, rank, world    # name -> [tensor of rank 0, 1, ...]
+
+    @staticmethod
+    def allocate(world, words=1 << 20, pool=1 << 18, ranks=1 << 16):
+        mk = lambda n, dt: [torch.zeros(n, dtype=dt).share_memory_() for _ in range(world)]  # noqa: E731
+        return {"words": mk(words, torch.uint8), "pool": mk(pool, torch.int64), "ranks": mk(ranks, torch.int32)}
+
+    def ensure(self, name, dtype, capacity):
+        t = self.bufs[name][self.rank]
+        assert t.dtype == dtype and capacity <= t.numel(), (name, capacity, t.numel())
+
+    def barrier(self, name):
+        import torch.distributed as dist
+        dist.barrier()
+
+    def local(self, name, count):
+        return self.bufs[name][self.rank][:count]
+
+    def scatter(self, name, send, send_off, send_cnt, dst_off):
+        for q in range(self.world):
+            c = int(send_cnt[q])
+            if c:
+                self.bufs[name][q][int(dst_off[q]):int(dst_off[q]) + c] = send[int(send_off[q]):int(send_off[q]) + c]

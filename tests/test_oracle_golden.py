@@ -5,7 +5,7 @@ oracle/_ref is present (build container, GPU box) the reference is also run live
 import numpy as np
 import pytest
 
-from conftest import assert_same_files, golden, golden_names
+from conftest import assert_same_files, golden, golden_dicz, golden_names
 from oracle import pfp_oracle as orc
 
 
@@ -22,6 +22,14 @@ def test_oracle_matches_golden(name):
     got = orc.parse(_text_of(c), c["w"], c["p"])
     assert_same_files(got, c, name)
     assert got.n_phrases == c["n_phrases"] and got.n_distinct == c["n_distinct"]
+
+
+@pytest.mark.parametrize("name", sorted(golden_dicz()))
+def test_oracle_dicz_matches_golden(name):
+    """-c: the oracle's .dicz rule against the file newscanNT.x -c wrote (newscan.cpp:410-413)."""
+    meta, dicz = golden_dicz()[name]
+    c = golden().case(name)
+    assert orc.dicz_of(orc.parse(_text_of(c), c["w"], c["p"]).dict, meta["w"]) == dicz
 
 
 def test_kr_hash_kat():

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_same_files, golden, golden_names
+from conftest import assert_same_files, golden, golden_dicz, golden_names
 from oracle import pfp_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -173,15 +173,58 @@ def test_stream_k2_equals_per_phrase_k2_64mb(pkg):
     assert_same_files(res[0], res[1], "stream vs per-phrase K2")
 
 
+@pytest.mark.parametrize("name", sorted(golden_dicz()))
+def test_compress_mode_dicz_golden(pkg, sc, name):
+    """-c against the .dicz the unmodified newscanNT.x -c wrote (tools/make_golden_dicz.py)."""
+    meta, dicz = golden_dicz()[name]
+    c = golden().case(name)
+    text = pkg.pfp.fasta_extract(c["input"])[0] if c["fasta"] else c["input"]
+    comp = sc.parse_host(text, c["w"], c["p"], compress=True)
+    assert comp.dict == dicz, f"{name}: .dicz differs ({len(comp.dict)} vs {len(dicz)} bytes)"
+    assert comp.parse == c["parse"] and comp.occ == c["occ"] and comp.last == c["last"]
+
+
 def test_compress_mode_dicz(pkg, sc):
-    """-c: words lose their last w bytes and the leading 0x02 (newscan.cpp:410-413)."""
+    """-c at a larger size: words lose their last w bytes and the leading 0x02 (newscan.cpp:410-413;
+    the rule is pinned to newscanNT.x -c by test_oracle_dicz_matches_golden)."""
     text = pkg.synth.pangenome_text(30_000, 5, 82).numpy().tobytes()
     w = 10
     plain = sc.parse_host(text, w, 100)
     comp = sc.parse_host(text, w, 100, compress=True)
-    words = plain.dict[:-1].split(b"\x01")[:-1]
-    want = b"".join((wd[:-w][1:] if wd[:1] == b"\x02" else wd[:-w]) + b"\x01" for wd in words) + b"\x00"
-    assert comp.dict == want and comp.parse == plain.parse and comp.occ == plain.occ
+    assert comp.dict == orc.dicz_of(plain.dict, w) and comp.parse == plain.parse and comp.occ == plain.occ
+
+
+@pytest.mark.parametrize("w,p,n", [(9000, 100, 400_000), (8192, 50, 300_000), (7000, 500, 600_000),
+                                   (40, 10, 300), (40, 10, 41), (33, 11, 2000), (65536, 100, 200_000)])
+def test_huge_windows_and_tiny_inputs_per_phrase_k2(pkg, sc, w, p, n):
+    """The per-phrase K2 path (w > 32): every phrase is longer than one fingerprint segment when
+    w >= 8192, and on tiny inputs most phrases end within the last bytes of the buffer -- both
+    used to overflow the list of phrases handed to the long-phrase kernel."""
+    text = pkg.synth.random_dna(n, 140 + w % 7).numpy().tobytes()
+    assert_same_files(sc.parse_host(text, w, p), orc.parse(text, w, p), f"w{w} p{p} n{n}")
+
+
+def test_verify_flag_catches_forced_collisions(pkg):
+    """PFPB200_F_VERIFY compares every phrase with its dictionary word byte for byte
+    (newscan.cpp:282-286).  With the fingerprints cut to 2 bits (test hook) almost all phrases
+    collide: without the flag the merge is silent, with it the parse must stop with E_COLLISION;
+    with full fingerprints the flag changes nothing."""
+    text = pkg.synth.pangenome_text(30_000, 6, 83).numpy().tobytes()
+    want = orc.parse(text, 10, 100)
+    s = pkg.pfp.Scanner(0)
+    assert_same_files(s.parse_host(text, 10, 100, verify=True), want, "verify on")
+    assert_same_files(s.fetch(s.parse_device(torch.from_numpy(np.frombuffer(text, np.uint8).copy()).cuda(),
+                                             10, 100, verify=True)), want, "verify on, device entry")
+    s.close()
+    os.environ["PFPB200_TEST_WEAK_FP"] = "1"
+    try:
+        weak = pkg.pfp.Scanner(0)
+    finally:
+        os.environ.pop("PFPB200_TEST_WEAK_FP", None)
+    with pytest.raises(pkg.pfp.PfpError) as e:
+        weak.parse_host(text, 10, 100, verify=True)
+    assert e.value.code == -6
+    weak.close()
 
 
 def test_bad_arguments(pkg, sc):

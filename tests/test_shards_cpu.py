@@ -37,7 +37,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, text, cuts, w, p, mode, q):
+def _worker(rank, world, port, text, cuts, w, p, mode, q, front=4096, shared=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -47,7 +47,10 @@ def _worker(rank, world, port, text, cuts, w, p, mode, q):
         from __graft_entry__ import load_package
         from mock_backend import MockBackend
         pkg = load_package()
-        job = pkg.shards.ShardedParser(None, world, rank, backend=MockBackend(), mode=mode, halo=64, front=4096)
+        job = pkg.shards.ShardedParser(None, world, rank, backend=MockBackend(), mode=mode, halo=64, front=front)
+        if shared is not None:        # the peer-memory exchange path, over shared host memory
+            from mock_backend import SharedMemExchange
+            job._peer = SharedMemExchange(shared, rank, world)
         shard = torch.from_numpy(np.frombuffer(text[cuts[rank]:cuts[rank + 1]], np.uint8).copy())
         job.set_text(shard)
         st = job.parse_device(w, p, sai=True)
@@ -58,12 +61,18 @@ def _worker(rank, world, port, text, cuts, w, p, mode, q):
         dist.destroy_process_group()
 
 
-def run_sharded(text, cuts, w, p, mode="replicate"):
+def run_sharded(text, cuts, w, p, mode="replicate", front=4096, peer=False):
     world = len(cuts) - 1
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, text, cuts, w, p, mode, q)) for r in range(world)]
+    shared = None
+    if peer:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from mock_backend import SharedMemExchange
+        shared = SharedMemExchange.allocate(world)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, text, cuts, w, p, mode, q, front, shared))
+             for r in range(world)]
     for pr in procs:
         pr.start()
     files, st = q.get(timeout=120)
@@ -98,3 +107,32 @@ def test_sharded_seam_without_triggers(pkg):
     want = orc.parse(text, 10, 100)
     for ext in FILES:
         assert files[ext] == getattr(want, ext), f".{ext} differs"
+
+
+def test_sharded_head_longer_than_the_reserved_front(pkg):
+    """The phrase straddling into the last shards starts far more bytes before them than the
+    buffer reserves in front (front = 256 here; 1 MB in production): the buffer grows instead of
+    the parse failing, and two whole shards lie inside the run."""
+    a = pkg.synth.random_dna(2000, 4).numpy().tobytes()
+    text = a + b"N" * 9000 + a[:1500]
+    cuts = [0, 2500, 5000, 8000, len(text)]     # shards 1 and 2 lie inside the N run
+    for mode in ("partition", "replicate"):
+        files, _ = run_sharded(text, cuts, 10, 100, mode, front=256)
+        want = orc.parse(text, 10, 100)
+        for ext in FILES:
+            assert files[ext] == getattr(want, ext), f".{ext} differs ({mode})"
+
+
+@pytest.mark.parametrize("world,w,p", [(2, 10, 100), (3, 10, 100), (4, 6, 50)])
+def test_sharded_peer_memory_exchange_offsets(pkg, world, w, p):
+    """mode "partition" through the peer-memory branch of _merge_partitioned (the default on the
+    GPUs): every rank stores its routed words straight into the owners' buffers behind the
+    segments of the lower ranks, and the ranks travel back the same way."""
+    text = pkg.synth.pangenome_text(1200, 7, 11).numpy().tobytes()
+    n = len(text)
+    cuts = [0] + [n * k // world - 5 * k for k in range(1, world)] + [n]
+    files, st = run_sharded(text, cuts, w, p, "partition", peer=True)
+    want = orc.parse(text, w, p)
+    for ext in FILES:
+        assert files[ext] == getattr(want, ext), f".{ext} differs (world {world})"
+    assert st["n_phrases"] == want.n_phrases and st["n_distinct"] == want.n_distinct
