@@ -16,7 +16,8 @@ static void usage(const char *exe, const pfpb200_opts *o) {
     printf("\t-w W\tsliding window size, def. %u\n", o->w);
     printf("\t-p M\tmodulo for defining phrases, def. %u\n", o->p);
     printf("\t-t M\tnumber of .last/.sai segments to write (helper threads of the reference), def. none \n");
-    printf("\t-g G\tCUDA device index, def. 0\n");
+    printf("\t-g G\tCUDA device index, or a comma-separated list (e.g. 0,1,2,3): the text is\n"
+           "\t    \tsharded over the listed GPUs, def. 0\n");
     printf("\t-h  \tshow help and exit\n");
     printf("\t-s  \tcompute suffix array info\n");
     printf("\t-f  \tread a FASTA/FASTQ file\n");
@@ -37,7 +38,7 @@ static long int_arg(const char *s) {
 
 int main(int argc, char **argv) {
     pfpb200_opts o = {10, 100, 0, 0};
-    int device = 0, verbose = 0, c;
+    int devices[PFPB200_MAX_RANKS] = {0}, n_dev = 1, verbose = 0, c;
     long w = 10, p = 100, nseg = 0;
     puts("==== Command line:");
     for (int i = 0; i < argc; i++) printf(" %s", argv[i]);
@@ -52,7 +53,13 @@ int main(int argc, char **argv) {
             case 'V': o.flags |= PFPB200_F_VERIFY; break;
             case 'f': o.flags |= PFPB200_F_FASTA; break;
             case 't': nseg = int_arg(optarg); break;
-            case 'g': device = atoi(optarg); break;
+            case 'g': {
+                n_dev = 0;
+                for (char *tok = strtok(optarg, ","); tok && n_dev < PFPB200_MAX_RANKS; tok = strtok(NULL, ","))
+                    devices[n_dev++] = (int)int_arg(tok);
+                if (n_dev == 0) { puts("Invalid device list"); exit(1); }
+                break;
+            }
             case 'v': verbose++; o.flags |= PFPB200_F_VERBOSE; break;
             case 'h': usage(argv[0], &o); break;
             default: puts("Unknown option. Use -h for help."); exit(1);
@@ -69,17 +76,33 @@ int main(int argc, char **argv) {
     printf("Stop word modulus: %u\n", o.p);
     time_t start = time(NULL);
     pfpb200_ctx *ctx = NULL;
-    int rc = pfpb200_create(device, &ctx);
-    if (rc != PFPB200_OK) {
-        fprintf(stderr, "gpuscan: cannot use CUDA device %d: %s\n", device, pfpb200_strerror(rc));
-        return 1;
-    }
+    pfpb200_multi *multi = NULL;
     pfpb200_stats st;
-    rc = pfpb200_parse_file(ctx, path, &o, &st);
-    if (rc != PFPB200_OK) {
-        fprintf(stderr, "gpuscan: %s: %s\n", pfpb200_strerror(rc), pfpb200_last_error(ctx));
-        pfpb200_destroy(ctx);
-        return 1;
+    int rc;
+    if (n_dev > 1) {           /* one host thread per GPU, complete files at exit (newscan -t T) */
+        rc = pfpb200_multi_create(n_dev, devices, &multi);
+        if (rc != PFPB200_OK) {
+            fprintf(stderr, "gpuscan: cannot use the %d listed CUDA devices: %s\n", n_dev, pfpb200_strerror(rc));
+            return 1;
+        }
+        rc = pfpb200_multi_parse_file(multi, path, &o, &st);
+        if (rc != PFPB200_OK) {
+            fprintf(stderr, "gpuscan: %s: %s\n", pfpb200_strerror(rc), pfpb200_multi_last_error(multi));
+            pfpb200_multi_destroy(multi);
+            return 1;
+        }
+    } else {
+        rc = pfpb200_create(devices[0], &ctx);
+        if (rc != PFPB200_OK) {
+            fprintf(stderr, "gpuscan: cannot use CUDA device %d: %s\n", devices[0], pfpb200_strerror(rc));
+            return 1;
+        }
+        rc = pfpb200_parse_file(ctx, path, &o, &st);
+        if (rc != PFPB200_OK) {
+            fprintf(stderr, "gpuscan: %s: %s\n", pfpb200_strerror(rc), pfpb200_last_error(ctx));
+            pfpb200_destroy(ctx);
+            return 1;
+        }
     }
     printf("Total input symbols: %llu\n", (unsigned long long)st.n_text);
     printf("Found %llu distinct words\n", (unsigned long long)st.n_distinct);
@@ -90,8 +113,20 @@ int main(int argc, char **argv) {
            st.ms_total, st.ms_scan, st.ms_emit, st.ms_hash, st.ms_dedup, st.ms_rank, st.rank_rounds,
            st.ms_dict, st.ms_remap, st.ms_h2d, st.ms_d2h, st.launches);
     printf("File read: %.3f s, file write: %.3f s\n", st.sec_read, st.sec_write);
+    if (multi && verbose) {
+        static const char *names[PFPB200_N_PHASES] = {"start", "h2d", "scan", "seams", "words", "splitters", "route",
+                                                      "exchange", "merge", "ranks-back", "remap", "d2h"};
+        float ms[PFPB200_MAX_RANKS * PFPB200_N_PHASES];
+        int k = pfpb200_multi_phase_ms(multi, ms, PFPB200_MAX_RANKS * PFPB200_N_PHASES);
+        for (int r = 0; r * PFPB200_N_PHASES < k; r++) {
+            printf("GPU %d:", devices[r]);
+            for (int ph = 1; ph < PFPB200_N_PHASES; ph++) printf(" %s %.3f", names[ph], ms[r * PFPB200_N_PHASES + ph]);
+            printf(" ms\n");
+        }
+    }
     printf("==== Elapsed time: %.0f wall clock seconds\n", difftime(time(NULL), start));
     pfpb200_destroy(ctx);
+    pfpb200_multi_destroy(multi);
     (void)verbose;
     return 0;
 }

@@ -40,6 +40,16 @@ __global__ void __launch_bounds__(256) first_invalid_k(const u8 *__restrict__ t,
     }
 }
 
+// *d_first (device u64, caller-initialised to n) = first position of text[0..n) holding a byte
+// <= 0x02, where the reference stops reading (newscan.cpp:364)
+int pfp_first_invalid(pfpb200_ctx *ctx, const u8 *d_text, u64 n, u64 *d_first) {
+    if (n == 0) return PFPB200_OK;
+    first_invalid_k<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_text, n,
+                                                               reinterpret_cast<unsigned long long *>(d_first));
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
 extern "C" int pfpb200_abi_version(void) { return PFPB200_ABI_VERSION; }
 
 extern "C" const char *pfpb200_strerror(int code) {

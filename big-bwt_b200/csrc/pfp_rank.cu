@@ -1021,6 +1021,11 @@ extern "C" int pfp_route_impl(pfpb200_ctx *ctx, const Splitters &sp, u32 n_ranks
     }
     out->words = owords;
     out->pool = opool; out->perm = perm;
+    for (u32 q = 0; q < PFPB200_MAX_RANKS; q++) {
+        ctx->sh.route_words_to[q] = hc[q];
+        ctx->sh.route_pool_to[q] = hc[PFPB200_MAX_RANKS + q];
+    }
+    ctx->sh.route_perm = perm;
     // free what the caller does not need; the rest is promoted to `held` by the caller
     u32 *perm_other = (perm == v0) ? v1 : v0;
     PFP_TRY(pfp_free_now(ctx, k0));
@@ -1029,5 +1034,47 @@ extern "C" int pfp_route_impl(pfpb200_ctx *ctx, const Splitters &sp, u32 n_ranks
     PFP_TRY(pfp_free_now(ctx, cnt));
     PFP_TRY(pfp_free_now(ctx, ooff));
     PFP_TRY(pfp_free_now(ctx, ouwords));
+    return PFPB200_OK;
+}
+
+// ---- ranks travelling back (range-partitioned merge) ------------------------------------------------------
+// back[i] = rank, inside its owner's range, of the word this shard routed to position i; the
+// global rank adds the number of distinct words in the ranges below that owner.
+struct OwnerBase {
+    u64 so[PFPB200_MAX_RANKS + 1];        // routed positions [so[q], so[q+1]) went to owner q
+    u32 base[PFPB200_MAX_RANKS];
+    u32 n;
+};
+
+__global__ void ranks_unroute_k(const u32 *__restrict__ perm, const u32 *__restrict__ back, u64 d,
+                                const OwnerBase B, u32 *__restrict__ rank_of_word) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    u32 q = 0;
+    while (q + 1 < B.n && i >= B.so[q + 1]) q++;
+    rank_of_word[perm[i]] = back[i] + B.base[q];
+}
+
+extern "C" int pfpb200_shard_ranks_back(pfpb200_ctx *ctx, uint32_t n_ranks, const uint32_t *d_back,
+                                        const uint64_t *rank_base, const uint32_t **d_rank_of_word) {
+    if (!ctx || !d_rank_of_word || n_ranks < 1 || n_ranks > PFPB200_MAX_RANKS || !rank_base) return PFPB200_E_ARG;
+    *d_rank_of_word = nullptr;
+    const u64 d = ctx->sh.d;
+    if (d == 0) return PFPB200_OK;
+    if (!ctx->sh.route_perm || !d_back) return pfp_fail(ctx, PFPB200_E_ARG, "shard_ranks_back before shard_route");
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    OwnerBase B;
+    memset(&B, 0, sizeof(B));
+    B.n = n_ranks;
+    for (u32 q = 0; q < n_ranks; q++) {
+        B.so[q + 1] = B.so[q] + ctx->sh.route_words_to[q];
+        if (rank_base[q] > 0x7FFFFFFFull) return pfp_fail(ctx, PFPB200_E_LIMIT, "more than 2^31-2 distinct words");
+        B.base[q] = (u32)rank_base[q];
+    }
+    u32 *out = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &out, d, true));
+    ranks_unroute_k<<<pfp_blocks(d, 256), 256, 0, ctx->stream>>>(ctx->sh.route_perm, d_back, d, B, out);
+    PFP_LAUNCHED(ctx);
+    *d_rank_of_word = out;
     return PFPB200_OK;
 }

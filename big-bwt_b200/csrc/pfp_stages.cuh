@@ -85,6 +85,8 @@ int pfp_dict_stage(pfpb200_ctx *ctx, const DictArrays &D, const u32 *order, u32 
                    u8 **dict, u64 *dict_bytes, u32 **occ, u32 **rank_of_uid);
 int pfp_remap_stage(pfpb200_ctx *ctx, const u32 *uid, const u32 *rank_of_uid, u64 P, u32 *parse);
 
+int pfp_first_invalid(pfpb200_ctx *ctx, const u8 *d_text, u64 n, u64 *d_first);
+
 // ---- sharded parsing building blocks ------------------------------------------------------------------------
 int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays &ph, u64 *wfpa,
                        u64 *wfpb);

@@ -81,6 +81,9 @@ SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_p
            "pfpb200_shard_scan", "pfpb200_shard_words", "pfpb200_dict_merge", "pfpb200_shard_remap",
            "pfpb200_shard_first_keys", "pfpb200_shard_route", "pfpb200_shard_route_plan",
            "pfpb200_shard_route_push", "pfpb200_dict_merge_words",
+           "pfpb200_shard_ranks_back", "pfpb200_multi_create", "pfpb200_multi_destroy", "pfpb200_multi_n_gpus",
+           "pfpb200_multi_parse_host", "pfpb200_multi_parse_file", "pfpb200_multi_last_error",
+           "pfpb200_multi_phase_ms",
            "pfpb200_launch_count", "pfpb200_last_error", "pfpb200_abi_version"]
 
 
@@ -119,6 +122,18 @@ def load_library():
     L.pfpb200_abi_version.restype = C.c_int
     L.pfpb200_launch_count.argtypes = [vp]
     L.pfpb200_launch_count.restype = C.c_uint32
+    L.pfpb200_multi_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+    L.pfpb200_multi_create.restype = C.c_int
+    L.pfpb200_multi_destroy.argtypes = [vp]
+    L.pfpb200_multi_destroy.restype = None
+    L.pfpb200_multi_parse_host.argtypes = [vp, vp, u64, C.POINTER(Opts), C.POINTER(Outputs), C.POINTER(Stats)]
+    L.pfpb200_multi_parse_host.restype = C.c_int
+    L.pfpb200_multi_parse_file.argtypes = [vp, C.c_char_p, C.POINTER(Opts), C.POINTER(Stats)]
+    L.pfpb200_multi_parse_file.restype = C.c_int
+    L.pfpb200_multi_last_error.argtypes = [vp]
+    L.pfpb200_multi_last_error.restype = C.c_char_p
+    L.pfpb200_multi_phase_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    L.pfpb200_multi_phase_ms.restype = C.c_int
     _lib = L
     return L
 
@@ -255,3 +270,67 @@ class Scanner:
         k = cnt.value
         pos = np.frombuffer(self.to_host(ptr.value, 8 * k), dtype=np.uint64)
         return pos, ms.value
+
+
+PHASES = ("start", "h2d", "scan", "seams", "words", "splitters", "route", "exchange", "merge", "ranks_back",
+          "remap", "d2h")
+
+
+class MultiScanner:
+    """Several GPUs of one box behind one call (pfpb200_multi_*): the drop-in for `newscan.x -t T`.
+    One process, one host thread per GPU inside the library; no torch, no NCCL."""
+
+    def __init__(self, gpu_ids):
+        self.L = load_library()
+        ids = (C.c_int * len(gpu_ids))(*gpu_ids)
+        h = C.c_void_p()
+        rc = self.L.pfpb200_multi_create(len(gpu_ids), ids, C.byref(h))
+        if rc != 0:
+            raise PfpError(rc, f"cannot create contexts on CUDA devices {list(gpu_ids)}: "
+                               f"{self.L.pfpb200_strerror(rc).decode()}")
+        self.h, self.gpu_ids, self.stats = h, list(gpu_ids), Stats()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pfpb200_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PfpError(rc, self.L.pfpb200_multi_last_error(self.h).decode(errors="replace"))
+
+    def parse_host(self, text, w=10, p=100, sai=True, compress=False, verify=False, copy=True):
+        a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) \
+            else np.ascontiguousarray(text, dtype=np.uint8)
+        return self.parse_host_ptr(a.ctypes.data if a.size else 0, a.size, w, p, sai, compress, verify, copy)
+
+    def parse_host_ptr(self, ptr, n, w=10, p=100, sai=True, compress=False, verify=False, copy=False):
+        o = Opts(w, p, _flags(sai, False, compress, verify=verify), 0)
+        out = Outputs()
+        self._check(self.L.pfpb200_multi_parse_host(self.h, C.c_void_p(ptr), n, C.byref(o), C.byref(out),
+                                                    C.byref(self.stats)))
+        if not copy:
+            return out
+        P, d = out.n_phrases, out.n_distinct
+        s = C.string_at
+        return PfpFiles(dict=s(out.dict, out.dict_bytes), occ=s(out.occ, 4 * d), parse=s(out.parse, 4 * P),
+                        last=s(out.last, P), sai=s(out.sai, 5 * P) if out.sai else b"",
+                        stats=self.stats.as_dict())
+
+    def parse_file(self, path, w=10, p=100, sai=False, fasta=False, compress=False, nseg=0) -> dict:
+        o = Opts(w, p, _flags(sai, fasta, compress), nseg)
+        self._check(self.L.pfpb200_multi_parse_file(self.h, os.fsencode(path), C.byref(o), C.byref(self.stats)))
+        return self.stats.as_dict()
+
+    def phase_ms(self):
+        """{phase: [ms of rank 0, rank 1, ...]} of the last parse."""
+        n = len(self.gpu_ids) * len(PHASES)
+        buf = (C.c_float * n)()
+        k = self.L.pfpb200_multi_phase_ms(self.h, buf, n)
+        return {ph: [buf[r * len(PHASES) + i] for r in range(k // len(PHASES))] for i, ph in enumerate(PHASES)}

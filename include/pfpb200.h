@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PFPB200_ABI_VERSION 1
+#define PFPB200_ABI_VERSION 2
 
 /* ---- error codes (reference behaviour: message + exit(1), utils.c:12-16) ------------------ */
 #define PFPB200_OK            0
@@ -237,6 +237,37 @@ int pfpb200_shard_route_push(pfpb200_ctx *ctx, uint32_t n_ranks, const uint64_t 
 int pfpb200_dict_merge_words(pfpb200_ctx *ctx, uint64_t n_in, const pfpb200_word *words,
                              const uint64_t *pool, uint64_t pool_words, uint32_t w, uint32_t flags,
                              pfpb200_merged *out, float *ms);
+
+/* Ranks travelling back in the range-partitioned merge: d_back[i] = rank, inside its owner's
+ * range, of the word pfpb200_shard_route put at routed position i; rank_base[q] = number of
+ * distinct words in the ranges below owner q.  *d_rank_of_word (context-owned) = global 1-based
+ * rank of every local word, ready for pfpb200_shard_remap. */
+int pfpb200_shard_ranks_back(pfpb200_ctx *ctx, uint32_t n_ranks, const uint32_t *d_back,
+                             const uint64_t *rank_base, const uint32_t **d_rank_of_word);
+
+/* ---- several GPUs of one box behind one call ------------------------------------------------ *
+ * Reference analogue: `newscan.x -t T` / `pscan.x -t T` -- one process, T helper threads over
+ * contiguous ranges of the input, complete outputs at return (newscan.hpp:230-337,
+ * pscan.hpp:114-165, bigbwt:71-78).  One host thread per listed GPU drives the pfpb200_shard_*
+ * stages; the dictionary words travel between the GPUs as peer-to-peer DMA over NVLink.  gpu_ids
+ * NULL = devices 0..n_gpus-1; a device may be listed more than once (its shards time-share it).
+ * Outputs: the five whole streams in pinned host memory owned by the handle (valid until the next
+ * parse on it), byte-identical to the single-GPU entry points for every n_gpus. */
+typedef struct pfpb200_multi pfpb200_multi;
+int  pfpb200_multi_create(int n_gpus, const int *gpu_ids, pfpb200_multi **m);
+void pfpb200_multi_destroy(pfpb200_multi *m);
+int  pfpb200_multi_n_gpus(const pfpb200_multi *m);
+int  pfpb200_multi_parse_host(pfpb200_multi *m, const uint8_t *text, uint64_t n_text,
+                              const pfpb200_opts *opts, pfpb200_outputs *host_out, pfpb200_stats *stats);
+/* newscan.x main() on several GPUs: reads `path`, writes the same files as pfpb200_parse_file. */
+int  pfpb200_multi_parse_file(pfpb200_multi *m, const char *path, const pfpb200_opts *opts,
+                              pfpb200_stats *stats);
+const char *pfpb200_multi_last_error(const pfpb200_multi *m);
+/* Per-rank timeline of the last parse: out[rank * PFPB200_N_PHASES + k] = milliseconds rank spent
+ * in phase k (start, h2d, scan, seams, words, splitters, route, exchange, merge, ranks-back, remap,
+ * d2h; a phase with a barrier includes waiting for the slowest rank).  Returns values written. */
+#define PFPB200_N_PHASES 12
+int  pfpb200_multi_phase_ms(const pfpb200_multi *m, float *out, int cap);
 
 /* Kernels launched on this context since the start of the current parse (the last
  * pfpb200_parse_* / pfpb200_shard_scan call). */

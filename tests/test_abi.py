@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for n in names:
         assert hasattr(L, n), f"libpfpb200.so does not export {n}"
     assert set(names) == set(pkg.pfp.SYMBOLS)
-    assert L.pfpb200_abi_version() == 1
+    assert L.pfpb200_abi_version() == 2
 
 
 def test_struct_layouts_match_header(pkg):
