@@ -2,8 +2,12 @@
 // orchestration of the stages K1..K5 for one GPU.
 #include "pfp_common.cuh"
 #include "pfp_stages.cuh"
+#include <errno.h>
+#include <fcntl.h>
 #include <stdlib.h>
+#include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 extern "C" {
 int pfp_io_read_file(const char *path, int gz_ok, uint8_t **buf, uint64_t *n, char *err, size_t errlen);
@@ -135,6 +139,7 @@ extern "C" void pfpb200_destroy(pfpb200_ctx *ctx) {
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->d_keys) cudaFree(ctx->d_keys);
     if (ctx->dna_table) cudaFree(ctx->dna_table);
+    pfp_io_destroy(ctx);
     for (int i = 0; i < 5; i++)
         if (ctx->pin_buf[i]) cudaFreeHost(ctx->pin_buf[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -411,41 +416,144 @@ extern "C" int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_
     return PFPB200_OK;
 }
 
+// the five files straight from the device outputs, D2H chunks overlapped with the writes
+static int write_outputs_from_device(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *o,
+                                     const pfpb200_outputs &dv) {
+    char name[4096];
+    auto put = [&](const char *ext, int seg, const void *p, u64 bytes) -> int {
+        if (seg < 0) snprintf(name, sizeof(name), "%s.%s", path, ext);              // utils.c:33-41
+        else snprintf(name, sizeof(name), "%s.%d.%s", path, seg, ext);              // utils.c:44-54
+        return pfp_device_to_file(ctx, name, p, bytes);
+    };
+    const u64 P = dv.n_phrases;
+    PFP_TRY(put((o->flags & PFPB200_F_COMPRESS) ? "dicz" : "dict", -1, dv.dict, dv.dict_bytes));
+    PFP_TRY(put("occ", -1, dv.occ, 4 * dv.n_distinct));
+    PFP_TRY(put("parse", -1, dv.parse, 4 * P));
+    const int T = o->nseg;
+    if (T <= 0) {
+        PFP_TRY(put("last", -1, dv.last, P));
+        if (dv.sai) PFP_TRY(put("sai", -1, dv.sai, PFP_IBYTES * P));
+    } else {
+        // newscan.hpp:274-276: one .last/.sai segment per helper thread; bwtparse -t T reads them
+        // back to back (bwtparse.c:179,195; utils.c:57-105), so any split is equivalent
+        const u64 per = (P + (u64)T - 1) / (u64)T;
+        for (int s = 0; s < T; s++) {
+            u64 a = (u64)s * per, b = a + per;
+            if (a > P) a = P;
+            if (b > P) b = P;
+            PFP_TRY(put("last", s, dv.last + a, b - a));
+            if (dv.sai) PFP_TRY(put("sai", s, dv.sai + PFP_IBYTES * a, PFP_IBYTES * (b - a)));
+        }
+    }
+    return PFPB200_OK;
+}
+
+// parse_host semantics for text that is already on the device: cut at the first byte <= 0x02
+static int cut_and_parse_device(pfpb200_ctx *ctx, const u8 *d_text, u64 n_text, const pfpb200_opts *opts,
+                                pfpb200_outputs *dv, pfpb200_stats *stats) {
+    u64 n = n_text;
+    if (n_text) {
+        set_u64_k<<<1, 1, 0, ctx->stream>>>(&ctx->d_flags[14], n_text);
+        PFP_LAUNCHED(ctx);
+        PFP_TRY(pfp_first_invalid(ctx, d_text, n_text, &ctx->d_flags[14]));
+        PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[14], &ctx->d_flags[14], sizeof(u64), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        n = ctx->h_flags[14];
+    }
+    if (n < n_text) fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
+    return parse_device_impl(ctx, d_text, n, opts, dv, stats);
+}
+
 extern "C" int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts,
                                   pfpb200_stats *stats) {
     PFP_TRY(check_opts(ctx, opts));
     if (!path) return pfp_fail(ctx, PFPB200_E_ARG, "null path");
-    double t0 = wall_sec();
-    uint8_t *file = nullptr;
-    uint64_t fn = 0;
-    if (pfp_io_read_file(path, (opts->flags & PFPB200_F_FASTA) != 0, &file, &fn, ctx->err, sizeof(ctx->err)) != 0)
-        return PFPB200_E_IO;
-    const uint8_t *text = file;
-    uint64_t n = fn;
-    uint8_t *seq = nullptr;
-    if (opts->flags & PFPB200_F_FASTA) {
-        seq = (uint8_t *)malloc(fn ? fn : 1);
-        if (!seq) { free(file); return pfp_fail(ctx, PFPB200_E_NOMEM, "out of memory"); }
-        int trunc = 0;
-        n = pfpb200_fasta_extract(file, fn, seq, &trunc);
-        if (trunc) fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
-        free(file);
-        file = nullptr;
-        text = seq;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const double t0 = wall_sec();
+    const bool fasta = (opts->flags & PFPB200_F_FASTA) != 0;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return pfp_fail(ctx, PFPB200_E_IO, "%s: %s", path, strerror(errno));
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); return pfp_fail(ctx, PFPB200_E_IO, "%s: %s", path, strerror(errno)); }
+    const u64 fsize = (u64)sb.st_size;
+    bool gz = false;
+    if (fasta && fsize >= 2) {       // gzip input, as the reference's gzread takes it (newscan.cpp:332-336)
+        unsigned char mg[2] = {0, 0};
+        if (pread(fd, mg, 2, 0) == 2) gz = mg[0] == 0x1f && mg[1] == 0x8b;
     }
-    double t1 = wall_sec();
-    pfpb200_outputs ho;
-    int rc = pfpb200_parse_host(ctx, text, n, opts, &ho, stats);
-    free(file);
-    free(seq);
-    if (rc != PFPB200_OK) return rc;
-    double t2 = wall_sec();
-    if (pfp_io_write_outputs(path, opts, &ho, ctx->err, sizeof(ctx->err)) != 0) return PFPB200_E_IO;
+    PFP_TRY(begin_call(ctx));
+    pfpb200_outputs dv;
+    memset(&dv, 0, sizeof(dv));
+    double t1 = t0;
+    int rc = PFPB200_OK;
+    auto run = [&]() -> int {
+        u8 *d_text = nullptr;
+        u64 n_text = 0;
+        bool on_device = false;
+        if (!gz) {
+            // the file goes to HBM through the pinned ring; it is never held in host memory
+            // (scratch: the text lives until the parse is done, the raw FASTA bytes until K0 is)
+            u8 *d_file = nullptr;
+            PFP_TRY(pfp_alloc(ctx, (void **)&d_file, fsize + 16));
+            PFP_TRY(pfp_file_to_device(ctx, fd, 0, fsize, d_file));
+            if (!fasta) { d_text = d_file; n_text = fsize; on_device = true; }
+            else {
+                int supported = 0;
+                PFP_TRY(pfp_fasta_device(ctx, d_file, fsize, &d_text, &n_text, &supported, false));    // K0
+                on_device = supported != 0;
+                PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                PFP_TRY(pfp_free_now(ctx, d_file));
+            }
+        }
+        if (!on_device) {
+            // gzip, FASTQ, CRLF, ...: the host reader with all of kseq's corner cases (pfp_io.c)
+            uint8_t *text = nullptr;
+            uint64_t n = 0;
+            int trunc = 0;
+            if (pfpb200_read_input(path, opts->flags, &text, &n, &trunc) != PFPB200_OK)
+                return pfp_fail(ctx, PFPB200_E_IO, "%s: cannot read", path);
+            if (trunc) fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
+            int r2 = pfp_alloc(ctx, (void **)&d_text, n + 16);
+            if (r2 == PFPB200_OK && n && cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                r2 = pfp_fail(ctx, PFPB200_E_CUDA, "host-to-device copy of the input failed");
+            if (r2 == PFPB200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                r2 = pfp_fail(ctx, PFPB200_E_CUDA, "host-to-device copy of the input failed");
+            pfpb200_free_host(text);
+            PFP_TRY(r2);
+            n_text = n;
+        }
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        t1 = wall_sec();
+        PFP_TRY(cut_and_parse_device(ctx, d_text, n_text, opts, &dv, stats));
+        return PFPB200_OK;
+    };
+    rc = run();
+    close(fd);
+    if (rc != PFPB200_OK) { pfp_release_scratch(ctx); return rc; }
+    const double t2 = wall_sec();
+    PFP_TRY(write_outputs_from_device(ctx, path, opts, dv));
     if (stats) {
         stats->sec_read = (float)(t1 - t0);
         stats->sec_write = (float)(wall_sec() - t2);
     }
+    pfp_release_held(ctx);
     return PFPB200_OK;
+}
+
+// K0 alone, for tests and callers that hold FASTA bytes in HBM: *d_text (context-owned, valid until
+// the next parse) = the text of `-f` mode; *supported = 0 when the bytes need the host reader
+// (pfpb200_fasta_extract) -- FASTQ, '\r', bytes <= 0x02 / 0xFF, no '>' at offset 0.
+extern "C" int pfpb200_fasta_extract_device(pfpb200_ctx *ctx, const uint8_t *d_file, uint64_t n,
+                                            const uint8_t **d_text, uint64_t *n_text, int *supported) {
+    if (!ctx || !d_text || !n_text || !supported || (n && !d_file)) return PFPB200_E_ARG;
+    PFP_TRY(begin_call(ctx));
+    u8 *out = nullptr;
+    int rc = pfp_fasta_device(ctx, d_file, n, &out, n_text, supported, true);
+    cudaStreamSynchronize(ctx->stream);
+    pfp_release_scratch(ctx);
+    *d_text = out;
+    return rc;
 }
 
 extern "C" int pfpb200_scan_triggers(pfpb200_ctx *ctx, const uint8_t *d_buf, uint64_t n_buf,

@@ -44,8 +44,19 @@ struct ScanBits {
     u32 max_tile_cnt;   // largest tile_cnt
 };
 
+// pinned ring of the overlapped file I/O (pfp_ingest.cu): IO_THREADS workers, two slots each
+constexpr int PFP_IO_THREADS = 4;
+constexpr size_t PFP_IO_CHUNK = (size_t)8 << 20;
+struct PfpIo {
+    bool ready = false;
+    void *slot[PFP_IO_THREADS][2] = {{nullptr}};
+    cudaEvent_t ev[PFP_IO_THREADS][2] = {{nullptr}};
+    cudaStream_t stream[PFP_IO_THREADS] = {nullptr};
+};
+
 struct pfpb200_ctx {
     int device = 0;
+    PfpIo io;
     PfpArena arena;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;

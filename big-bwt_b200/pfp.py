@@ -75,7 +75,8 @@ class PfpFiles:
 _lib = None
 
 SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_parse_device",
-           "pfpb200_parse_host", "pfpb200_parse_file", "pfpb200_fasta_extract", "pfpb200_read_input",
+           "pfpb200_parse_host", "pfpb200_parse_file", "pfpb200_fasta_extract", "pfpb200_fasta_extract_device",
+           "pfpb200_read_input",
            "pfpb200_free_host",
            "pfpb200_scan_triggers", "pfpb200_memcpy_d2h", "pfpb200_strerror",
            "pfpb200_shard_scan", "pfpb200_shard_words", "pfpb200_dict_merge", "pfpb200_shard_remap",
@@ -257,6 +258,19 @@ class Scanner:
         o = Opts(w, p, _flags(sai, fasta, compress), nseg)
         self._check(self.L.pfpb200_parse_file(self.h, os.fsencode(path), C.byref(o), C.byref(self.stats)))
         return self.stats.as_dict()
+
+    # -- K0 alone: FASTA bytes in HBM -> text in HBM ------------------------------------------------------
+    def fasta_extract_device(self, file_dev):
+        """(text bytes or None, supported) for FASTA bytes held in a CUDA uint8 tensor."""
+        self.L.pfpb200_fasta_extract_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p),
+                                                        C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        self.L.pfpb200_fasta_extract_device.restype = C.c_int
+        ptr, n, ok = C.c_void_p(), C.c_uint64(), C.c_int()
+        self._check(self.L.pfpb200_fasta_extract_device(self.h, C.c_void_p(file_dev.data_ptr() if file_dev.numel() else 0),
+                                                        file_dev.numel(), C.byref(ptr), C.byref(n), C.byref(ok)))
+        if not ok.value:
+            return None, False
+        return self.to_host(ptr.value, n.value), True
 
     # -- K1 alone ---------------------------------------------------------------------------------------
     def scan_triggers(self, buf, w=10, p=100, buf_pos0=0, own_lo=0, own_hi=None):

@@ -117,7 +117,10 @@ int pfpb200_parse_host(pfpb200_ctx *ctx, const uint8_t *text, uint64_t n_text,
 
 /* newscan.x main() (newscan.cpp:569-650): reads `path` (plain or FASTA per opts->flags),
  * parses on the GPU and writes <path>.dict|.dicz .occ .parse .last [.sai] (segmented
- * .last/.sai when opts->nseg > 0). */
+ * .last/.sai when opts->nseg > 0).  The file streams into HBM through a ring of pinned chunks
+ * (reads, copies and the FASTA extraction on the device overlap; it is never held in host
+ * memory, like the reference's byte-wise reader, newscan.cpp:332-374) and the outputs stream
+ * back into the files the same way. */
 int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts,
                        pfpb200_stats *stats);
 
@@ -125,6 +128,13 @@ int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *o
  * newscan.cpp:338-349), host side.  `out` must hold n bytes; returns text length and sets
  * *truncated when an invalid byte ended the input. */
 uint64_t pfpb200_fasta_extract(const uint8_t *file, uint64_t n, uint8_t *out, int *truncated);
+
+/* K0: the same extraction on the device, for FASTA bytes already in HBM (what pfpb200_parse_file
+ * runs after streaming the file in).  *d_text is owned by the context (valid until its next
+ * call).  *supported = 0: the bytes hold something beyond plain multi-line FASTA (FASTQ records,
+ * '\r', bytes <= 0x02 or 0xFF, junk in front of the first '>') and need pfpb200_fasta_extract. */
+int pfpb200_fasta_extract_device(pfpb200_ctx *ctx, const uint8_t *d_file, uint64_t n,
+                                 const uint8_t **d_text, uint64_t *n_text, int *supported);
 
 /* The text T that pfpb200_parse_file() parses for `path`, in host memory (release it with
  * pfpb200_free_host): the file bytes, or with PFPB200_F_FASTA the extraction above of a plain or
