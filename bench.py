@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the byte-exact output check after the timed region")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-t2", action="store_true", help="skip the file-to-files wall clock of gpuscan.x (N=1 only)")
     ap.add_argument("--merge", default="partition", choices=["partition", "replicate"],
                     help="multi-GPU dictionary merge: range-partitioned all-to-all or replicated all-gather")
     return ap.parse_args()
@@ -316,6 +317,53 @@ def parity_check(job, pkg, synth, world, rank, local, dev, merge):
             "sha256": {k: hashlib.sha256(v).hexdigest()[:16] for k, v in got.items()}}
 
 
+# ------------------------------------------------------------------------------------------------
+# T2: page-cache-warm FASTA file -> five files closed, wall clock of the gpuscan.x process
+# ------------------------------------------------------------------------------------------------
+def t2_file_to_files(a, pkg, synth, dev):
+    """Writes the workload as a one-record-per-haplotype, 60-column FASTA (what `bigbwt -f` is
+    given), runs `gpuscan.x <file> -w 10 -p 100 -s -f` twice as a subprocess -- process start, CUDA
+    context creation, streaming read, K0, parse, streaming write all inside the wall clock -- and
+    reports the faster run with the tool's own breakdown."""
+    import re
+    tmp = tempfile.mkdtemp(prefix="pfpt2_")
+    try:
+        path = os.path.join(tmp, "workload.fa")
+        t0 = time.perf_counter()
+        n_text = 0
+        with open(path, "wb") as f:
+            for k, rec in enumerate(synth.pangenome_records(a.base_len, a.haplotypes, SEED, device=dev)):
+                r = rec.cpu().numpy()
+                n_text += r.size
+                synth.to_fasta_np(r, f"hap{k}").tofile(f)
+        gen_s = time.perf_counter() - t0
+        fsize = os.path.getsize(path)
+        runs = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run([pkg.pfp.CLI_PATH, path, "-w", str(W), "-p", str(P), "-s", "-f"],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"failed": r.returncode, "stderr": r.stderr[-300:]}
+            io = re.search(r"File read: ([0-9.]+) s, file write: ([0-9.]+) s", r.stdout)
+            gp = re.search(r"GPU parse: ([0-9.]+) ms", r.stdout)
+            runs.append({"seconds": dt, "read_s": float(io.group(1)) if io else None,
+                         "write_s": float(io.group(2)) if io else None,
+                         "gpu_parse_ms": float(gp.group(1)) if gp else None})
+        best = min(runs, key=lambda x: x["seconds"])
+        out_bytes = sum(os.path.getsize(path + "." + e) for e in ("dict", "occ", "parse", "last", "sai"))
+        return {"value": n_text / best["seconds"] / 1e9, "unit": UNIT, "seconds": best["seconds"],
+                "read_and_k0_s": best["read_s"], "gpu_parse_ms": best["gpu_parse_ms"], "write_s": best["write_s"],
+                "other_s": best["seconds"] - (best["read_s"] or 0) - (best["write_s"] or 0) - (best["gpu_parse_ms"] or 0) / 1e3,
+                "fasta_bytes": fsize, "text_bytes": n_text, "output_bytes": out_bytes, "runs": len(runs),
+                "how": "wall clock of the gpuscan.x process (start, CUDA context, streaming read + K0, parse, streaming "
+                       "write) on a page-cache-warm 60-column FASTA of the workload; 'other' = process start + CUDA init",
+                "fasta_generation_s": gen_s}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     a = parse_args()
     from __graft_entry__ import load_package
@@ -436,6 +484,12 @@ def main():
     if not a.no_parity:
         parity = parity_check(job, pkg, synth, world, rank, local, dev, a.merge)
 
+    t2 = None
+    if world == 1 and not a.no_t2 and a.workload == "pangenome":
+        job.release_text()
+        torch.cuda.empty_cache()
+        t2 = t2_file_to_files(a, pkg, synth, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -483,6 +537,8 @@ def main():
         line["per_rank_phase_ms"] = per_rank
     if parity is not None:
         line["parity_check"] = parity
+    if t2 is not None:
+        line["t2_file_to_files"] = t2
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

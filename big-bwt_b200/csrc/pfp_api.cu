@@ -548,7 +548,7 @@ extern "C" int pfpb200_fasta_extract_device(pfpb200_ctx *ctx, const uint8_t *d_f
                                             const uint8_t **d_text, uint64_t *n_text, int *supported) {
     if (!ctx || !d_text || !n_text || !supported || (n && !d_file)) return PFPB200_E_ARG;
     PFP_TRY(begin_call(ctx));
-    u8 *out = nullptr;
+    u8 *out = nullptr;                 // null: an arena buffer held by the context
     int rc = pfp_fasta_device(ctx, d_file, n, &out, n_text, supported, true);
     cudaStreamSynchronize(ctx->stream);
     pfp_release_scratch(ctx);

@@ -439,10 +439,12 @@ __global__ void fasta_first_byte_k(const u8 *__restrict__ f, u32 *__restrict__ f
     if (f[0] != '>') atomicOr(flags, K0_BAD);      // kseq skips junk in front of the first '>' / '@'
 }
 
-// d_file[0..n) (FASTA bytes in HBM) -> *d_text (scratch of ctx, n bytes), *n_text.  *supported = 0:
-// the file needs the host reader, nothing was produced.
+// d_file[0..n) (FASTA bytes in HBM) -> *d_text, *n_text.  *d_text non-null on entry: the caller's
+// buffer (>= n + 16 bytes) is filled; else an arena buffer of ctx (held or scratch).
+// *supported = 0: the file needs the host reader, nothing was produced.
 int pfp_fasta_device(pfpb200_ctx *ctx, const u8 *d_file, u64 n, u8 **d_text, u64 *n_text, int *supported,
                      bool held) {
+    u8 *const user_out = *d_text;
     *d_text = nullptr;
     *n_text = 0;
     *supported = 1;
@@ -473,14 +475,14 @@ int pfp_fasta_device(pfpb200_ctx *ctx, const u8 *d_file, u64 n, u8 **d_text, u64
     if (h[0] & K0_BAD) {
         *supported = 0;
     } else {
-        u8 *out = nullptr;
-        PFP_TRY(pfp_alloc(ctx, (void **)&out, kept + 16, held));
+        u8 *out = user_out;
+        if (!out) PFP_TRY(pfp_alloc(ctx, (void **)&out, kept + 16, held));
         fasta_emit_k<<<ntiles, K0_T, 0, ctx->stream>>>(d_file, n, tstate, toff, out, flags);
         PFP_LAUNCHED(ctx);
         // a line starting with '@' or '+' (FASTQ) is only recognised now that the states are known
         PFP_CUDA(ctx, cudaMemcpyAsync(h, flags, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (h[0] & K0_BAD) { *supported = 0; PFP_TRY(pfp_free_now(ctx, out)); }
+        if (h[0] & K0_BAD) { *supported = 0; if (!user_out) PFP_TRY(pfp_free_now(ctx, out)); }
         else { *d_text = out; *n_text = kept; }
     }
     PFP_TRY(pfp_free_now(ctx, tsum));

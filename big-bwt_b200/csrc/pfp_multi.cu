@@ -22,7 +22,11 @@
 // single-GPU test box exercises this file.
 #include "pfp_common.cuh"
 #include "pfp_stages.cuh"
+#include <errno.h>
+#include <fcntl.h>
 #include <stdlib.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -97,8 +101,13 @@ struct pfpb200_multi {
     std::atomic<int> failed{0};
     std::mutex err_mu;
     char err[512] = {0};
-    // the current job
+    // the current job: where the text comes from
+    //   text     : host memory (pfpb200_multi_parse_host)
+    //   src_fd   : a plain-text file, every rank reads its own range through its pinned ring
+    //   src_dev  : device memory of rank 0 (the FASTA file after K0), shards travel peer to peer
     const u8 *text = nullptr;
+    int src_fd = -1;
+    const u8 *src_dev = nullptr;
     u64 n_text = 0, n_eff = 0;
     int n_active = 0;                     // shards in use (short texts use fewer)
     pfpb200_opts opts{};
@@ -200,9 +209,15 @@ void rank_main(pfpb200_multi *m, int g) {
             multi_fail(m, g, PFPB200_E_NOMEM, "device allocation of the shard failed");
             return;
         }
-        if (R.front + R.n_local)
-            MR_CUDA(cudaMemcpyAsync(R.buf, m->text + (R.pos0 - R.front), (size_t)(R.front + R.n_local),
-                                    cudaMemcpyHostToDevice, st));
+        const u64 from = R.pos0 - R.front, bytes = R.front + R.n_local;
+        if (bytes == 0) return;
+        if (m->text) {
+            MR_CUDA(cudaMemcpyAsync(R.buf, m->text + from, (size_t)bytes, cudaMemcpyHostToDevice, st));
+        } else if (m->src_dev) {
+            MR_CUDA(cudaMemcpyPeerAsync(R.buf, R.device, m->src_dev + from, m->r[0].device, (size_t)bytes, st));
+        } else {
+            MR_LIB(pfp_file_to_device(R.ctx, m->src_fd, from, bytes, R.buf));
+        }
     };
     [&]() {
         if (!ok()) return;
@@ -546,15 +561,12 @@ extern "C" int pfpb200_multi_phase_ms(const pfpb200_multi *m, float *out, int ca
     return k;
 }
 
-extern "C" int pfpb200_multi_parse_host(pfpb200_multi *m, const uint8_t *text, uint64_t n_text,
-                                        const pfpb200_opts *opts, pfpb200_outputs *host_out,
-                                        pfpb200_stats *stats) {
-    int rc = check_multi_opts(m, opts);
-    if (rc != PFPB200_OK) return rc;
-    if (!host_out || (n_text && !text)) return PFPB200_E_ARG;
+// one parse of n_text bytes from the source set in m (text / src_fd / src_dev)
+static int multi_run(pfpb200_multi *m, uint64_t n_text, const pfpb200_opts *opts, pfpb200_outputs *host_out,
+                     pfpb200_stats *stats) {
+    int rc;
     memset(host_out, 0, sizeof(*host_out));
     if (stats) memset(stats, 0, sizeof(*stats));
-    m->text = text;
     m->n_text = n_text;
     m->opts = *opts;
     m->failed.store(0);
@@ -596,25 +608,151 @@ extern "C" int pfpb200_multi_parse_host(pfpb200_multi *m, const uint8_t *text, u
     return PFPB200_OK;
 }
 
+extern "C" int pfpb200_multi_parse_host(pfpb200_multi *m, const uint8_t *text, uint64_t n_text,
+                                        const pfpb200_opts *opts, pfpb200_outputs *host_out,
+                                        pfpb200_stats *stats) {
+    int rc = check_multi_opts(m, opts);
+    if (rc != PFPB200_OK) return rc;
+    if (!host_out || (n_text && !text)) return PFPB200_E_ARG;
+    static const u8 empty = 0;
+    m->text = n_text ? text : &empty;
+    m->src_fd = -1;
+    m->src_dev = nullptr;
+    return multi_run(m, n_text, opts, host_out, stats);
+}
+
+// host buffer -> file, a few threads pwrite()-ing disjoint chunks
+static int host_to_file(const char *name, const void *p, u64 bytes, char *err, size_t errlen) {
+    int fd = open(name, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) { snprintf(err, errlen, "%s: %s", name, strerror(errno)); return -1; }
+    const u64 chunk = (u64)16 << 20;
+    const u64 nchunks = (bytes + chunk - 1) / chunk;
+    const int nt = (int)std::min<u64>(4, std::max<u64>(1, nchunks));
+    std::atomic<int> bad{0};
+    auto worker = [&](int t) {
+        for (u64 c = (u64)t; c < nchunks; c += (u64)nt) {
+            const u64 o = c * chunk, len = std::min(chunk, bytes - o);
+            u64 done = 0;
+            while (done < len) {
+                ssize_t r = pwrite(fd, (const char *)p + o + done, (size_t)(len - done), (off_t)(o + done));
+                if (r < 0) { if (errno == EINTR) continue; bad.store(1); return; }
+                done += (u64)r;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &t : th) t.join();
+    if (close(fd) != 0) bad.store(1);
+    if (bad.load()) { snprintf(err, errlen, "%s: write error", name); return -1; }
+    return 0;
+}
+
+static int multi_write_outputs(pfpb200_multi *m, const char *path, const pfpb200_opts *o, const pfpb200_outputs &ho) {
+    char name[4096];
+    auto put = [&](const char *ext, int seg, const void *p, u64 bytes) -> int {
+        if (seg < 0) snprintf(name, sizeof(name), "%s.%s", path, ext);              // utils.c:33-41
+        else snprintf(name, sizeof(name), "%s.%d.%s", path, seg, ext);              // utils.c:44-54
+        return host_to_file(name, p, bytes, m->err, sizeof(m->err));
+    };
+    const u64 P = ho.n_phrases;
+    if (put((o->flags & PFPB200_F_COMPRESS) ? "dicz" : "dict", -1, ho.dict, ho.dict_bytes)) return -1;
+    if (put("occ", -1, ho.occ, 4 * ho.n_distinct)) return -1;
+    if (put("parse", -1, ho.parse, 4 * P)) return -1;
+    const int T = o->nseg;
+    if (T <= 0) {
+        if (put("last", -1, ho.last, P)) return -1;
+        if (ho.sai && put("sai", -1, ho.sai, PFP_IBYTES * P)) return -1;
+    } else {                                  // newscan.hpp:274-276; bwtparse.c:179,195
+        const u64 per = (P + (u64)T - 1) / (u64)T;
+        for (int s = 0; s < T; s++) {
+            u64 a = std::min(P, (u64)s * per), b = std::min(P, a + per);
+            if (put("last", s, ho.last + a, b - a)) return -1;
+            if (ho.sai && put("sai", s, ho.sai + PFP_IBYTES * a, PFP_IBYTES * (b - a))) return -1;
+        }
+    }
+    return 0;
+}
+
+// newscan.x main() on several GPUs.  Plain text: every rank reads its own range of the file through
+// its pinned ring.  FASTA: rank 0 streams the file in and runs K0; the shards of the extracted
+// text then travel to the other GPUs peer to peer (NVLink).  gzip / FASTQ / CRLF input takes the
+// host reader.
 extern "C" int pfpb200_multi_parse_file(pfpb200_multi *m, const char *path, const pfpb200_opts *opts,
                                         pfpb200_stats *stats) {
     int rc = check_multi_opts(m, opts);
     if (rc != PFPB200_OK) return rc;
     if (!path) return PFPB200_E_ARG;
     const double t0 = wall_sec();
-    uint8_t *text = nullptr;
-    uint64_t n = 0;
-    int trunc = 0;
-    rc = pfpb200_read_input(path, opts->flags, &text, &n, &trunc);
-    if (rc != PFPB200_OK) { snprintf(m->err, sizeof(m->err), "cannot read %s", path); return rc; }
-    if (trunc) fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
+    const bool fasta = (opts->flags & PFPB200_F_FASTA) != 0;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { snprintf(m->err, sizeof(m->err), "%s: %s", path, strerror(errno)); return PFPB200_E_IO; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { snprintf(m->err, sizeof(m->err), "%s: %s", path, strerror(errno)); close(fd); return PFPB200_E_IO; }
+    const u64 fsize = (u64)sb.st_size;
+    bool gz = false;
+    if (fasta && fsize >= 2) {
+        unsigned char mg[2] = {0, 0};
+        if (pread(fd, mg, 2, 0) == 2) gz = mg[0] == 0x1f && mg[1] == 0x8b;
+    }
+    m->text = nullptr;
+    m->src_fd = -1;
+    m->src_dev = nullptr;
+    u64 n = 0;
+    u8 *d_text0 = nullptr;                     // rank 0's copy of the extracted text (FASTA)
+    uint8_t *host_text = nullptr;
+    Rank &R0 = m->r[0];
+    if (!fasta) {
+        m->src_fd = fd;
+        n = fsize;
+    } else if (!gz && fsize > 0) {
+        cudaSetDevice(R0.device);
+        u8 *d_file = nullptr;
+        int supported = 0;
+        u64 nt = 0;
+        if (cudaMalloc(&d_file, fsize + 16) != cudaSuccess || cudaMalloc(&d_text0, fsize + 32) != cudaSuccess) {
+            cudaGetLastError();
+            if (d_file) cudaFree(d_file);
+            if (d_text0) cudaFree(d_text0);
+            close(fd);
+            snprintf(m->err, sizeof(m->err), "device allocation for the FASTA file failed");
+            return PFPB200_E_NOMEM;
+        }
+        rc = pfp_file_to_device(R0.ctx, fd, 0, fsize, d_file);
+        u8 *out = d_text0;
+        if (rc == PFPB200_OK) rc = pfp_fasta_device(R0.ctx, d_file, fsize, &out, &nt, &supported, false);   // K0
+        cudaStreamSynchronize(R0.ctx->stream);
+        pfp_release_scratch(R0.ctx);
+        cudaFree(d_file);
+        if (rc != PFPB200_OK) {
+            snprintf(m->err, sizeof(m->err), "%s", pfpb200_last_error(R0.ctx));
+            cudaFree(d_text0);
+            close(fd);
+            return rc;
+        }
+        if (supported) { m->src_dev = d_text0; n = nt; }
+        else { cudaFree(d_text0); d_text0 = nullptr; }
+    }
+    if (fasta && !m->src_dev && !(fsize == 0)) {             // gzip, FASTQ, CRLF, ...: the host reader (pfp_io.c)
+        int trunc = 0;
+        rc = pfpb200_read_input(path, opts->flags, &host_text, &n, &trunc);
+        if (rc != PFPB200_OK) { snprintf(m->err, sizeof(m->err), "cannot read %s", path); close(fd); return rc; }
+        if (trunc) fprintf(stderr, "Invalid char found in input file: no additional chars will be read\n");
+        m->text = host_text;
+    }
+    static const u8 empty = 0;
+    if (n == 0 && !m->text) { m->text = &empty; m->src_fd = -1; m->src_dev = nullptr; }
     const double t1 = wall_sec();
     pfpb200_outputs ho;
-    rc = pfpb200_multi_parse_host(m, text, n, opts, &ho, stats);
-    pfpb200_free_host(text);
+    rc = multi_run(m, n, opts, &ho, stats);
+    close(fd);
+    if (host_text) pfpb200_free_host(host_text);
+    if (d_text0) { cudaSetDevice(R0.device); cudaFree(d_text0); }
+    m->text = nullptr; m->src_fd = -1; m->src_dev = nullptr;
     if (rc != PFPB200_OK) return rc;
     const double t2 = wall_sec();
-    if (pfp_io_write_outputs(path, opts, &ho, m->err, sizeof(m->err)) != 0) return PFPB200_E_IO;
+    if (multi_write_outputs(m, path, opts, ho) != 0) return PFPB200_E_IO;
     if (stats) {
         stats->sec_read = (float)(t1 - t0);
         stats->sec_write = (float)(wall_sec() - t2);

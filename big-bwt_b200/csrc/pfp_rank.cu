@@ -1078,3 +1078,36 @@ extern "C" int pfpb200_shard_ranks_back(pfpb200_ctx *ctx, uint32_t n_ranks, cons
     *d_rank_of_word = out;
     return PFPB200_OK;
 }
+
+// ---- self-check: the dictionary is strictly increasing (std::sort order, newscan.cpp:387-390,636) ---------
+// One thread per adjacent pair of a .dict byte stream (words end in 0x01): word i must be
+// strictly smaller than word i+1 in unsigned-byte order, a proper prefix counting as smaller.
+__global__ void dict_order_check_k(const u8 *__restrict__ dict, const u64 *__restrict__ seps, u64 d,
+                                   unsigned long long *__restrict__ bad) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= d) return;
+    const u64 a0 = i ? seps[i - 1] + 1 : 0, a1 = seps[i];          // word i   = dict[a0, a1)
+    const u64 b0 = a1 + 1, b1 = seps[i + 1];                        // word i+1 = dict[b0, b1)
+    const u64 la = a1 - a0, lb = b1 - b0;
+    const u64 m = la < lb ? la : lb;
+    u64 k = 0;
+    while (k < m && dict[a0 + k] == dict[b0 + k]) k++;
+    const bool less = k < m ? dict[a0 + k] < dict[b0 + k] : la < lb;
+    if (!less) atomicAdd(bad, 1ull);
+}
+
+extern "C" int pfpb200_check_dict_order(pfpb200_ctx *ctx, const uint8_t *d_dict, const uint64_t *d_seps,
+                                        uint64_t n_words, uint64_t *n_bad) {
+    if (!ctx || !n_bad || (n_words && (!d_dict || !d_seps))) return PFPB200_E_ARG;
+    *n_bad = 0;
+    if (n_words < 2) return PFPB200_OK;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[13], 0, sizeof(u64), ctx->stream));
+    dict_order_check_k<<<pfp_blocks(n_words - 1, 256), 256, 0, ctx->stream>>>(
+        d_dict, d_seps, n_words, reinterpret_cast<unsigned long long *>(&ctx->d_flags[13]));
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[13], &ctx->d_flags[13], sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_bad = ctx->h_flags[13];
+    return PFPB200_OK;
+}

@@ -85,6 +85,7 @@ SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_p
            "pfpb200_shard_ranks_back", "pfpb200_multi_create", "pfpb200_multi_destroy", "pfpb200_multi_n_gpus",
            "pfpb200_multi_parse_host", "pfpb200_multi_parse_file", "pfpb200_multi_last_error",
            "pfpb200_multi_phase_ms",
+           "pfpb200_check_dict_order",
            "pfpb200_launch_count", "pfpb200_last_error", "pfpb200_abi_version"]
 
 
@@ -258,6 +259,17 @@ class Scanner:
         o = Opts(w, p, _flags(sai, fasta, compress), nseg)
         self._check(self.L.pfpb200_parse_file(self.h, os.fsencode(path), C.byref(o), C.byref(self.stats)))
         return self.stats.as_dict()
+
+    def check_dict_order(self, dict_dev, seps_dev) -> int:
+        """Adjacent pairs of the .dict stream (CUDA uint8 tensor) that are not strictly increasing;
+        seps_dev: int64 CUDA tensor with the positions of the 0x01 terminators."""
+        self.L.pfpb200_check_dict_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                    C.POINTER(C.c_uint64)]
+        self.L.pfpb200_check_dict_order.restype = C.c_int
+        bad = C.c_uint64()
+        self._check(self.L.pfpb200_check_dict_order(self.h, C.c_void_p(dict_dev.data_ptr()),
+                                                    C.c_void_p(seps_dev.data_ptr()), seps_dev.numel(), C.byref(bad)))
+        return bad.value
 
     # -- K0 alone: FASTA bytes in HBM -> text in HBM ------------------------------------------------------
     def fasta_extract_device(self, file_dev):

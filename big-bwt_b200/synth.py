@@ -115,6 +115,27 @@ def pangenome_text(base_len: int, n_hap: int, seed: int, device="cpu",
     return torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=device)
 
 
+# BASELINE.json configs[0] names the reference's bundled yeast.fasta, which is not in the mount
+# (SURVEY section 0).  Stand-in of the same shape: the 16 chromosomes + mitochondrion of S. cerevisiae
+# S288C by length (12.16 Mbp), i.i.d. bases with 38 % GC.
+YEAST_LENGTHS = (230218, 813184, 316620, 1531933, 576874, 270161, 1090940, 562643, 439888, 745751, 666816,
+                 1078177, 924431, 784333, 1091291, 948066, 85779)
+YEAST_NAMES = tuple("chr" + r for r in ("I II III IV V VI VII VIII IX X XI XII XIII XIV XV XVI".split())) + ("chrM",)
+
+
+def yeast_like_records(seed: int = 1, device="cpu"):
+    """The 17 sequences (uint8 tensors) of the yeast-shaped stand-in."""
+    out = []
+    for k, n in enumerate(YEAST_LENGTHS):
+        i = torch.arange(n, dtype=torch.int64, device=device)
+        u = _lsr(_mix(i ^ _s64(_mix_int((seed << 8) ^ (k + 1)))), 44)          # 20 random bits
+        # A 31 %, C 19 %, G 19 %, T 31 %
+        code = (u >= 325058).to(torch.int64) + (u >= 524288).to(torch.int64) + (u >= 723518).to(torch.int64)
+        lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+        out.append(lut[code])
+    return out
+
+
 def to_fasta(records, names=None, width: int = 60, newline: bytes = b"\n") -> bytes:
     """Wrap sequences (uint8 arrays/tensors/bytes) as FASTA records with `width`-column lines."""
     chunks = []

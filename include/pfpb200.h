@@ -279,6 +279,13 @@ const char *pfpb200_multi_last_error(const pfpb200_multi *m);
 #define PFPB200_N_PHASES 12
 int  pfpb200_multi_phase_ms(const pfpb200_multi *m, float *out, int cap);
 
+/* Self-check of a .dict byte stream in device memory: number of adjacent word pairs that are NOT
+ * strictly increasing in unsigned-byte order (the std::sort(pstringCompare) order of
+ * newscan.cpp:387-390,636; the reference asserts its invariants the same way).  d_seps: ascending
+ * positions of the n_words 0x01 terminators. */
+int pfpb200_check_dict_order(pfpb200_ctx *ctx, const uint8_t *d_dict, const uint64_t *d_seps,
+                             uint64_t n_words, uint64_t *n_bad);
+
 /* Kernels launched on this context since the start of the current parse (the last
  * pfpb200_parse_* / pfpb200_shard_scan call). */
 uint32_t pfpb200_launch_count(const pfpb200_ctx *ctx);

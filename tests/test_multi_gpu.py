@@ -154,6 +154,14 @@ def test_cli_multi_gpu_files_match_reference(pkg):
             subprocess.run([orc.ref_exe("newscanNT.x"), ref, "-w", "10", "-p", "100", "-s"] + extra, check=True,
                            stdout=subprocess.PIPE)
             assert_same_files(orc.collect_files(ours), orc.collect_files(ref), f"cli -g {devs} fasta={fasta}")
+        # gzip-compressed FASTA goes through the host reader (zlib, as the reference's gzread)
+        import gzip
+        gzp = os.path.join(tmp, "ours.gz")
+        with gzip.open(gzp, "wb") as f:
+            f.write(pkg.synth.to_fasta(recs))
+        subprocess.run([pkg.pfp.CLI_PATH, gzp, "-w", "10", "-p", "100", "-s", "-f", "-g", devs], check=True,
+                       stdout=subprocess.PIPE)
+        assert_same_files(orc.collect_files(gzp), orc.collect_files(os.path.join(tmp, "ref1")), "cli multi gzip")
         seg = os.path.join(tmp, "seg")
         shutil.copy(os.path.join(tmp, "ref0"), seg)
         subprocess.run([pkg.pfp.CLI_PATH, seg, "-w", "10", "-p", "100", "-s", "-g", devs, "-t", "2"], check=True,

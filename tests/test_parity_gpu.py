@@ -298,3 +298,38 @@ def test_cli_files_and_bwt_match_reference(pkg):
                           "cli gzip")
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+@pytest.mark.skipif(not (orc.have_ref() and orc.have_ref("simplebwt")), reason="oracle/_ref not built")
+def test_config1_yeast_shaped_fasta_to_bwt(pkg):
+    """BASELINE config 1 (`bigbwt yeast.fasta -w 10 -p 100`; the bundled file is absent from the
+    mount, so a stand-in of its shape: 17 records, 12.16 Mbp, 60-column FASTA).  gpuscan.x replaces
+    the scanner; the UNCHANGED bwtparse + pfbwtNT.x turn its files into the .bwt/.sa of the
+    all-reference chain, and the .bwt equals the one SACA-K (simplebwt) computes from the extracted
+    text -- the check `bigbwt -c` does (bigbwt:176-195; on the extracted text)."""
+    recs = [r.numpy() for r in pkg.synth.yeast_like_records(1)]
+    assert len(recs) == 17 and 12_000_000 < sum(r.size for r in recs) < 12_300_000
+    fa = b"".join(pkg.synth.to_fasta_np(r, f"{nm} stand-in").tobytes() for r, nm in zip(recs, pkg.synth.YEAST_NAMES))
+    tmp = tempfile.mkdtemp(prefix="pfpyeast_")
+    try:
+        ours, ref, txt = (os.path.join(tmp, x) for x in ("ours.fa", "ref.fa", "text"))
+        for pth in (ours, ref):
+            with open(pth, "wb") as f:
+                f.write(fa)
+        run = lambda cmd: subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)  # noqa: E731
+        run([pkg.pfp.CLI_PATH, ours, "-w", "10", "-p", "100", "-s", "-f"])
+        run([orc.ref_exe("newscanNT.x"), ref, "-w", "10", "-p", "100", "-s", "-f"])
+        assert_same_files(orc.collect_files(ours), orc.collect_files(ref), "config 1 scanner files")
+        for base in (ours, ref):
+            run([orc.ref_exe("bwtparse"), base, "-s"])
+            run([orc.ref_exe("pfbwtNT.x"), "-w", "10", base, "-S"])
+        for ext in ("bwt", "sa"):
+            assert open(ours + "." + ext, "rb").read() == open(ref + "." + ext, "rb").read(), ext
+        text, trunc = pkg.pfp.read_input(ours, fasta=True)
+        assert not trunc and text == b"".join(r.tobytes() for r in recs)
+        with open(txt, "wb") as f:
+            f.write(text)
+        run([orc.ref_exe("simplebwt"), txt])
+        assert open(ours + ".bwt", "rb").read() == open(txt + ".Bwt", "rb").read(), "BWT differs from SACA-K"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)

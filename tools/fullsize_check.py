@@ -7,8 +7,11 @@ host reconstruction of a text prefix from .dict + .parse):
   * sum(.occ) == #phrases, bincount(.parse) == .occ, every rank in 1..d
   * .sai strictly increasing, last value n + w; .last[j] == T[sai[j] - w - 1]
   * every phrase end is a trigger: T[sai-w .. sai) hashes to 0 mod p (re-computed with torch)
-  * .dict: d words, strictly increasing (sampled adjacent pairs), 0x01 terminators, final 0x00
+  * .dict: d words, EVERY adjacent pair strictly increasing (device kernel), 0x01 terminators, final 0x00
   * unparse of the first 200 000 phrases == the text prefix
+and, where tests/golden/fullsize_sha256.json holds them (tools/make_fullsize_digests.py ran the
+unmodified newscanNT.x on the same full-size text in the build container), BYTE-EXACT parity:
+sha256 of each of the five streams == the reference's.
 usage: fullsize_check.py [--config pangenome|random|sweep|all] [--small]
 Prints one JSON line per case; exit status 1 on any failed property.
 """
@@ -40,7 +43,25 @@ def window_hash_mod_p(text, ends, w, p):
     return h % p
 
 
-def check_case(sc, text, w, p, name, sample_pairs=200_000, prefix_phrases=200_000):
+def load_digests():
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fullsize_sha256.json")) as f:
+            return json.load(f)
+    except OSError:
+        return {"cases": {}, "texts": {}}
+
+
+def sha_dev(ptr, nbytes):
+    """sha256 of a device buffer (copied to the host in 256 MB pieces)."""
+    import hashlib
+    h = hashlib.sha256()
+    step = 1 << 28
+    for o in range(0, nbytes, step):
+        h.update(view(ptr + o, min(step, nbytes - o)).cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def check_case(sc, text, w, p, name, digest_key=None, text_key=None, prefix_phrases=200_000):
     n = text.numel()
     sc.parse_device(text, w, p, sai=True)               # warm-up: arena growth, table sizing hint
     torch.cuda.synchronize()
@@ -85,13 +106,12 @@ def check_case(sc, text, w, p, name, sample_pairs=200_000, prefix_phrases=200_00
     seps = np.flatnonzero(dic == 1)
     if seps.size != d: fails.append("#0x01 != distinct")
     starts = np.concatenate([[0], seps[:-1] + 1])
-    rng = np.random.default_rng(7)
-    idx = np.unique(rng.integers(0, max(d - 1, 1), min(sample_pairs, max(d - 1, 0))))
-    bad = 0
-    for i in idx:
-        a = dic[starts[i]:seps[i]].tobytes(); b = dic[starts[i + 1]:seps[i + 1]].tobytes()
-        bad += not (a < b)
-    if bad: fails.append(f".dict order violated in {bad} sampled pairs")
+    dd = view(out.dict, out.dict_bytes)
+    seps_dev = torch.nonzero(dd == 1).flatten()
+    bad = sc.check_dict_order(dd, seps_dev) if seps_dev.numel() == d else -1
+    res["dict_pairs_checked"] = max(d - 1, 0)
+    if bad: fails.append(f".dict order violated in {bad} adjacent pairs")
+    del seps_dev
     k = min(P, prefix_phrases)
     ranks = parse[:k].cpu().numpy()
     parts = []
@@ -101,6 +121,23 @@ def check_case(sc, text, w, p, name, sample_pairs=200_000, prefix_phrases=200_00
     rec = np.concatenate(parts)[1:]
     if k == P: rec = rec[:len(rec) - w]
     if not np.array_equal(rec, text[:rec.size].cpu().numpy()): fails.append("unparse(prefix) != text prefix")
+    # byte-exact parity with the reference at full size, through digests
+    dg = load_digests()
+    if text_key and text_key in dg["texts"]:
+        t_sha = sha_dev(text.data_ptr(), n)
+        res["text_sha256_matches_cpu_generator"] = t_sha == dg["texts"][text_key]["sha256"]
+        if not res["text_sha256_matches_cpu_generator"]: fails.append("the GPU generator's text differs from the CPU generator's")
+    if digest_key and digest_key in dg["cases"]:
+        want = dg["cases"][digest_key]["sha256"]
+        sizes = {"dict": out.dict_bytes, "occ": 4 * d, "parse": 4 * P, "last": P, "sai": 5 * P}
+        ptrs = {"dict": out.dict, "occ": out.occ, "parse": out.parse, "last": out.last, "sai": out.sai}
+        got = {e: sha_dev(ptrs[e], sizes[e]) for e in want}
+        res["sha256_vs_reference"] = {e: got[e] == want[e] for e in want}
+        res["sha256"] = {e: got[e][:16] for e in got}
+        for e in want:
+            if got[e] != want[e]: fails.append(f".{e} sha256 differs from newscanNT.x")
+    else:
+        res["sha256_vs_reference"] = None
     res["ok"] = not fails
     res["fails"] = fails
     print(json.dumps(res), flush=True)
@@ -120,16 +157,18 @@ def main():
     if a.config in ("pangenome", "sweep", "all"):
         text = pkg.synth.pangenome_text(40_000_000 // scale, 100, 2, device="cuda")
         if a.config in ("pangenome", "all"):
-            ok &= check_case(sc, text, 10, 100, "config2 pangenome 100 x 40 Mbp")
+            ok &= check_case(sc, text, 10, 100, "config2 pangenome 100 x 40 Mbp",
+                             digest_key=None if a.small else "config2 w10 p100", text_key=None if a.small else "pangenome")
         if a.config in ("sweep", "all"):
             for w in (6, 10, 16, 32):
                 for p in (50, 100, 500, 1000):
-                    ok &= check_case(sc, text, w, p, "config5 sweep")
+                    ok &= check_case(sc, text, w, p, "config5 sweep", digest_key=None if a.small else f"sweep w{w} p{p}")
         del text
         torch.cuda.empty_cache()
     if a.config in ("random", "all"):
         text = pkg.synth.random_dna(8_000_000_000 // scale, 4, device="cuda")
-        ok &= check_case(sc, text, 10, 100, "config4 random ACGT 8 GB")
+        ok &= check_case(sc, text, 10, 100, "config4 random ACGT 8 GB",
+                         digest_key=None if a.small else "config4 random 8 GB w10 p100", text_key=None if a.small else "random")
     sc.close()
     sys.exit(0 if ok else 1)
 
