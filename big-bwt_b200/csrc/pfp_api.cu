@@ -95,6 +95,8 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     { const char *ev = getenv("PFPB200_LEGACY_K2"); ctx->legacy_k2 = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_K1"); ctx->k1_mode = (ev && strcmp(ev, "rolling") == 0) ? 1 : 0; }
     { const char *ev = getenv("PFPB200_TEST_WEAK_FP"); ctx->weak_fp = (ev && atoi(ev) != 0) ? 1u : 0u; }
+    { const char *ev = getenv("PFPB200_FUSE_K3"); ctx->fuse_k3 = ev && atoi(ev) != 0; }
+    { const char *ev = getenv("PFPB200_TABLE_SCALE"); if (ev && atof(ev) >= 1.2) ctx->table_scale = atof(ev); }
     { const char *ev = getenv("PFPB200_K1_MIX"); ctx->k1_mix = ev ? atoi(ev) : 0; }
     { const char *ev = getenv("PFPB200_K2_WINDOW"); ctx->k2_window = ev ? atoi(ev) : 0; }
     auto bail = [&](int code) { pfpb200_destroy(ctx); return code; };
@@ -237,15 +239,21 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
         // K2: positions, .last, .sai and fingerprints in one pass over text + bits
         PhraseArrays ph{};
         ph.ends = ends;
-        PFP_TRY(pfp_alloc_t(ctx, &ph.rec, P));
         PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
         if (o->flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
         TextView tv{d_text, n, 0, (i64)n};
-        if (pfp_stream_ok(sb, w) && !ctx->legacy_k2) {
-            PFP_TRY(pfp_stream_stage(ctx, sb, tv, ph, P, -1, w, true));
-        } else {                                                        // any window size
-            PFP_TRY(pfp_scan_emit(ctx, sb, ends));
-            PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, -1, w));
+        DictArrays D;
+        const bool stream = pfp_stream_ok(sb, w) && !ctx->legacy_k2;
+        const bool fused = stream && ctx->fuse_k3;                      // K3 + pool inside the K2 pass (A/B)
+        if (fused) {
+            PFP_TRY(pfp_words_fused_stage(ctx, sb, tv, ph, P, -1, w, true, &D));
+        } else {
+            PFP_TRY(pfp_alloc_t(ctx, &ph.rec, P));
+            if (stream) PFP_TRY(pfp_stream_stage(ctx, sb, tv, ph, P, -1, w, true));
+            else {                                                      // any window size
+                PFP_TRY(pfp_scan_emit(ctx, sb, ends));
+                PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, -1, w));
+            }
         }
         PFP_TRY(pfp_scan_bits_free(ctx, &sb));
         tm.mark(ctx->stream);                                           // 2
@@ -266,11 +274,12 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
             PFP_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
             ctx->early_done = true;
         }
-        // K3
-        DictArrays D;
-        PFP_TRY(pfp_dedup_stage(ctx, ph, P, -1, w, &D));
-        PFP_TRY(pfp_free_now(ctx, ph.rec));
-        PFP_TRY(pfp_pool_stage(ctx, tv, ends, -1, w, &D));
+        // K3 (when it did not run inside K2)
+        if (!fused) {
+            PFP_TRY(pfp_dedup_stage(ctx, ph, P, -1, w, &D));
+            PFP_TRY(pfp_free_now(ctx, ph.rec));
+            PFP_TRY(pfp_pool_stage(ctx, tv, ends, -1, w, &D));
+        }
         if (o->flags & PFPB200_F_VERIFY) PFP_TRY(pfp_verify_stage(ctx, tv, ends, -1, w, P, D));
         tm.mark(ctx->stream);                                           // 3
         // K4
@@ -677,17 +686,22 @@ extern "C" int pfpb200_shard_words(pfpb200_ctx *ctx, int64_t first_start, pfpb20
         PFP_TRY(pfp_alloc_t(ctx, &ph.last, P, true));
         if (o.flags & PFPB200_F_SAI) PFP_TRY(pfp_alloc_t(ctx, &ph.sai, P * PFP_IBYTES, true));
         TextView tv{sh.d_buf, sh.n_buf, (i64)sh.buf_pos0, (i64)sh.n_global};
-        if (pfp_stream_ok(ctx->sh.bits, w) && !ctx->legacy_k2)
-            PFP_TRY(pfp_stream_stage(ctx, ctx->sh.bits, tv, ph, P, first_start, w, !ctx->sh.ends_emitted));
-        else PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, first_start, w));
         DictArrays D;
-        PFP_TRY(pfp_dedup_stage(ctx, ph, P, first_start, w, &D));
+        const bool stream = pfp_stream_ok(ctx->sh.bits, w) && !ctx->legacy_k2;
+        const bool fused = stream && ctx->fuse_k3;
+        if (fused) {                       // K2 + K3 + pool in one pass; creators leave their fingerprints in rec
+            PFP_TRY(pfp_words_fused_stage(ctx, ctx->sh.bits, tv, ph, P, first_start, w, !ctx->sh.ends_emitted, &D));
+        } else {
+            if (stream) PFP_TRY(pfp_stream_stage(ctx, ctx->sh.bits, tv, ph, P, first_start, w, !ctx->sh.ends_emitted));
+            else PFP_TRY(pfp_hash_stage(ctx, tv, ph, P, first_start, w));
+            PFP_TRY(pfp_dedup_stage(ctx, ph, P, first_start, w, &D));
+        }
         u64 *wfpa = nullptr, *wfpb = nullptr;
         PFP_TRY(pfp_alloc_t(ctx, &wfpa, D.d));
         PFP_TRY(pfp_alloc_t(ctx, &wfpb, D.d));
         PFP_TRY(pfp_gather_word_fp(ctx, D, ph, wfpa, wfpb));
         PFP_TRY(pfp_free_now(ctx, ph.rec));
-        PFP_TRY(pfp_pool_stage(ctx, tv, ends, first_start, w, &D));
+        if (!fused) PFP_TRY(pfp_pool_stage(ctx, tv, ends, first_start, w, &D));
         PFP_TRY(pfp_free_now(ctx, D.rep));
         if (o.flags & PFPB200_F_VERIFY) PFP_TRY(pfp_verify_stage(ctx, tv, ends, first_start, w, P, D));
         PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));

@@ -65,7 +65,10 @@ struct pfpb200_ctx {
     int k1_mode = 0;               // PFPB200_K1=rolling: always the rolling-arithmetic scan kernel (A/B)
     u32 *dna_table = nullptr;      // 4^w-bit trigger table of (dna_w, dna_p) for the DNA scan (w <= 10)
     u32 dna_w = 0, dna_p = 0;
+    bool fuse_k3 = false;          // PFPB200_FUSE_K3=1: K3 + pool fused into the K2 pass (A/B; measured slower, see pfp_stream.cu)
+    double pool_ratio = 0.0;       // pool bytes / text bytes of the previous parse (pool sizing hint of the fused K2+K3)
     bool legacy_k2 = false;        // PFPB200_LEGACY_K2=1: per-phrase K2 kernels (A/B measurements)
+    double table_scale = 2.0;      // PFPB200_TABLE_SCALE: dictionary table slots per expected word (A/B)
     u32 weak_fp = 0;               // PFPB200_TEST_WEAK_FP=1 (tests): 2-bit fingerprints, so that PFPB200_F_VERIFY has collisions to catch
     int k1_mix = 0;                // PFPB200_K1_MIX: every k-th row of the table scan by arithmetic (A/B)
     int k2_window = 0;             // PFPB200_K2_WINDOW: shared-memory text window in phrase_hash_k (A/B)
@@ -109,6 +112,7 @@ struct pfpb200_ctx {
 #define PFP_ERRBIT_LIMIT 2ull
 #define PFP_ERRBIT_INTERNAL 4ull
 #define PFP_ERRBIT_TABLE_FULL 8ull
+#define PFP_ERRBIT_POOL_FULL 16ull
 
 int pfp_fail(pfpb200_ctx *ctx, int code, const char *fmt, ...);
 

@@ -17,6 +17,7 @@
 #include "pfp_common.cuh"
 #include "pfp_stages.cuh"
 #include "pfp_fp.cuh"
+#include "pfp_table.cuh"
 #include <stdlib.h>
 
 // 16 bytes of a phrase at phrase offset o (multiple of 16), zero beyond the phrase end.
@@ -269,7 +270,9 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
                                                            const u32 *__restrict__ keytab,
                                                            const u32 *__restrict__ long_list,
                                                            const u32 *__restrict__ long_count, u32 long_cap,
-                                                           u64 *__restrict__ flags) {
+                                                           u64 *__restrict__ flags,
+                                                           PhraseFp *__restrict__ rec_compact /* non-null: record of
+                                                           the q-th listed phrase goes to rec_compact[q] */) {
     __shared__ __align__(16) u32 sk[NH_KEY_WORDS];
     for (int i = threadIdx.x; i < NH_KEY_WORDS; i += PH_T) sk[i] = keytab[i];
     __syncthreads();
@@ -303,58 +306,22 @@ __global__ void __launch_bounds__(PH_T) phrase_hash_long_k(TextView tv, PhraseAr
         }
         if (lane == 0) {
             if (len > 0xFFFFFFFFull) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_LIMIT);
-            store_rec(ph.rec, j, fa, fb);
+            if (rec_compact) store_rec(rec_compact, q, fa, fb);
+            else store_rec(ph.rec, j, fa, fb);
         }
     }
 }
 
-// ---- K3: dictionary table ----------------------------------------------------------------------------
-// Open addressing, linear probing, 16-byte slots {key, occurrences, check}; key 0 = empty.
-// A warp first groups its lanes by key (match.any) so that runs of identical phrases cost one
-// atomic per warp instead of 32.  `chk` is a 32-bit digest of the full 128-bit fingerprint and
-// the length, independent of the key: every phrase that lands in a slot must agree with it, or
-// the parse stops with PFPB200_E_COLLISION (the reference compares strings, newscan.cpp:282-286).
-struct __align__(16) DictSlot { u64 key; u32 uid1; u32 chk; };   // uid1 = word id + 1; 0 until its creator stored it
-constexpr u32 TABLE_MAX_PROBES = 2048;
-constexpr u32 UID_PENDING = 0x80000000u;       // uid[j] = UID_PENDING | slot: resolved by table_pending_k
-
-__device__ __forceinline__ u32 check_of(const PhraseFp &r) {
-    u64 x = (r.fpa + 0x632BE59BD9B4E019ULL) * 0xD1342543DE82EF95ULL;
-    x ^= (rotl64(r.fpb, 23) + 0x2545F4914F6CDD1DULL) * 0xAF251AF3B0F025B5ULL;
-    x ^= x >> 29;
-    u32 c = (u32)(x ^ (x >> 32));
-    return c ? c : 1u;
-}
-
+// ---- K3: dictionary table (slot layout and the probe loop: pfp_table.cuh) --------------------------------
 __global__ void table_init_k(DictSlot *__restrict__ tab, u64 cap) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap) *reinterpret_cast<uint4 *>(tab + i) = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// One probe sequence: a plain 16-byte load of the slot first -- on repetitive inputs nine phrases
-// in ten find their word already there, read its id from the slot and finish with one
-// fire-and-forget add to its count -- and a CAS only on an empty slot.  The thread that wins the
-// CAS is the word's creator: it draws the next word id from a counter (ids are dense, in creation
-// order: no flag / scan / compaction passes over the table afterwards), stores it in the slot and
-// records itself as the word's representative occurrence.
-struct Probe { u64 slot; bool placed; bool creator; u32 seen_chk; u32 seen_uid1; };
-
-__device__ __forceinline__ Probe table_probe(DictSlot *__restrict__ tab, u64 cap, u64 slot, uint4 sv, u64 k) {
-    Probe r{slot, false, false, 0u, 0u};
-    u32 probes = 0;
-    for (;;) {
-        const u64 key = ((u64)sv.y << 32) | sv.x;
-        if (key == k) { r.placed = true; r.seen_uid1 = sv.z; r.seen_chk = sv.w; break; }
-        if (key == 0ull) {
-            const u64 prev = atomicCAS((unsigned long long *)&tab[r.slot].key, 0ull, (unsigned long long)k);
-            if (prev == 0ull) { r.placed = true; r.creator = true; break; }
-            if (prev == k) { r.placed = true; break; }
-        }
-        if (++probes > TABLE_MAX_PROBES) break;               // table too small for this input
-        r.slot = (r.slot + 1 == cap) ? 0 : r.slot + 1;
-        sv = __ldcg(reinterpret_cast<const uint4 *>(tab + r.slot));
-    }
-    return r;
+int pfp_table_init(pfpb200_ctx *ctx, DictSlot *tab, u64 cap) {
+    table_init_k<<<pfp_blocks(cap, 256), 256, 0, ctx->stream>>>(tab, cap);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
 }
 
 constexpr int TI_ITEMS = 2;      // phrases per thread: their first probes are in flight together
@@ -521,16 +488,21 @@ __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__re
                                                     const u32 *__restrict__ rep,
                                                     const u32 *__restrict__ ulen,
                                                     const u64 *__restrict__ uoff, u64 d,
-                                                    u64 *__restrict__ pool) {
+                                                    u64 *__restrict__ pool,
+                                                    const u32 *__restrict__ ulist /* null: words 0..d-1 */,
+                                                    const u32 *__restrict__ ucount, u64 pool_cap) {
     const u32 li = threadIdx.x & (PC_GROUP - 1);
-    for (u64 u = (u64)blockIdx.x * PC_PER_BLOCK + (threadIdx.x / PC_GROUP); u < d;
-         u += (u64)gridDim.x * PC_PER_BLOCK) {
+    if (ulist) d = *ucount;
+    for (u64 x = (u64)blockIdx.x * PC_PER_BLOCK + (threadIdx.x / PC_GROUP); x < d;
+         x += (u64)gridDim.x * PC_PER_BLOCK) {
+        const u64 u = ulist ? ulist[x] : x;
         u64 j = rep[u];
         i64 e = (i64)ends[j];
         i64 s0 = (j == 0) ? first_start : (i64)ends[j - 1] - (i64)w + 1;
         u64 len = ulen[u];
         bool special = (s0 < 0) || (e >= tv.n_global);
         u64 nw = (len + 7) >> 3;
+        if (uoff[u] + nw > pool_cap) continue;                 // the caller sees PFP_ERRBIT_POOL_FULL and reruns
         u64 *dst = pool + uoff[u];
         for (u64 k = li; k < nw; k += PC_GROUP) dst[k] = phrase_word8(tv, s0, len, k, special);
     }
@@ -588,19 +560,96 @@ __global__ void __launch_bounds__(PH_T) verify_entries_k(u64 n, const u32 *__res
     }
 }
 
+// The few phrases the fused streaming pass leaves to the list kernel (the buffer's first phrase, a
+// final phrase at the virtual border, phrases open behind their tile or longer than a key
+// segment): one thread each, same table, same id / pool cursors.  A creator notes its word in
+// `created`, whose bytes pool_copy_k then fetches from the text.
+__global__ void table_insert_list_k(const PhraseFp *__restrict__ rec_small, const u32 *__restrict__ list,
+                                    const u32 *__restrict__ list_count, u32 list_cap,
+                                    DictSlot *__restrict__ tab, u64 cap, const u64 *__restrict__ ends,
+                                    i64 first_start, u32 w, u32 weak, u32 *__restrict__ uid,
+                                    u32 *__restrict__ rep, u32 *__restrict__ ulen, u32 *__restrict__ uwords,
+                                    u32 *__restrict__ count, u64 *__restrict__ uoff,
+                                    PhraseFp *__restrict__ rec_full, u32 *__restrict__ created,
+                                    u32 *__restrict__ created_count, u64 *__restrict__ flags) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(*list_count, list_cap)) return;
+    const u64 j = list[i];
+    PhraseFp r = rec_small[i];
+    if (weak) { r.fpa &= 3ull; r.fpb = 0; }
+    const u64 k = sort_key_of(r.fpa, r.fpb);
+    const u32 chk = check_of(r);
+    const u64 s0 = __umul64hi(k, cap);
+    const Probe pr = table_probe(tab, cap, s0, __ldcg(reinterpret_cast<const uint4 *>(tab + s0)), k);
+    if (!pr.placed) { atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_TABLE_FULL); uid[j] = 0; return; }
+    u32 seen = pr.seen_chk;
+    if (pr.creator) {
+        const i64 st = j ? (i64)ends[j - 1] - (i64)w + 1 : first_start;
+        const u32 len = (u32)((i64)ends[j] - st + 1);
+        const u32 uw = (len + 7) >> 3;
+        const u32 u = (u32)atomicAdd((unsigned long long *)&flags[1], 1ull);
+        const u64 off = atomicAdd((unsigned long long *)&flags[7], (unsigned long long)uw);
+        atomicMax((unsigned long long *)&flags[2], (unsigned long long)len);
+        atomicAdd((unsigned long long *)&flags[3], (unsigned long long)len);
+        rep[u] = (u32)j; ulen[u] = len; uwords[u] = uw; uoff[u] = off;
+        tab[pr.slot].uid1 = u + 1;
+        uid[j] = u;
+        atomicAdd(&count[u], 1u);
+        created[atomicAdd(created_count, 1u)] = u;
+        if (rec_full) store_rec(rec_full, j, r.fpa, r.fpb);
+    } else if (pr.seen_uid1) {
+        uid[j] = pr.seen_uid1 - 1;
+        atomicAdd(&count[pr.seen_uid1 - 1], 1u);
+    } else {
+        uid[j] = UID_PENDING | (u32)pr.slot;
+        atomicOr((unsigned long long *)&flags[6], 1ull);
+    }
+    if (seen == 0u) seen = atomicCAS(&tab[pr.slot].chk, 0u, chk);
+    if (seen != 0u && seen != chk) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_COLLISION);
+}
+
+// insert the listed phrases (fingerprints in rec_small, list order) and copy the bytes of the words
+// they created into the pool
+int pfp_insert_list(pfpb200_ctx *ctx, const TextView &tv, const PhraseFp *rec_small, const u32 *list,
+                    const u32 *list_count, u64 list_cap, void *tab, u64 cap, const u64 *ends, i64 first_start,
+                    u32 w, const DictArrays &D, u64 pool_cap, PhraseFp *rec_full) {
+    u32 *created = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &created, (size_t)list_cap + 1));
+    u32 *ccount = created + list_cap;
+    PFP_CUDA(ctx, cudaMemsetAsync(ccount, 0, sizeof(u32), ctx->stream));
+    const u32 lc = (u32)(list_cap < 0xFFFFFFFFull ? list_cap : 0xFFFFFFFFull);
+    table_insert_list_k<<<pfp_blocks(list_cap, 128), 128, 0, ctx->stream>>>(
+        rec_small, list, list_count, lc, (DictSlot *)tab, cap, ends, first_start, w, ctx->weak_fp, D.uid, D.rep, D.ulen,
+        D.uwords, D.count, D.uoff, rec_full, created, ccount, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    u64 want = (list_cap + PC_PER_BLOCK - 1) / PC_PER_BLOCK;
+    u64 maxb = (u64)ctx->sm_count * 8;
+    pool_copy_k<<<(u32)(want < maxb ? (want ? want : 1) : maxb), PH_T, 0, ctx->stream>>>(
+        tv, ends, first_start, w, D.rep, D.ulen, D.uoff, 0, D.pool, created, ccount, pool_cap);
+    PFP_LAUNCHED(ctx);
+    PFP_TRY(pfp_free_now(ctx, created));
+    return PFPB200_OK;
+}
+
+int pfp_table_pending(pfpb200_ctx *ctx, const void *tab, u64 P, u32 *uid, u32 *count) {
+    table_pending_k<<<pfp_blocks(P, 256), 256, 0, ctx->stream>>>((const DictSlot *)tab, P, nullptr, uid, count, ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    return PFPB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
 // fingerprints of the phrases listed in long_list[0..*long_count): any length, any position
 int pfp_hash_list(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph, i64 first_start, u32 w,
-                  const u32 *long_list, const u32 *long_count, u64 max_count) {
+                  const u32 *long_list, const u32 *long_count, u64 max_count, PhraseFp *rec_compact) {
     u64 want = (max_count + PH_WARPS - 1) / PH_WARPS;
     u64 maxb = (u64)ctx->sm_count * 8;
     u32 nlb = (u32)(want < maxb ? want : maxb);
     if (nlb == 0) nlb = 1;
     phrase_hash_long_k<<<nlb, PH_T, 0, ctx->stream>>>(tv, ph, first_start, w, ctx->d_keys, long_list,
                                                       long_count, (u32)(max_count < 0xFFFFFFFFull ? max_count : 0xFFFFFFFFull),
-                                                      ctx->d_flags);
+                                                      ctx->d_flags, rec_compact);
     PFP_LAUNCHED(ctx);
     return PFPB200_OK;
 }
@@ -638,7 +687,7 @@ int pfp_hash_stage(pfpb200_ctx *ctx, const TextView &tv, const PhraseArrays &ph,
     phrase_hash_k<<<nb, PH_T, use_window ? PH_WARPS * PH_WIN : 0, ctx->stream>>>(
         tv, ph, P, first_start, w, ctx->d_keys, long_list, long_count, (u32)cap, ctx->d_flags, use_window);
     PFP_LAUNCHED(ctx);
-    PFP_TRY(pfp_hash_list(ctx, tv, ph, first_start, w, long_list, long_count, cap));
+    PFP_TRY(pfp_hash_list(ctx, tv, ph, first_start, w, long_list, long_count, cap, nullptr));
     PFP_TRY(pfp_free_now(ctx, long_list));
     PFP_TRY(pfp_free_now(ctx, long_count));
     return PFPB200_OK;
@@ -662,7 +711,7 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, i64 first_s
     for (int attempt = 0;; attempt++) {
         double want = (double)P * 1.5;
         if (attempt == 0 && ctx->dedup_ratio > 0.0) {
-            double guess = ctx->dedup_ratio * (double)P * 2.0;
+            double guess = ctx->dedup_ratio * (double)P * ctx->table_scale;
             if (guess < want) want = guess;
         }
         cap = (u64)want + 1024;
@@ -734,7 +783,7 @@ int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 fi
     u32 nb = (u32)(want < maxb ? want : maxb);
     if (nb == 0) nb = 1;
     pool_copy_k<<<nb, PH_T, 0, ctx->stream>>>(tv, ends, first_start, w, D->rep, D->ulen, D->uoff, d,
-                                              D->pool);
+                                              D->pool, nullptr, nullptr, D->pool_words);
     PFP_LAUNCHED(ctx);
     return PFPB200_OK;
 }

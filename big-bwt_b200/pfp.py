@@ -262,7 +262,8 @@ class Scanner:
 
     def check_dict_order(self, dict_dev, seps_dev) -> int:
         """Adjacent pairs of the .dict stream (CUDA uint8 tensor) that are not strictly increasing;
-        seps_dev: int64 CUDA tensor with the positions of the 0x01 terminators."""
+        seps_dev: int64 CUDA tensor with the positions of the 0x01 terminators.  The library works on
+        its own stream: synchronise the stream that produced the tensors first."""
         self.L.pfpb200_check_dict_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                                     C.POINTER(C.c_uint64)]
         self.L.pfpb200_check_dict_order.restype = C.c_int

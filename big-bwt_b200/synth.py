@@ -110,9 +110,21 @@ def pangenome_records(base_len: int, n_hap: int, seed: int, device="cpu", first_
 
 def pangenome_text(base_len: int, n_hap: int, seed: int, device="cpu",
                    first_hap: int = 0) -> torch.Tensor:
-    """Concatenated haplotypes = the text T the parser sees for the FASTA of these records."""
-    parts = list(pangenome_records(base_len, n_hap, seed, device, first_hap))
-    return torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=device)
+    """Concatenated haplotypes = the text T the parser sees for the FASTA of these records.
+    Written haplotype by haplotype into one buffer (a 64 GB shard must not exist twice)."""
+    if n_hap <= 0:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    # a haplotype is at most base_len * (1 + insertion rate) long: 0.1 % of the sites mutate, one in
+    # ten of those inserts a base; 0.05 % of slack per haplotype is 5 times that
+    cap = n_hap * (base_len + base_len // 2000 + 1024)
+    out = torch.empty(cap, dtype=torch.uint8, device=device)
+    pos = 0
+    for rec in pangenome_records(base_len, n_hap, seed, device, first_hap):
+        n = rec.numel()
+        out[pos:pos + n] = rec
+        pos += n
+        del rec
+    return out[:pos]
 
 
 # BASELINE.json configs[0] names the reference's bundled yeast.fasta, which is not in the mount

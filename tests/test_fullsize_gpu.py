@@ -56,7 +56,9 @@ def test_dict_order_check_kernel(pkg, sc):
 
     def bad(ws):
         d = torch.from_numpy(__import__("numpy").frombuffer(b"".join(x + b"\x01" for x in ws) + b"\x00", dtype="uint8").copy()).cuda()
-        return sc.check_dict_order(d, torch.nonzero(d == 1).flatten())
+        seps = torch.nonzero(d == 1).flatten()
+        torch.cuda.synchronize()                         # the library runs on its own stream
+        return sc.check_dict_order(d, seps)
     assert bad(words) == 0
     assert bad(words[::-1]) == len(words) - 1
     assert bad(words[:3] + [words[2]] + words[3:]) == 1          # a duplicate is not strictly increasing

@@ -173,6 +173,26 @@ def test_stream_k2_equals_per_phrase_k2_64mb(pkg):
     assert_same_files(res[0], res[1], "stream vs per-phrase K2")
 
 
+def test_fused_k3_equals_split_k3_64mb(pkg):
+    """The dictionary insert fused into the streaming K2 pass (PFPB200_FUSE_K3=1, an A/B path) against
+    K3 as its own kernels behind K2 (the default): same five streams, on a repetitive and on a
+    random text (the random one overflows the first pool / table guess and reruns the pass)."""
+    texts = [pkg.synth.pangenome_text(4_000_000, 16, 134).cuda(), pkg.synth.random_dna(48_000_000, 135, device="cuda")]
+    for t in texts:
+        res = []
+        for fuse in ("1", "0"):
+            os.environ["PFPB200_FUSE_K3"] = fuse
+            try:
+                s = pkg.pfp.Scanner(0)
+            finally:
+                os.environ.pop("PFPB200_FUSE_K3", None)
+            for _ in range(2):               # second parse: table and pool sized from the first
+                got = s.fetch(s.parse_device(t, 10, 100, sai=True))
+            res.append(got)
+            s.close()
+        assert_same_files(res[0], res[1], "fused vs split K3")
+
+
 @pytest.mark.parametrize("name", sorted(golden_dicz()))
 def test_compress_mode_dicz_golden(pkg, sc, name):
     """-c against the .dicz the unmodified newscanNT.x -c wrote (tools/make_golden_dicz.py)."""

@@ -108,6 +108,7 @@ def check_case(sc, text, w, p, name, digest_key=None, text_key=None, prefix_phra
     starts = np.concatenate([[0], seps[:-1] + 1])
     dd = view(out.dict, out.dict_bytes)
     seps_dev = torch.nonzero(dd == 1).flatten()
+    torch.cuda.synchronize()                             # the library runs on its own stream
     bad = sc.check_dict_order(dd, seps_dev) if seps_dev.numel() == d else -1
     res["dict_pairs_checked"] = max(d - 1, 0)
     if bad: fails.append(f".dict order violated in {bad} adjacent pairs")
