@@ -95,6 +95,7 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     { const char *ev = getenv("PFPB200_LEGACY_K2"); ctx->legacy_k2 = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_K1"); ctx->k1_mode = (ev && strcmp(ev, "rolling") == 0) ? 1 : 0; }
     { const char *ev = getenv("PFPB200_TEST_WEAK_FP"); ctx->weak_fp = (ev && atoi(ev) != 0) ? 1u : 0u; }
+    { const char *ev = getenv("PFPB200_RANK_CHUNK_PASSES"); ctx->rank_chunk_passes = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_FUSE_K3"); ctx->fuse_k3 = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_TABLE_SCALE"); if (ev && atof(ev) >= 1.2) ctx->table_scale = atof(ev); }
     { const char *ev = getenv("PFPB200_K1_MIX"); ctx->k1_mix = ev ? atoi(ev) : 0; }

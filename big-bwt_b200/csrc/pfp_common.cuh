@@ -65,6 +65,7 @@ struct pfpb200_ctx {
     int k1_mode = 0;               // PFPB200_K1=rolling: always the rolling-arithmetic scan kernel (A/B)
     u32 *dna_table = nullptr;      // 4^w-bit trigger table of (dna_w, dna_p) for the DNA scan (w <= 10)
     u32 dna_w = 0, dna_p = 0;
+    bool rank_chunk_passes = false;  // PFPB200_RANK_CHUNK_PASSES=1: mid-size tie groups by chunk passes instead of LCP walks (A/B)
     bool fuse_k3 = false;          // PFPB200_FUSE_K3=1: K3 + pool fused into the K2 pass (A/B; measured slower, see pfp_stream.cu)
     double pool_ratio = 0.0;       // pool bytes / text bytes of the previous parse (pool sizing hint of the fused K2+K3)
     bool legacy_k2 = false;        // PFPB200_LEGACY_K2=1: per-phrase K2 kernels (A/B measurements)

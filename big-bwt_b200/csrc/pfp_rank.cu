@@ -511,6 +511,148 @@ __global__ void __launch_bounds__(256) rank_mid_k(const u32 *__restrict__ hp,
     }
 }
 
+// ---- LCP-aware refinement of mid-size tie groups (33..256 words), one warp per group ----------------------
+// The multikey-quicksort passes above advance ONE 8-byte chunk per pass; a family of variants of
+// one long phrase (p = 1000: words of a kilobyte, a hundred of them differing in one base each)
+// then costs a pass -- a memory round trip, a scan and two moves of the group -- per chunk of
+// shared prefix.  Here a round costs one walk per word instead: every word of a range walks along
+// the range's FIRST word (its head) until they differ, at chunk c with own chunk v against the
+// head's h.  For two words x, y below the head (v < h): c_x < c_y  =>  x[c_x] < head[c_x] = y[c_x],
+// so x < y; with equal c the chunks decide; above the head the order in c is reversed.  So
+//      (below: c ascending, v ascending) < head < (above: c descending, v ascending)
+// is the lexicographic order of the range, up to ties (same c, same v), which agree on c + 1
+// chunks and form the ranges of the next round.  One bitonic sort of the group by
+// (range, class/c, v) per round; a family is done in two or three rounds whatever its length.
+constexpr u32 LCP_MAX = 256;                  // words per group
+constexpr u32 LCP_WALK = 4;                   // chunks fetched per memory round trip of a walk
+
+struct LcpSort {
+    u64 ka[LCP_MAX];                          // sort key, high part: range start << 32 | class-and-depth code
+    u64 kb[LCP_MAX];                          // low part: the word's chunk where it leaves the head
+    u32 uid[2][LCP_MAX];
+    u32 off[2][LCP_MAX];                      // pool offset (8-byte words)
+    u32 wn[2][LCP_MAX];                       // length in 8-byte words
+    u32 dep[LCP_MAX];                         // at a range start: chunks the range is known to share
+    u16 lo[LCP_MAX];                          // range start of every position
+    u16 pay[LCP_MAX];                         // position before the sort
+};
+
+__global__ void __launch_bounds__(256) rank_lcp_k(const u32 *__restrict__ hp, const u32 *__restrict__ list,
+                                                  const u32 *__restrict__ count, const u32 *__restrict__ depth,
+                                                  const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
+                                                  const u32 *__restrict__ uwords, u32 max_chunks,
+                                                  u32 *__restrict__ ord, u64 *__restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char lcp_raw[];
+    const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    LcpSort &S = reinterpret_cast<LcpSort *>(lcp_raw)[wp];
+    const u32 n = *count;
+    for (u32 gq = blockIdx.x * 8 + wp; gq < n; gq += gridDim.x * 8) {
+        const u32 g = list[gq];
+        const u32 s = hp[g], m = hp[g + 1] - s;
+        u32 M = 32;                                           // bitonic size: next power of two
+        while (M < m) M <<= 1;
+        int cur = 0;
+        __syncwarp();
+        for (u32 p = lane; p < m; p += 32) {
+            const u32 u = ord[s + p];
+            S.uid[0][p] = u; S.off[0][p] = (u32)uoff[u]; S.wn[0][p] = uwords[u];
+            S.lo[p] = 0;
+        }
+        if (lane == 0) S.dep[0] = depth[s];
+        __syncwarp();
+        for (u32 round = 0;; round++) {
+            // ---- 1. every word of a range of two or more walks along the range's head ---------------------
+            int any = 0, bad = 0;
+            for (u32 p = lane; p < M; p += 32) {
+                u64 ka = ~0ull, kb = 0;                        // padding sorts behind everything
+                if (p < m) {
+                    const u32 l = S.lo[p];
+                    const bool single = (p == l) && (p + 1 >= m || S.lo[p + 1] != l);
+                    u32 code = 0x80000000u;                   // the head of its range (or a finished word)
+                    if (!single && p != l) {
+                        const u64 *mine = pool + S.off[cur][p], *head = pool + S.off[cur][l];
+                        const u32 wm = S.wn[cur][p], wh = S.wn[cur][l];
+                        u32 c = S.dep[l];
+                        u64 v = 0, h = 0;
+                        for (;;) {
+                            u64 a[LCP_WALK], b[LCP_WALK];
+#pragma unroll
+                            for (u32 i = 0; i < LCP_WALK; i++) {
+                                a[i] = (c + i < wm) ? __ldg(mine + c + i) : 0ull;
+                                b[i] = (c + i < wh) ? __ldg(head + c + i) : 0ull;
+                            }
+                            bool found = false;
+#pragma unroll
+                            for (u32 i = 0; i < LCP_WALK; i++)
+                                if (!found && a[i] != b[i]) { found = true; c += i; v = bswap64(a[i]); h = bswap64(b[i]); }
+                            if (found) break;
+                            c += LCP_WALK;
+                            if (c >= max_chunks) { bad = 1; break; }      // two equal words: cannot happen
+                        }
+                        code = v < h ? c : 0xFFFFFFFFu - c;
+                        kb = v;
+                    }
+                    any |= single ? 0 : 1;
+                    ka = ((u64)l << 32) | code;
+                }
+                S.ka[p] = ka; S.kb[p] = kb; S.pay[p] = (u16)p;
+            }
+            if (__any_sync(0xffffffffu, bad)) {
+                if (lane == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
+                break;
+            }
+            if (!__any_sync(0xffffffffu, any)) break;
+            __syncwarp();
+            // ---- 2. bitonic sort of the group by (range start, class/depth code, chunk) ------------------
+            for (u32 k = 2; k <= M; k <<= 1) {
+                for (u32 j = k >> 1; j > 0; j >>= 1) {
+                    for (u32 i = lane; i < M; i += 32) {
+                        const u32 x = i ^ j;
+                        if (x > i) {
+                            const u64 a0 = S.ka[i], a1 = S.ka[x], b0 = S.kb[i], b1 = S.kb[x];
+                            const bool gt = a0 > a1 || (a0 == a1 && b0 > b1);
+                            if (gt == ((i & k) == 0)) {
+                                S.ka[i] = a1; S.ka[x] = a0; S.kb[i] = b1; S.kb[x] = b0;
+                                const u16 t = S.pay[i]; S.pay[i] = S.pay[x]; S.pay[x] = t;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            // ---- 3. move the words; ranges of the next round = runs of equal keys ----------------------
+            u32 carry = 0;                                    // start of the range running into this block of 32
+            for (u32 b0 = 0; b0 < m; b0 += 32) {
+                const u32 p = b0 + lane;
+                bool start = false;
+                if (p < m) {
+                    const u32 q = S.pay[p];
+                    S.uid[cur ^ 1][p] = S.uid[cur][q];
+                    S.off[cur ^ 1][p] = S.off[cur][q];
+                    S.wn[cur ^ 1][p] = S.wn[cur][q];
+                    start = p == 0 || S.ka[p] != S.ka[p - 1] || S.kb[p] != S.kb[p - 1];
+                }
+                const u32 sm = __ballot_sync(0xffffffffu, start);
+                if (p < m) {
+                    const u32 below = sm & (0xFFFFFFFFu >> (31 - lane));      // starts at or below my lane
+                    const u32 l = below ? b0 + (31 - __clz(below)) : carry;
+                    S.lo[p] = (u16)l;
+                    if (start) {                              // depth of a new range: its members left their old head
+                        const u32 code = (u32)S.ka[p];        // at the same chunk c with the same chunk value
+                        const u32 c = code < 0x80000000u ? code : 0xFFFFFFFFu - code;
+                        S.dep[p] = code == 0x80000000u ? 0u : c + 1;
+                    }
+                }
+                if (sm) carry = b0 + (31 - __clz(sm));
+            }
+            __syncwarp();
+            cur ^= 1;
+        }
+        __syncwarp();
+        for (u32 p = lane; p < m; p += 32) ord[s + p] = S.uid[cur][p];
+    }
+}
+
 __global__ void __launch_bounds__(256) rank_cta_k(const u32 *__restrict__ hp,
                                                   const u32 *__restrict__ list,
                                                   const u32 *__restrict__ count,
@@ -536,6 +678,8 @@ int pfp_rank_init(pfpb200_ctx *ctx) {
                                        (int)sizeof(TieSort<LOCAL_MAX>)));
     PFP_CUDA(ctx, cudaFuncSetAttribute(rank_mid_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(8 * sizeof(TieSort<MID_MAX>))));
+    PFP_CUDA(ctx, cudaFuncSetAttribute(rank_lcp_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(8 * sizeof(LcpSort))));
     return PFPB200_OK;
 }
 
@@ -652,8 +796,12 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
         rank_warp_k<<<nbw, 256, 0, ctx->stream>>>(hp, d_nheads, depth, D.pool, D.uoff, D.uwords, max_chunks,
                                                   ord, ctx->d_flags);
         PFP_LAUNCHED(ctx);
-        rank_mid_k<<<ctx->sm_count * 4, 256, 8 * sizeof(TieSort<MID_MAX>), ctx->stream>>>(
-            hp, mid_list, counts, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
+        if (ctx->rank_chunk_passes)      // A/B: one 8-byte chunk per pass (the kernel rank_lcp_k replaced)
+            rank_mid_k<<<ctx->sm_count * 4, 256, 8 * sizeof(TieSort<MID_MAX>), ctx->stream>>>(
+                hp, mid_list, counts, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
+        else
+            rank_lcp_k<<<ctx->sm_count * 4, 256, 8 * sizeof(LcpSort), ctx->stream>>>(
+                hp, mid_list, counts, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
         PFP_LAUNCHED(ctx);
         rank_cta_k<<<ctx->sm_count * 4, 256, sizeof(TieSort<LOCAL_MAX>), ctx->stream>>>(
             hp, big_list, counts + 1, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);

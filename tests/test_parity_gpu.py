@@ -173,6 +173,23 @@ def test_stream_k2_equals_per_phrase_k2_64mb(pkg):
     assert_same_files(res[0], res[1], "stream vs per-phrase K2")
 
 
+@pytest.mark.parametrize("w,p", [(10, 500), (16, 1000), (10, 100)])
+def test_rank_lcp_walks_on_large_families(pkg, w, p):
+    """Families of near-identical long words (many haplotypes, large p): tie groups of 33..256 words
+    are ranked by LCP walks against the group's head (rank_lcp_k).  Against the oracle, and against
+    the chunk-pass kernel it replaced (PFPB200_RANK_CHUNK_PASSES=1)."""
+    text = pkg.synth.pangenome_text(150_000, 150, 136).numpy().tobytes()
+    want = orc.parse(text, w, p)
+    for chunk_passes in ("0", "1"):
+        os.environ["PFPB200_RANK_CHUNK_PASSES"] = chunk_passes
+        try:
+            s = pkg.pfp.Scanner(0)
+        finally:
+            os.environ.pop("PFPB200_RANK_CHUNK_PASSES", None)
+        assert_same_files(s.parse_host(text, w, p), want, f"families w{w} p{p} chunk_passes={chunk_passes}")
+        s.close()
+
+
 def test_fused_k3_equals_split_k3_64mb(pkg):
     """The dictionary insert fused into the streaming K2 pass (PFPB200_FUSE_K3=1, an A/B path) against
     K3 as its own kernels behind K2 (the default): same five streams, on a repetitive and on a
