@@ -784,23 +784,103 @@ extern "C" int pfpb200_dict_merge(pfpb200_ctx *ctx, uint64_t n_in, const uint64_
 extern "C" int pfp_unpack_words(pfpb200_ctx *ctx, const pfpb200_word *in, u64 n, u64 *fpa, u64 *fpb,
                                 u32 *len, u32 *count, u32 *uwords);
 
+// The merge of received words in two halves, so that the exchange of the pool BYTES can overlap the
+// dedup, which only needs the 32-byte word records: _begin dedups (table, counts, representative
+// entry of every word), _finish ranks the distinct words and writes .dict/.occ once the bytes are there.
+extern "C" int pfpb200_dict_merge_begin(pfpb200_ctx *ctx, uint64_t n_in, const pfpb200_word *words, float *ms) {
+    if (!ctx || (n_in && !words)) return PFPB200_E_ARG;
+    if (ms) *ms = 0;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, PFP_FLAG_SLOTS * sizeof(u64), ctx->stream));
+    ctx->mg.n_in = n_in;
+    ctx->mg.d = 0;
+    if (n_in == 0) return PFPB200_OK;
+    CallTimer tm(ctx->stream);
+    auto run = [&]() -> int {
+        u64 *fpa = nullptr, *fpb = nullptr;
+        u32 *len = nullptr, *count = nullptr, *uwords = nullptr;
+        PFP_TRY(pfp_alloc_t(ctx, &fpa, n_in));
+        PFP_TRY(pfp_alloc_t(ctx, &fpb, n_in));
+        PFP_TRY(pfp_alloc_t(ctx, &len, n_in));
+        PFP_TRY(pfp_alloc_t(ctx, &count, n_in));
+        PFP_TRY(pfp_alloc_t(ctx, &uwords, n_in));
+        PFP_TRY(pfp_unpack_words(ctx, words, n_in, fpa, fpb, len, count, uwords));
+        DictArrays D;
+        u32 *uid_of_entry = nullptr;
+        PFP_TRY(pfp_merge_stage(ctx, n_in, fpa, fpb, len, count, uwords, nullptr, 0, false, &D, &uid_of_entry));
+        PFP_TRY(pfp_free_now(ctx, fpa));
+        PFP_TRY(pfp_free_now(ctx, fpb));
+        PFP_TRY(pfp_free_now(ctx, count));
+        ctx->mg.d = D.d; ctx->mg.sum_len = D.sum_len; ctx->mg.max_len = D.max_len;
+        ctx->mg.uid_of_entry = uid_of_entry; ctx->mg.rep = D.rep; ctx->mg.count = D.count;
+        ctx->mg.ulen = D.ulen; ctx->mg.uwords = D.uwords; ctx->mg.uoff = D.uoff;
+        ctx->mg.len_in = len; ctx->mg.uwords_in = uwords;
+        return PFPB200_OK;
+    };
+    int rc = run();
+    float t = tm.stop();
+    if (rc != PFPB200_OK) { pfp_release_scratch(ctx); ctx->mg.n_in = 0; return rc; }
+    promote_scratch(ctx);                 // the dictionary arrays live until _finish (and the next parse)
+    if (ms) *ms = t;
+    return PFPB200_OK;
+}
+
+extern "C" int pfpb200_dict_merge_finish(pfpb200_ctx *ctx, const uint64_t *pool, uint64_t pool_words, uint32_t w,
+                                         uint32_t flags, pfpb200_merged *out, float *ms) {
+    if (!ctx || !out) return PFPB200_E_ARG;
+    memset(out, 0, sizeof(*out));
+    if (ms) *ms = 0;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    CallTimer tm(ctx->stream);
+    const u64 n_in = ctx->mg.n_in;
+    auto run = [&]() -> int {
+        if (n_in == 0) {
+            u8 *dict = nullptr;
+            PFP_TRY(pfp_alloc_t(ctx, &dict, 1, true));
+            PFP_CUDA(ctx, cudaMemsetAsync(dict, 0, 1, ctx->stream));
+            out->dict = dict; out->dict_bytes = 1;
+            return PFPB200_OK;
+        }
+        if (!pool) return pfp_fail(ctx, PFPB200_E_ARG, "dict_merge_finish: null pool");
+        DictArrays D;
+        D.d = ctx->mg.d; D.sum_len = ctx->mg.sum_len; D.max_len = ctx->mg.max_len;
+        D.uid = ctx->mg.uid_of_entry; D.rep = ctx->mg.rep; D.count = ctx->mg.count; D.ulen = ctx->mg.ulen;
+        D.uwords = ctx->mg.uwords; D.uoff = ctx->mg.uoff;
+        D.pool = const_cast<u64 *>(pool); D.pool_words = pool_words;
+        if (flags & PFPB200_F_VERIFY)
+            PFP_TRY(pfp_merge_verify(ctx, n_in, ctx->mg.uid_of_entry, D.rep, ctx->mg.len_in, ctx->mg.uwords_in, pool));
+        u32 *order = nullptr, rounds = 0;
+        PFP_TRY(pfp_rank_stage(ctx, D, &order, &rounds));
+        u8 *dict = nullptr;
+        u32 *occ = nullptr, *rank_of_uid = nullptr, *rank_of_entry = nullptr;
+        u64 dict_bytes = 0;
+        PFP_TRY(pfp_dict_stage(ctx, D, order, (flags & PFPB200_F_COMPRESS) ? w : 0, &dict, &dict_bytes, &occ,
+                               &rank_of_uid));
+        PFP_TRY(pfp_alloc_t(ctx, &rank_of_entry, n_in, true));
+        PFP_TRY(pfp_remap_stage(ctx, ctx->mg.uid_of_entry, rank_of_uid, n_in, rank_of_entry));
+        PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PFP_CUDA(ctx, cudaGetLastError());
+        out->n_distinct = D.d; out->dict_bytes = dict_bytes; out->sum_word_len = D.sum_len;
+        out->dict = dict; out->occ = occ; out->rank_of_entry = rank_of_entry;
+        return PFPB200_OK;
+    };
+    int rc = run();
+    float t = tm.stop();
+    pfp_release_scratch(ctx);
+    ctx->mg.n_in = 0;
+    if (ms) *ms = t;
+    return rc;
+}
+
 extern "C" int pfpb200_dict_merge_words(pfpb200_ctx *ctx, uint64_t n_in, const pfpb200_word *words,
                                         const uint64_t *pool, uint64_t pool_words, uint32_t w,
                                         uint32_t flags, pfpb200_merged *out, float *ms) {
     if (!ctx || !out || (n_in && !words)) return PFPB200_E_ARG;
-    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
-    u64 *fpa = nullptr, *fpb = nullptr;
-    u32 *len = nullptr, *count = nullptr, *uwords = nullptr;
-    if (n_in) {
-        // the separate arrays must outlive the merge's own scratch release: hold them
-        PFP_TRY(pfp_alloc_t(ctx, &fpa, n_in, true));
-        PFP_TRY(pfp_alloc_t(ctx, &fpb, n_in, true));
-        PFP_TRY(pfp_alloc_t(ctx, &len, n_in, true));
-        PFP_TRY(pfp_alloc_t(ctx, &count, n_in, true));
-        PFP_TRY(pfp_alloc_t(ctx, &uwords, n_in, true));
-        PFP_TRY(pfp_unpack_words(ctx, words, n_in, fpa, fpb, len, count, uwords));
-    }
-    return pfpb200_dict_merge(ctx, n_in, fpa, fpb, len, count, uwords, pool, pool_words, w, flags, out, ms);
+    float a = 0, b = 0;
+    PFP_TRY(pfpb200_dict_merge_begin(ctx, n_in, words, &a));
+    int rc = pfpb200_dict_merge_finish(ctx, pool, pool_words, w, flags, out, &b);
+    if (ms) *ms = a + b;
+    return rc;
 }
 
 extern "C" int pfpb200_shard_remap(pfpb200_ctx *ctx, const uint32_t *d_rank_of_word, const uint32_t **d_parse,

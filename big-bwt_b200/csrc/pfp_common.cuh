@@ -89,6 +89,14 @@ struct pfpb200_ctx {
     u32 *d_keys = nullptr;         // NH key table (phrase fingerprints)
     u64 *d_flags = nullptr;        // [0] error bits, [1..] counters read back by the host
     u64 *h_flags = nullptr;        // pinned mirror
+    // state carried from pfpb200_dict_merge_begin to pfpb200_dict_merge_finish
+    struct {
+        u64 n_in = 0, d = 0, sum_len = 0;
+        u32 max_len = 0;
+        u32 *uid_of_entry = nullptr, *rep = nullptr, *count = nullptr, *ulen = nullptr, *uwords = nullptr;
+        u64 *uoff = nullptr;
+        const u32 *len_in = nullptr, *uwords_in = nullptr;
+    } mg;
     // state carried between the pfpb200_shard_* calls of one sharded parse
     struct {
         pfpb200_shard desc;

@@ -74,7 +74,8 @@ struct Rank {
     pfpb200_word *rx_words = nullptr; size_t rx_words_cap = 0;
     u64 *rx_pool = nullptr; size_t rx_pool_cap = 0;
     u32 *rx_ranks = nullptr; size_t rx_ranks_cap = 0;
-    cudaEvent_t ev_sent = nullptr, ev_back = nullptr;
+    cudaEvent_t ev_sent = nullptr, ev_back = nullptr, ev_routed = nullptr, ev_pool = nullptr;
+    cudaStream_t side = nullptr;          // the pool bytes travel here while the owners dedup the word records
     cudaEvent_t ev_phase[PH_COUNT] = {nullptr};
     u64 *d_small = nullptr, *h_small = nullptr;   // 16 u64 of device / pinned scratch
     u64 *h_sample = nullptr;              // pinned, MULTI_SAMPLE keys
@@ -341,36 +342,47 @@ void rank_main(pfpb200_multi *m, int g) {
     }();
     m->bar.wait();
 
-    // ---- 8. exchange: one DMA per (owner, buffer), straight into the owner's memory ------------------
+    // ---- 8. exchange: one DMA per (owner, buffer), straight into the owner's memory.  The 32-byte
+    //         word records go first on the main stream; the pool bytes follow on a side stream and
+    //         are still travelling while the owners dedup the records (step 9a needs nothing else)
+    cudaEventRecord(R.ev_routed, st);
+    cudaStreamWaitEvent(R.side, R.ev_routed, 0);
     [&]() {
         if (!ok() || R.n_words == 0) return;
         std::vector<u64> sw(G + 1, 0), sp(G + 1, 0);           // my routed segments, in owner order
         for (int q = 0; q < G; q++) { sw[q + 1] = sw[q] + R.words_to[q]; sp[q + 1] = sp[q] + R.pool_to[q]; }
-        for (int i = 0; i < G; i++) {
-            const int q = (g + i) % G;                      // start with myself, then round the ring
-            Rank &O = m->r[q];
-            u64 w_off = 0, p_off = 0;                       // my slot: behind the segments of the lower ranks
-            for (int src = 0; src < g; src++) { w_off += m->r[src].words_to[q]; p_off += m->r[src].pool_to[q]; }
-            if (R.words_to[q])
-                MR_CUDA(cudaMemcpyPeerAsync(O.rx_words + w_off, O.device, R.rt.words + sw[q], R.device,
-                                            (size_t)R.words_to[q] * sizeof(pfpb200_word), st));
-            if (R.pool_to[q])
-                MR_CUDA(cudaMemcpyPeerAsync(O.rx_pool + p_off, O.device, R.rt.pool + sp[q], R.device,
-                                            (size_t)R.pool_to[q] * sizeof(u64), st));
-        }
+        for (int pass = 0; pass < 2; pass++)
+            for (int i = 0; i < G; i++) {
+                const int q = (g + i) % G;                  // start with myself, then round the ring
+                Rank &O = m->r[q];
+                u64 w_off = 0, p_off = 0;                   // my slot: behind the segments of the lower ranks
+                for (int src = 0; src < g; src++) { w_off += m->r[src].words_to[q]; p_off += m->r[src].pool_to[q]; }
+                if (pass == 0 && R.words_to[q])
+                    MR_CUDA(cudaMemcpyPeerAsync(O.rx_words + w_off, O.device, R.rt.words + sw[q], R.device,
+                                                (size_t)R.words_to[q] * sizeof(pfpb200_word), st));
+                if (pass == 1 && R.pool_to[q])
+                    MR_CUDA(cudaMemcpyPeerAsync(O.rx_pool + p_off, O.device, R.rt.pool + sp[q], R.device,
+                                                (size_t)R.pool_to[q] * sizeof(u64), R.side));
+            }
     }();
     cudaEventRecord(R.ev_sent, st);
+    cudaEventRecord(R.ev_pool, R.side);
     m->bar.wait();
     for (int src = 0; src < G; src++)
         if (src != g) cudaStreamWaitEvent(st, m->r[src].ev_sent, 0);
     mark(R, PH_EXCHANGE);
 
-    // ---- 9. merge: dedup + rank + .dict/.occ of the owned range ------------------------------------------
+    // ---- 9. merge: (a) dedup of the received records, (b) once the bytes are here: rank + .dict/.occ -----
     memset(&R.mg, 0, sizeof(R.mg));
     [&]() {
         if (!ok()) return;
-        MR_LIB(pfpb200_dict_merge_words(R.ctx, recv_w, R.rx_words, R.rx_pool, recv_p, w,
-                                        m->opts.flags & (PFPB200_F_COMPRESS | PFPB200_F_VERIFY), &R.mg, nullptr));
+        MR_LIB(pfpb200_dict_merge_begin(R.ctx, recv_w, R.rx_words, nullptr));
+    }();
+    for (int src = 0; src < G; src++) cudaStreamWaitEvent(st, m->r[src].ev_pool, 0);
+    [&]() {
+        if (!ok()) return;
+        MR_LIB(pfpb200_dict_merge_finish(R.ctx, R.rx_pool, recv_p, w,
+                                         m->opts.flags & (PFPB200_F_COMPRESS | PFPB200_F_VERIFY), &R.mg, nullptr));
     }();
     R.n_distinct = R.mg.n_distinct;
     R.sum_word_len = R.mg.sum_word_len;
@@ -459,6 +471,7 @@ void rank_main(pfpb200_multi *m, int g) {
     }();
     mark(R, PH_D2H);
     cudaStreamSynchronize(st);
+    cudaStreamSynchronize(R.side);
     if (ok()) {
         for (int k = 1; k < PH_COUNT; k++) {
             float t = 0;
@@ -501,6 +514,9 @@ extern "C" int pfpb200_multi_create(int n_gpus, const int *gpu_ids, pfpb200_mult
         bool ok = cudaSetDevice(R.device) == cudaSuccess &&
                   cudaEventCreateWithFlags(&R.ev_sent, cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&R.ev_back, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&R.ev_routed, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&R.ev_pool, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&R.side, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaMalloc(&R.d_small, 16 * sizeof(u64)) == cudaSuccess &&
                   cudaHostAlloc(&R.h_small, 16 * sizeof(u64), cudaHostAllocPortable) == cudaSuccess &&
                   cudaHostAlloc(&R.h_sample, MULTI_SAMPLE * sizeof(u64), cudaHostAllocPortable) == cudaSuccess;
@@ -540,6 +556,9 @@ extern "C" void pfpb200_multi_destroy(pfpb200_multi *m) {
         if (R.h_sample) cudaFreeHost(R.h_sample);
         if (R.ev_sent) cudaEventDestroy(R.ev_sent);
         if (R.ev_back) cudaEventDestroy(R.ev_back);
+        if (R.ev_routed) cudaEventDestroy(R.ev_routed);
+        if (R.ev_pool) cudaEventDestroy(R.ev_pool);
+        if (R.side) { cudaStreamSynchronize(R.side); cudaStreamDestroy(R.side); }
         for (int k = 0; k < PH_COUNT; k++)
             if (R.ev_phase[k]) cudaEventDestroy(R.ev_phase[k]);
         pfpb200_destroy(R.ctx);

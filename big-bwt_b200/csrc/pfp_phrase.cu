@@ -788,6 +788,26 @@ int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 fi
     return PFPB200_OK;
 }
 
+// PFPB200_F_VERIFY for a merge whose pool arrived after the dedup (pfpb200_dict_merge_finish)
+int pfp_merge_verify(pfpb200_ctx *ctx, u64 n, const u32 *uid_of_entry, const u32 *rep, const u32 *len_in,
+                     const u32 *uwords_in, const u64 *pool) {
+    if (n == 0) return PFPB200_OK;
+    u64 *in_off = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &in_off, n));
+    PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, uwords_in, in_off, n, nullptr));
+    u64 want = (n + PH_WARPS - 1) / PH_WARPS;
+    u64 maxb = (u64)ctx->sm_count * 32;
+    verify_entries_k<<<(u32)(want < maxb ? want : maxb), PH_T, 0, ctx->stream>>>(n, uid_of_entry, rep, len_in, in_off, pool,
+                                                                                ctx->d_flags);
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PFP_TRY(pfp_free_now(ctx, in_off));
+    if (ctx->h_flags[0] & PFP_ERRBIT_COLLISION)
+        return pfp_fail(ctx, PFPB200_E_COLLISION, "two different words share a fingerprint (found by the verify pass)");
+    return PFPB200_OK;
+}
+
 // PFPB200_F_VERIFY for a parse: after the pool exists.  The caller reads flags[0] back.
 int pfp_verify_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w, u64 P,
                      const DictArrays &D) {

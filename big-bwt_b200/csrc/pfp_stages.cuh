@@ -109,5 +109,7 @@ int pfp_gather_word_fp(pfpb200_ctx *ctx, const DictArrays &D, const PhraseArrays
 int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, const u32 *len,
                     const u32 *count_in, const u32 *uwords_in, const u64 *pool, u64 pool_words,
                     bool verify, DictArrays *D, u32 **uid_of_entry);
+int pfp_merge_verify(pfpb200_ctx *ctx, u64 n, const u32 *uid_of_entry, const u32 *rep, const u32 *len_in,
+                     const u32 *uwords_in, const u64 *pool);
 int pfp_verify_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w, u64 P,
                      const DictArrays &D);

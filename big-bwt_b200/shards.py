@@ -145,6 +145,10 @@ class CudaBackend:
         L.pfpb200_shard_route_push.argtypes = [vp, u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float)]
         L.pfpb200_shard_route_push.restype = C.c_int
         L.pfpb200_dict_merge_words.restype = C.c_int
+        L.pfpb200_dict_merge_begin.argtypes = [vp, u64, vp, C.POINTER(C.c_float)]
+        L.pfpb200_dict_merge_begin.restype = C.c_int
+        L.pfpb200_dict_merge_finish.argtypes = [vp, vp, u64, u32, u32, C.POINTER(Merged), C.POINTER(C.c_float)]
+        L.pfpb200_dict_merge_finish.restype = C.c_int
         for f in (L.pfpb200_shard_scan, L.pfpb200_shard_words, L.pfpb200_dict_merge, L.pfpb200_shard_remap,
                   L.pfpb200_shard_first_keys, L.pfpb200_shard_route):
             f.restype = C.c_int
@@ -234,6 +238,26 @@ class CudaBackend:
                 "occ": dev_tensor(m.occ, m.n_distinct, torch.int32, dev),
                 "rank_of_entry": dev_tensor(m.rank_of_entry, n_in, torch.int32, dev)}
 
+    def dict_merge_begin(self, words):
+        """Global dedup of the received 32-byte word records (no bytes needed yet)."""
+        ms = C.c_float()
+        self._merge_n_in = words.numel() // 32
+        self.scanner._check(self.L.pfpb200_dict_merge_begin(self.h, self._merge_n_in, words.data_ptr(), C.byref(ms)))
+        self.ms["merge"] = ms.value
+
+    def dict_merge_finish(self, pool, w, compress=False, verify=False):
+        """Ranking + .dict/.occ of the deduplicated words, once their bytes have arrived."""
+        m, ms = Merged(), C.c_float()
+        self.scanner._check(self.L.pfpb200_dict_merge_finish(
+            self.h, pool.data_ptr(), pool.numel(), w,
+            (pfp.F_COMPRESS if compress else 0) | (pfp.F_VERIFY if verify else 0), C.byref(m), C.byref(ms)))
+        self.ms["merge"] = self.ms.get("merge", 0.0) + ms.value
+        dev = self.dev
+        return {"n_distinct": m.n_distinct, "sum_word_len": m.sum_word_len,
+                "dict": dev_tensor(m.dict, m.dict_bytes, torch.uint8, dev),
+                "occ": dev_tensor(m.occ, m.n_distinct, torch.int32, dev),
+                "rank_of_entry": dev_tensor(m.rank_of_entry, self._merge_n_in, torch.int32, dev)}
+
     def shard_remap(self, rank_of_word, n_phrases):
         out, ms = C.c_void_p(), C.c_float()
         self.scanner._check(self.L.pfpb200_shard_remap(self.h, rank_of_word.data_ptr(), C.byref(out), C.byref(ms)))
@@ -299,8 +323,15 @@ class PeerExchange:
         """Device addresses of every rank's buffer `name` as mapped into this process."""
         return [int(p) for p in self.bufs[name][1].buffer_ptrs]
 
-    def scatter(self, name, send, send_off, send_cnt, dst_off):
-        """send[send_off[q] : +send_cnt[q]] -> rank q's buffer `name` at element dst_off[q]."""
+    def join(self):
+        """The current stream waits for the copies issued by scatter(..., wait=False)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def scatter(self, name, send, send_off, send_cnt, dst_off, wait=True):
+        """send[send_off[q] : +send_cnt[q]] -> rank q's buffer `name` at element dst_off[q].
+        wait=False: the copies run on the side streams while the current stream goes on; join() later."""
         t, h, cap = self.bufs[name]
         cur = torch.cuda.current_stream(self.dev)
         for i in range(self.world):
@@ -313,8 +344,9 @@ class PeerExchange:
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 dst.copy_(send[int(send_off[q]):int(send_off[q]) + c], non_blocking=True)
-        for st in self.streams:
-            cur.wait_stream(st)
+        if wait:
+            for st in self.streams:
+                cur.wait_stream(st)
 
 
 class ShardedParser:
@@ -627,6 +659,7 @@ class ShardedParser:
         recv_w = [M[q][g] for q in range(G)]
         recv_p = [M[q][G + g] for q in range(G)]
         self._mark("route")
+        split = False                                   # pool bytes overlapped with the dedup of the records
         if peer is not None:
             need_w = max(sum(M[src][q] for src in range(G)) for q in range(G))
             need_p = max(sum(M[src][G + q] for src in range(G)) for q in range(G))
@@ -650,18 +683,28 @@ class ShardedParser:
                 send_words = rt["words"] if rt else torch.empty(0, dtype=torch.uint8, device=dev)
                 send_pool = rt["pool"] if rt else torch.empty(0, dtype=torch.int64, device=dev)
                 peer.scatter("words", send_words, 32 * so_w, [32 * c for c in words_to], [32 * o for o in w_off])
-                peer.scatter("pool", send_pool, so_p, pool_to, p_off)
-            peer.barrier("words")                       # everything addressed to me has landed
+                split = hasattr(be, "dict_merge_begin") and hasattr(peer, "join")
+                # the pool bytes travel on the side streams while the owners dedup the word records
+                peer.scatter("pool", send_pool, so_p, pool_to, p_off, **({"wait": False} if split else {}))
+            peer.barrier("words")                       # the word records addressed to me have landed
             got_words = peer.local("words", 32 * sum(recv_w))
             got_pool = peer.local("pool", sum(recv_p))
+            if not fused and split:
+                self._mark("exchange")
+                be.dict_merge_begin(got_words)
+                peer.join()
+                peer.barrier("words")                   # ... and now the pool bytes
         else:
             # NCCL grouped send/recv: the 32-byte word records and the pool bytes
             send_words = rt["words"] if rt else torch.empty(0, dtype=torch.uint8, device=dev)
             send_pool = rt["pool"] if rt else torch.empty(0, dtype=torch.int64, device=dev)
             got_words = self._all_to_all_v(send_words, [32 * c for c in words_to], [32 * c for c in recv_w])
             got_pool = self._all_to_all_v(send_pool, pool_to, recv_p)
-        self._mark("exchange")
-        m = be.dict_merge_words(got_words, got_pool, w, compress, verify)
+        if peer is not None and not fused and split:
+            m = be.dict_merge_finish(got_pool, w, compress, verify)
+        else:
+            self._mark("exchange")
+            m = be.dict_merge_words(got_words, got_pool, w, compress, verify)
         self._mark("merge")
         piece = m["dict"] if g == G - 1 else m["dict"][:-1]                 # only the last piece ends in 0x00
         tot = self._all_gather_i64([m["n_distinct"], int(piece.numel()), m["sum_word_len"], wd["n_phrases"]])

@@ -286,6 +286,13 @@ int  pfpb200_multi_phase_ms(const pfpb200_multi *m, float *out, int cap);
 int pfpb200_check_dict_order(pfpb200_ctx *ctx, const uint8_t *d_dict, const uint64_t *d_seps,
                              uint64_t n_words, uint64_t *n_bad);
 
+/* pfpb200_dict_merge_words in two halves, so that the exchange of the pool bytes overlaps the
+ * dedup: _begin needs only the 32-byte word records (global dedup: table, counts); _finish, called
+ * once the pool bytes have arrived, ranks the distinct words and writes .dict/.occ. */
+int pfpb200_dict_merge_begin(pfpb200_ctx *ctx, uint64_t n_in, const pfpb200_word *words, float *ms);
+int pfpb200_dict_merge_finish(pfpb200_ctx *ctx, const uint64_t *pool, uint64_t pool_words, uint32_t w,
+                              uint32_t flags, pfpb200_merged *out, float *ms);
+
 /* Kernels launched on this context since the start of the current parse (the last
  * pfpb200_parse_* / pfpb200_shard_scan call). */
 uint32_t pfpb200_launch_count(const pfpb200_ctx *ctx);
