@@ -95,6 +95,7 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     { const char *ev = getenv("PFPB200_LEGACY_K2"); ctx->legacy_k2 = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_K1"); ctx->k1_mode = (ev && strcmp(ev, "rolling") == 0) ? 1 : 0; }
     { const char *ev = getenv("PFPB200_TEST_WEAK_FP"); ctx->weak_fp = (ev && atoi(ev) != 0) ? 1u : 0u; }
+    { const char *ev = getenv("PFPB200_RANK_FULL_SORT"); ctx->rank_full_sort = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_RANK_CHUNK_PASSES"); ctx->rank_chunk_passes = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_FUSE_K3"); ctx->fuse_k3 = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_TABLE_SCALE"); if (ev && atof(ev) >= 1.2) ctx->table_scale = atof(ev); }
@@ -122,6 +123,10 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     set_u64_k<<<1, 1, 0, ctx->stream>>>(&ctx->d_flags[15], 1);
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         return bail(PFPB200_E_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_aux0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_aux1, cudaEventDisableTiming) != cudaSuccess)
+        return bail(PFPB200_E_CUDA);
     // per-device kernel attributes and constants of every stage (see pfp_common.cuh)
     if (pfp_scan_init(ctx) || pfp_stream_init(ctx) || pfp_phrase_init(ctx) || pfp_prims_init(ctx) ||
         pfp_rank_init(ctx))
@@ -146,6 +151,9 @@ extern "C" void pfpb200_destroy(pfpb200_ctx *ctx) {
     for (int i = 0; i < 5; i++)
         if (ctx->pin_buf[i]) cudaFreeHost(ctx->pin_buf[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->ev_aux0) cudaEventDestroy(ctx->ev_aux0);
+    if (ctx->ev_aux1) cudaEventDestroy(ctx->ev_aux1);
     if (ctx->ev_k2) cudaEventDestroy(ctx->ev_k2);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     delete ctx;
@@ -290,13 +298,12 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
         u8 *dict = nullptr;
         u32 *occ = nullptr, *rank_of_uid = nullptr;
         u64 dict_bytes = 0;
-        PFP_TRY(pfp_dict_stage(ctx, D, order, (o->flags & PFPB200_F_COMPRESS) ? w : 0, &dict,
-                               &dict_bytes, &occ, &rank_of_uid));
-        tm.mark(ctx->stream);                                           // 5
-        // K5
+        // K5 (remap) runs on the aux stream beside the .dict gather: it only needs the ranks
         u32 *parse = nullptr;
         PFP_TRY(pfp_alloc_t(ctx, &parse, P, true));
-        PFP_TRY(pfp_remap_stage(ctx, D.uid, rank_of_uid, P, parse));
+        PFP_TRY(pfp_dict_stage(ctx, D, order, (o->flags & PFPB200_F_COMPRESS) ? w : 0, &dict,
+                               &dict_bytes, &occ, &rank_of_uid, D.uid, P, parse));
+        tm.mark(ctx->stream);                                           // 5
         tm.mark(ctx->stream);                                           // 6
         PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -854,10 +861,9 @@ extern "C" int pfpb200_dict_merge_finish(pfpb200_ctx *ctx, const uint64_t *pool,
         u8 *dict = nullptr;
         u32 *occ = nullptr, *rank_of_uid = nullptr, *rank_of_entry = nullptr;
         u64 dict_bytes = 0;
-        PFP_TRY(pfp_dict_stage(ctx, D, order, (flags & PFPB200_F_COMPRESS) ? w : 0, &dict, &dict_bytes, &occ,
-                               &rank_of_uid));
         PFP_TRY(pfp_alloc_t(ctx, &rank_of_entry, n_in, true));
-        PFP_TRY(pfp_remap_stage(ctx, ctx->mg.uid_of_entry, rank_of_uid, n_in, rank_of_entry));
+        PFP_TRY(pfp_dict_stage(ctx, D, order, (flags & PFPB200_F_COMPRESS) ? w : 0, &dict, &dict_bytes, &occ,
+                               &rank_of_uid, ctx->mg.uid_of_entry, n_in, rank_of_entry));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         PFP_CUDA(ctx, cudaGetLastError());
         out->n_distinct = D.d; out->dict_bytes = dict_bytes; out->sum_word_len = D.sum_len;

@@ -65,6 +65,7 @@ struct pfpb200_ctx {
     int k1_mode = 0;               // PFPB200_K1=rolling: always the rolling-arithmetic scan kernel (A/B)
     u32 *dna_table = nullptr;      // 4^w-bit trigger table of (dna_w, dna_p) for the DNA scan (w <= 10)
     u32 dna_w = 0, dna_p = 0;
+    bool rank_full_sort = false;     // PFPB200_RANK_FULL_SORT=1: radix-sort all 64 bits of the first key (A/B)
     bool rank_chunk_passes = false;  // PFPB200_RANK_CHUNK_PASSES=1: mid-size tie groups by chunk passes instead of LCP walks (A/B)
     bool fuse_k3 = false;          // PFPB200_FUSE_K3=1: K3 + pool fused into the K2 pass (A/B; measured slower, see pfp_stream.cu)
     double pool_ratio = 0.0;       // pool bytes / text bytes of the previous parse (pool sizing hint of the fused K2+K3)
@@ -81,6 +82,9 @@ struct pfpb200_ctx {
     size_t pin_cap[5] = {0, 0, 0, 0, 0};                                 // kept and grown across calls
     // parse_host: .last/.sai are final after K2 and travel to the host on a second stream while
     // the dictionary stages run
+    // K5 (remap) needs only the ranks: it runs here while the .dict bytes are gathered on the main stream
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_k2 = nullptr, ev_copy = nullptr;
     bool early_copy = false;       // set by parse_host for the duration of the call

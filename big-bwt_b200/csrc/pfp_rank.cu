@@ -110,12 +110,17 @@ __global__ void rank_keys0_k(const u64 *__restrict__ pool, const u64 *__restrict
     vals[u] = (u32)u;
 }
 
-__global__ void rank_heads0_k(const u64 *__restrict__ ks, u64 d, const AlphaMap *__restrict__ am,
+// Only the key bits [begin_bit, 64) were sorted (enough to tell d words apart; the rest is left to
+// the tie kernels, which compare whole chunks anyway): groups and their known common depth follow
+// from those bits alone.
+__global__ void rank_heads0_k(const u64 *__restrict__ ks, u64 d, const AlphaMap *__restrict__ am, u32 begin_bit,
                               u8 *__restrict__ head, u32 *__restrict__ depth) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d) return;
-    head[i] = (i == 0 || ks[i] != ks[i - 1]) ? 1 : 0;
-    depth[i] = am->depth0;
+    head[i] = (i == 0 || (ks[i] >> begin_bit) != (ks[i - 1] >> begin_bit)) ? 1 : 0;
+    const u32 chars = (64u - begin_bit) / am->bits;           // whole symbols inside the sorted bits
+    const u32 d0 = chars / 8u;                                // whole 8-byte chunks they cover
+    depth[i] = d0 < am->depth0 ? d0 : am->depth0;
 }
 
 // ---- tie groups ------------------------------------------------------------------------------------------
@@ -268,17 +273,18 @@ __global__ void __launch_bounds__(256) rank_window_k(const u32 *__restrict__ hp,
 
 // groups of 2..32 words that straddle a window border: one warp each
 __global__ void __launch_bounds__(256) rank_warp_k(const u32 *__restrict__ hp,
-                                                   const u32 *__restrict__ nheads,
+                                                   const u32 *__restrict__ list,
+                                                   const u32 *__restrict__ count,
                                                    const u32 *__restrict__ depth,
                                                    const u64 *pool, const u64 *uoff, const u32 *uwords,
                                                    u32 max_chunks, u32 *__restrict__ ord,
                                                    u64 *__restrict__ flags) {
     const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const u32 ng = *nheads;
+    const u32 ng = *count;
     const u32 nwarps = gridDim.x * 8;
-    for (u32 g = blockIdx.x * 8 + wp; g < ng; g += nwarps) {
+    for (u32 q = blockIdx.x * 8 + wp; q < ng; q += nwarps) {
+        const u32 g = list[q];
         const u32 s = hp[g], m = hp[g + 1] - s;
-        if (m < 2 || m > WARP_MAX || (s >> 5) == ((s + m - 1) >> 5)) continue;   // inside a window: done
         const bool mem = lane < m;
         const u32 uid = mem ? ord[s + lane] : 0;
         const u64 *wptr = pool + (mem ? uoff[uid] : 0);
@@ -483,12 +489,16 @@ __device__ __forceinline__ void tie_refine(TieSort<CAP> &S, u64 *sm_v, u32 *sm_f
 // lists of the groups for the two shared-memory kernels
 __global__ void rank_lists_k(const u32 *__restrict__ hp, const u32 *__restrict__ nheads, u64 d,
                              u32 *__restrict__ mid_list, u32 *__restrict__ big_list,
-                             u32 *__restrict__ counts /* [0]=mid, [1]=big */) {
+                             u32 *__restrict__ warp_list,
+                             u32 *__restrict__ counts /* [0]=mid, [1]=big, [2]=warp */) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d || g >= *nheads) return;
-    u32 m = hp[g + 1] - hp[g];
-    if (m > WARP_MAX && m <= MID_MAX) mid_list[atomicAdd(&counts[0], 1u)] = (u32)g;
-    else if (m > MID_MAX && m <= LOCAL_MAX) big_list[atomicAdd(&counts[1], 1u)] = (u32)g;
+    const u32 s = hp[g], m = hp[g + 1] - s;
+    if (m < 2) return;
+    if (m <= WARP_MAX) {                      // inside one window of 32 positions: rank_window_k has it
+        if ((s >> 5) != ((s + m - 1) >> 5)) warp_list[atomicAdd(&counts[2], 1u)] = (u32)g;
+    } else if (m <= MID_MAX) mid_list[atomicAdd(&counts[0], 1u)] = (u32)g;
+    else if (m <= LOCAL_MAX) big_list[atomicAdd(&counts[1], 1u)] = (u32)g;
 }
 
 __global__ void __launch_bounds__(256) rank_mid_k(const u32 *__restrict__ hp,
@@ -523,133 +533,335 @@ __global__ void __launch_bounds__(256) rank_mid_k(const u32 *__restrict__ hp,
 // is the lexicographic order of the range, up to ties (same c, same v), which agree on c + 1
 // chunks and form the ranges of the next round.  One bitonic sort of the group by
 // (range, class/c, v) per round; a family is done in two or three rounds whatever its length.
-constexpr u32 LCP_MAX = 256;                  // words per group
+constexpr u32 LCP_MAX = 256;                  // words per group finished by one warp
 constexpr u32 LCP_WALK = 4;                   // chunks fetched per memory round trip of a walk
+constexpr u32 LCP_HEAD = 1u << 20;            // class-and-depth code of a range's head / a finished word
+constexpr u32 LCP_MAX_CHUNKS = LCP_HEAD - 1;  // longer words (8 MB) take the chunk-pass kernels
 
+// sort key of a word inside its group: ka = range start << 21 | code, code = c (left the head at
+// chunk c, below it), LCP_HEAD (the head), 2^21 - 1 - c (above it); kb = the word's chunk at c
+template <u32 CAP>
 struct LcpSort {
-    u64 ka[LCP_MAX];                          // sort key, high part: range start << 32 | class-and-depth code
-    u64 kb[LCP_MAX];                          // low part: the word's chunk where it leaves the head
-    u32 uid[2][LCP_MAX];
-    u32 off[2][LCP_MAX];                      // pool offset (8-byte words)
-    u32 wn[2][LCP_MAX];                       // length in 8-byte words
-    u32 dep[LCP_MAX];                         // at a range start: chunks the range is known to share
-    u16 lo[LCP_MAX];                          // range start of every position
-    u16 pay[LCP_MAX];                         // position before the sort
+    u64 kb[CAP];
+    u32 ka[CAP];
+    u32 uid[CAP];
+    u32 off[CAP];                             // pool offset (8-byte words)
+    u32 wn[CAP];                              // length in 8-byte words
+    u32 dep[CAP];                             // at a range start: chunks the range is known to share
+    u16 lo[CAP];                              // range start of every position
+    u16 pay[CAP];                             // position before the sort; then: 1 = a range starts here
+    unsigned long long best;                  // occurrences << 32 | position of the group's most frequent word
 };
 
-__global__ void __launch_bounds__(256) rank_lcp_k(const u32 *__restrict__ hp, const u32 *__restrict__ list,
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ bool lcp_less(u32 a0, u64 b0, u32 a1, u64 b1) { return a0 < a1 || (a0 == a1 && b0 < b1); }
+
+// compare-exchange of the (ka, kb, pay) held by two lanes (partner = lane ^ j), ascending iff `up`
+__device__ __forceinline__ void lcp_cx_shfl(u32 &ka, u64 &kb, u32 &pay, u32 j, bool up, bool lower) {
+    const u32 oa = __shfl_xor_sync(0xffffffffu, ka, j);
+    const u64 ob = __shfl_xor_sync(0xffffffffu, kb, j);
+    const u32 op = __shfl_xor_sync(0xffffffffu, pay, j);
+    const bool mine_less = lcp_less(ka, kb, oa, ob);
+    // the lower lane keeps the smaller key in an ascending block, the larger one in a descending block
+    const bool keep = (mine_less == lower) == up;
+    if (!keep && !(ka == oa && kb == ob)) { ka = oa; kb = ob; pay = op; }
+}
+
+// compare-exchange inside a lane: elements e and e ^ DJ (partner distance DJ * 32 positions)
+template <int E, int DJ>
+__device__ __forceinline__ void lcp_cx_lane(u32 (&ka)[E], u64 (&kb)[E], u32 (&pay)[E], u32 lane, u32 k) {
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int x = e ^ DJ;
+        if (x > e && x < E) {
+            const bool up = (((u32)e * 32 + lane) & k) == 0;
+            if (lcp_less(ka[x], kb[x], ka[e], kb[e]) == up) {
+                const u32 ta = ka[e]; ka[e] = ka[x]; ka[x] = ta;
+                const u64 tb = kb[e]; kb[e] = kb[x]; kb[x] = tb;
+                const u32 tp = pay[e]; pay[e] = pay[x]; pay[x] = tp;
+            }
+        }
+    }
+}
+
+// bitonic sort of E*32 keys held E per lane (position e*32 + lane) entirely in registers: partners
+// at distance < 32 are reached by shuffles, the others sit in the same lane.  The (k, j) loops stay
+// loops: fully unrolled, the four instantiations are tens of thousands of instructions and the
+// kernel stalls on instruction fetch (measured: 69 % of the stall samples).
+template <int E>
+__device__ __forceinline__ void lcp_bitonic_regs(u32 (&ka)[E], u64 (&kb)[E], u32 (&pay)[E], u32 lane) {
+#pragma unroll 1
+    for (u32 k = 2; k <= (u32)E * 32; k <<= 1) {
+#pragma unroll 1
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const u32 dj = j >> 5;
+                if (dj == 1) lcp_cx_lane<E, 1>(ka, kb, pay, lane, k);
+                else if (dj == 2) lcp_cx_lane<E, 2>(ka, kb, pay, lane, k);
+                else lcp_cx_lane<E, 4>(ka, kb, pay, lane, k);
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const bool up = (((u32)e * 32 + lane) & k) == 0;
+                    lcp_cx_shfl(ka[e], kb[e], pay[e], j, up, (lane & j) == 0);
+                }
+            }
+        }
+    }
+}
+
+template <int E>
+__device__ __noinline__ void lcp_sort_regs(LcpSort<LCP_MAX> &S, u32 lane) {
+    u32 ka[E], pay[E];
+    u64 kb[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) { ka[e] = S.ka[e * 32 + lane]; kb[e] = S.kb[e * 32 + lane]; pay[e] = S.pay[e * 32 + lane]; }
+    lcp_bitonic_regs<E>(ka, kb, pay, lane);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < E; e++) { S.ka[e * 32 + lane] = ka[e]; S.kb[e * 32 + lane] = kb[e]; S.pay[e * 32 + lane] = (u16)pay[e]; }
+}
+
+// One group of m words (hp range [s, s+m)) by the NT threads of a team (a warp, or a CTA).
+template <int NT, u32 CAP>
+__device__ __forceinline__ void lcp_refine(LcpSort<CAP> &S, u32 t, u32 s, u32 m, u32 r0, const u64 *__restrict__ pool,
+                                           const u64 *__restrict__ uoff, const u32 *__restrict__ uwords,
+                                           const u32 *__restrict__ occ_of_word, u32 max_chunks,
+                                           u32 *__restrict__ ord, u64 *__restrict__ flags) {
+    u32 M = 32;                                               // bitonic size: next power of two
+    while (M < m) M <<= 1;
+    if (t == 0) S.best = 0ull;
+    tie_sync<NT>();
+    {   // the words of the group: ids first, then their offsets / lengths (independent loads in flight together)
+        constexpr u32 EM = CAP / NT;
+        u32 us[EM];
+#pragma unroll
+        for (u32 e = 0; e < EM; e++) { const u32 p = e * NT + t; us[e] = p < m ? ord[s + p] : 0u; }
+#pragma unroll
+        for (u32 e = 0; e < EM; e++) {
+            const u32 p = e * NT + t;
+            if (p < m) {
+                const u32 o = (u32)uoff[us[e]];
+                S.uid[p] = us[e]; S.off[p] = o; S.wn[p] = uwords[us[e]];
+                S.lo[p] = 0;
+                prefetch_l2(pool + o + r0);                   // where the first walk starts
+                atomicMax(&S.best, ((unsigned long long)occ_of_word[us[e]] << 32) | p);
+            }
+        }
+    }
+    if (t == 0) S.dep[0] = r0;
+    tie_sync<NT>();
+    // The head of the first round is the group's MOST FREQUENT word.  Any member would do for
+    // correctness; but a tie group is typically a family -- one consensus phrase and its variants,
+    // each differing from the consensus in one place -- and against the consensus every variant
+    // leaves at its own place (one round), while against a variant everything that mutates
+    // behind the variant's place leaves together and has to be split again, round after round.
+    if (t == 0) {
+        const u32 b = (u32)(S.best & 0xFFFFFFFFull);
+        if (b != 0 && b < m) {
+            const u32 u0 = S.uid[0], o0 = S.off[0], w0 = S.wn[0];
+            S.uid[0] = S.uid[b]; S.off[0] = S.off[b]; S.wn[0] = S.wn[b];
+            S.uid[b] = u0; S.off[b] = o0; S.wn[b] = w0;
+        }
+    }
+    tie_sync<NT>();
+    for (u32 round = 0;; round++) {
+        // ---- 1. every word of a range of two or more walks along the range's head -------------------------
+        // (the chunks where the walks start are requested for ALL of a thread's words first: the walks
+        //  of one thread run one after the other, and each would otherwise wait for DRAM on its own)
+        if (round > 0)
+            for (u32 p = t; p < m; p += NT) {
+                const u32 l = S.lo[p];
+                if (p != l) prefetch_l2(pool + S.off[p] + S.dep[l]);
+            }
+        int any = 0, bad = 0;
+        u32 na = 0;                                           // words still tied (NT == 32: exact, for all lanes)
+        for (u32 p = t; p < M; p += NT) {
+            u32 ka = 0xFFFFFFFFu;                             // padding sorts behind everything
+            u64 kb = 0;
+            bool active = false;
+            if (p < m) {
+                const u32 l = S.lo[p];
+                const bool single = (p == l) && (p + 1 >= m || S.lo[p + 1] != l);
+                active = !single;
+                u32 code = LCP_HEAD;
+                if (active && p != l) {
+                    const u64 *mine = pool + S.off[p], *head = pool + S.off[l];
+                    const u32 wm = S.wn[p], wh = S.wn[l];
+                    u32 c = S.dep[l];
+                    u64 v = 0, h = 0;
+                    for (;;) {
+                        u64 a[LCP_WALK], b[LCP_WALK];
+#pragma unroll
+                        for (u32 i = 0; i < LCP_WALK; i++) {
+                            a[i] = (c + i < wm) ? __ldg(mine + c + i) : 0ull;
+                            b[i] = (c + i < wh) ? __ldg(head + c + i) : 0ull;
+                        }
+                        bool found = false;
+#pragma unroll
+                        for (u32 i = 0; i < LCP_WALK; i++)
+                            if (!found && a[i] != b[i]) { found = true; c += i; v = bswap64(a[i]); h = bswap64(b[i]); }
+                        if (found) break;
+                        c += LCP_WALK;
+                        prefetch_l2(mine + c + LCP_WALK);     // one batch ahead
+                        if (c >= max_chunks) { bad = 1; break; }          // two equal words: cannot happen
+                    }
+                    code = v < h ? c : 2u * LCP_HEAD - 1u - c;
+                    kb = v;
+                }
+                ka = (l << 21) | code;
+            }
+            if (NT == 32) na += __popc(__ballot_sync(0xffffffffu, active));
+            any |= active ? 1 : 0;
+            S.ka[p] = ka; S.kb[p] = kb; S.pay[p] = (u16)p;
+        }
+        if (tie_any<NT>(bad)) {
+            if (t == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
+            break;
+        }
+        if (!tie_any<NT>(any)) break;
+        // ---- 2. sort the group by (range start, class/depth code, chunk) -------------------------------------
+        if (NT == 32 && na <= 48) {
+            // few words are still tied (every round but the first): each finds its place among the
+            // words of its range by counting the smaller ones
+            u16 np[LCP_MAX / 32];
+#pragma unroll
+            for (u32 e = 0; e < LCP_MAX / 32; e++) {
+                const u32 p = e * 32 + t;
+                np[e] = (u16)p;
+                if (p < m) {
+                    const u32 l = S.lo[p];
+                    const bool single = (p == l) && (p + 1 >= m || S.lo[p + 1] != l);
+                    if (!single) {
+                        const u32 a0 = S.ka[p];
+                        const u64 b0 = S.kb[p];
+                        u32 rank = 0;
+                        for (u32 q = l; q < m && S.lo[q] == l; q++) {
+                            const u32 a1 = S.ka[q];
+                            const u64 b1 = S.kb[q];
+                            rank += (lcp_less(a1, b1, a0, b0) || (a1 == a0 && b1 == b0 && q < p)) ? 1u : 0u;
+                        }
+                        np[e] = (u16)(l + rank);
+                    }
+                }
+            }
+            // pay[new position] = old position, keys move along
+            u32 ka[LCP_MAX / 32];
+            u64 kb[LCP_MAX / 32];
+#pragma unroll
+            for (u32 e = 0; e < LCP_MAX / 32; e++) {
+                const u32 p = e * 32 + t;
+                if (p < m) { ka[e] = S.ka[p]; kb[e] = S.kb[p]; }
+            }
+            __syncwarp();
+#pragma unroll
+            for (u32 e = 0; e < LCP_MAX / 32; e++) {
+                const u32 p = e * 32 + t;
+                if (p < m) { S.ka[np[e]] = ka[e]; S.kb[np[e]] = kb[e]; S.pay[np[e]] = (u16)p; }
+            }
+            __syncwarp();
+        } else if (NT == 32) {
+            __syncwarp();
+            LcpSort<LCP_MAX> &W = reinterpret_cast<LcpSort<LCP_MAX> &>(S);
+            if (M == 32) lcp_sort_regs<1>(W, t);
+            else if (M == 64) lcp_sort_regs<2>(W, t);
+            else if (M == 128) lcp_sort_regs<4>(W, t);
+            else lcp_sort_regs<8>(W, t);
+            __syncwarp();
+        } else {
+            tie_sync<NT>();
+            for (u32 k = 2; k <= M; k <<= 1) {
+                for (u32 j = k >> 1; j > 0; j >>= 1) {
+                    for (u32 i = t; i < M; i += NT) {
+                        const u32 x = i ^ j;
+                        if (x > i) {
+                            const u32 a0 = S.ka[i], a1 = S.ka[x];
+                            const u64 b0 = S.kb[i], b1 = S.kb[x];
+                            if (lcp_less(a1, b1, a0, b0) == ((i & k) == 0)) {
+                                S.ka[i] = a1; S.ka[x] = a0; S.kb[i] = b1; S.kb[x] = b0;
+                                const u16 tp = S.pay[i]; S.pay[i] = S.pay[x]; S.pay[x] = tp;
+                            }
+                        }
+                    }
+                    tie_sync<NT>();
+                }
+            }
+        }
+        // ---- 3. move the words; ranges of the next round = runs of equal keys ---------------------------------
+        {
+            constexpr u32 EM = CAP / NT;
+            u32 mu[EM], mo[EM], mw[EM];
+#pragma unroll
+            for (u32 e = 0; e < EM; e++) {
+                const u32 p = e * NT + t;
+                if (p < m) { const u32 q = S.pay[p]; mu[e] = S.uid[q]; mo[e] = S.off[q]; mw[e] = S.wn[q]; }
+            }
+            tie_sync<NT>();
+#pragma unroll
+            for (u32 e = 0; e < EM; e++) {
+                const u32 p = e * NT + t;
+                if (p < m) {
+                    S.uid[p] = mu[e]; S.off[p] = mo[e]; S.wn[p] = mw[e];
+                    const bool start = p == 0 || S.ka[p] != S.ka[p - 1] || S.kb[p] != S.kb[p - 1];
+                    S.pay[p] = start ? 1 : 0;
+                    if (start) {                              // depth of a new range: its members left their old
+                        const u32 code = S.ka[p] & (2u * LCP_HEAD - 1u);    // head at the same chunk c
+                        const u32 c = code < LCP_HEAD ? code : 2u * LCP_HEAD - 1u - code;
+                        S.dep[p] = code == LCP_HEAD ? 0u : c + 1;
+                    }
+                }
+            }
+            tie_sync<NT>();
+            if (t < 32) {                                     // range start of every position: one warp, ballots
+                u32 carry = 0;
+                for (u32 b0 = 0; b0 < m; b0 += 32) {
+                    const u32 p = b0 + t;
+                    const u32 sm = __ballot_sync(0xffffffffu, p < m && S.pay[p] != 0);
+                    if (p < m) {
+                        const u32 below = sm & (0xFFFFFFFFu >> (31 - t));
+                        S.lo[p] = (u16)(below ? b0 + (31 - __clz(below)) : carry);
+                    }
+                    if (sm) carry = b0 + (31 - __clz(sm));
+                }
+            }
+            tie_sync<NT>();
+        }
+    }
+    tie_sync<NT>();
+    for (u32 p = t; p < m; p += NT) ord[s + p] = S.uid[p];
+}
+
+// groups of 33..256 words: one warp each
+__global__ void __launch_bounds__(256, 3) rank_lcp_k(const u32 *__restrict__ hp, const u32 *__restrict__ list,
                                                   const u32 *__restrict__ count, const u32 *__restrict__ depth,
                                                   const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
-                                                  const u32 *__restrict__ uwords, u32 max_chunks,
-                                                  u32 *__restrict__ ord, u64 *__restrict__ flags) {
+                                                  const u32 *__restrict__ uwords, const u32 *__restrict__ occ_of_word,
+                                                  u32 max_chunks, u32 *__restrict__ ord, u64 *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char lcp_raw[];
     const u32 lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    LcpSort &S = reinterpret_cast<LcpSort *>(lcp_raw)[wp];
+    LcpSort<LCP_MAX> &S = reinterpret_cast<LcpSort<LCP_MAX> *>(lcp_raw)[wp];
     const u32 n = *count;
     for (u32 gq = blockIdx.x * 8 + wp; gq < n; gq += gridDim.x * 8) {
         const u32 g = list[gq];
         const u32 s = hp[g], m = hp[g + 1] - s;
-        u32 M = 32;                                           // bitonic size: next power of two
-        while (M < m) M <<= 1;
-        int cur = 0;
-        __syncwarp();
-        for (u32 p = lane; p < m; p += 32) {
-            const u32 u = ord[s + p];
-            S.uid[0][p] = u; S.off[0][p] = (u32)uoff[u]; S.wn[0][p] = uwords[u];
-            S.lo[p] = 0;
-        }
-        if (lane == 0) S.dep[0] = depth[s];
-        __syncwarp();
-        for (u32 round = 0;; round++) {
-            // ---- 1. every word of a range of two or more walks along the range's head ---------------------
-            int any = 0, bad = 0;
-            for (u32 p = lane; p < M; p += 32) {
-                u64 ka = ~0ull, kb = 0;                        // padding sorts behind everything
-                if (p < m) {
-                    const u32 l = S.lo[p];
-                    const bool single = (p == l) && (p + 1 >= m || S.lo[p + 1] != l);
-                    u32 code = 0x80000000u;                   // the head of its range (or a finished word)
-                    if (!single && p != l) {
-                        const u64 *mine = pool + S.off[cur][p], *head = pool + S.off[cur][l];
-                        const u32 wm = S.wn[cur][p], wh = S.wn[cur][l];
-                        u32 c = S.dep[l];
-                        u64 v = 0, h = 0;
-                        for (;;) {
-                            u64 a[LCP_WALK], b[LCP_WALK];
-#pragma unroll
-                            for (u32 i = 0; i < LCP_WALK; i++) {
-                                a[i] = (c + i < wm) ? __ldg(mine + c + i) : 0ull;
-                                b[i] = (c + i < wh) ? __ldg(head + c + i) : 0ull;
-                            }
-                            bool found = false;
-#pragma unroll
-                            for (u32 i = 0; i < LCP_WALK; i++)
-                                if (!found && a[i] != b[i]) { found = true; c += i; v = bswap64(a[i]); h = bswap64(b[i]); }
-                            if (found) break;
-                            c += LCP_WALK;
-                            if (c >= max_chunks) { bad = 1; break; }      // two equal words: cannot happen
-                        }
-                        code = v < h ? c : 0xFFFFFFFFu - c;
-                        kb = v;
-                    }
-                    any |= single ? 0 : 1;
-                    ka = ((u64)l << 32) | code;
-                }
-                S.ka[p] = ka; S.kb[p] = kb; S.pay[p] = (u16)p;
-            }
-            if (__any_sync(0xffffffffu, bad)) {
-                if (lane == 0) atomicOr((unsigned long long *)&flags[0], PFP_ERRBIT_INTERNAL);
-                break;
-            }
-            if (!__any_sync(0xffffffffu, any)) break;
-            __syncwarp();
-            // ---- 2. bitonic sort of the group by (range start, class/depth code, chunk) ------------------
-            for (u32 k = 2; k <= M; k <<= 1) {
-                for (u32 j = k >> 1; j > 0; j >>= 1) {
-                    for (u32 i = lane; i < M; i += 32) {
-                        const u32 x = i ^ j;
-                        if (x > i) {
-                            const u64 a0 = S.ka[i], a1 = S.ka[x], b0 = S.kb[i], b1 = S.kb[x];
-                            const bool gt = a0 > a1 || (a0 == a1 && b0 > b1);
-                            if (gt == ((i & k) == 0)) {
-                                S.ka[i] = a1; S.ka[x] = a0; S.kb[i] = b1; S.kb[x] = b0;
-                                const u16 t = S.pay[i]; S.pay[i] = S.pay[x]; S.pay[x] = t;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            // ---- 3. move the words; ranges of the next round = runs of equal keys ----------------------
-            u32 carry = 0;                                    // start of the range running into this block of 32
-            for (u32 b0 = 0; b0 < m; b0 += 32) {
-                const u32 p = b0 + lane;
-                bool start = false;
-                if (p < m) {
-                    const u32 q = S.pay[p];
-                    S.uid[cur ^ 1][p] = S.uid[cur][q];
-                    S.off[cur ^ 1][p] = S.off[cur][q];
-                    S.wn[cur ^ 1][p] = S.wn[cur][q];
-                    start = p == 0 || S.ka[p] != S.ka[p - 1] || S.kb[p] != S.kb[p - 1];
-                }
-                const u32 sm = __ballot_sync(0xffffffffu, start);
-                if (p < m) {
-                    const u32 below = sm & (0xFFFFFFFFu >> (31 - lane));      // starts at or below my lane
-                    const u32 l = below ? b0 + (31 - __clz(below)) : carry;
-                    S.lo[p] = (u16)l;
-                    if (start) {                              // depth of a new range: its members left their old head
-                        const u32 code = (u32)S.ka[p];        // at the same chunk c with the same chunk value
-                        const u32 c = code < 0x80000000u ? code : 0xFFFFFFFFu - code;
-                        S.dep[p] = code == 0x80000000u ? 0u : c + 1;
-                    }
-                }
-                if (sm) carry = b0 + (31 - __clz(sm));
-            }
-            __syncwarp();
-            cur ^= 1;
-        }
-        __syncwarp();
-        for (u32 p = lane; p < m; p += 32) ord[s + p] = S.uid[cur][p];
+        lcp_refine<32, LCP_MAX>(S, lane, s, m, depth[s], pool, uoff, uwords, occ_of_word, max_chunks, ord, flags);
+    }
+}
+
+// groups of 257..2048 words: one CTA each
+__global__ void __launch_bounds__(256) rank_lcp_cta_k(const u32 *__restrict__ hp, const u32 *__restrict__ list,
+                                                      const u32 *__restrict__ count, const u32 *__restrict__ depth,
+                                                      const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
+                                                      const u32 *__restrict__ uwords, const u32 *__restrict__ occ_of_word,
+                                                      u32 max_chunks, u32 *__restrict__ ord, u64 *__restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char lcp_cta_raw[];
+    LcpSort<LOCAL_MAX> &S = *reinterpret_cast<LcpSort<LOCAL_MAX> *>(lcp_cta_raw);
+    const u32 n = *count;
+    for (u32 gq = blockIdx.x; gq < n; gq += gridDim.x) {
+        const u32 g = list[gq];
+        const u32 s = hp[g], m = hp[g + 1] - s;
+        lcp_refine<256, LOCAL_MAX>(S, threadIdx.x, s, m, depth[s], pool, uoff, uwords, occ_of_word, max_chunks, ord, flags);
     }
 }
 
@@ -679,7 +891,9 @@ int pfp_rank_init(pfpb200_ctx *ctx) {
     PFP_CUDA(ctx, cudaFuncSetAttribute(rank_mid_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(8 * sizeof(TieSort<MID_MAX>))));
     PFP_CUDA(ctx, cudaFuncSetAttribute(rank_lcp_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(8 * sizeof(LcpSort))));
+                                       (int)(8 * sizeof(LcpSort<LCP_MAX>))));
+    PFP_CUDA(ctx, cudaFuncSetAttribute(rank_lcp_cta_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(LcpSort<LOCAL_MAX>)));
     return PFPB200_OK;
 }
 
@@ -714,8 +928,18 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
     PFP_LAUNCHED(ctx);
     rank_keys0_k<<<nbd, TB, 0, ctx->stream>>>(D.pool, D.uoff, D.ulen, d, am, k0, v0);
     PFP_LAUNCHED(ctx);
-    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, d, 0, 64, &ks, &vs));
-    rank_heads0_k<<<nbd, TB, 0, ctx->stream>>>(ks, d, am, head, depth);
+    // LSD passes only over the top 2 log2(d) + 2 key bits (whole bytes): with fewer, unrelated
+    // words start to collide by chance (measured on 8 GB of random text: sorting 40 of 64 bits
+    // saved 3 ms of sort passes and cost 9 ms of tie groups); with these, 6 or 7 passes instead
+    // of 8 for 4 M .. 100 M words.  Words that agree on the sorted bits form the tie groups; the
+    // tie kernels compare whole chunks, so nothing is lost.
+    int lg = 1;
+    while (lg < 32 && (1ull << lg) < d) lg++;
+    int sort_bits = (2 * lg + 2 + 7) / 8 * 8;
+    if (sort_bits > 64 || ctx->rank_full_sort) sort_bits = 64;
+    const int begin_bit = 64 - sort_bits;
+    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, d, begin_bit, 64, &ks, &vs));
+    rank_heads0_k<<<nbd, TB, 0, ctx->stream>>>(ks, d, am, (u32)begin_bit, head, depth);
     PFP_LAUNCHED(ctx);
     PFP_CUDA(ctx, cudaMemcpyAsync(ord, vs, d * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
 
@@ -780,9 +1004,10 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
     // finish every remaining tie group on chip
     if (d >= 2) {
         u32 *mid_list = v1, *big_list = v0;      // sort buffers are free again
+        u32 *warp_list = reinterpret_cast<u32 *>(k1);
         u32 *counts = reinterpret_cast<u32 *>(&ctx->d_flags[5]);
-        PFP_CUDA(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(u32), ctx->stream));
-        rank_lists_k<<<nbd, TB, 0, ctx->stream>>>(hp, d_nheads, d, mid_list, big_list, counts);
+        PFP_CUDA(ctx, cudaMemsetAsync(counts, 0, 4 * sizeof(u32), ctx->stream));
+        rank_lists_k<<<nbd, TB, 0, ctx->stream>>>(hp, d_nheads, d, mid_list, big_list, warp_list, counts);
         PFP_LAUNCHED(ctx);
         u64 want = (d / 2 + 7) / 8;
         u64 maxb = (u64)ctx->sm_count * 16;
@@ -793,18 +1018,24 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
         PFP_LAUNCHED(ctx);
         // (a second pass over windows shifted by 16 for the groups straddling a border was measured:
         //  it costs what it saves -- the kernels are bound by their chains of dependent loads)
-        rank_warp_k<<<nbw, 256, 0, ctx->stream>>>(hp, d_nheads, depth, D.pool, D.uoff, D.uwords, max_chunks,
+        rank_warp_k<<<nbw, 256, 0, ctx->stream>>>(hp, warp_list, counts + 2, depth, D.pool, D.uoff, D.uwords, max_chunks,
                                                   ord, ctx->d_flags);
         PFP_LAUNCHED(ctx);
-        if (ctx->rank_chunk_passes)      // A/B: one 8-byte chunk per pass (the kernel rank_lcp_k replaced)
+        // A/B (and words of 8 MB and more): one 8-byte chunk per pass, the kernels the LCP walks replaced
+        const bool chunk_passes = ctx->rank_chunk_passes || max_chunks >= LCP_MAX_CHUNKS;
+        if (chunk_passes)
             rank_mid_k<<<ctx->sm_count * 4, 256, 8 * sizeof(TieSort<MID_MAX>), ctx->stream>>>(
                 hp, mid_list, counts, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
         else
-            rank_lcp_k<<<ctx->sm_count * 4, 256, 8 * sizeof(LcpSort), ctx->stream>>>(
-                hp, mid_list, counts, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
+            rank_lcp_k<<<ctx->sm_count * 6, 256, 8 * sizeof(LcpSort<LCP_MAX>), ctx->stream>>>(
+                hp, mid_list, counts, depth, D.pool, D.uoff, D.uwords, D.count, max_chunks, ord, ctx->d_flags);
         PFP_LAUNCHED(ctx);
-        rank_cta_k<<<ctx->sm_count * 4, 256, sizeof(TieSort<LOCAL_MAX>), ctx->stream>>>(
-            hp, big_list, counts + 1, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
+        if (chunk_passes)
+            rank_cta_k<<<ctx->sm_count * 4, 256, sizeof(TieSort<LOCAL_MAX>), ctx->stream>>>(
+                hp, big_list, counts + 1, depth, D.pool, D.uoff, D.uwords, max_chunks, ord, ctx->d_flags);
+        else
+            rank_lcp_cta_k<<<ctx->sm_count * 3, 256, sizeof(LcpSort<LOCAL_MAX>), ctx->stream>>>(
+                hp, big_list, counts + 1, depth, D.pool, D.uoff, D.uwords, D.count, max_chunks, ord, ctx->d_flags);
         PFP_LAUNCHED(ctx);
         PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(u64), cudaMemcpyDeviceToHost,
                                       ctx->stream));
@@ -886,8 +1117,15 @@ __global__ void __launch_bounds__(DC_T) dict_copy_k(const u32 *__restrict__ ord,
     }
 }
 
+__global__ void remap_k(const u32 *__restrict__ uid, const u32 *__restrict__ rank_of_uid, u64 P,
+                        u32 *__restrict__ parse);
+
+// remap_uid / remap_out non-null: K5 (remap_out[j] = rank of remap_uid[j], j < remap_n) is launched
+// on the context's aux stream as soon as the ranks exist and runs beside the .dict gather; the
+// main stream waits for it before this function returns.
 int pfp_dict_stage(pfpb200_ctx *ctx, const DictArrays &D, const u32 *order, u32 strip_w, u8 **dict,
-                   u64 *dict_bytes, u32 **occ, u32 **rank_of_uid) {
+                   u64 *dict_bytes, u32 **occ, u32 **rank_of_uid, const u32 *remap_uid, u64 remap_n,
+                   u32 *remap_out) {
     const int TB = 256;
     const u64 d = D.d;
     u32 *dl = nullptr;
@@ -898,6 +1136,14 @@ int pfp_dict_stage(pfpb200_ctx *ctx, const DictArrays &D, const u32 *order, u32 
     PFP_TRY(pfp_alloc_t(ctx, &doff, d));
     dict_layout_k<<<pfp_blocks(d, TB), TB, 0, ctx->stream>>>(order, d, D, strip_w, *rank_of_uid, *occ, dl);
     PFP_LAUNCHED(ctx);
+    const bool side_remap = remap_uid && remap_out && remap_n;
+    if (side_remap) {
+        PFP_CUDA(ctx, cudaEventRecord(ctx->ev_aux0, ctx->stream));
+        PFP_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux0, 0));
+        remap_k<<<pfp_blocks(remap_n, 256), 256, 0, ctx->aux_stream>>>(remap_uid, *rank_of_uid, remap_n, remap_out);
+        PFP_LAUNCHED(ctx);
+        PFP_CUDA(ctx, cudaEventRecord(ctx->ev_aux1, ctx->aux_stream));
+    }
     PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, dl, doff, d, &ctx->d_flags[1]));
     PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[1], &ctx->d_flags[1], sizeof(u64),
                                   cudaMemcpyDeviceToHost, ctx->stream));
@@ -911,6 +1157,7 @@ int pfp_dict_stage(pfpb200_ctx *ctx, const DictArrays &D, const u32 *order, u32 
     if (nb == 0) nb = 1;
     dict_copy_k<<<nb, DC_T, 0, ctx->stream>>>(order, doff, d, D, strip_w, total, *dict);
     PFP_LAUNCHED(ctx);
+    if (side_remap) PFP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux1, 0));
     PFP_TRY(pfp_free_now(ctx, dl));
     PFP_TRY(pfp_free_now(ctx, doff));
     return PFPB200_OK;

@@ -90,7 +90,8 @@ int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 fi
 int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *rounds);
 // .dict / .occ bytes and rank-per-uid from the order; outputs are `held` device buffers.
 int pfp_dict_stage(pfpb200_ctx *ctx, const DictArrays &D, const u32 *order, u32 strip_w,
-                   u8 **dict, u64 *dict_bytes, u32 **occ, u32 **rank_of_uid);
+                   u8 **dict, u64 *dict_bytes, u32 **occ, u32 **rank_of_uid,
+                   const u32 *remap_uid = nullptr, u64 remap_n = 0, u32 *remap_out = nullptr);
 int pfp_remap_stage(pfpb200_ctx *ctx, const u32 *uid, const u32 *rank_of_uid, u64 P, u32 *parse);
 
 int pfp_first_invalid(pfpb200_ctx *ctx, const u8 *d_text, u64 n, u64 *d_first);
