@@ -107,6 +107,13 @@ def main():
             except OSError:
                 pass
         os.remove(link)
+        if os.path.exists(OUT):                 # another instance may have written in the meantime
+            with open(OUT) as f:
+                disk = json.load(f)
+            for k in ("texts", "cases"):
+                merged = dict(disk.get(k, {}))
+                merged.update(res[k])
+                res[k] = merged
         with open(OUT, "w") as f:
             json.dump(res, f, indent=1)
 
