@@ -95,6 +95,7 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     { const char *ev = getenv("PFPB200_LEGACY_K2"); ctx->legacy_k2 = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_K1"); ctx->k1_mode = (ev && strcmp(ev, "rolling") == 0) ? 1 : 0; }
     { const char *ev = getenv("PFPB200_TEST_WEAK_FP"); ctx->weak_fp = (ev && atoi(ev) != 0) ? 1u : 0u; }
+    { const char *ev = getenv("PFPB200_NO_SCAN_ALPHA"); ctx->no_scan_alpha = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_RANK_FULL_SORT"); ctx->rank_full_sort = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_RANK_CHUNK_PASSES"); ctx->rank_chunk_passes = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_FUSE_K3"); ctx->fuse_k3 = ev && atoi(ev) != 0; }
@@ -111,7 +112,8 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     ctx->stream = ctx->own_stream;
     if (cudaMalloc(&ctx->d_flags, PFP_FLAG_SLOTS * sizeof(u64)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_flags, PFP_FLAG_SLOTS * sizeof(u64)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_keys, NH_KEY_WORDS * sizeof(u32)) != cudaSuccess)
+        cudaMalloc(&ctx->d_keys, NH_KEY_WORDS * sizeof(u32)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_alpha, 8 * sizeof(u32)) != cudaSuccess)
         return bail(PFPB200_E_NOMEM);
     u32 hk[NH_KEY_WORDS];
     u64 seed = 0x5bd1e9955bd1e995ULL;
@@ -147,6 +149,7 @@ extern "C" void pfpb200_destroy(pfpb200_ctx *ctx) {
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->d_keys) cudaFree(ctx->d_keys);
     if (ctx->dna_table) cudaFree(ctx->dna_table);
+    if (ctx->d_alpha) cudaFree(ctx->d_alpha);
     pfp_io_destroy(ctx);
     for (int i = 0; i < 5; i++)
         if (ctx->pin_buf[i]) cudaFreeHost(ctx->pin_buf[i]);
@@ -293,7 +296,7 @@ static int parse_device_impl(pfpb200_ctx *ctx, const u8 *d_text, u64 n, const pf
         tm.mark(ctx->stream);                                           // 3
         // K4
         u32 *order = nullptr, rounds = 0;
-        PFP_TRY(pfp_rank_stage(ctx, D, &order, &rounds));
+        PFP_TRY(pfp_rank_stage(ctx, D, &order, &rounds, ctx->alpha_valid && !ctx->no_scan_alpha));
         tm.mark(ctx->stream);                                           // 4
         u8 *dict = nullptr;
         u32 *occ = nullptr, *rank_of_uid = nullptr;

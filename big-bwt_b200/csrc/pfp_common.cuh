@@ -63,8 +63,14 @@ struct pfpb200_ctx {
     cudaStream_t stream = nullptr;
     u32 launches = 0;
     int k1_mode = 0;               // PFPB200_K1=rolling: always the rolling-arithmetic scan kernel (A/B)
+    // byte values present in the text, as a by-product of the DNA form of K1 (8 x 32 bits): rows that
+    // pass the table path hold only A C G T, the others record their bytes.  Valid for the words of
+    // a single-GPU parse; lets the ranking skip its own pass over the words' first bytes.
+    u32 *d_alpha = nullptr;
+    bool alpha_valid = false;
     u32 *dna_table = nullptr;      // 4^w-bit trigger table of (dna_w, dna_p) for the DNA scan (w <= 10)
     u32 dna_w = 0, dna_p = 0;
+    bool no_scan_alpha = false;      // PFPB200_NO_SCAN_ALPHA=1: the ranking finds the alphabet of the words itself (A/B)
     bool rank_full_sort = false;     // PFPB200_RANK_FULL_SORT=1: radix-sort all 64 bits of the first key (A/B)
     bool rank_chunk_passes = false;  // PFPB200_RANK_CHUNK_PASSES=1: mid-size tie groups by chunk passes instead of LCP walks (A/B)
     bool fuse_k3 = false;          // PFPB200_FUSE_K3=1: K3 + pool fused into the K2 pass (A/B; measured slower, see pfp_stream.cu)

@@ -122,9 +122,17 @@ int pfp_file_to_device(pfpb200_ctx *ctx, int fd, u64 off, u64 bytes, u8 *d_dst) 
 int pfp_device_to_file(pfpb200_ctx *ctx, const char *name, const void *d_src, u64 bytes) {
     int fd = open(name, O_WRONLY | O_CREAT | O_TRUNC, 0666);
     if (fd < 0) return pfp_fail(ctx, PFPB200_E_IO, "%s: %s", name, strerror(errno));
-    if (bytes == 0) { close(fd); return PFPB200_OK; }
+    int rc = pfp_device_to_fd(ctx, fd, 0, d_src, bytes, name);
+    if (close(fd) != 0 && rc == PFPB200_OK) rc = pfp_fail(ctx, PFPB200_E_IO, "%s: write error: %s", name, strerror(errno));
+    return rc;
+}
+
+// d_src[0..bytes) -> bytes [file_off, file_off + bytes) of the open file fd (several GPUs write
+// their pieces of one file side by side)
+int pfp_device_to_fd(pfpb200_ctx *ctx, int fd, u64 file_off, const void *d_src, u64 bytes, const char *name) {
+    if (bytes == 0) return PFPB200_OK;
     int rc = io_ensure(ctx);
-    if (rc != PFPB200_OK) { close(fd); return rc; }
+    if (rc != PFPB200_OK) return rc;
     PfpIo &io = ctx->io;
     const u64 nchunks = (bytes + IO_CHUNK - 1) / IO_CHUNK;
     int err[IO_THREADS] = {0};
@@ -148,7 +156,7 @@ int pfp_device_to_file(pfpb200_ctx *ctx, const char *name, const void *d_src, u6
             const u64 nxt = c + IO_THREADS;
             if (nxt < nchunks && !issue(nxt, s ^ 1)) { err[t] = 2; break; }
             if (cudaEventSynchronize(io.ev[t][s]) != cudaSuccess) { err[t] = 2; break; }
-            if (pwrite_all(fd, io.slot[t][s], mlen[s], (off_t)mine[s]) != 0) { err[t] = 1; break; }
+            if (pwrite_all(fd, io.slot[t][s], mlen[s], (off_t)(file_off + mine[s])) != 0) { err[t] = 1; break; }
         }
         cudaStreamSynchronize(io.stream[t]);
     };
@@ -159,7 +167,6 @@ int pfp_device_to_file(pfpb200_ctx *ctx, const char *name, const void *d_src, u6
     for (int t = 1; t < nt; t++) th[t].join();
     int bad = 0;
     for (int t = 0; t < nt; t++) bad |= err[t];
-    if (close(fd) != 0) bad |= 1;
     if (bad & 2) { cudaGetLastError(); return pfp_fail(ctx, PFPB200_E_CUDA, "%s: device-to-host copy failed", name); }
     if (bad & 1) return pfp_fail(ctx, PFPB200_E_IO, "%s: write error: %s", name, strerror(errno));
     return PFPB200_OK;

@@ -102,6 +102,7 @@ struct pfpb200_multi {
     std::atomic<int> failed{0};
     std::mutex err_mu;
     char err[512] = {0};
+    char io_err[512] = {0};
     // the current job: where the text comes from
     //   text     : host memory (pfpb200_multi_parse_host)
     //   src_fd   : a plain-text file, every rank reads its own range through its pinned ring
@@ -109,6 +110,7 @@ struct pfpb200_multi {
     const u8 *text = nullptr;
     int src_fd = -1;
     const u8 *src_dev = nullptr;
+    const char *out_path = nullptr;       // non-null: every rank writes its pieces straight into the five files
     u64 n_text = 0, n_eff = 0;
     int n_active = 0;                     // shards in use (short texts use fewer)
     pfpb200_opts opts{};
@@ -178,6 +180,88 @@ i64 first_phrase_start(const pfpb200_multi *m, int g, u32 w) {
     for (int q = g - 1; q >= 0; q--)
         if (m->r[q].n_trig > 0) return (i64)m->r[q].last_trig - (i64)w + 1;
     return -1;
+}
+
+// ---- files written by all ranks side by side -------------------------------------------------------------
+void stream_name(char *name, size_t cap, const char *path, const char *ext, int seg) {
+    if (seg < 0) snprintf(name, cap, "%s.%s", path, ext);                  // utils.c:33-41
+    else snprintf(name, cap, "%s.%d.%s", path, seg, ext);                  // utils.c:44-54
+}
+
+// phrases [a, b) of segment s when the P phrases are cut into T segments (newscan.hpp:274-276)
+void segment_range(u64 P, int T, int s, u64 *a, u64 *b) {
+    const u64 per = (P + (u64)T - 1) / (u64)T;
+    *a = std::min(P, (u64)s * per);
+    *b = std::min(P, *a + per);
+}
+
+int create_sized(pfpb200_multi *m, const char *name, u64 bytes) {
+    int fd = open(name, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0 || close(fd) != 0) {
+        snprintf(m->io_err, sizeof(m->io_err), "%.400s: %s", name, strerror(errno));
+        return -1;
+    }
+    return 0;
+}
+
+int multi_create_files(pfpb200_multi *m, u64 dict_bytes, u64 d, u64 P) {
+    char name[4096];
+    const pfpb200_opts &o = m->opts;
+    stream_name(name, sizeof(name), m->out_path, (o.flags & PFPB200_F_COMPRESS) ? "dicz" : "dict", -1);
+    if (create_sized(m, name, dict_bytes)) return -1;
+    stream_name(name, sizeof(name), m->out_path, "occ", -1);
+    if (create_sized(m, name, 4 * d)) return -1;
+    stream_name(name, sizeof(name), m->out_path, "parse", -1);
+    if (create_sized(m, name, 4 * P)) return -1;
+    const int T = o.nseg;
+    for (int s = (T > 0 ? 0 : -1); s < (T > 0 ? T : 0); s++) {
+        u64 a = 0, b = P;
+        if (T > 0) segment_range(P, T, s, &a, &b);
+        stream_name(name, sizeof(name), m->out_path, "last", s);
+        if (create_sized(m, name, b - a)) return -1;
+        if (o.flags & PFPB200_F_SAI) {
+            stream_name(name, sizeof(name), m->out_path, "sai", s);
+            if (create_sized(m, name, PFP_IBYTES * (b - a))) return -1;
+        }
+    }
+    return 0;
+}
+
+// device bytes -> [file_off, +bytes) of the named (existing) file
+int piece_to_file(Rank &R, const char *name, u64 file_off, const void *d_src, u64 bytes) {
+    if (bytes == 0) return PFPB200_OK;
+    int fd = open(name, O_WRONLY);
+    if (fd < 0) return pfp_fail(R.ctx, PFPB200_E_IO, "%s: %s", name, strerror(errno));
+    int rc = pfp_device_to_fd(R.ctx, fd, file_off, d_src, bytes, name);
+    if (close(fd) != 0 && rc == PFPB200_OK) rc = pfp_fail(R.ctx, PFPB200_E_IO, "%s: write error", name);
+    return rc;
+}
+
+// this rank's pieces of the five streams into the files rank 0 created
+int multi_write_pieces(pfpb200_multi *m, Rank &R, u64 off_dict, u64 off_d, u64 off_P) {
+    char name[4096];
+    const pfpb200_opts &o = m->opts;
+    stream_name(name, sizeof(name), m->out_path, (o.flags & PFPB200_F_COMPRESS) ? "dicz" : "dict", -1);
+    PFP_TRY(piece_to_file(R, name, off_dict, R.mg.dict, R.piece_bytes));
+    stream_name(name, sizeof(name), m->out_path, "occ", -1);
+    PFP_TRY(piece_to_file(R, name, 4 * off_d, R.mg.occ, 4 * R.n_distinct));
+    stream_name(name, sizeof(name), m->out_path, "parse", -1);
+    PFP_TRY(piece_to_file(R, name, 4 * off_P, R.d_parse, 4 * R.n_phrases));
+    const int T = o.nseg;
+    const u64 P = m->tot_phrases, lo = off_P, hi = off_P + R.n_phrases;
+    for (int s = (T > 0 ? 0 : -1); s < (T > 0 ? T : 0); s++) {
+        u64 a = 0, b = P;
+        if (T > 0) segment_range(P, T, s, &a, &b);
+        const u64 x = std::max(a, lo), y = std::min(b, hi);               // my phrases inside this segment
+        if (x >= y) continue;
+        stream_name(name, sizeof(name), m->out_path, "last", s);
+        PFP_TRY(piece_to_file(R, name, x - a, R.wd.last + (x - lo), y - x));
+        if (R.wd.sai) {
+            stream_name(name, sizeof(name), m->out_path, "sai", s);
+            PFP_TRY(piece_to_file(R, name, PFP_IBYTES * (x - a), R.wd.sai + PFP_IBYTES * (x - lo), PFP_IBYTES * (y - x)));
+        }
+    }
+    return PFPB200_OK;
 }
 
 template <typename T>
@@ -406,8 +490,12 @@ void rank_main(pfpb200_multi *m, int g) {
         m->tot_phrases = tp; m->tot_distinct = td; m->tot_dict = tb; m->tot_sum_len = ts;
         if (td > 0x7FFFFFFEull) multi_fail(m, g, PFPB200_E_LIMIT, "more than 2^31-2 distinct words");        // newscan.cpp:114
         else if (tp >= 0xFFFFFFFFull) multi_fail(m, g, PFPB200_E_LIMIT, "the parse contains more than 2^32-2 words");  // bigbwt:110-114
-        const size_t need[5] = {(size_t)tb, (size_t)td * 4, (size_t)tp * 4, (size_t)tp,
-                                (m->opts.flags & PFPB200_F_SAI) ? (size_t)tp * PFP_IBYTES : 0};
+        size_t need[5] = {(size_t)tb, (size_t)td * 4, (size_t)tp * 4, (size_t)tp,
+                          (m->opts.flags & PFPB200_F_SAI) ? (size_t)tp * PFP_IBYTES : 0};
+        if (m->out_path) {                 // files: created here at their final size, filled by all ranks
+            for (int k = 0; k < 5; k++) need[k] = 0;
+            if (ok() && multi_create_files(m, tb, td, tp) != 0) multi_fail(m, g, PFPB200_E_IO, m->io_err);
+        }
         for (int k = 0; k < 5 && ok(); k++) {
             if (need[k] <= m->pin_cap[k]) continue;
             if (m->pin[k]) cudaFreeHost(m->pin[k]);
@@ -451,7 +539,14 @@ void rank_main(pfpb200_multi *m, int g) {
     }();
     mark(R, PH_REMAP);
 
-    // ---- 12. my pieces of the five streams to the host ---------------------------------------------------------
+    // ---- 12. my pieces of the five streams: into the files, or to the host buffers ---------------------------
+    if (m->out_path) {
+        [&]() {
+            if (!ok()) return;
+            MR_CUDA(cudaStreamSynchronize(st));
+            MR_LIB(multi_write_pieces(m, R, off_dict, off_d, off_P));
+        }();
+    } else
     [&]() {
         if (!ok()) return;
         u8 *h_dict = (u8 *)m->pin[0];
@@ -640,64 +735,11 @@ extern "C" int pfpb200_multi_parse_host(pfpb200_multi *m, const uint8_t *text, u
     return multi_run(m, n_text, opts, host_out, stats);
 }
 
-// host buffer -> file, a few threads pwrite()-ing disjoint chunks
-static int host_to_file(const char *name, const void *p, u64 bytes, char *err, size_t errlen) {
-    int fd = open(name, O_WRONLY | O_CREAT | O_TRUNC, 0666);
-    if (fd < 0) { snprintf(err, errlen, "%s: %s", name, strerror(errno)); return -1; }
-    const u64 chunk = (u64)16 << 20;
-    const u64 nchunks = (bytes + chunk - 1) / chunk;
-    const int nt = (int)std::min<u64>(4, std::max<u64>(1, nchunks));
-    std::atomic<int> bad{0};
-    auto worker = [&](int t) {
-        for (u64 c = (u64)t; c < nchunks; c += (u64)nt) {
-            const u64 o = c * chunk, len = std::min(chunk, bytes - o);
-            u64 done = 0;
-            while (done < len) {
-                ssize_t r = pwrite(fd, (const char *)p + o + done, (size_t)(len - done), (off_t)(o + done));
-                if (r < 0) { if (errno == EINTR) continue; bad.store(1); return; }
-                done += (u64)r;
-            }
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
-    worker(0);
-    for (auto &t : th) t.join();
-    if (close(fd) != 0) bad.store(1);
-    if (bad.load()) { snprintf(err, errlen, "%s: write error", name); return -1; }
-    return 0;
-}
-
-static int multi_write_outputs(pfpb200_multi *m, const char *path, const pfpb200_opts *o, const pfpb200_outputs &ho) {
-    char name[4096];
-    auto put = [&](const char *ext, int seg, const void *p, u64 bytes) -> int {
-        if (seg < 0) snprintf(name, sizeof(name), "%s.%s", path, ext);              // utils.c:33-41
-        else snprintf(name, sizeof(name), "%s.%d.%s", path, seg, ext);              // utils.c:44-54
-        return host_to_file(name, p, bytes, m->err, sizeof(m->err));
-    };
-    const u64 P = ho.n_phrases;
-    if (put((o->flags & PFPB200_F_COMPRESS) ? "dicz" : "dict", -1, ho.dict, ho.dict_bytes)) return -1;
-    if (put("occ", -1, ho.occ, 4 * ho.n_distinct)) return -1;
-    if (put("parse", -1, ho.parse, 4 * P)) return -1;
-    const int T = o->nseg;
-    if (T <= 0) {
-        if (put("last", -1, ho.last, P)) return -1;
-        if (ho.sai && put("sai", -1, ho.sai, PFP_IBYTES * P)) return -1;
-    } else {                                  // newscan.hpp:274-276; bwtparse.c:179,195
-        const u64 per = (P + (u64)T - 1) / (u64)T;
-        for (int s = 0; s < T; s++) {
-            u64 a = std::min(P, (u64)s * per), b = std::min(P, a + per);
-            if (put("last", s, ho.last + a, b - a)) return -1;
-            if (ho.sai && put("sai", s, ho.sai + PFP_IBYTES * a, PFP_IBYTES * (b - a))) return -1;
-        }
-    }
-    return 0;
-}
-
 // newscan.x main() on several GPUs.  Plain text: every rank reads its own range of the file through
 // its pinned ring.  FASTA: rank 0 streams the file in and runs K0; the shards of the extracted
 // text then travel to the other GPUs peer to peer (NVLink).  gzip / FASTQ / CRLF input takes the
-// host reader.
+// host reader.  The outputs never gather on the host: rank 0 creates the five files at their final
+// size and every rank writes its pieces into them (its own pinned ring, D2H overlapped with pwrite).
 extern "C" int pfpb200_multi_parse_file(pfpb200_multi *m, const char *path, const pfpb200_opts *opts,
                                         pfpb200_stats *stats) {
     int rc = check_multi_opts(m, opts);
@@ -764,17 +806,17 @@ extern "C" int pfpb200_multi_parse_file(pfpb200_multi *m, const char *path, cons
     if (n == 0 && !m->text) { m->text = &empty; m->src_fd = -1; m->src_dev = nullptr; }
     const double t1 = wall_sec();
     pfpb200_outputs ho;
+    m->out_path = path;                   // every rank writes its pieces of the five files itself
     rc = multi_run(m, n, opts, &ho, stats);
+    m->out_path = nullptr;
     close(fd);
     if (host_text) pfpb200_free_host(host_text);
     if (d_text0) { cudaSetDevice(R0.device); cudaFree(d_text0); }
     m->text = nullptr; m->src_fd = -1; m->src_dev = nullptr;
     if (rc != PFPB200_OK) return rc;
-    const double t2 = wall_sec();
-    if (multi_write_outputs(m, path, opts, ho) != 0) return PFPB200_E_IO;
     if (stats) {
         stats->sec_read = (float)(t1 - t0);
-        stats->sec_write = (float)(wall_sec() - t2);
+        stats->sec_write = stats->ms_d2h * 1e-3f;       // the writes are the ranks' last phase
     }
     return PFPB200_OK;
 }

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256, 8) table_insert_k(const PhraseFp *__restr
                                                       u32 weak /* test hook: keep 2 fingerprint bits */,
                                                       u32 *__restrict__ uid, u32 *__restrict__ rep,
                                                       u32 *__restrict__ ulen, u32 *__restrict__ uwords,
-                                                      u32 *__restrict__ count,
+                                                      u32 *__restrict__ count, i64 *__restrict__ ustart /* may be null */,
                                                       u64 *__restrict__ flags /* [0] errors, [1] words, [2] max len, [3] sum len, [6] pending */) {
     const u32 lane = threadIdx.x & 31;
     const u64 base = (u64)blockIdx.x * (256 * TI_ITEMS) + threadIdx.x;
@@ -373,10 +373,11 @@ __global__ void __launch_bounds__(256, 8) table_insert_k(const PhraseFp *__restr
     u32 res[TI_ITEMS];                               // word id + 1, or UID_PENDING | slot
     u32 mine[TI_ITEMS];                              // creator: index among the CTA's new words
     u32 len[TI_ITEMS];                               // creator: length of the new word
+    i64 start[TI_ITEMS];                             // creator: where its phrase starts in the text
     u64 slot[TI_ITEMS];
 #pragma unroll
     for (int it = 0; it < TI_ITEMS; it++) {
-        res[it] = 0; mine[it] = 0xFFFFFFFFu; slot[it] = 0; len[it] = 0;
+        res[it] = 0; mine[it] = 0xFFFFFFFFu; slot[it] = 0; len[it] = 0; start[it] = 0;
         if (lead[it]) {
             const Probe pr = table_probe(tab, cap, __umul64hi(k[it], cap), sv[it], k[it]);
             if (pr.placed) {
@@ -388,6 +389,7 @@ __global__ void __launch_bounds__(256, 8) table_insert_k(const PhraseFp *__restr
                     else {
                         const i64 s0 = j ? (i64)ends[j - 1] - (i64)w + 1 : first_start;
                         len[it] = (u32)((i64)ends[j] - s0 + 1);     // > 2^32-1 was flagged by K2
+                        start[it] = s0;
                     }
                     mine[it] = atomicAdd(&s_new, 1u);
                     atomicMax(&s_max, len[it]);
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(256, 8) table_insert_k(const PhraseFp *__restr
         if (mine[it] != 0xFFFFFFFFu) {
             const u32 u = (u32)s_base + mine[it];
             rep[u] = (u32)j; ulen[u] = len[it]; uwords[u] = (len[it] + 7) >> 3;
+            if (ustart) ustart[u] = start[it];
             tab[slot[it]].uid1 = u + 1;
             res[it] = u + 1;
         }
@@ -490,17 +493,24 @@ __global__ void __launch_bounds__(PH_T) pool_copy_k(TextView tv, const u64 *__re
                                                     const u64 *__restrict__ uoff, u64 d,
                                                     u64 *__restrict__ pool,
                                                     const u32 *__restrict__ ulist /* null: words 0..d-1 */,
-                                                    const u32 *__restrict__ ucount, u64 pool_cap) {
+                                                    const u32 *__restrict__ ucount, u64 pool_cap,
+                                                    const i64 *__restrict__ ustart /* null: from rep and ends */) {
     const u32 li = threadIdx.x & (PC_GROUP - 1);
     if (ulist) d = *ucount;
     for (u64 x = (u64)blockIdx.x * PC_PER_BLOCK + (threadIdx.x / PC_GROUP); x < d;
          x += (u64)gridDim.x * PC_PER_BLOCK) {
         const u64 u = ulist ? ulist[x] : x;
-        u64 j = rep[u];
-        i64 e = (i64)ends[j];
-        i64 s0 = (j == 0) ? first_start : (i64)ends[j - 1] - (i64)w + 1;
-        u64 len = ulen[u];
-        bool special = (s0 < 0) || (e >= tv.n_global);
+        const u64 len = ulen[u];
+        i64 s0, e;
+        if (ustart) {                              // noted by the word's creator: no walk through rep and ends
+            s0 = ustart[u];
+            e = s0 + (i64)len - 1;
+        } else {
+            const u64 j = rep[u];
+            e = (i64)ends[j];
+            s0 = (j == 0) ? first_start : (i64)ends[j - 1] - (i64)w + 1;
+        }
+        const bool special = (s0 < 0) || (e >= tv.n_global);
         u64 nw = (len + 7) >> 3;
         if (uoff[u] + nw > pool_cap) continue;                 // the caller sees PFP_ERRBIT_POOL_FULL and reruns
         u64 *dst = pool + uoff[u];
@@ -625,7 +635,7 @@ int pfp_insert_list(pfpb200_ctx *ctx, const TextView &tv, const PhraseFp *rec_sm
     u64 want = (list_cap + PC_PER_BLOCK - 1) / PC_PER_BLOCK;
     u64 maxb = (u64)ctx->sm_count * 8;
     pool_copy_k<<<(u32)(want < maxb ? (want ? want : 1) : maxb), PH_T, 0, ctx->stream>>>(
-        tv, ends, first_start, w, D.rep, D.ulen, D.uoff, 0, D.pool, created, ccount, pool_cap);
+        tv, ends, first_start, w, D.rep, D.ulen, D.uoff, 0, D.pool, created, ccount, pool_cap, nullptr);
     PFP_LAUNCHED(ctx);
     PFP_TRY(pfp_free_now(ctx, created));
     return PFPB200_OK;
@@ -722,6 +732,7 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, i64 first_s
         PFP_TRY(pfp_alloc_t(ctx, &D->count, wcap));
         PFP_TRY(pfp_alloc_t(ctx, &D->ulen, wcap));
         PFP_TRY(pfp_alloc_t(ctx, &D->uwords, wcap));
+        PFP_TRY(pfp_alloc_t(ctx, &D->ustart, wcap));
         table_init_k<<<pfp_blocks(cap, TB), TB, 0, ctx->stream>>>(tab, cap);
         PFP_LAUNCHED(ctx);
         PFP_CUDA(ctx, cudaMemsetAsync(D->count, 0, wcap * sizeof(u32), ctx->stream));
@@ -729,7 +740,7 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, i64 first_s
         PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[6], 0, sizeof(u64), ctx->stream));
         table_insert_k<<<pfp_blocks(P, TB * TI_ITEMS), TB, 0, ctx->stream>>>(
             ph.rec, P, tab, cap, nullptr, nullptr, ph.ends, first_start, w, ctx->weak_fp, D->uid, D->rep, D->ulen, D->uwords,
-            D->count, ctx->d_flags);
+            D->count, D->ustart, ctx->d_flags);
         PFP_LAUNCHED(ctx);
         PFP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 7 * sizeof(u64), cudaMemcpyDeviceToHost,
                                       ctx->stream));
@@ -741,7 +752,7 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, i64 first_s
         if (!full) break;
         if (attempt > 0) return pfp_fail(ctx, PFPB200_E_INTERNAL, "dictionary table overflow");
         // undo and retry with the safe capacity
-        void *fr[] = {tab, D->rep, D->count, D->ulen, D->uwords};
+        void *fr[] = {tab, D->rep, D->count, D->ulen, D->uwords, D->ustart};
         for (void *q : fr) PFP_TRY(pfp_free_now(ctx, q));
         ctx->dedup_ratio = 0.0;
         const u64 keep = ctx->h_flags[0] & ~(PFP_ERRBIT_TABLE_FULL | PFP_ERRBIT_COLLISION);
@@ -783,7 +794,7 @@ int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 fi
     u32 nb = (u32)(want < maxb ? want : maxb);
     if (nb == 0) nb = 1;
     pool_copy_k<<<nb, PH_T, 0, ctx->stream>>>(tv, ends, first_start, w, D->rep, D->ulen, D->uoff, d,
-                                              D->pool, nullptr, nullptr, D->pool_words);
+                                              D->pool, nullptr, nullptr, D->pool_words, D->ustart);
     PFP_LAUNCHED(ctx);
     return PFPB200_OK;
 }
@@ -889,7 +900,7 @@ int pfp_merge_stage(pfpb200_ctx *ctx, u64 n, const u64 *fpa, const u64 *fpb, con
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[6], 0, sizeof(u64), ctx->stream));
     table_insert_k<<<pfp_blocks(n, TB * TI_ITEMS), TB, 0, ctx->stream>>>(
         rec, n, tab, cap, count_in, len, nullptr, 0, 0, ctx->weak_fp, *uid_of_entry, D->rep, D->ulen, D->uwords, D->count,
-        ctx->d_flags);
+        nullptr, ctx->d_flags);
     PFP_LAUNCHED(ctx);
     // stragglers (ids not stored yet when they looked) -- cheap, and saves a synchronisation to ask
     table_pending_k<<<pfp_blocks(n, TB), TB, 0, ctx->stream>>>(tab, n, count_in, *uid_of_entry, D->count,

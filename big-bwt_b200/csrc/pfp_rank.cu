@@ -66,8 +66,14 @@ __global__ void alpha_presence_k(const u64 *__restrict__ pool, const u64 *__rest
     if (threadIdx.x < 8 && sm[threadIdx.x]) atomicOr(&gmask[threadIdx.x], sm[threadIdx.x]);
 }
 
-__global__ void alpha_build_k(const u32 *__restrict__ gmask, AlphaMap *am) {
+// from_scan: the byte set comes from the DNA form of K1 over the whole text; the letters its table
+// path stands for and the virtual border symbol are added here
+__global__ void alpha_build_k(u32 *__restrict__ gmask, AlphaMap *am, int from_scan) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (from_scan) {
+        gmask[0] |= 1u << PFP_DOLLAR;
+        gmask[2] |= (1u << ('A' & 31)) | (1u << ('C' & 31)) | (1u << ('G' & 31)) | (1u << ('T' & 31));
+    }
     u32 sigma = 0;
     for (int q = 0; q < 8; q++) sigma += __popc(gmask[q]);
     u32 bits = 3;            // >= 3 so that the key never reaches past the probed 24 bytes
@@ -88,8 +94,9 @@ __global__ void alpha_build_k(const u32 *__restrict__ gmask, AlphaMap *am) {
 }
 
 __global__ void rank_keys0_k(const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
-                             const u32 *__restrict__ ulen, u64 d, const AlphaMap *__restrict__ am,
-                             u64 *__restrict__ keys, u32 *__restrict__ vals) {
+                             const u32 *__restrict__ ulen, const u32 *__restrict__ count, u64 d,
+                             const AlphaMap *__restrict__ am, u64 *__restrict__ keys, u32 *__restrict__ vals,
+                             WordMeta *__restrict__ meta) {
     __shared__ u8 lut[256];
     __shared__ u32 s_bits, s_chars;
     lut[threadIdx.x & 255] = am->lut[threadIdx.x & 255];
@@ -98,11 +105,17 @@ __global__ void rank_keys0_k(const u64 *__restrict__ pool, const u64 *__restrict
     u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= d) return;
     const u32 bits = s_bits, chars = s_chars, len = ulen[u];
+    const u64 off = uoff[u];
+    {
+        WordMeta wm;
+        wm.off = off; wm.len = len; wm.count = count[u];
+        meta[u] = wm;
+    }
     const u32 nc = len < chars ? len : chars;
     u64 key = 0;
     u64 v = 0;
     for (u32 i = 0; i < nc; i++) {
-        if ((i & 7) == 0) v = __ldg(pool + uoff[u] + (i >> 3));
+        if ((i & 7) == 0) v = __ldg(pool + off + (i >> 3));
         u32 c = (u32)(v >> (8 * (i & 7))) & 255u;
         key |= (u64)lut[c] << (64 - bits * (i + 1));
     }
@@ -897,7 +910,7 @@ int pfp_rank_init(pfpb200_ctx *ctx) {
     return PFPB200_OK;
 }
 
-int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *rounds) {
+int pfp_rank_stage(pfpb200_ctx *ctx, DictArrays &D, u32 **order, u32 *rounds, bool alpha_from_scan) {
     const int TB = 256;
     const u64 d = D.d;
     const u32 nbd = pfp_blocks(d, TB);
@@ -921,12 +934,17 @@ int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *roun
     PFP_TRY(pfp_alloc_t(ctx, &am, 1));
     PFP_TRY(pfp_alloc_t(ctx, &amask, 8));
     // first key: alphabet-compacted prefix, one global sort
-    PFP_CUDA(ctx, cudaMemsetAsync(amask, 0, 8 * sizeof(u32), ctx->stream));
-    alpha_presence_k<<<nbd, TB, 0, ctx->stream>>>(D.pool, D.uoff, D.ulen, d, amask);
+    if (alpha_from_scan) {             // K1 saw every byte of the text these words come from
+        PFP_CUDA(ctx, cudaMemcpyAsync(amask, ctx->d_alpha, 8 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        PFP_CUDA(ctx, cudaMemsetAsync(amask, 0, 8 * sizeof(u32), ctx->stream));
+        alpha_presence_k<<<nbd, TB, 0, ctx->stream>>>(D.pool, D.uoff, D.ulen, d, amask);
+        PFP_LAUNCHED(ctx);
+    }
+    alpha_build_k<<<1, 32, 0, ctx->stream>>>(amask, am, alpha_from_scan ? 1 : 0);
     PFP_LAUNCHED(ctx);
-    alpha_build_k<<<1, 32, 0, ctx->stream>>>(amask, am);
-    PFP_LAUNCHED(ctx);
-    rank_keys0_k<<<nbd, TB, 0, ctx->stream>>>(D.pool, D.uoff, D.ulen, d, am, k0, v0);
+    PFP_TRY(pfp_alloc_t(ctx, &D.meta, d));
+    rank_keys0_k<<<nbd, TB, 0, ctx->stream>>>(D.pool, D.uoff, D.ulen, D.count, d, am, k0, v0, D.meta);
     PFP_LAUNCHED(ctx);
     // LSD passes only over the top 2 log2(d) + 2 key bits (whole bytes): with fewer, unrelated
     // words start to collide by chance (measured on 8 GB of random text: sorting 40 of 64 bits
@@ -1071,9 +1089,10 @@ __global__ void dict_layout_k(const u32 *__restrict__ ord, u64 d, const DictArra
     if (i >= d) return;
     u32 u = ord[i];
     rank_of_uid[u] = (u32)i + 1;                     // 1-based (newscan.cpp:405,436)
-    occ[i] = D.count[u];                             // newscan.cpp:433
+    const uint4 mv = __ldg(reinterpret_cast<const uint4 *>(D.meta + u));     // one sector: offset, length, count
+    occ[i] = mv.w;                                   // newscan.cpp:433
     u32 skip, outlen;
-    out_span(D.pool, D.uoff[u], D.ulen[u], strip_w, &skip, &outlen);
+    out_span(D.pool, ((u64)mv.y << 32) | mv.x, mv.z, strip_w, &skip, &outlen);
     dl[i] = outlen + 1;                              // + EndOfWord (newscan.cpp:416)
 }
 
@@ -1093,8 +1112,9 @@ __global__ void __launch_bounds__(DC_T) dict_copy_k(const u32 *__restrict__ ord,
          i += (u64)gridDim.x * (DC_T / DC_GROUP)) {
         const u32 u = ord[i];
         u32 skip, outlen;
-        const u64 off = D.uoff[u];
-        out_span(D.pool, off, D.ulen[u], strip_w, &skip, &outlen);
+        const uint4 mv = __ldg(reinterpret_cast<const uint4 *>(D.meta + u));
+        const u64 off = ((u64)mv.y << 32) | mv.x;
+        out_span(D.pool, off, mv.z, strip_w, &skip, &outlen);
         const u64 *src64 = D.pool + off;
         const u8 *src = reinterpret_cast<const u8 *>(src64) + skip;
         u8 *dst = dict + doff[i];

@@ -227,8 +227,53 @@ __device__ __forceinline__ uint4 kd_load_unit(const uint4 *__restrict__ A, u64 q
     return make_uint4(0, 0, 0, 0);
 }
 
+// the byte values of a lane's 32 positions into the 256-bit set `alpha` (rows off the table path
+// only: kept out of line so that it costs the table path no registers)
+__device__ __noinline__ void kd_note_alphabet(uint4 u0, uint4 u1, u64 q, u64 q_text0, u64 q_end, u32 lane,
+                                               u32 *__restrict__ alpha) {
+    const u32 xs[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    u32 pm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const u32 c = (xs[i >> 2] >> (8 * (i & 3))) & 255u;
+        const bool in_text = q + i >= q_text0 && q + i < q_end;     // bytes in front of / behind the text are not text
+#pragma unroll
+        for (int k = 0; k < 8; k++) pm[k] |= (in_text && (c >> 5) == (u32)k) ? (1u << (c & 31)) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const u32 o = __reduce_or_sync(0xffffffffu, pm[k]);
+        if (lane == 0 && o) atomicOr(&alpha[k], o);
+    }
+}
+
 // byte j (-12 <= j < 32) of {three words in front, eight words of the lane}
 #define KD_BYTE(wd, j) (__byte_perm((wd)[((j) + 12) >> 2], 0u, 0x4440u | (((j) + 12) & 3)))
+
+// A row that holds something besides A C G T (or that an A/B run gives to the arithmetic): the
+// trigger bits of the lane's 32 positions by the rolling arithmetic of kr_scan_k, exact for any
+// bytes; and, when the row is not pure A C G T, its byte values go into the alphabet set.
+template <int W>
+__device__ __noinline__ u32 kd_row_by_arithmetic(uint4 u0, uint4 u1, u32 lane, pfp_scan_consts C, u64 q, u64 q_text0,
+                                                 u64 q_end, bool note, u32 *__restrict__ alpha) {
+    if (note) kd_note_alphabet(u0, u1, q, q_text0, q_end, lane, alpha);
+    u32 wd[11];
+    wd[0] = __shfl_up_sync(0xffffffffu, u1.y, 1);
+    wd[1] = __shfl_up_sync(0xffffffffu, u1.z, 1);
+    wd[2] = __shfl_up_sync(0xffffffffu, u1.w, 1);
+    if (lane == 0) { wd[0] = 0; wd[1] = 0; wd[2] = 0; }   // only used by word 0: nothing in front
+    wd[3] = u0.x; wd[4] = u0.y; wd[5] = u0.z; wd[6] = u0.w;
+    wd[7] = u1.x; wd[8] = u1.y; wd[9] = u1.z; wd[10] = u1.w;
+    u32 h = 0, m = 0;
+#pragma unroll
+    for (int j = -W; j < 0; j++) h = pfp_push(h, KD_BYTE(wd, j));
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        h = pfp_roll(h, KD_BYTE(wd, i), KD_BYTE(wd, i - W), C.negw);
+        if (pfp_is_trigger(h, C.pinv, C.pshift, C.plimit)) m |= 1u << i;
+    }
+    return m;
+}
 
 // Rows overlap by one lane: row r covers the 32-position words 31r .. 31r+31 of the bit array,
 // lane 0 only supplies the symbols in front of lane 1 (its word belongs to lane 31 of row r-1).
@@ -239,7 +284,8 @@ __global__ void __launch_bounds__(KD_T, 1) kr_scan_dna_k(const uint4 *__restrict
                                                          const u32 *__restrict__ table_g,
                                                          u32 *__restrict__ mask32,
                                                          u32 *__restrict__ tile_cnt, u64 nwords,
-                                                         u32 mix /* every mix-th row by arithmetic; 0: none */) {
+                                                         u32 mix /* every mix-th row by arithmetic; 0: none */,
+                                                         u32 *__restrict__ alpha /* 256-bit set of the byte values seen */) {
     extern __shared__ __align__(16) u32 tab[];
     constexpr u32 TWORDS = ((1u << (2 * W)) + 31) / 32;
     for (u32 i = threadIdx.x; i < TWORDS; i += KD_T) tab[i] = table_g[i];
@@ -293,22 +339,10 @@ __global__ void __launch_bounds__(KD_T, 1) kr_scan_dna_k(const uint4 *__restrict
                 m = __funnelshift_r(m, wd >> (v & 31), 1);        // bit i after 32 steps
             }
         } else {
-            // exact arithmetic on the bytes (kr_scan_k's inner loop on a 32-position run)
-            u32 wd[11];
-            wd[0] = __shfl_up_sync(0xffffffffu, u1.y, 1);
-            wd[1] = __shfl_up_sync(0xffffffffu, u1.z, 1);
-            wd[2] = __shfl_up_sync(0xffffffffu, u1.w, 1);
-            if (lane == 0) { wd[0] = 0; wd[1] = 0; wd[2] = 0; }   // only used by word 0: nothing in front
-            wd[3] = u0.x; wd[4] = u0.y; wd[5] = u0.z; wd[6] = u0.w;
-            wd[7] = u1.x; wd[8] = u1.y; wd[9] = u1.z; wd[10] = u1.w;
-            u32 h = 0;
-#pragma unroll
-            for (int j = -W; j < 0; j++) h = pfp_push(h, KD_BYTE(wd, j));
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                h = pfp_roll(h, KD_BYTE(wd, i), KD_BYTE(wd, i - W), C.negw);
-                if (pfp_is_trigger(h, C.pinv, C.pshift, C.plimit)) m |= 1u << i;
-            }
+            // a row off the table path (warp-uniform, rare): out of line, so that it costs the table
+            // path neither registers nor instruction-cache lines
+            m = kd_row_by_arithmetic<W>(u0, u1, lane, C, q, q_lo >= (u64)(W - 1) ? q_lo - (u64)(W - 1) : 0, q_end,
+                                        __any_sync(0xffffffffu, bad != 0), alpha);
         }
         const bool mine = (lane != 0 || row == 0) && word < nwords;
         if (q < q_lo || q + 32 > q_hi) m &= range_mask32(q, q_lo, q_hi);
@@ -381,7 +415,7 @@ static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A,
     const int mix = ctx->k1_mix;
     kr_scan_dna_k<W><<<ctx->sm_count, KD_T, smem, ctx->stream>>>(A, q_end, q_lo, q_hi, C, ctx->dna_table,
                                                                 reinterpret_cast<u32 *>(mask), tile_cnt, nwords,
-                                                                (u32)mix);
+                                                                (u32)mix, ctx->d_alpha);
     return cudaGetLastError();
 }
 #define KD_CASE(W) case W: le = launch_scan_dna<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
@@ -459,9 +493,12 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
     const bool dna = w <= (u32)KD_MAXW && ctx->k1_mode != 1;
     if (dna) PFP_TRY(ensure_dna_table(ctx, C));
     PFP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    ctx->alpha_valid = false;
     if (dna) {
         // the table form: bits and per-tile counts (added up by the warps) for every row
         PFP_CUDA(ctx, cudaMemsetAsync(tile_cnt, 0, (size_t)ntiles * sizeof(u32), ctx->stream));
+        PFP_CUDA(ctx, cudaMemsetAsync(ctx->d_alpha, 0, 8 * sizeof(u32), ctx->stream));
+        ctx->alpha_valid = buf_pos0 == 0 && own_lo == 0;       // the whole text of a single-GPU parse
         cudaError_t le = cudaSuccess;
         switch ((int)w) {
             KD_CASE(4) KD_CASE(5) KD_CASE(6) KD_CASE(7) KD_CASE(8) KD_CASE(9) KD_CASE(10)

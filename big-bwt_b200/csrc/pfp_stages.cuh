@@ -36,10 +36,17 @@ struct PhraseArrays {
 };
 
 // ---- dictionary arrays (d entries, in fingerprint-key order = "uid" order) ---------------------------
+// what the .dict/.occ emission needs of a word, in one 16-byte record: a gather by rank then
+// touches one sector per word instead of three (written by the ranking's key pass, which reads
+// these fields of every word anyway)
+struct __align__(16) WordMeta { u64 off; u32 len; u32 count; };
+
 struct DictArrays {
     u64 d = 0;
+    WordMeta *meta = nullptr;   // [d] filled by pfp_rank_stage
     u32 *uid = nullptr;     // [P] phrase -> uid
     u32 *rep = nullptr;     // [d] first phrase index of the word
+    i64 *ustart = nullptr;  // [d] global text position of that phrase's first byte (may be -1: virtual border)
     u32 *count = nullptr;   // [d] occurrences
     u32 *ulen = nullptr;    // [d] length in bytes
     u32 *uwords = nullptr;  // [d] length in 8-byte pool words
@@ -87,7 +94,7 @@ int pfp_dedup_stage(pfpb200_ctx *ctx, const PhraseArrays &ph, u64 P, i64 first_s
 int pfp_pool_stage(pfpb200_ctx *ctx, const TextView &tv, const u64 *ends, i64 first_start, u32 w,
                    DictArrays *D);
 // Lexicographic order of the d pool words: order[i] = uid of the word of rank i+1.
-int pfp_rank_stage(pfpb200_ctx *ctx, const DictArrays &D, u32 **order, u32 *rounds);
+int pfp_rank_stage(pfpb200_ctx *ctx, DictArrays &D, u32 **order, u32 *rounds, bool alpha_from_scan = false);
 // .dict / .occ bytes and rank-per-uid from the order; outputs are `held` device buffers.
 int pfp_dict_stage(pfpb200_ctx *ctx, const DictArrays &D, const u32 *order, u32 strip_w,
                    u8 **dict, u64 *dict_bytes, u32 **occ, u32 **rank_of_uid,
@@ -99,6 +106,7 @@ int pfp_first_invalid(pfpb200_ctx *ctx, const u8 *d_text, u64 n, u64 *d_first);
 // ---- overlapped file I/O and K0 (pfp_ingest.cu) ------------------------------------------------------------
 int pfp_file_to_device(pfpb200_ctx *ctx, int fd, u64 off, u64 bytes, u8 *d_dst);
 int pfp_device_to_file(pfpb200_ctx *ctx, const char *name, const void *d_src, u64 bytes);
+int pfp_device_to_fd(pfpb200_ctx *ctx, int fd, u64 file_off, const void *d_src, u64 bytes, const char *name);
 void pfp_io_destroy(pfpb200_ctx *ctx);
 // FASTA bytes in HBM -> the text T of `-f` mode (kseq.h:177-218); *supported = 0: host reader needed
 int pfp_fasta_device(pfpb200_ctx *ctx, const u8 *d_file, u64 n, u8 **d_text, u64 *n_text, int *supported,
