@@ -383,13 +383,8 @@ void rank_main(pfpb200_multi *m, int g) {
     R.n_sample = 0;
     [&]() {
         if (!ok() || R.n_words == 0) return;
-        const u64 *keys = nullptr;
-        MR_LIB(pfpb200_shard_first_keys(R.ctx, &keys));
-        const u64 step = std::max<u64>(1, R.n_words / MULTI_SAMPLE);
-        const u32 k = (u32)std::min<u64>(MULTI_SAMPLE, (R.n_words + step - 1) / step);
-        MR_CUDA(cudaMemcpy2DAsync(R.h_sample, sizeof(u64), keys, step * sizeof(u64), sizeof(u64), k,
-                                  cudaMemcpyDeviceToHost, st));
-        MR_CUDA(cudaStreamSynchronize(st));
+        u32 k = 0;
+        MR_LIB(pfpb200_shard_sample_keys(R.ctx, MULTI_SAMPLE, R.h_sample, &k));
         R.n_sample = k;
     }();
     m->bar.wait();

@@ -1283,6 +1283,34 @@ __global__ void __launch_bounds__(256) route_pool_k(const u32 *__restrict__ perm
     }
 }
 
+// keys of every step-th word only: what the splitter sample needs
+__global__ void sample_keys_k(const u64 *__restrict__ pool, const u64 *__restrict__ uoff,
+                              const u32 *__restrict__ uwords, u64 d, u64 step, u32 n, u64 *__restrict__ keys) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 u = (u64)i * step;
+    keys[i] = u < d ? word_key(pool, uoff, uwords, (u32)u, 0) : 0ull;
+}
+
+extern "C" int pfpb200_shard_sample_keys(pfpb200_ctx *ctx, uint32_t max_samples, uint64_t *h_keys, uint32_t *n_keys) {
+    if (!ctx || !h_keys || !n_keys || max_samples == 0) return PFPB200_E_ARG;
+    *n_keys = 0;
+    const u64 d = ctx->sh.d;
+    if (d == 0) return PFPB200_OK;
+    PFP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const u64 step = d / max_samples ? d / max_samples : 1;
+    const u32 n = (u32)((d + step - 1) / step < max_samples ? (d + step - 1) / step : max_samples);
+    u64 *keys = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &keys, n));
+    sample_keys_k<<<pfp_blocks(n, 256), 256, 0, ctx->stream>>>(ctx->sh.pool, ctx->sh.uoff, ctx->sh.uwords, d, step, n, keys);
+    PFP_LAUNCHED(ctx);
+    PFP_CUDA(ctx, cudaMemcpyAsync(h_keys, keys, (size_t)n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PFP_TRY(pfp_free_now(ctx, keys));
+    *n_keys = n;
+    return PFPB200_OK;
+}
+
 extern "C" int pfp_first_keys_impl(pfpb200_ctx *ctx, u64 **keys) {
     const u64 d = ctx->sh.d;
     PFP_TRY(pfp_alloc_t(ctx, keys, d, true));

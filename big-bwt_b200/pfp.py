@@ -80,7 +80,7 @@ SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_p
            "pfpb200_free_host",
            "pfpb200_scan_triggers", "pfpb200_memcpy_d2h", "pfpb200_strerror",
            "pfpb200_shard_scan", "pfpb200_shard_words", "pfpb200_dict_merge", "pfpb200_shard_remap",
-           "pfpb200_shard_first_keys", "pfpb200_shard_route", "pfpb200_shard_route_plan",
+           "pfpb200_shard_first_keys", "pfpb200_shard_sample_keys", "pfpb200_shard_route", "pfpb200_shard_route_plan",
            "pfpb200_shard_route_push", "pfpb200_dict_merge_words", "pfpb200_dict_merge_begin",
            "pfpb200_dict_merge_finish",
            "pfpb200_shard_ranks_back", "pfpb200_multi_create", "pfpb200_multi_destroy", "pfpb200_multi_n_gpus",

@@ -194,6 +194,25 @@ class CudaBackend:
         self.scanner._check(self.L.pfpb200_shard_first_keys(self.h, C.byref(out)))
         return dev_tensor(out.value, wd["n_words"], torch.int64, self.dev)
 
+    def sample_keys(self, max_samples: int) -> np.ndarray:
+        """First keys of (up to) max_samples evenly spaced words of the local dictionary (host)."""
+        self.L.pfpb200_shard_sample_keys.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+        self.L.pfpb200_shard_sample_keys.restype = C.c_int
+        out = np.zeros(max_samples, dtype=np.uint64)
+        n = C.c_uint32()
+        self.scanner._check(self.L.pfpb200_shard_sample_keys(self.h, max_samples, C.c_void_p(out.ctypes.data), C.byref(n)))
+        return out[:n.value]
+
+    def ranks_back(self, n_ranks, back, rank_base, n_words):
+        """Global rank of every local word from the ranks that came back in routed order."""
+        self.L.pfpb200_shard_ranks_back.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64),
+                                                    C.POINTER(C.c_void_p)]
+        self.L.pfpb200_shard_ranks_back.restype = C.c_int
+        base = (C.c_uint64 * n_ranks)(*rank_base)
+        out = C.c_void_p()
+        self.scanner._check(self.L.pfpb200_shard_ranks_back(self.h, n_ranks, C.c_void_p(back.data_ptr()), base, C.byref(out)))
+        return dev_tensor(out.value, n_words, torch.int32, self.dev)
+
     def route(self, wd, splitters: np.ndarray, n_ranks: int):
         rt, ms = Routed(), C.c_float()
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
@@ -621,8 +640,12 @@ class ShardedParser:
         dev = self.buf.device
         samp = torch.zeros(self.SAMPLE + 1, dtype=torch.int64, device=dev)
         k = 0
-        if d:
-            keys = be.first_keys(wd)          # uid order = fingerprint order: any stride is a random sample
+        if d and hasattr(be, "sample_keys"):  # keys of the sampled words only, straight to the host and back
+            pick = torch.from_numpy(be.sample_keys(self.SAMPLE).view(np.int64))
+            k = int(pick.numel())
+            samp[:k] = pick.to(dev)
+        elif d:
+            keys = be.first_keys(wd)          # uid order = creation order: any stride is a sample
             step = max(1, d // self.SAMPLE)
             pick = keys[::step][:self.SAMPLE]
             k = int(pick.numel())
@@ -710,7 +733,10 @@ class ShardedParser:
         tot = self._all_gather_i64([m["n_distinct"], int(piece.numel()), m["sum_word_len"], wd["n_phrases"]])
         nd = [r[0] for r in tot]
         offset = sum(nd[:g])
-        ranks = m["rank_of_entry"] + offset if m["rank_of_entry"].numel() else m["rank_of_entry"]
+        c_back = peer is not None and hasattr(be, "ranks_back")     # offsets and un-routing in one library kernel
+        ranks = m["rank_of_entry"]
+        if not c_back and ranks.numel():
+            ranks = ranks + offset
         if peer is not None:
             # the ranks of the records that came from rank q go back to q, behind what q routed to
             # the owners below me
@@ -721,9 +747,16 @@ class ShardedParser:
             back = peer.local("ranks", wd["n_words"])
         else:
             back = self._all_to_all_v(ranks.to(torch.int32), recv_w, words_to)  # routed order
-        rank_of_word = torch.empty(wd["n_words"], dtype=torch.int32, device=dev)
-        if rt:
-            rank_of_word[rt["perm"].long()] = back
+        if c_back and rt and not fused:
+            rank_of_word = be.ranks_back(G, back, [sum(nd[:q]) for q in range(G)], wd["n_words"])
+        else:
+            if c_back and back.numel():         # (fused push keeps its own routing state: offsets here)
+                so = np.concatenate([[0], np.cumsum(words_to)]).astype(np.int64)
+                for q in range(G):
+                    back[so[q]:so[q + 1]] += sum(nd[:q])
+            rank_of_word = torch.empty(wd["n_words"], dtype=torch.int32, device=dev)
+            if rt:
+                rank_of_word[rt["perm"].long()] = back
         self._mark("ranks_back")
         return {"dict": piece, "occ": m["occ"], "n_distinct": sum(nd), "rank_of_word": rank_of_word,
                 "totals": {"n_phrases": sum(r[3] for r in tot), "n_distinct": sum(nd),

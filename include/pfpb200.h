@@ -213,6 +213,10 @@ int pfpb200_shard_remap(pfpb200_ctx *ctx, const uint32_t *d_rank_of_word, const 
  * pfpb200_shard_words call; used to sample range splitters. */
 int pfpb200_shard_first_keys(pfpb200_ctx *ctx, const uint64_t **d_keys);
 
+/* The splitter sample directly: the keys of (up to) max_samples evenly spaced words of the last
+ * pfpb200_shard_words call, in HOST memory (h_keys must hold max_samples values). */
+int pfpb200_shard_sample_keys(pfpb200_ctx *ctx, uint32_t max_samples, uint64_t *h_keys, uint32_t *n_keys);
+
 typedef struct pfpb200_word {       /* one dictionary word on the wire: 32 bytes                 */
     uint64_t fpa, fpb;              /* 128-bit fingerprint                                       */
     uint32_t len, count, uwords;    /* bytes, occurrences, 8-byte pool words                     */
