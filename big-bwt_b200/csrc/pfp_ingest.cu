@@ -122,6 +122,7 @@ int pfp_file_to_device(pfpb200_ctx *ctx, int fd, u64 off, u64 bytes, u8 *d_dst) 
 int pfp_device_to_file(pfpb200_ctx *ctx, const char *name, const void *d_src, u64 bytes) {
     int fd = open(name, O_WRONLY | O_CREAT | O_TRUNC, 0666);
     if (fd < 0) return pfp_fail(ctx, PFPB200_E_IO, "%s: %s", name, strerror(errno));
+    if (bytes && ftruncate(fd, (off_t)bytes) != 0) { /* the writers extend the file themselves then */ }
     int rc = pfp_device_to_fd(ctx, fd, 0, d_src, bytes, name);
     if (close(fd) != 0 && rc == PFPB200_OK) rc = pfp_fail(ctx, PFPB200_E_IO, "%s: write error: %s", name, strerror(errno));
     return rc;

@@ -290,6 +290,9 @@ void rank_main(pfpb200_multi *m, int g) {
 
     // ---- 1. shard (+front) to the device; first invalid byte of the shard ---------------------------
     auto upload = [&]() {
+        // the working set of a shard (trigger bits, positions, records, table, pool, sort buffers,
+        // the owned range's dictionary) in one slab, before the stages ask for it piece by piece
+        pfp_arena_reserve(R.ctx, (size_t)(R.n_local + R.n_local / 2) + ((size_t)256 << 20));
         if (!ensure_dev(&R.buf, &R.buf_cap, (size_t)(R.front + R.n_local + 64))) {
             multi_fail(m, g, PFPB200_E_NOMEM, "device allocation of the shard failed");
             return;
@@ -596,11 +599,23 @@ extern "C" int pfpb200_multi_create(int n_gpus, const int *gpu_ids, pfpb200_mult
     m->r.resize(n_gpus);
     m->bar.n = n_gpus;
     int rc = PFPB200_OK;
+    {   // the CUDA contexts of the devices come up side by side (a third of a second each)
+        std::vector<std::thread> th;
+        std::vector<int> rcs(n_gpus, PFPB200_OK);
+        for (int g = 0; g < n_gpus; g++) m->r[g].device = gpu_ids ? gpu_ids[g] : g;
+        for (int g = 0; g < n_gpus; g++) {
+            bool first = true;                       // one thread per distinct device; repeats follow in order
+            for (int q = 0; q < g; q++) first = first && m->r[q].device != m->r[g].device;
+            if (first) th.emplace_back([m, g, n_gpus, &rcs]() {
+                for (int q = g; q < n_gpus; q++)
+                    if (m->r[q].device == m->r[g].device) rcs[q] = pfpb200_create(m->r[q].device, &m->r[q].ctx);
+            });
+        }
+        for (auto &t : th) t.join();
+        for (int g = 0; g < n_gpus; g++) if (rcs[g] != PFPB200_OK && rc == PFPB200_OK) rc = rcs[g];
+    }
     for (int g = 0; g < n_gpus && rc == PFPB200_OK; g++) {
         Rank &R = m->r[g];
-        R.device = gpu_ids ? gpu_ids[g] : g;
-        rc = pfpb200_create(R.device, &R.ctx);
-        if (rc != PFPB200_OK) break;
         bool ok = cudaSetDevice(R.device) == cudaSuccess &&
                   cudaEventCreateWithFlags(&R.ev_sent, cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&R.ev_back, cudaEventDisableTiming) == cudaSuccess &&

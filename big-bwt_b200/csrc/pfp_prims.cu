@@ -124,6 +124,20 @@ int pfp_alloc(pfpb200_ctx *ctx, void **p, size_t bytes, bool held) {
     return PFPB200_OK;
 }
 
+// One slab of `bytes` up front (when the arena holds less): a parse whose size is known then reaches
+// the driver once instead of at every stage -- with peer access enabled every cudaMalloc is mapped
+// into all the peer GPUs, tens of milliseconds each.  Best effort: a failure leaves the arena as it is.
+void pfp_arena_reserve(pfpb200_ctx *ctx, size_t bytes) {
+    PfpArena &A = ctx->arena;
+    if (A.total >= bytes) return;
+    size_t want = ((bytes - A.total) + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    void *base = nullptr;
+    if (cudaMalloc(&base, want) != cudaSuccess) { cudaGetLastError(); return; }
+    A.slabs.push_back({(char *)base, want});
+    A.total += want;
+    arena_insert_free(A, {(char *)base, want});
+}
+
 int pfp_free_now(pfpb200_ctx *ctx, void *p) {
     if (!p) return PFPB200_OK;
     for (size_t i = 0; i < ctx->scratch.size(); i++)
