@@ -245,8 +245,9 @@ def load_peaks():
 
 
 def scan_kernel_name():
-    """K1 of the benchmarked configuration (w=10): the table form unless PFPB200_K1=rolling."""
-    return "kr_scan_k<10>" if os.environ.get("PFPB200_K1") == "rolling" else "kr_scan_dna_k<10>"
+    """K1 of the benchmarked configuration (w=10): the interval form unless PFPB200_K1=rolling / table."""
+    mode = os.environ.get("PFPB200_K1")
+    return "kr_scan_k<10>" if mode == "rolling" else "kr_scan_dna_k<10>" if mode == "table" else "kr_scan_iv_k<10>"
 
 
 def load_traffic(n_text):

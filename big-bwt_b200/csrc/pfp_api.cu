@@ -93,7 +93,7 @@ extern "C" int pfpb200_create(int device, pfpb200_ctx **out) {
     if (!ctx) return PFPB200_E_NOMEM;
     ctx->device = device;
     { const char *ev = getenv("PFPB200_LEGACY_K2"); ctx->legacy_k2 = ev && atoi(ev) != 0; }
-    { const char *ev = getenv("PFPB200_K1"); ctx->k1_mode = (ev && strcmp(ev, "rolling") == 0) ? 1 : 0; }
+    { const char *ev = getenv("PFPB200_K1"); ctx->k1_mode = (ev && strcmp(ev, "rolling") == 0) ? 1 : (ev && strcmp(ev, "table") == 0) ? 2 : 0; }
     { const char *ev = getenv("PFPB200_TEST_WEAK_FP"); ctx->weak_fp = (ev && atoi(ev) != 0) ? 1u : 0u; }
     { const char *ev = getenv("PFPB200_NO_SCAN_ALPHA"); ctx->no_scan_alpha = ev && atoi(ev) != 0; }
     { const char *ev = getenv("PFPB200_RANK_FULL_SORT"); ctx->rank_full_sort = ev && atoi(ev) != 0; }
@@ -150,6 +150,8 @@ extern "C" void pfpb200_destroy(pfpb200_ctx *ctx) {
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->d_keys) cudaFree(ctx->d_keys);
     if (ctx->dna_table) cudaFree(ctx->dna_table);
+    if (ctx->iv_etab) cudaFree(ctx->iv_etab);
+    if (ctx->iv_xtab) cudaFree(ctx->iv_xtab);
     if (ctx->d_alpha) cudaFree(ctx->d_alpha);
     pfp_io_destroy(ctx);
     for (int i = 0; i < 5; i++)

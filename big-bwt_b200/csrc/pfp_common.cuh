@@ -62,7 +62,7 @@ struct pfpb200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     u32 launches = 0;
-    int k1_mode = 0;               // PFPB200_K1=rolling: always the rolling-arithmetic scan kernel (A/B)
+    int k1_mode = 0;               // PFPB200_K1=rolling: always the rolling-arithmetic scan kernel; =table: the 4^w-bit table form (A/B)
     // byte values present in the text, as a by-product of the DNA form of K1 (8 x 32 bits): rows that
     // pass the table path hold only A C G T, the others record their bytes.  Valid for the words of
     // a single-GPU parse; lets the ranking skip its own pass over the words' first bytes.
@@ -70,6 +70,9 @@ struct pfpb200_ctx {
     bool alpha_valid = false;
     u32 *dna_table = nullptr;      // 4^w-bit trigger table of (dna_w, dna_p) for the DNA scan (w <= 10)
     u32 dna_w = 0, dna_p = 0;
+    u32 *iv_etab = nullptr;        // interval form of the DNA scan: 1024 x {a16 + 2, b16} of (iv_w, iv_p)
+    uint2 *iv_xtab = nullptr;      //   and the exact partial hashes {Ah, Bl}
+    u32 iv_w = 0, iv_p = 0, iv_cthr = 0;
     bool no_scan_alpha = false;      // PFPB200_NO_SCAN_ALPHA=1: the ranking finds the alphabet of the words itself (A/B)
     bool rank_full_sort = false;     // PFPB200_RANK_FULL_SORT=1: radix-sort all 64 bits of the first key (A/B)
     bool rank_chunk_passes = false;  // PFPB200_RANK_CHUNK_PASSES=1: mid-size tie groups by chunk passes instead of LCP walks (A/B)

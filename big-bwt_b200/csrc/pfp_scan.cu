@@ -211,7 +211,9 @@ __device__ __forceinline__ u32 dna_pack4(u32 x, u32 &bad) {
     const u32 y = shr_fma(x, 1) & 0x03030303u;
     const u32 z = y | shr_fma(y, 4);                          // nibbles: (c0,c1) in byte 0, (c2,c3) in byte 2
     const u32 sel = __byte_perm(z, 0u, 0x4420u);              // c0,c1,c2,c3 as the low four nibbles
-    bad |= __byte_perm(KD_LETTERS, 0u, sel) ^ x;
+    u32 dec;                                                  // raw PRMT: every selector nibble is < 4, nothing to mask
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(dec) : "r"(KD_LETTERS), "r"(0u), "r"(sel));
+    bad |= dec ^ x;
     return y * 0x01041040u;
 }
 __device__ __forceinline__ u32 dna_pack16(const uint4 &v, u32 &bad) {
@@ -361,6 +363,185 @@ __global__ void __launch_bounds__(KD_T, 1) kr_scan_dna_k(const uint4 *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1a, interval form (w <= 10, p < PW) -- the default for DNA text since round 2.
+//
+// The bit-table form above pays 3.6 shared-memory wavefronts per position (32 random words in 32
+// banks).  This form needs ONE conflict-free wavefront, from two facts about the hash:
+//  (1) it is LINEAR: H(window) = (Ah[hi] + Bl[lo]) mod PW, hi / lo = the codes of the w-5 older
+//      and the 5 newest symbols; and the hi block of the window ending at i IS the lo block of
+//      the window ending at i-5, so ONE table of 4^5 = 1024 entries, indexed by the 5-symbol block
+//      ending at a position, serves both halves: one look-up per position, each used twice;
+//  (2) "H mod p == 0" becomes an INTERVAL test after multiplying by u = p^-1 mod PW: H = k p with
+//      0 <= k <= K = (PW-1)/p  <=>  (H u mod PW) <= K, and H u = Ah u + Bl u (mod PW).
+//      Scaled by 2^16/PW the reduction mod PW is the wrap of 16-bit addition: with
+//      a16 = floor(Ah u 2^16/PW), b16 = floor(Bl u 2^16/PW), t = (a16 + b16) mod 2^16, the true
+//      scaled sum lies in [t, t+2) (mod 2^16), so every trigger has (t + 2) mod 2^16 < theta + 4,
+//      theta = (K+1) 2^16/PW.  One entry holds (a16 + 2) in its high and b16 in its low half:
+//            T = (E[i] << 16) + E[i-5];   candidate  <=>  T < (floor(theta) + 4) << 16
+//      -- one multiply-add and one compare per position.  The table is 4 KB, so it is replicated
+//      32 times (word 32 x + lane): every lane reads its own bank.
+// Candidates (all triggers + 6e-5 of the positions for p = 100) are then decided EXACTLY from the
+// full 32-bit partial hashes {Ah, Bl} (a second, unreplicated 8 KB table) with the same
+// pfp_is_trigger() as everywhere else, so the trigger set is identical for every input; rows
+// holding anything besides A C G T go to the rolling arithmetic as in the bit-table form.
+// tests/test_arith.py::test_interval_form_* models both tables in numpy over all 4^10 windows.
+// ------------------------------------------------------------------------------------------------
+constexpr u32 KE_ENT = 1024;                                        // 5-symbol blocks
+constexpr size_t KE_SMEM = (size_t)KE_ENT * 32 * 4 + (size_t)KE_ENT * 8;   // replicated E + exact {Ah, Bl}
+
+__global__ void dna_etab_k(pfp_scan_consts C, u32 uinv, u32 *__restrict__ etab, uint2 *__restrict__ xtab) {
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= KE_ENT) return;
+    u64 bl = 0, ah = 0;
+    for (int j = 0; j < 5; j++) {                                    // symbol j of the block, j = 0 oldest
+        const u64 c = (KD_LETTERS >> (8 * ((x >> (2 * j)) & 3u))) & 255u;
+        if ((int)C.w - 5 + j >= 0) bl = (bl * 256 + c) % PFP_PW;     // as the lo block: window symbol w-5+j
+        if ((int)C.w - 10 + j >= 0) ah = (ah * 256 + c) % PFP_PW;    // as the hi block: window symbol w-10+j
+    }
+    for (int j = 0; j < 5; j++) ah = (ah * 256) % PFP_PW;            // the hi block stands 5 symbols higher
+    xtab[x] = make_uint2((u32)ah, (u32)bl);
+    const u64 as = (ah * uinv) % PFP_PW, bs = (bl * uinv) % PFP_PW;
+    const u32 a16 = (u32)((as << 16) / PFP_PW), b16 = (u32)((bs << 16) / PFP_PW);
+    etab[x] = (((a16 + 2u) & 0xFFFFu) << 16) | b16;
+}
+
+// (bits [b, b+10) of the 96-bit stream {S[0], S[1], S[2]}) << 7, other bits undefined
+template <int B>
+__device__ __forceinline__ u32 ke_block_x128(const u32 (&S)[3]) {
+    constexpr int k = B >> 5, sh = B & 31;
+    if constexpr (sh < 7) return S[k] * kd_pow2[7 - sh];                      // IMAD (FMA pipe)
+    else if constexpr (sh + 10 <= 32) return shr_fma(S[k], sh - 7);           // IMAD.HI
+    else return __funnelshift_r(S[k], S[k + 1], sh - 7);                      // SHF (ALU pipe), 4 of 16
+}
+
+template <int I>
+__device__ __forceinline__ u32 ke_lookup(const u32 (&S)[3], const unsigned char *rep_lane) {
+    const u32 v = ke_block_x128<2 * (I + 12)>(S);                   // block of the symbols I-4 .. I
+    return *reinterpret_cast<const u32 *>(rep_lane + (v & 0x1FF80u));
+}
+
+// trigger bits of a lane's 32 positions; S = {16 symbols in front, 32 own symbols}, 2 bits each
+__device__ __forceinline__ u32 ke_row_bits(const u32 (&S)[3], const unsigned char *rep_lane,
+                                           const uint2 *__restrict__ xt, const pfp_scan_consts &C, u32 cthr) {
+    u32 E[37];                                                       // E[5 + i]: block ending at position i
+#define KE_L(I) E[5 + I] = ke_lookup<I>(S, rep_lane);
+    KE_L(27) KE_L(28) KE_L(29) KE_L(30) KE_L(31)
+    KE_L(0) KE_L(1) KE_L(2) KE_L(3) KE_L(4) KE_L(5) KE_L(6) KE_L(7) KE_L(8) KE_L(9) KE_L(10) KE_L(11) KE_L(12)
+    KE_L(13) KE_L(14) KE_L(15) KE_L(16) KE_L(17) KE_L(18) KE_L(19) KE_L(20) KE_L(21) KE_L(22) KE_L(23) KE_L(24)
+    KE_L(25) KE_L(26)
+#undef KE_L
+#pragma unroll
+    for (int j = 0; j < 5; j++) E[j] = __shfl_up_sync(0xffffffffu, E[32 + j], 1);   // blocks ending at -5 .. -1
+    u32 m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const u32 T = E[5 + i] * kd_pow2[16] + E[i];
+        asm("{\n\t.reg .pred c;\n\tsetp.lt.u32 c, %1, %2;\n\t@c or.b32 %0, %0, %3;\n\t}"
+            : "+r"(m) : "r"(T), "r"(cthr), "r"(1u << i));
+    }
+    // candidates -> triggers, exactly (about one candidate per three lanes and row for p = 100)
+    u32 cand = m;
+    while (cand) {
+        const u32 bit = cand & (0u - cand);
+        cand ^= bit;
+        const u32 o = 2u * (u32)(31 - __clz(bit)) + 14u;             // first stream bit of the window's hi block
+        const bool k0 = o < 32u, k2 = o >= 64u;
+        const u32 lo = k0 ? S[0] : (k2 ? S[2] : S[1]);
+        const u32 hi = k0 ? S[1] : S[2];                             // k2: o + 20 <= 96, the upper word is not reached
+        const u32 v = __funnelshift_r(lo, hi, o);                    // (shift taken mod 32) 20 bits: hi block, lo block
+        u32 h = xt[v & 1023u].x + xt[(v >> 10) & 1023u].y;
+        h = min(h, h - PFP_PW);
+        if (!pfp_is_trigger(h, C.pinv, C.pshift, C.plimit)) m ^= bit;
+    }
+    return m;
+}
+
+// first and last rows of a buffer: words outside the bit array, positions outside [q_lo, q_hi)
+__device__ __noinline__ u32 ke_clip_row(u32 m, u32 word, u64 q_lo, u64 q_hi) {
+    const u64 q = (u64)word * 32;
+    if (q < q_lo || q + 32 > q_hi) m &= range_mask32(q, q_lo, q_hi);
+    return m;
+}
+
+template <int W>
+__global__ void __launch_bounds__(KD_T, 1) kr_scan_iv_k(const uint4 *__restrict__ A, u64 q_end, u64 q_lo,
+                                                        u64 q_hi, pfp_scan_consts C,
+                                                        const u32 *__restrict__ etab_g,
+                                                        const uint2 *__restrict__ xtab_g, u32 cthr,
+                                                        u32 *__restrict__ mask32,
+                                                        u32 *__restrict__ tile_cnt, u32 nwords,
+                                                        u32 fast_lo, u32 fast_n /* rows [fast_lo, fast_lo + fast_n): nothing to clip */,
+                                                        u32 *__restrict__ alpha) {
+    extern __shared__ __align__(16) u32 ke_sm[];
+    u32 *rep = ke_sm;
+    uint2 *xt = reinterpret_cast<uint2 *>(ke_sm + KE_ENT * 32);
+    for (u32 i = threadIdx.x; i < KE_ENT * 32; i += KD_T) rep[i] = etab_g[i >> 5];
+    for (u32 i = threadIdx.x; i < KE_ENT; i += KD_T) xt[i] = xtab_g[i];
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31;
+    const unsigned char *rep_lane = reinterpret_cast<const unsigned char *>(rep) + lane * 4;
+    const u32 nrows = (nwords + 30) / 31;
+    const u32 wstride = gridDim.x * (KD_T / 32);
+    u32 row = blockIdx.x * (KD_T / 32) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const unsigned char *A8 = reinterpret_cast<const unsigned char *>(A);
+    uint4 n0, n1;
+    {
+        const u64 q = ((u64)row * 31 + lane) * 32;
+        n0 = kd_load_unit(A, q_end, (i64)q);
+        n1 = kd_load_unit(A, q_end, (i64)q + 16);
+    }
+    for (; row < nrows; row += wstride) {
+        const uint4 u0 = n0, u1 = n1;
+        const u32 word = row * 31 + lane;                            // my 32 positions = bit-array word `word`
+        const bool fast = row - fast_lo < fast_n;
+        const u32 nrow = row + wstride;
+        if (nrow - fast_lo < fast_n) {                               // interior row: no bounds to check
+            const uint4 *pn = reinterpret_cast<const uint4 *>(A8 + ((u64)nrow * 31 + lane) * 32);
+            n0 = __ldg(pn);
+            n1 = __ldg(pn + 1);
+        } else if (nrow < nrows) {
+            const u64 nq = ((u64)nrow * 31 + lane) * 32;
+            n0 = kd_load_unit(A, q_end, (i64)nq);
+            n1 = kd_load_unit(A, q_end, (i64)nq + 16);
+        }
+        u32 bad = 0;
+        const u32 S1 = dna_pack16(u0, bad), S2 = dna_pack16(u1, bad);
+        const u32 S0 = __shfl_up_sync(0xffffffffu, S2, 1);          // the 16 symbols in front of my run
+        const bool any_bad = __any_sync(0xffffffffu, bad != 0);
+        u32 m;
+        if (!any_bad) {
+            const u32 S[3] = {S0, S1, S2};
+            m = ke_row_bits(S, rep_lane, xt, C, cthr);
+        } else {
+            const u64 q = (u64)word * 32;
+            m = kd_row_by_arithmetic<W>(u0, u1, lane, C, q, q_lo >= (u64)(W - 1) ? q_lo - (u64)(W - 1) : 0, q_end,
+                                        true, alpha);
+        }
+        bool mine = lane != 0;
+        if (!fast) {
+            mine = (lane != 0 || row == 0) && word < nwords;
+            m = ke_clip_row(m, word, q_lo, q_hi);
+        }
+        if (!mine) m = 0;
+        if (mine) mask32[word] = m;
+        // per-tile counts: the words 31 row + 1 .. 31 row + 31 of a row lie in at most two tiles (1024 words each)
+        const u32 c = __popc(m);
+        const u32 t0 = (row * 31 + 1) >> 10, t1 = (row * 31 + 31) >> 10;
+        const u32 call = __reduce_add_sync(0xffffffffu, c);
+        if (t0 == t1) {
+            if (lane == 0 && call) atomicAdd(&tile_cnt[t0], call);
+        } else {
+            const u32 c1 = __reduce_add_sync(0xffffffffu, (word >> 10) == t1 && lane != 0 ? c : 0u);
+            if (lane == 0) {
+                if (call - c1) atomicAdd(&tile_cnt[t0], call - c1);
+                if (c1) atomicAdd(&tile_cnt[t1], c1);
+            }
+        }
+    }
+}
+
 // K1c: bits -> ascending global positions
 __global__ void __launch_bounds__(K1_T) kr_emit_k(const uint4 *__restrict__ mask,
                                                   const u64 *__restrict__ tile_off,
@@ -420,12 +601,32 @@ static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A,
 }
 #define KD_CASE(W) case W: le = launch_scan_dna<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
 
+template <int W>
+static cudaError_t launch_scan_iv(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
+                                  const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
+    const u32 nwords = ntiles * (u32)(K1_TILE / 32);      // every word of every tile gets written
+    // rows that need no clipping: all 1024 positions inside [q_lo, q_hi) and inside whole 16-byte units
+    const u64 lim = q_hi < (q_end & ~(u64)15) ? q_hi : (q_end & ~(u64)15);
+    u64 f_lo = (q_lo + 991) / 992;
+    if (f_lo < 1) f_lo = 1;
+    const u64 f_hi = lim >= 1024 ? (lim - 1024) / 992 + 1 : 0;
+    const u32 fast_lo = (u32)f_lo, fast_n = f_hi > f_lo ? (u32)(f_hi - f_lo) : 0u;
+    kr_scan_iv_k<W><<<ctx->sm_count, KD_T, KE_SMEM, ctx->stream>>>(A, q_end, q_lo, q_hi, C, ctx->iv_etab, ctx->iv_xtab,
+                                                                   ctx->iv_cthr, reinterpret_cast<u32 *>(mask),
+                                                                   tile_cnt, nwords, fast_lo, fast_n, ctx->d_alpha);
+    return cudaGetLastError();
+}
+#define KE_CASE(W) case W: le = launch_scan_iv<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
+
 template <int W> static cudaError_t scan_attr() {
     cudaError_t e = cudaFuncSetAttribute(kr_scan_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
     if (e == cudaSuccess && W <= KD_MAXW)
         e = cudaFuncSetAttribute(kr_scan_dna_k<(W <= KD_MAXW ? W : KD_MAXW)>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((((size_t)1 << (2 * (W <= KD_MAXW ? W : KD_MAXW))) + 31) / 32 * 4));
+    if (e == cudaSuccess && W <= KD_MAXW)
+        e = cudaFuncSetAttribute(kr_scan_iv_k<(W <= KD_MAXW ? W : KD_MAXW)>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KE_SMEM);
     return e;
 }
 
@@ -452,6 +653,36 @@ static int ensure_dna_table(pfpb200_ctx *ctx, const pfp_scan_consts &C) {
     PFP_LAUNCHED(ctx);
     ctx->dna_w = C.w;
     ctx->dna_p = C.p;
+    return PFPB200_OK;
+}
+
+// p^-1 modulo the prime PW (extended Euclid); 0 when p is a multiple of PW
+static u32 inverse_mod_pw(u32 p) {
+    i64 r0 = PFP_PW, r1 = p % PFP_PW, t0 = 0, t1 = 1;
+    if (r1 == 0) return 0;
+    while (r1) {
+        const i64 qq = r0 / r1;
+        const i64 r2 = r0 - qq * r1; r0 = r1; r1 = r2;
+        const i64 t2 = t0 - qq * t1; t0 = t1; t1 = t2;
+    }
+    return (u32)(t0 < 0 ? t0 + PFP_PW : t0);
+}
+
+// the two 1024-entry tables of the interval form for (w, p), cached in the context
+static int ensure_iv_tables(pfpb200_ctx *ctx, const pfp_scan_consts &C) {
+    if (ctx->iv_etab && ctx->iv_w == C.w && ctx->iv_p == C.p) return PFPB200_OK;
+    if (!ctx->iv_etab) {
+        PFP_CUDA(ctx, cudaMalloc(&ctx->iv_etab, KE_ENT * sizeof(u32)));
+        PFP_CUDA(ctx, cudaMalloc(&ctx->iv_xtab, KE_ENT * sizeof(uint2)));
+    }
+    const u32 uinv = inverse_mod_pw(C.p);
+    dna_etab_k<<<KE_ENT / 256, 256, 0, ctx->stream>>>(C, uinv, ctx->iv_etab, ctx->iv_xtab);
+    PFP_LAUNCHED(ctx);
+    // theta = (K + 1) 2^16 / PW, K = (PW - 1) / p: every trigger has T < (floor(theta) + 4) << 16
+    const u64 theta = (((u64)(PFP_PW - 1) / C.p + 1) << 16) / PFP_PW;
+    ctx->iv_cthr = (u32)((theta + 4) << 16);
+    ctx->iv_w = C.w;
+    ctx->iv_p = C.p;
     return PFPB200_OK;
 }
 
@@ -491,7 +722,10 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
     if (!evs.ok) return pfp_fail(ctx, PFPB200_E_CUDA, "cudaEventCreate failed");
     const cudaEvent_t e0 = evs[0], e1 = evs[1];
     const bool dna = w <= (u32)KD_MAXW && ctx->k1_mode != 1;
-    if (dna) PFP_TRY(ensure_dna_table(ctx, C));
+    // interval form: p must be invertible modulo PW and the threshold must leave the 16-bit range alone
+    const bool iv = dna && ctx->k1_mode == 0 && p >= 10 && p < PFP_PW && (u64)ntiles * (K1_TILE / 32) < 0xFFFFFF00ull;
+    if (iv) PFP_TRY(ensure_iv_tables(ctx, C));
+    else if (dna) PFP_TRY(ensure_dna_table(ctx, C));
     PFP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     ctx->alpha_valid = false;
     if (dna) {
@@ -500,13 +734,20 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
         PFP_CUDA(ctx, cudaMemsetAsync(ctx->d_alpha, 0, 8 * sizeof(u32), ctx->stream));
         ctx->alpha_valid = buf_pos0 == 0 && own_lo == 0;       // the whole text of a single-GPU parse
         cudaError_t le = cudaSuccess;
-        switch ((int)w) {
-            KD_CASE(4) KD_CASE(5) KD_CASE(6) KD_CASE(7) KD_CASE(8) KD_CASE(9) KD_CASE(10)
-            default: le = cudaErrorInvalidValue;
+        if (iv) {
+            switch ((int)w) {
+                KE_CASE(4) KE_CASE(5) KE_CASE(6) KE_CASE(7) KE_CASE(8) KE_CASE(9) KE_CASE(10)
+                default: le = cudaErrorInvalidValue;
+            }
+        } else {
+            switch ((int)w) {
+                KD_CASE(4) KD_CASE(5) KD_CASE(6) KD_CASE(7) KD_CASE(8) KD_CASE(9) KD_CASE(10)
+                default: le = cudaErrorInvalidValue;
+            }
         }
         ctx->launches++;
         if (le != cudaSuccess)
-            return pfp_fail(ctx, PFPB200_E_CUDA, "kr_scan_dna_k launch: %s", cudaGetErrorString(le));
+            return pfp_fail(ctx, PFPB200_E_CUDA, "%s launch: %s", iv ? "kr_scan_iv_k" : "kr_scan_dna_k", cudaGetErrorString(le));
     } else {
         switch (w <= K1_MAXW_FAST ? (int)w : 0) {
             K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7) K1_CASE(8) K1_CASE(9) K1_CASE(10)

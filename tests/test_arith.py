@@ -101,3 +101,46 @@ def test_table_form_of_the_scan_equals_the_rolling_hash(pkg, w, p):
     got = np.flatnonzero(table[idx]) + (w - 1)
     want = orc.triggers(text.tobytes(), w, p)
     assert np.array_equal(got.astype(np.uint64), want)
+
+
+# ---- the interval form of the scan (kr_scan_iv_k): both tables modelled in numpy over ALL 4^10 windows ----
+def _interval_tables(w, p):
+    """What dna_etab_k builds: per 5-symbol block x the exact partial hashes Ah (x as the w-5 older
+    symbols of a window, 5 places up) and Bl (x as the 5 newest), and E = (a16 + 2) << 16 | b16 with
+    a16 = floor(Ah u 2^16 / PW), b16 = floor(Bl u 2^16 / PW), u = p^-1 mod PW."""
+    letters = np.array([65, 67, 84, 71], dtype=np.int64)
+    x = np.arange(1024, dtype=np.int64)
+    bl = np.zeros(1024, dtype=np.int64)
+    ah = np.zeros(1024, dtype=np.int64)
+    for j in range(5):
+        c = letters[(x >> (2 * j)) & 3]
+        if w - 5 + j >= 0:
+            bl = (bl * 256 + c) % PW
+        if w - 10 + j >= 0:
+            ah = (ah * 256 + c) % PW
+    ah = (ah * pow(256, 5, PW)) % PW
+    u = pow(p, -1, PW)
+    a_s = np.array([(int(a) * u) % PW for a in ah], dtype=np.int64)
+    b_s = np.array([(int(b) * u) % PW for b in bl], dtype=np.int64)
+    e = ((((a_s << 16) // PW + 2) & 0xFFFF) << 16) | ((b_s << 16) // PW)
+    theta = ((((PW - 1) // p) + 1) << 16) // PW
+    return ah, bl, e.astype(np.uint64), (theta + 4) << 16
+
+
+@pytest.mark.parametrize("w,p", [(4, 10), (5, 11), (6, 50), (7, 99991), (8, 16), (9, 1000), (10, 10), (10, 100),
+                                 (10, 65536), (10, 1999999), (10, PW - 1)])
+def test_interval_form_candidates_cover_every_trigger(w, p):
+    ah, bl, e, cthr = _interval_tables(w, p)
+    assert cthr < 1 << 32
+    idx = np.arange(1 << 20, dtype=np.int64)             # a window of 10 symbols, oldest in the lowest bits
+    hi, lo = idx & 1023, idx >> 10
+    letters = np.array([65, 67, 84, 71], dtype=np.int64)
+    h = np.zeros_like(idx)
+    for k in range(10 - w, 10):                           # the last w symbols are the window
+        h = (h * 256 + letters[(idx >> (2 * k)) & 3]) % PW
+    assert np.array_equal((ah[hi] + bl[lo]) % PW, h)      # linearity: the exact tables of the second stage
+    trig = (h % p) == 0
+    t = ((e[lo] << np.uint64(16)) + e[hi]) & np.uint64(0xFFFFFFFF)
+    cand = t < np.uint64(cthr)
+    assert not np.any(trig & ~cand)                       # no trigger is missed by the 16-bit interval test
+    assert cand.sum() - trig.sum() <= 200                 # and next to nothing else passes it

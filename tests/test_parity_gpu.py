@@ -54,6 +54,41 @@ def test_trigger_scan_vs_oracle(pkg, sc, w, p):
         assert np.array_equal(got, want), f"w={w} p={p} off={off}: {len(got)} vs {len(want)}"
 
 
+@pytest.mark.parametrize("w,p", [(4, 10), (5, 11), (6, 64), (7, 16), (8, 33), (9, 1000), (10, 10), (10, 100),
+                                 (10, 65536), (10, 99991), (10, 1999999), (10, 3999999946)])
+def test_interval_form_scan_vs_oracle_and_other_forms(pkg, w, p):
+    """K1's interval form (kr_scan_iv_k, the default for w <= 10) against the oracle and against the
+    bit-table and rolling forms, on DNA with rows that leave the table path (N runs, lower case,
+    a newline) and at misaligned starts.  p >= PW (last case) has no inverse: the library falls back."""
+    n = 700_000
+    text = pkg.synth.random_dna(n, 77 + w).numpy().copy()
+    text[100_000:103_000] = ord("N")
+    text[300_010:300_050] |= 0x20            # lower case
+    text[500_000] = ord("\n")
+    text[n - 5] = ord("N")
+    want = orc.triggers(text.tobytes(), w, p)
+    for mode in ("", "table", "rolling"):
+        old = os.environ.get("PFPB200_K1")
+        if mode:
+            os.environ["PFPB200_K1"] = mode
+        else:
+            os.environ.pop("PFPB200_K1", None)
+        try:
+            s = pkg.pfp.Scanner(0)
+        finally:
+            if old is None:
+                os.environ.pop("PFPB200_K1", None)
+            else:
+                os.environ["PFPB200_K1"] = old
+        try:
+            for off in (0, 5, 16):
+                buf = torch.from_numpy(np.concatenate([np.zeros(off, np.uint8), text])).cuda()
+                got, _ = s.scan_triggers(buf[off:], w, p)
+                assert np.array_equal(got, want), f"mode={mode or 'interval'} w={w} p={p} off={off}: {len(got)} vs {len(want)}"
+        finally:
+            s.close()
+
+
 def test_trigger_scan_shard_with_halo(pkg, sc):
     """A shard [lo,hi) scanned from a buffer with a left halo gives exactly the global triggers
     in [lo,hi) (pscan.hpp:44-108 semantics, sequential first-window rule)."""
