@@ -73,6 +73,7 @@ struct pfpb200_ctx {
     u32 *iv_etab = nullptr;        // interval form of the DNA scan: 1024 x {a16 + 2, b16} of (iv_w, iv_p)
     uint2 *iv_xtab = nullptr;      //   and the exact partial hashes {Ah, Bl}
     u32 iv_w = 0, iv_p = 0, iv_cthr = 0;
+    int iv_skip = 0;               // > 0: the last scan found text that is not DNA, use the rolling kernel for this many calls
     bool no_scan_alpha = false;      // PFPB200_NO_SCAN_ALPHA=1: the ranking finds the alphabet of the words itself (A/B)
     bool rank_full_sort = false;     // PFPB200_RANK_FULL_SORT=1: radix-sort all 64 bits of the first key (A/B)
     bool rank_chunk_passes = false;  // PFPB200_RANK_CHUNK_PASSES=1: mid-size tie groups by chunk passes instead of LCP walks (A/B)

@@ -457,22 +457,18 @@ __device__ __forceinline__ u32 ke_row_bits(const u32 (&S)[3], const unsigned cha
     return m;
 }
 
-// first and last rows of a buffer: words outside the bit array, positions outside [q_lo, q_hi)
-__device__ __noinline__ u32 ke_clip_row(u32 m, u32 word, u64 q_lo, u64 q_hi) {
-    const u64 q = (u64)word * 32;
-    if (q < q_lo || q + 32 > q_hi) m &= range_mask32(q, q_lo, q_hi);
-    return m;
-}
-
-template <int W>
-__global__ void __launch_bounds__(KD_T, 1) kr_scan_iv_k(const uint4 *__restrict__ A, u64 q_end, u64 q_lo,
-                                                        u64 q_hi, pfp_scan_consts C,
-                                                        const u32 *__restrict__ etab_g,
-                                                        const uint2 *__restrict__ xtab_g, u32 cthr,
-                                                        u32 *__restrict__ mask32,
-                                                        u32 *__restrict__ tile_cnt, u32 nwords,
-                                                        u32 fast_lo, u32 fast_n /* rows [fast_lo, fast_lo + fast_n): nothing to clip */,
-                                                        u32 *__restrict__ alpha) {
+// The interior rows of the buffer (every position inside [q_lo, q_hi), whole 16-byte units): one
+// persistent 1024-thread CTA per SM, every warp walks a CONTIGUOUS run of rows (a running pointer
+// instead of 64-bit index arithmetic; the per-tile trigger counts are kept per lane and flushed
+// when the lane's word leaves its tile).  Rows overlap by one lane as in the bit-table form.
+// A row holding anything besides A C G T is not handled here: its number goes to `redo` and
+// kr_scan_rows_k does it by the rolling arithmetic -- this loop has no calls and no clipping.
+__global__ void __launch_bounds__(KD_T, 1) kr_scan_ivf_k(const unsigned char *__restrict__ A8, pfp_scan_consts C,
+                                                         const u32 *__restrict__ etab_g,
+                                                         const uint2 *__restrict__ xtab_g, u32 cthr,
+                                                         u32 *__restrict__ mask32, u32 *__restrict__ tile_cnt,
+                                                         u32 row_lo, u32 n_rows,
+                                                         u32 *__restrict__ redo, u32 *__restrict__ redo_n) {
     extern __shared__ __align__(16) u32 ke_sm[];
     u32 *rep = ke_sm;
     uint2 *xt = reinterpret_cast<uint2 *>(ke_sm + KE_ENT * 32);
@@ -481,63 +477,72 @@ __global__ void __launch_bounds__(KD_T, 1) kr_scan_iv_k(const uint4 *__restrict_
     __syncthreads();
     const u32 lane = threadIdx.x & 31;
     const unsigned char *rep_lane = reinterpret_cast<const unsigned char *>(rep) + lane * 4;
-    const u32 nrows = (nwords + 30) / 31;
-    const u32 wstride = gridDim.x * (KD_T / 32);
-    u32 row = blockIdx.x * (KD_T / 32) + (threadIdx.x >> 5);
-    if (row >= nrows) return;
-    const unsigned char *A8 = reinterpret_cast<const unsigned char *>(A);
-    uint4 n0, n1;
-    {
-        const u64 q = ((u64)row * 31 + lane) * 32;
-        n0 = kd_load_unit(A, q_end, (i64)q);
-        n1 = kd_load_unit(A, q_end, (i64)q + 16);
-    }
-    for (; row < nrows; row += wstride) {
-        const uint4 u0 = n0, u1 = n1;
-        const u32 word = row * 31 + lane;                            // my 32 positions = bit-array word `word`
-        const bool fast = row - fast_lo < fast_n;
-        const u32 nrow = row + wstride;
-        if (nrow - fast_lo < fast_n) {                               // interior row: no bounds to check
-            const uint4 *pn = reinterpret_cast<const uint4 *>(A8 + ((u64)nrow * 31 + lane) * 32);
-            n0 = __ldg(pn);
-            n1 = __ldg(pn + 1);
-        } else if (nrow < nrows) {
-            const u64 nq = ((u64)nrow * 31 + lane) * 32;
-            n0 = kd_load_unit(A, q_end, (i64)nq);
-            n1 = kd_load_unit(A, q_end, (i64)nq + 16);
-        }
+    const u32 g = blockIdx.x * (KD_T / 32) + (threadIdx.x >> 5), nw = gridDim.x * (KD_T / 32);
+    const u32 r0 = row_lo + (u32)((u64)g * n_rows / nw), r1 = row_lo + (u32)((u64)(g + 1) * n_rows / nw);
+    if (r0 >= r1) return;
+    u32 word = r0 * 31 + lane;                                       // my 32 positions = bit-array word `word`
+    const uint4 *p = reinterpret_cast<const uint4 *>(A8 + (u64)word * 32);
+    u32 *pm = mask32 + word;
+    u32 acc = 0;                                                     // triggers of my words in tile word >> 10
+    uint4 u0 = __ldg(p), u1 = __ldg(p + 1);
+    for (u32 row = r0; row < r1; row++) {
         u32 bad = 0;
         const u32 S1 = dna_pack16(u0, bad), S2 = dna_pack16(u1, bad);
+        // the bytes are packed: their registers take the next row, which has the rest of this one to arrive
+        p += 62;
+        if (row + 1 < r1) { u0 = __ldg(p); u1 = __ldg(p + 1); }
         const u32 S0 = __shfl_up_sync(0xffffffffu, S2, 1);          // the 16 symbols in front of my run
-        const bool any_bad = __any_sync(0xffffffffu, bad != 0);
-        u32 m;
-        if (!any_bad) {
+        if (!__any_sync(0xffffffffu, bad != 0)) {
             const u32 S[3] = {S0, S1, S2};
-            m = ke_row_bits(S, rep_lane, xt, C, cthr);
-        } else {
-            const u64 q = (u64)word * 32;
-            m = kd_row_by_arithmetic<W>(u0, u1, lane, C, q, q_lo >= (u64)(W - 1) ? q_lo - (u64)(W - 1) : 0, q_end,
-                                        true, alpha);
+            const u32 m = ke_row_bits(S, rep_lane, xt, C, cthr);
+            if (lane != 0) {
+                *pm = m;
+                acc += __popc(m);
+            }
+        } else if (lane == 0) {
+            redo[atomicAdd(redo_n, 1u)] = row;
         }
-        bool mine = lane != 0;
-        if (!fast) {
-            mine = (lane != 0 || row == 0) && word < nwords;
-            m = ke_clip_row(m, word, q_lo, q_hi);
+        const u32 nword = word + 31;
+        if (((nword ^ word) >> 10) != 0 && acc) {                    // my next word lies in the next tile
+            atomicAdd(&tile_cnt[word >> 10], acc);
+            acc = 0;
         }
+        word = nword;
+        pm += 31;
+    }
+    if (acc) atomicAdd(&tile_cnt[(word - 31) >> 10], acc);
+}
+
+// The rows the loop above does not take: the first and last rows of the buffer (clipped to
+// [q_lo, q_hi), partial 16-byte units, the padding words of the last tile) and the rows of the
+// `redo` list, by the rolling arithmetic -- exact for any bytes.
+template <int W>
+__global__ void __launch_bounds__(256) kr_scan_rows_k(const uint4 *__restrict__ A, u64 q_end, u64 q_lo, u64 q_hi,
+                                                      pfp_scan_consts C, u32 *__restrict__ mask32,
+                                                      u32 *__restrict__ tile_cnt, u32 nwords, u32 nrows,
+                                                      u32 fast_lo, u32 fast_n, const u32 *__restrict__ redo,
+                                                      const u32 *__restrict__ redo_n, u32 *__restrict__ alpha) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 nb = nrows - fast_n, total = nb + *redo_n;
+    for (u32 idx = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); idx < total; idx += gridDim.x * (blockDim.x / 32)) {
+        const u32 row = idx < fast_lo ? idx : idx < nb ? idx + fast_n : redo[idx - nb];
+        const u32 word = row * 31 + lane;
+        const u64 q = (u64)word * 32;
+        const uint4 u0 = kd_load_unit(A, q_end, (i64)q), u1 = kd_load_unit(A, q_end, (i64)q + 16);
+        u32 m = kd_row_by_arithmetic<W>(u0, u1, lane, C, q, q_lo >= (u64)(W - 1) ? q_lo - (u64)(W - 1) : 0, q_end, true, alpha);
+        const bool mine = (lane != 0 || row == 0) && word < nwords;
+        if (q < q_lo || q + 32 > q_hi) m &= range_mask32(q, q_lo, q_hi);
         if (!mine) m = 0;
         if (mine) mask32[word] = m;
-        // per-tile counts: the words 31 row + 1 .. 31 row + 31 of a row lie in at most two tiles (1024 words each)
+        // per-tile counts: the words of a row lie in at most two tiles
         const u32 c = __popc(m);
-        const u32 t0 = (row * 31 + 1) >> 10, t1 = (row * 31 + 31) >> 10;
-        const u32 call = __reduce_add_sync(0xffffffffu, c);
-        if (t0 == t1) {
-            if (lane == 0 && call) atomicAdd(&tile_cnt[t0], call);
-        } else {
-            const u32 c1 = __reduce_add_sync(0xffffffffu, (word >> 10) == t1 && lane != 0 ? c : 0u);
-            if (lane == 0) {
-                if (call - c1) atomicAdd(&tile_cnt[t0], call - c1);
-                if (c1) atomicAdd(&tile_cnt[t1], c1);
-            }
+        const u32 t0 = (row * 31 + 1) >> 10;
+        const bool in0 = (word >> 10) == t0 || lane == 0;
+        const u32 c0 = __reduce_add_sync(0xffffffffu, in0 ? c : 0u);
+        const u32 c1 = __reduce_add_sync(0xffffffffu, in0 ? 0u : c);
+        if (lane == 0) {
+            if (c0) atomicAdd(&tile_cnt[t0], c0);
+            if (c1) atomicAdd(&tile_cnt[t0 + 1], c1);
         }
     }
 }
@@ -603,20 +608,31 @@ static cudaError_t launch_scan_dna(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A,
 
 template <int W>
 static cudaError_t launch_scan_iv(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, u64 q_end, u64 q_lo, u64 q_hi,
-                                  const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt) {
+                                  const pfp_scan_consts &C, uint4 *mask, u32 *tile_cnt, u32 *redo) {
     const u32 nwords = ntiles * (u32)(K1_TILE / 32);      // every word of every tile gets written
+    const u32 nrows = (nwords + 30) / 31;
     // rows that need no clipping: all 1024 positions inside [q_lo, q_hi) and inside whole 16-byte units
     const u64 lim = q_hi < (q_end & ~(u64)15) ? q_hi : (q_end & ~(u64)15);
     u64 f_lo = (q_lo + 991) / 992;
     if (f_lo < 1) f_lo = 1;
     const u64 f_hi = lim >= 1024 ? (lim - 1024) / 992 + 1 : 0;
-    const u32 fast_lo = (u32)f_lo, fast_n = f_hi > f_lo ? (u32)(f_hi - f_lo) : 0u;
-    kr_scan_iv_k<W><<<ctx->sm_count, KD_T, KE_SMEM, ctx->stream>>>(A, q_end, q_lo, q_hi, C, ctx->iv_etab, ctx->iv_xtab,
-                                                                   ctx->iv_cthr, reinterpret_cast<u32 *>(mask),
-                                                                   tile_cnt, nwords, fast_lo, fast_n, ctx->d_alpha);
+    const u32 fast_lo = f_hi > f_lo ? (u32)f_lo : 0u, fast_n = f_hi > f_lo ? (u32)(f_hi - f_lo) : 0u;
+    u32 *redo_n = reinterpret_cast<u32 *>(&ctx->d_flags[3]);
+    if (fast_n) {
+        kr_scan_ivf_k<<<ctx->sm_count, KD_T, KE_SMEM, ctx->stream>>>(reinterpret_cast<const unsigned char *>(A), C,
+                                                                    ctx->iv_etab, ctx->iv_xtab, ctx->iv_cthr,
+                                                                    reinterpret_cast<u32 *>(mask), tile_cnt,
+                                                                    fast_lo, fast_n, redo, redo_n);
+        ctx->launches++;
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    kr_scan_rows_k<W><<<ctx->sm_count, 256, 0, ctx->stream>>>(A, q_end, q_lo, q_hi, C, reinterpret_cast<u32 *>(mask),
+                                                              tile_cnt, nwords, nrows, fast_lo, fast_n, redo, redo_n,
+                                                              ctx->d_alpha);
     return cudaGetLastError();
 }
-#define KE_CASE(W) case W: le = launch_scan_iv<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt); break;
+#define KE_CASE(W) case W: le = launch_scan_iv<W>(ctx, ntiles, A, q_end, q_lo, q_hi, C, mask, tile_cnt, redo); break;
 
 template <int W> static cudaError_t scan_attr() {
     cudaError_t e = cudaFuncSetAttribute(kr_scan_k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
@@ -624,9 +640,6 @@ template <int W> static cudaError_t scan_attr() {
         e = cudaFuncSetAttribute(kr_scan_dna_k<(W <= KD_MAXW ? W : KD_MAXW)>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((((size_t)1 << (2 * (W <= KD_MAXW ? W : KD_MAXW))) + 31) / 32 * 4));
-    if (e == cudaSuccess && W <= KD_MAXW)
-        e = cudaFuncSetAttribute(kr_scan_iv_k<(W <= KD_MAXW ? W : KD_MAXW)>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KE_SMEM);
     return e;
 }
 
@@ -637,6 +650,7 @@ int pfp_scan_init(pfpb200_ctx *ctx) {
     K1_ATTR(11) K1_ATTR(12) K1_ATTR(13) K1_ATTR(14) K1_ATTR(15) K1_ATTR(16)
     K1_ATTR(20) K1_ATTR(24) K1_ATTR(28) K1_ATTR(31) K1_ATTR(32)
 #undef K1_ATTR
+    PFP_CUDA(ctx, cudaFuncSetAttribute(kr_scan_ivf_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KE_SMEM));
     u32 h[33];
     for (int i = 0; i < 32; i++) h[i] = 1u << i;
     h[32] = 0;
@@ -721,11 +735,19 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
     PfpEvents evs(2);
     if (!evs.ok) return pfp_fail(ctx, PFPB200_E_CUDA, "cudaEventCreate failed");
     const cudaEvent_t e0 = evs[0], e1 = evs[1];
-    const bool dna = w <= (u32)KD_MAXW && ctx->k1_mode != 1;
+    // a text that is not DNA (most rows of the previous scan went to the arithmetic) is scanned by the
+    // rolling kernel directly; the interval form is tried again every eighth call
+    const bool not_dna = ctx->k1_mode == 0 && ctx->iv_skip > 0 && ctx->iv_skip-- > 0;
+    const bool dna = w <= (u32)KD_MAXW && ctx->k1_mode != 1 && !not_dna;
     // interval form: p must be invertible modulo PW and the threshold must leave the 16-bit range alone
     const bool iv = dna && ctx->k1_mode == 0 && p >= 10 && p < PFP_PW && (u64)ntiles * (K1_TILE / 32) < 0xFFFFFF00ull;
-    if (iv) PFP_TRY(ensure_iv_tables(ctx, C));
-    else if (dna) PFP_TRY(ensure_dna_table(ctx, C));
+    u32 *redo = nullptr;                                   // rows the interval form hands to the arithmetic
+    if (iv) {
+        PFP_TRY(ensure_iv_tables(ctx, C));
+        PFP_TRY(pfp_alloc_t(ctx, &redo, (size_t)ntiles * (K1_TILE / 32) / 31 + 2, false));
+    } else if (dna) {
+        PFP_TRY(ensure_dna_table(ctx, C));
+    }
     PFP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     ctx->alpha_valid = false;
     if (dna) {
@@ -733,6 +755,7 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
         PFP_CUDA(ctx, cudaMemsetAsync(tile_cnt, 0, (size_t)ntiles * sizeof(u32), ctx->stream));
         PFP_CUDA(ctx, cudaMemsetAsync(ctx->d_alpha, 0, 8 * sizeof(u32), ctx->stream));
         ctx->alpha_valid = buf_pos0 == 0 && own_lo == 0;       // the whole text of a single-GPU parse
+        if (iv) PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[3], 0, sizeof(u64), ctx->stream));
         cudaError_t le = cudaSuccess;
         if (iv) {
             switch ((int)w) {
@@ -747,7 +770,7 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
         }
         ctx->launches++;
         if (le != cudaSuccess)
-            return pfp_fail(ctx, PFPB200_E_CUDA, "%s launch: %s", iv ? "kr_scan_iv_k" : "kr_scan_dna_k", cudaGetErrorString(le));
+            return pfp_fail(ctx, PFPB200_E_CUDA, "%s launch: %s", iv ? "kr_scan_ivf_k / kr_scan_rows_k" : "kr_scan_dna_k", cudaGetErrorString(le));
     } else {
         switch (w <= K1_MAXW_FAST ? (int)w : 0) {
             K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7) K1_CASE(8) K1_CASE(9) K1_CASE(10)
@@ -760,6 +783,7 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
         PFP_LAUNCHED(ctx);
     }
     PFP_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    if (redo) PFP_TRY(pfp_free_now(ctx, redo));
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[5], 0, sizeof(u64), ctx->stream));
     PFP_TRY(pfp_exclusive_scan_u32_u64(ctx, tile_cnt, tile_off, ntiles, &ctx->d_flags[1]));
     tile_max_k<<<ctx->sm_count, 256, 0, ctx->stream>>>(tile_cnt, ntiles,
@@ -775,6 +799,7 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
     sb->mask = mask; sb->tile_cnt = tile_cnt; sb->tile_off = tile_off;
     sb->total = ctx->h_flags[1];
     sb->max_tile_cnt = (u32)ctx->h_flags[5];
+    if (iv && (u64)(u32)ctx->h_flags[3] * 4 > (u64)ntiles * (K1_TILE / 32) / 31) ctx->iv_skip = 7;
     return PFPB200_OK;
 }
 
