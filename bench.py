@@ -247,7 +247,7 @@ def load_peaks():
 def scan_kernel_name():
     """K1 of the benchmarked configuration (w=10): the interval form unless PFPB200_K1=rolling / table."""
     mode = os.environ.get("PFPB200_K1")
-    return "kr_scan_k<10>" if mode == "rolling" else "kr_scan_dna_k<10>" if mode == "table" else "kr_scan_iv_k<10>"
+    return "kr_scan_k<10>" if mode == "rolling" else "kr_scan_dna_k<10>" if mode == "table" else "kr_scan_ivf_k"
 
 
 def load_traffic(n_text):
