@@ -158,6 +158,7 @@ void pfp_release_scratch(pfpb200_ctx *ctx) {
 void pfp_release_held(pfpb200_ctx *ctx) {
     for (void *p : ctx->held) arena_give(ctx->arena, p);
     ctx->held.clear();
+    ctx->bp_out[0] = ctx->bp_out[1] = ctx->bp_out[2] = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libpfpb200.so")
 CLI_PATH = os.path.join(PKG_DIR, "gpuscan.x")
+BWTPARSE_CLI_PATH = os.path.join(PKG_DIR, "gpubwtparse.x")
 
 F_SAI, F_FASTA, F_COMPRESS, F_VERBOSE, F_VERIFY = 1, 2, 4, 8, 16
 
@@ -53,6 +54,25 @@ class Outputs(C.Structure):
                 ("last", C.c_void_p), ("sai", C.c_void_p)]
 
 
+class BwtParseResult(C.Structure):
+    """include/pfpb200.h: pfpb200_bwtparse_result."""
+    _fields_ = [("ilist", C.c_void_p), ("bwlast", C.c_void_p), ("bwsai", C.c_void_p), ("n_out", C.c_uint64),
+                ("alphabet", C.c_uint64), ("rounds", C.c_uint32), ("launches", C.c_uint32),
+                ("ms_sa", C.c_float), ("ms_lists", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ilist", "bwlast", "bwsai")}
+
+
+@dataclass
+class BwtParseFiles:
+    """.ilist / .bwlast / .bwsai as bytes (host copies)."""
+    ilist: bytes
+    bwlast: bytes
+    bwsai: bytes
+    stats: dict = field(default_factory=dict)
+
+
 @dataclass
 class PfpFiles:
     """The five output streams as bytes (host copies)."""
@@ -87,6 +107,7 @@ SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_p
            "pfpb200_multi_parse_host", "pfpb200_multi_parse_file", "pfpb200_multi_last_error",
            "pfpb200_multi_phase_ms",
            "pfpb200_check_dict_order",
+           "pfpb200_bwtparse_device", "pfpb200_bwtparse_host", "pfpb200_bwtparse_file",
            "pfpb200_launch_count", "pfpb200_last_error", "pfpb200_abi_version"]
 
 
@@ -125,6 +146,12 @@ def load_library():
     L.pfpb200_abi_version.restype = C.c_int
     L.pfpb200_launch_count.argtypes = [vp]
     L.pfpb200_launch_count.restype = C.c_uint32
+    L.pfpb200_bwtparse_device.argtypes = [vp, vp, u64, vp, vp, C.POINTER(BwtParseResult)]
+    L.pfpb200_bwtparse_device.restype = C.c_int
+    L.pfpb200_bwtparse_host.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, C.POINTER(BwtParseResult)]
+    L.pfpb200_bwtparse_host.restype = C.c_int
+    L.pfpb200_bwtparse_file.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(BwtParseResult)]
+    L.pfpb200_bwtparse_file.restype = C.c_int
     L.pfpb200_multi_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
     L.pfpb200_multi_create.restype = C.c_int
     L.pfpb200_multi_destroy.argtypes = [vp]
@@ -260,6 +287,36 @@ class Scanner:
         o = Opts(w, p, _flags(sai, fasta, compress), nseg)
         self._check(self.L.pfpb200_parse_file(self.h, os.fsencode(path), C.byref(o), C.byref(self.stats)))
         return self.stats.as_dict()
+
+    # -- the stage after the parse: bwtparse (bwtparse.c) ---------------------------------------------
+    def bwtparse_device(self, parse_ptr: int, n: int, last_ptr: int, sai_ptr: int | None = None) -> BwtParseResult:
+        """Device pointers in (e.g. the Outputs of parse_device on this scanner), device pointers out."""
+        r = BwtParseResult()
+        self._check(self.L.pfpb200_bwtparse_device(self.h, C.c_void_p(parse_ptr), n, C.c_void_p(last_ptr),
+                                                   C.c_void_p(sai_ptr or 0), C.byref(r)))
+        return r
+
+    def bwtparse_host(self, parse: bytes, last: bytes, sai: bytes | None = None) -> BwtParseFiles:
+        """.parse / .last / .sai bytes in, .ilist / .bwlast / .bwsai bytes out."""
+        pa = np.frombuffer(parse, dtype=np.uint32)
+        la = np.frombuffer(last, dtype=np.uint8)
+        n = pa.size
+        sa = np.frombuffer(sai, dtype=np.uint8) if sai else None
+        il = np.empty(n + 1, dtype=np.uint32)
+        bl = np.empty(n + 1, dtype=np.uint8)
+        bs = np.empty(5 * (n + 1), dtype=np.uint8) if sai else None
+        r = BwtParseResult()
+        self._check(self.L.pfpb200_bwtparse_host(self.h, C.c_void_p(pa.ctypes.data if n else 0), n,
+                                                 C.c_void_p(la.ctypes.data if n else 0),
+                                                 C.c_void_p(sa.ctypes.data) if sai else None,
+                                                 C.c_void_p(il.ctypes.data), C.c_void_p(bl.ctypes.data),
+                                                 C.c_void_p(bs.ctypes.data) if sai else None, C.byref(r)))
+        return BwtParseFiles(il.tobytes(), bl.tobytes(), bs.tobytes() if sai else b"", r.as_dict())
+
+    def bwtparse_file(self, basename, sai=False, nseg=0) -> dict:
+        r = BwtParseResult()
+        self._check(self.L.pfpb200_bwtparse_file(self.h, os.fsencode(basename), 1 if sai else 0, nseg, C.byref(r)))
+        return r.as_dict()
 
     def check_dict_order(self, dict_dev, seps_dev) -> int:
         """Adjacent pairs of the .dict stream (CUDA uint8 tensor) that are not strictly increasing;

@@ -301,6 +301,41 @@ int pfpb200_dict_merge_finish(pfpb200_ctx *ctx, const uint64_t *pool, uint64_t p
  * pfpb200_parse_* / pfpb200_shard_scan call). */
 uint32_t pfpb200_launch_count(const pfpb200_ctx *ctx);
 
+/* ---- the stage after the parse: bwtparse ---------------------------------- *
+ * Replaces main() of bwtparse.c (:218-322): the suffix array of the parse T[0..n] (n symbols of
+ * .parse + the end symbol 0, sacak_int(), bwtparse.c:162-174), its BWT, and from them
+ *   .ilist  : for every parse symbol in alphabetical order (end symbol first) the BWT positions
+ *             where it occurs -- (n+1) u32 (bwtparse.c:276-306)
+ *   .bwlast : .last permuted by the suffix array -- n+1 bytes (:243-262)
+ *   .bwsai  : .sai permuted the same way -- 5 (n+1) bytes, with -s (:247,:256,:266)
+ * exactly as pfbwt*.x reads them.  Limits as the reference: 2 <= n <= 2^32-2 (bwtparse.c:101,241).
+ * The result's device pointers are owned by the context and stay valid until its next
+ * pfpb200_bwtparse_* or parse call; the outputs of a previous parse on the same context stay valid
+ * across this call, so pfpb200_parse_device -> pfpb200_bwtparse_device chains without a copy. */
+typedef struct pfpb200_bwtparse_result {
+    const uint32_t *ilist;     /* [n_out] device                                                 */
+    const uint8_t  *bwlast;    /* [n_out] device                                                 */
+    const uint8_t  *bwsai;     /* [5 n_out] device, NULL without .sai input                      */
+    uint64_t n_out;            /* n + 1: "ilist positions written"                               */
+    uint64_t alphabet;         /* largest parse symbol + 1 (the k+1 of bwtparse.c:233)           */
+    uint32_t rounds;           /* prefix-doubling rounds of the suffix sort                      */
+    uint32_t launches;         /* kernels launched                                               */
+    float ms_sa, ms_lists, ms_total;   /* CUDA-event times: suffix array; BWT + lists; both      */
+} pfpb200_bwtparse_result;
+
+int pfpb200_bwtparse_device(pfpb200_ctx *ctx, const uint32_t *d_parse, uint64_t n_phrases,
+                            const uint8_t *d_last, const uint8_t *d_sai /* may be NULL */,
+                            pfpb200_bwtparse_result *res);
+/* host buffers in, host buffers out: ilist[n+1], bwlast[n+1], bwsai[5(n+1)] (NULL iff sai is NULL) */
+int pfpb200_bwtparse_host(pfpb200_ctx *ctx, const uint32_t *parse, uint64_t n_phrases,
+                          const uint8_t *last, const uint8_t *sai, uint32_t *ilist, uint8_t *bwlast,
+                          uint8_t *bwsai, pfpb200_bwtparse_result *res);
+/* `bwtparse <basename> [-s] [-t nseg]`: reads <basename>.parse, .last and (sa_info) .sai -- as nseg
+ * segment files <basename>.<i>.last|sai when nseg > 0 (utils.c:57-110) -- and writes .ilist,
+ * .bwlast and .bwsai (the device copies stay available through res, as above). */
+int pfpb200_bwtparse_file(pfpb200_ctx *ctx, const char *basename, int sa_info, int nseg,
+                          pfpb200_bwtparse_result *res);
+
 const char *pfpb200_strerror(int code);
 /* Message of the last failure on this context (CUDA error string, file name, ...). */
 const char *pfpb200_last_error(const pfpb200_ctx *ctx);

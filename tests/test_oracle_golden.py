@@ -2,6 +2,8 @@
 
 The golden fixtures were produced by the unmodified newscanNT.x (tools/make_golden.py); when
 oracle/_ref is present (build container, GPU box) the reference is also run live."""
+import os
+
 import numpy as np
 import pytest
 
@@ -68,3 +70,32 @@ def test_fasta_extract_matches_live_reference(pkg):
     text, trunc = orc.fasta_extract(fa)
     assert not trunc and text == b"".join(r.tobytes() for r in recs)
     assert_same_files(orc.parse(text), orc.run_reference(fa, fasta=True), "fasta live")
+
+
+# ---- the bwtparse stage: oracle/bwtparse_oracle.py against the reference binary ----
+def _bwtparse_golden():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_bwtparse.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    return {n: {f: (z[f"{n}/{f}"].tobytes() if z[f"{n}/{f}"].ndim else int(z[f"{n}/{f}"]))
+                for f in ("w", "p", "parse", "last", "sai", "occ", "ilist", "bwlast", "bwsai")} for n in names}
+
+
+def test_bwtparse_oracle_matches_golden():
+    from oracle import bwtparse_oracle as bo
+    cases = _bwtparse_golden()
+    assert len(cases) >= 6
+    for name, c in cases.items():
+        il, bl, bs = bo.bwtparse(c["parse"], c["last"], c["sai"])
+        assert il == c["ilist"] and bl == c["bwlast"] and bs == c["bwsai"], name
+        il2, bl2, bs2 = bo.bwtparse(c["parse"], c["last"], None)
+        assert il2 == c["ilist"] and bl2 == c["bwlast"] and bs2 == b"", name
+
+
+@pytest.mark.skipif(not orc.have_ref("bwtparse"), reason="oracle/_ref not built")
+def test_bwtparse_oracle_matches_live_reference(pkg):
+    from oracle import bwtparse_oracle as bo
+    text = pkg.synth.pangenome_text(30000, 10, 77).numpy().tobytes()
+    f = orc.parse(text, 8, 40)
+    for nseg in (0, 3):
+        want = bo.run_reference(f.parse, f.last, f.sai, f.occ, nseg=nseg)
+        assert bo.bwtparse(f.parse, f.last, f.sai) == want, f"nseg={nseg}"
