@@ -159,6 +159,7 @@ void pfp_release_held(pfpb200_ctx *ctx) {
     for (void *p : ctx->held) arena_give(ctx->arena, p);
     ctx->held.clear();
     ctx->bp_out[0] = ctx->bp_out[1] = ctx->bp_out[2] = nullptr;
+    ctx->up_out = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------

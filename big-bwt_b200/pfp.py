@@ -17,6 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libpfpb200.so")
 CLI_PATH = os.path.join(PKG_DIR, "gpuscan.x")
 BWTPARSE_CLI_PATH = os.path.join(PKG_DIR, "gpubwtparse.x")
+UNPARSE_CLI_PATH = os.path.join(PKG_DIR, "gpuunparse.x")
 
 F_SAI, F_FASTA, F_COMPRESS, F_VERBOSE, F_VERIFY = 1, 2, 4, 8, 16
 
@@ -108,6 +109,7 @@ SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_p
            "pfpb200_multi_phase_ms",
            "pfpb200_check_dict_order",
            "pfpb200_bwtparse_device", "pfpb200_bwtparse_host", "pfpb200_bwtparse_file",
+           "pfpb200_unparse_device", "pfpb200_unparse_file",
            "pfpb200_launch_count", "pfpb200_last_error", "pfpb200_abi_version"]
 
 
@@ -317,6 +319,27 @@ class Scanner:
         r = BwtParseResult()
         self._check(self.L.pfpb200_bwtparse_file(self.h, os.fsencode(basename), 1 if sai else 0, nseg, C.byref(r)))
         return r.as_dict()
+
+    # -- the inverse of the parse: unparse (unparse.c) ---------------------------------------------------
+    def unparse_device(self, dict_ptr: int, dict_bytes: int, parse_ptr: int, n: int, strip_w: int = 0):
+        """(device pointer, length, ms) of the text rebuilt from .dicz (strip_w = 0) or .dict (strip_w = w)
+        bytes and the parse, all in HBM."""
+        self.L.pfpb200_unparse_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64,
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+        self.L.pfpb200_unparse_device.restype = C.c_int
+        ptr, nt, ms = C.c_void_p(), C.c_uint64(), C.c_float()
+        self._check(self.L.pfpb200_unparse_device(self.h, C.c_void_p(dict_ptr), dict_bytes, strip_w, C.c_void_p(parse_ptr),
+                                                  n, C.byref(ptr), C.byref(nt), C.byref(ms)))
+        return ptr.value, nt.value, ms.value
+
+    def unparse_file(self, basename, outname=None) -> dict:
+        self.L.pfpb200_unparse_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64),
+                                                C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+        self.L.pfpb200_unparse_file.restype = C.c_int
+        nw, nt, ms = C.c_uint64(), C.c_uint64(), C.c_float()
+        self._check(self.L.pfpb200_unparse_file(self.h, os.fsencode(basename), os.fsencode(outname) if outname else None,
+                                                C.byref(nw), C.byref(nt), C.byref(ms)))
+        return {"n_words": nw.value, "n_text": nt.value, "ms": ms.value}
 
     def check_dict_order(self, dict_dev, seps_dev) -> int:
         """Adjacent pairs of the .dict stream (CUDA uint8 tensor) that are not strictly increasing;

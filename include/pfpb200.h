@@ -336,6 +336,20 @@ int pfpb200_bwtparse_host(pfpb200_ctx *ctx, const uint32_t *parse, uint64_t n_ph
 int pfpb200_bwtparse_file(pfpb200_ctx *ctx, const char *basename, int sa_info, int nseg,
                           pfpb200_bwtparse_result *res);
 
+/* ---- the inverse of the parse: unparse ------------------------------------ *
+ * Replaces main() of unparse.c (:76-137): the text is the concatenation, over the symbols of
+ * .parse, of the words of .dicz (`newscan -c`, newscan.cpp:410-413: words without their last w
+ * bytes, the first one without its leading 0x02).  strip_w = 0: d_dict holds .dicz bytes;
+ * strip_w = w > 0: d_dict holds plain .dict bytes and the same bytes are skipped on the fly.
+ * *d_text is owned by the context (valid until its next unparse or parse call); the outputs of a
+ * previous parse on the same context stay valid, so parse -> unparse runs without a copy. */
+int pfpb200_unparse_device(pfpb200_ctx *ctx, const uint8_t *d_dict, uint64_t dict_bytes, uint32_t strip_w,
+                           const uint32_t *d_parse, uint64_t n_phrases, const uint8_t **d_text,
+                           uint64_t *n_text, float *ms);
+/* `unparse <basename> [-o outname]`: <basename>.dicz + <basename>.parse -> outname (NULL: <basename>.out) */
+int pfpb200_unparse_file(pfpb200_ctx *ctx, const char *basename, const char *outname, uint64_t *n_words,
+                         uint64_t *n_text, float *ms);
+
 const char *pfpb200_strerror(int code);
 /* Message of the last failure on this context (CUDA error string, file name, ...). */
 const char *pfpb200_last_error(const pfpb200_ctx *ctx);

@@ -8,7 +8,8 @@ host reconstruction of a text prefix from .dict + .parse):
   * .sai strictly increasing, last value n + w; .last[j] == T[sai[j] - w - 1]
   * every phrase end is a trigger: T[sai-w .. sai) hashes to 0 mod p (re-computed with torch)
   * .dict: d words, EVERY adjacent pair strictly increasing (device kernel), 0x01 terminators, final 0x00
-  * unparse of the first 200 000 phrases == the text prefix
+  * unparse of the first 200 000 phrases == the text prefix (host), and the FULL round trip on the device:
+    pfpb200_unparse_device(.dict, .parse) == text, every byte
 and, where tests/golden/fullsize_sha256.json holds them (tools/make_fullsize_digests.py ran the
 unmodified newscanNT.x on the same full-size text in the build container), BYTE-EXACT parity:
 sha256 of each of the five streams == the reference's.
@@ -139,6 +140,19 @@ def check_case(sc, text, w, p, name, digest_key=None, text_key=None, prefix_phra
             if got[e] != want[e]: fails.append(f".{e} sha256 differs from newscanNT.x")
     else:
         res["sha256_vs_reference"] = None
+    # the round trip at full size, every byte, on the device: unparse(.dict, .parse) == text
+    # (pfpb200_unparse_device keeps the outputs of the parse alive; reference: unparse.c)
+    del parse, occ, last, sai, pos
+    torch.cuda.empty_cache()
+    try:
+        ptr, nt, ms_up = sc.unparse_device(out.dict, out.dict_bytes, out.parse, P, strip_w=w)
+        torch.cuda.synchronize()
+        same = nt == n and bool(torch.equal(view(ptr, nt), text))
+        res["unparse_round_trip"] = {"bytes": nt, "ms": round(ms_up, 3), "ok": same}
+        if not same: fails.append("unparse(.dict, .parse) != text")
+    except Exception as e:  # noqa: BLE001
+        res["unparse_round_trip"] = {"error": str(e)[:200]}
+        fails.append("unparse failed")
     res["ok"] = not fails
     res["fails"] = fails
     print(json.dumps(res), flush=True)
