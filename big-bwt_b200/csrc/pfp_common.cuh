@@ -70,8 +70,8 @@ struct pfpb200_ctx {
     bool alpha_valid = false;
     u32 *dna_table = nullptr;      // 4^w-bit trigger table of (dna_w, dna_p) for the DNA scan (w <= 10)
     u32 dna_w = 0, dna_p = 0;
-    u32 *iv_etab = nullptr;        // interval form of the DNA scan: 1024 x {a16 + 2, b16} of (iv_w, iv_p)
-    uint2 *iv_xtab = nullptr;      //   and the exact partial hashes {Ah, Bl}
+    void *iv_etab = nullptr;       // interval form of the DNA scan, tables of (iv_w, iv_p): 1024 x {a16 + 2, b16} (w <= 10)
+    void *iv_xtab = nullptr;       //   or 256 x {f1 f0, f3 f2} (w <= 16); and the exact partial hashes {Ah, Bl} / {F0..F3}
     u32 iv_w = 0, iv_p = 0, iv_cthr = 0;
     int iv_skip = 0;               // > 0: the last scan found text that is not DNA, use the rolling kernel for this many calls
     bool no_scan_alpha = false;      // PFPB200_NO_SCAN_ALPHA=1: the ranking finds the alphabet of the words itself (A/B)

@@ -249,8 +249,8 @@ __device__ __noinline__ void kd_note_alphabet(uint4 u0, uint4 u1, u64 q, u64 q_t
     }
 }
 
-// byte j (-12 <= j < 32) of {three words in front, eight words of the lane}
-#define KD_BYTE(wd, j) (__byte_perm((wd)[((j) + 12) >> 2], 0u, 0x4440u | (((j) + 12) & 3)))
+// byte j (-16 <= j < 32) of {four words in front, eight words of the lane}
+#define KD_BYTE(wd, j) (__byte_perm((wd)[((j) + 16) >> 2], 0u, 0x4440u | (((j) + 16) & 3)))
 
 // A row that holds something besides A C G T (or that an A/B run gives to the arithmetic): the
 // trigger bits of the lane's 32 positions by the rolling arithmetic of kr_scan_k, exact for any
@@ -259,13 +259,14 @@ template <int W>
 __device__ __noinline__ u32 kd_row_by_arithmetic(uint4 u0, uint4 u1, u32 lane, pfp_scan_consts C, u64 q, u64 q_text0,
                                                  u64 q_end, bool note, u32 *__restrict__ alpha) {
     if (note) kd_note_alphabet(u0, u1, q, q_text0, q_end, lane, alpha);
-    u32 wd[11];
-    wd[0] = __shfl_up_sync(0xffffffffu, u1.y, 1);
-    wd[1] = __shfl_up_sync(0xffffffffu, u1.z, 1);
-    wd[2] = __shfl_up_sync(0xffffffffu, u1.w, 1);
-    if (lane == 0) { wd[0] = 0; wd[1] = 0; wd[2] = 0; }   // only used by word 0: nothing in front
-    wd[3] = u0.x; wd[4] = u0.y; wd[5] = u0.z; wd[6] = u0.w;
-    wd[7] = u1.x; wd[8] = u1.y; wd[9] = u1.z; wd[10] = u1.w;
+    u32 wd[12];
+    wd[0] = __shfl_up_sync(0xffffffffu, u1.x, 1);
+    wd[1] = __shfl_up_sync(0xffffffffu, u1.y, 1);
+    wd[2] = __shfl_up_sync(0xffffffffu, u1.z, 1);
+    wd[3] = __shfl_up_sync(0xffffffffu, u1.w, 1);
+    if (lane == 0) { wd[0] = 0; wd[1] = 0; wd[2] = 0; wd[3] = 0; }   // only used by word 0: nothing in front
+    wd[4] = u0.x; wd[5] = u0.y; wd[6] = u0.z; wd[7] = u0.w;
+    wd[8] = u1.x; wd[9] = u1.y; wd[10] = u1.z; wd[11] = u1.w;
     u32 h = 0, m = 0;
 #pragma unroll
     for (int j = -W; j < 0; j++) h = pfp_push(h, KD_BYTE(wd, j));
@@ -406,19 +407,93 @@ __global__ void dna_etab_k(pfp_scan_consts C, u32 uinv, u32 *__restrict__ etab, 
     etab[x] = (((a16 + 2u) & 0xFFFFu) << 16) | b16;
 }
 
-// (bits [b, b+10) of the 96-bit stream {S[0], S[1], S[2]}) << 7, other bits undefined
-template <int B>
+// (bits [b, b+NB) of the 96-bit stream {S[0], S[1], S[2]}) << 7, other bits undefined
+template <int B, int NB = 10>
 __device__ __forceinline__ u32 ke_block_x128(const u32 (&S)[3]) {
     constexpr int k = B >> 5, sh = B & 31;
     if constexpr (sh < 7) return S[k] * kd_pow2[7 - sh];                      // IMAD (FMA pipe)
-    else if constexpr (sh + 10 <= 32) return shr_fma(S[k], sh - 7);           // IMAD.HI
-    else return __funnelshift_r(S[k], S[k + 1], sh - 7);                      // SHF (ALU pipe), 4 of 16
+    else if constexpr (sh + NB <= 32) return shr_fma(S[k], sh - 7);           // IMAD.HI
+    else return __funnelshift_r(S[k], S[k + 1], sh - 7);                      // SHF (ALU pipe), a few of 16
 }
 
 template <int I>
 __device__ __forceinline__ u32 ke_lookup(const u32 (&S)[3], const unsigned char *rep_lane) {
     const u32 v = ke_block_x128<2 * (I + 12)>(S);                   // block of the symbols I-4 .. I
     return *reinterpret_cast<const u32 *>(rep_lane + (v & 0x1FF80u));
+}
+
+// ---- 11 <= w <= 16: FOUR blocks of 4 symbols (256 entries of 8 bytes, 16 replicas: every lane of a
+// half warp reads its own pair of banks).  The block ending at a position serves the windows
+// ending 0, 4, 8 and 12 positions later in roles 0..3; entry = {lo: f1 << 16 | f0, hi: f3 << 16 | f2},
+//     T = (lo[i] << 16) + lo[i-4] + (hi[i-8] << 16) + hi[i-12]
+// (the low halves add up to garbage that may carry once into the high half: with four floors the
+// true scaled sum lies in [t-1, t+4), the table carries a bias of 5 and the threshold is
+// floor(theta) + 7).  Candidates are decided exactly from the four exact partial hashes.
+constexpr u32 K4_ENT = 256;
+constexpr size_t K4_SMEM = (size_t)K4_ENT * 16 * 8 + (size_t)K4_ENT * 16;
+
+__global__ void dna_etab4_k(pfp_scan_consts C, u32 uinv, uint2 *__restrict__ etab, uint4 *__restrict__ xtab) {
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= K4_ENT) return;
+    u32 F[4], f16[4];
+    for (int r = 0; r < 4; r++) {                                    // role r: the block ends 4 r symbols before the window's end
+        u64 h = 0;
+        for (int j = 0; j < 4; j++) {                                // symbol j of the block, j = 0 oldest
+            const u32 dist = 4u * r + (3u - j);                      // distance from the window's last symbol
+            if (dist >= C.w) continue;
+            u64 c = (KD_LETTERS >> (8 * ((x >> (2 * j)) & 3u))) & 255u;
+            for (u32 k = 0; k < dist; k++) c = (c * 256) % PFP_PW;
+            h = (h + c) % PFP_PW;
+        }
+        F[r] = (u32)h;
+        f16[r] = (u32)((((h * uinv) % PFP_PW) << 16) / PFP_PW);
+    }
+    xtab[x] = make_uint4(F[0], F[1], F[2], F[3]);
+    etab[x] = make_uint2((f16[1] << 16) | f16[0], (((f16[3] + 5u) & 0xFFFFu) << 16) | f16[2]);
+}
+
+template <int I>
+__device__ __forceinline__ uint2 k4_lookup(const u32 (&S)[3], const unsigned char *rep_lane) {
+    const u32 v = ke_block_x128<2 * (I + 13), 8>(S);                // block of the symbols I-3 .. I
+    return *reinterpret_cast<const uint2 *>(rep_lane + (v & 0x7F80u));
+}
+
+__device__ __forceinline__ u32 k4_row_bits(const u32 (&S)[3], const unsigned char *rep_lane,
+                                           const uint4 *__restrict__ xt, const pfp_scan_consts &C, u32 cthr) {
+    u32 L[36], H[44];                                                // L[4 + i], H[12 + i]: block ending at position i
+#define K4_L(I) { const uint2 e = k4_lookup<I>(S, rep_lane); L[4 + I] = e.x; H[12 + I] = e.y; }
+    K4_L(20) K4_L(21) K4_L(22) K4_L(23) K4_L(24) K4_L(25) K4_L(26) K4_L(27) K4_L(28) K4_L(29) K4_L(30) K4_L(31)
+    K4_L(0) K4_L(1) K4_L(2) K4_L(3) K4_L(4) K4_L(5) K4_L(6) K4_L(7) K4_L(8) K4_L(9) K4_L(10) K4_L(11) K4_L(12)
+    K4_L(13) K4_L(14) K4_L(15) K4_L(16) K4_L(17) K4_L(18) K4_L(19)
+#undef K4_L
+#pragma unroll
+    for (int j = 0; j < 12; j++) H[j] = __shfl_up_sync(0xffffffffu, H[32 + j], 1);   // blocks ending at -12 .. -1
+#pragma unroll
+    for (int j = 0; j < 4; j++) L[j] = __shfl_up_sync(0xffffffffu, L[32 + j], 1);    // blocks ending at -4 .. -1
+    u32 m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const u32 T = (L[4 + i] * kd_pow2[16] + L[i]) + (H[4 + i] * kd_pow2[16] + H[i]);
+        asm("{\n\t.reg .pred c;\n\tsetp.lt.u32 c, %1, %2;\n\t@c or.b32 %0, %0, %3;\n\t}"
+            : "+r"(m) : "r"(T), "r"(cthr), "r"(1u << i));
+    }
+    u32 cand = m;
+    while (cand) {
+        const u32 bit = cand & (0u - cand);
+        cand ^= bit;
+        const u32 o = 2u * (u32)(31 - __clz(bit)) + 2u;              // first stream bit of the 16 symbols ending here
+        const bool k0 = o < 32u, k2 = o >= 64u;
+        const u32 lo = k0 ? S[0] : (k2 ? S[2] : S[1]);
+        const u32 hi = k0 ? S[1] : S[2];                             // k2: o = 64, shift 0, the upper word is not used
+        const u32 v = __funnelshift_r(lo, hi, o);                    // 32 bits: roles 3, 2, 1, 0 from the low byte up
+        u32 a = xt[v >> 24].x + xt[(v >> 16) & 255u].y, b = xt[(v >> 8) & 255u].z + xt[v & 255u].w;
+        a = min(a, a - PFP_PW);
+        b = min(b, b - PFP_PW);
+        u32 h = a + b;
+        h = min(h, h - PFP_PW);
+        if (!pfp_is_trigger(h, C.pinv, C.pshift, C.plimit)) m ^= bit;
+    }
+    return m;
 }
 
 // trigger bits of a lane's 32 positions; S = {16 symbols in front, 32 own symbols}, 2 bits each
@@ -463,20 +538,34 @@ __device__ __forceinline__ u32 ke_row_bits(const u32 (&S)[3], const unsigned cha
 // when the lane's word leaves its tile).  Rows overlap by one lane as in the bit-table form.
 // A row holding anything besides A C G T is not handled here: its number goes to `redo` and
 // kr_scan_rows_k does it by the rolling arithmetic -- this loop has no calls and no clipping.
+// BLK = 5: two blocks of 5 symbols (w <= 10); BLK = 4: four blocks of 4 symbols (11 <= w <= 16)
+template <int BLK>
 __global__ void __launch_bounds__(KD_T, 1) kr_scan_ivf_k(const unsigned char *__restrict__ A8, pfp_scan_consts C,
-                                                         const u32 *__restrict__ etab_g,
-                                                         const uint2 *__restrict__ xtab_g, u32 cthr,
+                                                         const void *__restrict__ etab_g,
+                                                         const void *__restrict__ xtab_g, u32 cthr,
                                                          u32 *__restrict__ mask32, u32 *__restrict__ tile_cnt,
                                                          u32 row_lo, u32 n_rows,
                                                          u32 *__restrict__ redo, u32 *__restrict__ redo_n) {
     extern __shared__ __align__(16) u32 ke_sm[];
-    u32 *rep = ke_sm;
-    uint2 *xt = reinterpret_cast<uint2 *>(ke_sm + KE_ENT * 32);
-    for (u32 i = threadIdx.x; i < KE_ENT * 32; i += KD_T) rep[i] = etab_g[i >> 5];
-    for (u32 i = threadIdx.x; i < KE_ENT; i += KD_T) xt[i] = xtab_g[i];
-    __syncthreads();
     const u32 lane = threadIdx.x & 31;
-    const unsigned char *rep_lane = reinterpret_cast<const unsigned char *>(rep) + lane * 4;
+    const unsigned char *rep_lane;
+    const void *xt_v;
+    if constexpr (BLK == 5) {
+        u32 *rep = ke_sm;
+        uint2 *xt = reinterpret_cast<uint2 *>(ke_sm + KE_ENT * 32);
+        for (u32 i = threadIdx.x; i < KE_ENT * 32; i += KD_T) rep[i] = static_cast<const u32 *>(etab_g)[i >> 5];
+        for (u32 i = threadIdx.x; i < KE_ENT; i += KD_T) xt[i] = static_cast<const uint2 *>(xtab_g)[i];
+        rep_lane = reinterpret_cast<const unsigned char *>(rep) + lane * 4;
+        xt_v = xt;
+    } else {
+        uint2 *rep = reinterpret_cast<uint2 *>(ke_sm);
+        uint4 *xt = reinterpret_cast<uint4 *>(ke_sm + K4_ENT * 16 * 2);
+        for (u32 i = threadIdx.x; i < K4_ENT * 16; i += KD_T) rep[i] = static_cast<const uint2 *>(etab_g)[i >> 4];
+        for (u32 i = threadIdx.x; i < K4_ENT; i += KD_T) xt[i] = static_cast<const uint4 *>(xtab_g)[i];
+        rep_lane = reinterpret_cast<const unsigned char *>(rep) + (lane & 15) * 8;
+        xt_v = xt;
+    }
+    __syncthreads();
     const u32 g = blockIdx.x * (KD_T / 32) + (threadIdx.x >> 5), nw = gridDim.x * (KD_T / 32);
     const u32 r0 = row_lo + (u32)((u64)g * n_rows / nw), r1 = row_lo + (u32)((u64)(g + 1) * n_rows / nw);
     if (r0 >= r1) return;
@@ -494,7 +583,9 @@ __global__ void __launch_bounds__(KD_T, 1) kr_scan_ivf_k(const unsigned char *__
         const u32 S0 = __shfl_up_sync(0xffffffffu, S2, 1);          // the 16 symbols in front of my run
         if (!__any_sync(0xffffffffu, bad != 0)) {
             const u32 S[3] = {S0, S1, S2};
-            const u32 m = ke_row_bits(S, rep_lane, xt, C, cthr);
+            u32 m;
+            if constexpr (BLK == 5) m = ke_row_bits(S, rep_lane, static_cast<const uint2 *>(xt_v), C, cthr);
+            else m = k4_row_bits(S, rep_lane, static_cast<const uint4 *>(xt_v), C, cthr);
             if (lane != 0) {
                 *pm = m;
                 acc += __popc(m);
@@ -619,10 +710,16 @@ static cudaError_t launch_scan_iv(pfpb200_ctx *ctx, u32 ntiles, const uint4 *A, 
     const u32 fast_lo = f_hi > f_lo ? (u32)f_lo : 0u, fast_n = f_hi > f_lo ? (u32)(f_hi - f_lo) : 0u;
     u32 *redo_n = reinterpret_cast<u32 *>(&ctx->d_flags[3]);
     if (fast_n) {
-        kr_scan_ivf_k<<<ctx->sm_count, KD_T, KE_SMEM, ctx->stream>>>(reinterpret_cast<const unsigned char *>(A), C,
-                                                                    ctx->iv_etab, ctx->iv_xtab, ctx->iv_cthr,
-                                                                    reinterpret_cast<u32 *>(mask), tile_cnt,
-                                                                    fast_lo, fast_n, redo, redo_n);
+        if (W <= 10)
+            kr_scan_ivf_k<5><<<ctx->sm_count, KD_T, KE_SMEM, ctx->stream>>>(reinterpret_cast<const unsigned char *>(A), C,
+                                                                           ctx->iv_etab, ctx->iv_xtab, ctx->iv_cthr,
+                                                                           reinterpret_cast<u32 *>(mask), tile_cnt,
+                                                                           fast_lo, fast_n, redo, redo_n);
+        else
+            kr_scan_ivf_k<4><<<ctx->sm_count, KD_T, K4_SMEM, ctx->stream>>>(reinterpret_cast<const unsigned char *>(A), C,
+                                                                           ctx->iv_etab, ctx->iv_xtab, ctx->iv_cthr,
+                                                                           reinterpret_cast<u32 *>(mask), tile_cnt,
+                                                                           fast_lo, fast_n, redo, redo_n);
         ctx->launches++;
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -650,7 +747,8 @@ int pfp_scan_init(pfpb200_ctx *ctx) {
     K1_ATTR(11) K1_ATTR(12) K1_ATTR(13) K1_ATTR(14) K1_ATTR(15) K1_ATTR(16)
     K1_ATTR(20) K1_ATTR(24) K1_ATTR(28) K1_ATTR(31) K1_ATTR(32)
 #undef K1_ATTR
-    PFP_CUDA(ctx, cudaFuncSetAttribute(kr_scan_ivf_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KE_SMEM));
+    PFP_CUDA(ctx, cudaFuncSetAttribute(kr_scan_ivf_k<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KE_SMEM));
+    PFP_CUDA(ctx, cudaFuncSetAttribute(kr_scan_ivf_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K4_SMEM));
     u32 h[33];
     for (int i = 0; i < 32; i++) h[i] = 1u << i;
     h[32] = 0;
@@ -685,16 +783,23 @@ static u32 inverse_mod_pw(u32 p) {
 // the two 1024-entry tables of the interval form for (w, p), cached in the context
 static int ensure_iv_tables(pfpb200_ctx *ctx, const pfp_scan_consts &C) {
     if (ctx->iv_etab && ctx->iv_w == C.w && ctx->iv_p == C.p) return PFPB200_OK;
-    if (!ctx->iv_etab) {
+    if (!ctx->iv_etab) {                                    // room for either scheme: 1024 x 4 / 256 x 8 and 1024 x 8 / 256 x 16 bytes
         PFP_CUDA(ctx, cudaMalloc(&ctx->iv_etab, KE_ENT * sizeof(u32)));
         PFP_CUDA(ctx, cudaMalloc(&ctx->iv_xtab, KE_ENT * sizeof(uint2)));
     }
     const u32 uinv = inverse_mod_pw(C.p);
-    dna_etab_k<<<KE_ENT / 256, 256, 0, ctx->stream>>>(C, uinv, ctx->iv_etab, ctx->iv_xtab);
-    PFP_LAUNCHED(ctx);
-    // theta = (K + 1) 2^16 / PW, K = (PW - 1) / p: every trigger has T < (floor(theta) + 4) << 16
+    // theta = (K + 1) 2^16 / PW, K = (PW - 1) / p: every trigger has T < (floor(theta) + 4) << 16 (+ 7 with four blocks)
     const u64 theta = (((u64)(PFP_PW - 1) / C.p + 1) << 16) / PFP_PW;
-    ctx->iv_cthr = (u32)((theta + 4) << 16);
+    if (C.w <= (u32)KD_MAXW) {
+        dna_etab_k<<<KE_ENT / 256, 256, 0, ctx->stream>>>(C, uinv, static_cast<u32 *>(ctx->iv_etab),
+                                                          static_cast<uint2 *>(ctx->iv_xtab));
+        ctx->iv_cthr = (u32)((theta + 4) << 16);
+    } else {
+        dna_etab4_k<<<1, K4_ENT, 0, ctx->stream>>>(C, uinv, static_cast<uint2 *>(ctx->iv_etab),
+                                                   static_cast<uint4 *>(ctx->iv_xtab));
+        ctx->iv_cthr = (u32)((theta + 7) << 16);
+    }
+    PFP_LAUNCHED(ctx);
     ctx->iv_w = C.w;
     ctx->iv_p = C.p;
     return PFPB200_OK;
@@ -738,9 +843,10 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
     // a text that is not DNA (most rows of the previous scan went to the arithmetic) is scanned by the
     // rolling kernel directly; the interval form is tried again every eighth call
     const bool not_dna = ctx->k1_mode == 0 && ctx->iv_skip > 0 && ctx->iv_skip-- > 0;
-    const bool dna = w <= (u32)KD_MAXW && ctx->k1_mode != 1 && !not_dna;
-    // interval form: p must be invertible modulo PW and the threshold must leave the 16-bit range alone
-    const bool iv = dna && ctx->k1_mode == 0 && p >= 10 && p < PFP_PW && (u64)ntiles * (K1_TILE / 32) < 0xFFFFFF00ull;
+    // interval form (w <= 16): p must be invertible modulo PW and the threshold must leave the 16-bit range alone
+    const bool iv = w <= 16 && ctx->k1_mode == 0 && !not_dna && p >= 10 && p < PFP_PW &&
+                    (u64)ntiles * (K1_TILE / 32) < 0xFFFFFF00ull;
+    const bool dna = iv || (w <= (u32)KD_MAXW && ctx->k1_mode != 1 && !not_dna);
     u32 *redo = nullptr;                                   // rows the interval form hands to the arithmetic
     if (iv) {
         PFP_TRY(ensure_iv_tables(ctx, C));
@@ -760,6 +866,7 @@ int pfp_scan_bits(pfpb200_ctx *ctx, const u8 *d_buf, u64 n_buf, u64 buf_pos0, u6
         if (iv) {
             switch ((int)w) {
                 KE_CASE(4) KE_CASE(5) KE_CASE(6) KE_CASE(7) KE_CASE(8) KE_CASE(9) KE_CASE(10)
+                KE_CASE(11) KE_CASE(12) KE_CASE(13) KE_CASE(14) KE_CASE(15) KE_CASE(16)
                 default: le = cudaErrorInvalidValue;
             }
         } else {

@@ -144,3 +144,42 @@ def test_interval_form_candidates_cover_every_trigger(w, p):
     cand = t < np.uint64(cthr)
     assert not np.any(trig & ~cand)                       # no trigger is missed by the 16-bit interval test
     assert cand.sum() - trig.sum() <= 200                 # and next to nothing else passes it
+
+
+def _interval_tables4(w, p):
+    """What dna_etab4_k builds for 11 <= w <= 16: per 4-symbol block x and role r (the block ends 4 r
+    symbols before the window's end) the exact partial hash F[r][x] and f16 = floor(F u 2^16 / PW)."""
+    letters = np.array([65, 67, 84, 71], dtype=np.int64)
+    x = np.arange(256, dtype=np.int64)
+    F = np.zeros((4, 256), dtype=np.int64)
+    for r in range(4):
+        for j in range(4):
+            dist = 4 * r + (3 - j)
+            if dist < w:
+                F[r] = (F[r] + letters[(x >> (2 * j)) & 3] * pow(256, dist, PW)) % PW
+    u = pow(p, -1, PW)
+    f16 = np.array([[((int(a) * u) % PW << 16) // PW for a in F[r]] for r in range(4)], dtype=np.int64)
+    lo = (f16[1] << 16) | f16[0]
+    hi = (((f16[3] + 5) & 0xFFFF) << 16) | f16[2]
+    theta = ((((PW - 1) // p) + 1) << 16) // PW
+    return F, lo, hi, (theta + 7) << 16
+
+
+@pytest.mark.parametrize("w,p", [(11, 100), (12, 50), (13, 1000), (14, 10), (15, 500), (16, 100), (16, 10), (16, 65536)])
+def test_interval_form_four_blocks_candidates_cover_every_trigger(w, p):
+    F, lo, hi, cthr = _interval_tables4(w, p)
+    assert cthr < 1 << 32
+    rng = np.random.default_rng(1000 * w + p)
+    n = 4_000_000
+    codes = rng.integers(0, 4, (n, 16))                                   # 16 symbols, oldest first
+    letters = np.array([65, 67, 84, 71], dtype=np.int64)
+    h = np.zeros(n, dtype=np.int64)
+    for k in range(16 - w, 16):
+        h = (h * 256 + letters[codes[:, k]]) % PW
+    xs = [sum(codes[:, 15 - 4 * r - (3 - j)] << (2 * j) for j in range(4)) for r in range(4)]    # block of role r
+    assert np.array_equal((F[0][xs[0]] + F[1][xs[1]] + F[2][xs[2]] + F[3][xs[3]]) % PW, h)       # linearity
+    trig = (h % p) == 0
+    t = ((lo[xs[0]] << 16) + lo[xs[1]] + (hi[xs[2]] << 16) + hi[xs[3]]) & 0xFFFFFFFF
+    cand = t < cthr
+    assert not np.any(trig & ~cand)
+    assert cand.sum() - trig.sum() <= 2000

@@ -55,9 +55,11 @@ def test_trigger_scan_vs_oracle(pkg, sc, w, p):
 
 
 @pytest.mark.parametrize("w,p", [(4, 10), (5, 11), (6, 64), (7, 16), (8, 33), (9, 1000), (10, 10), (10, 100),
-                                 (10, 65536), (10, 99991), (10, 1999999), (10, 3999999946)])
+                                 (10, 65536), (10, 99991), (10, 1999999), (10, 3999999946),
+                                 (11, 100), (12, 50), (13, 1000), (14, 10), (15, 500), (16, 100), (16, 500), (16, 65536)])
 def test_interval_form_scan_vs_oracle_and_other_forms(pkg, w, p):
-    """K1's interval form (kr_scan_iv_k, the default for w <= 10) against the oracle and against the
+    """K1's interval form (kr_scan_ivf_k: two 5-symbol blocks for w <= 10, four 4-symbol blocks for
+    w <= 16) against the oracle and against the
     bit-table and rolling forms, on DNA with rows that leave the table path (N runs, lower case,
     a newline) and at misaligned starts.  p >= PW (last case) has no inverse: the library falls back."""
     n = 700_000
