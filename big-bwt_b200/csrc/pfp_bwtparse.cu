@@ -10,9 +10,11 @@
 //     -- the end symbol is unique and the smallest, so no suffix is a prefix of another and a
 //     position past the end never has to be compared (its rank is read as 0).  A round is: keys
 //     from ranks (one gather), radix passes over exactly 2 ceil(log2 N) key bits, group flags,
-//     a scan, a scatter of the new ranks.  It stops as soon as every suffix has its own rank.  A
-//     repetitive pan-genome parse needs log2(longest repeat in phrases) + 1 rounds (9 for 100
-//     haplotypes at 0.1 % divergence, at most 32).
+//     a scan, the new ranks.  A suffix's rank is the POSITION where its group starts, so ranks stay
+//     valid while only some groups are refined: a suffix alone in its group is final and leaves
+//     the active list (Larsson-Sadakane discarding) -- the last rounds sort a few per cent of the
+//     suffixes.  It stops when the active list is empty.  A repetitive pan-genome parse needs
+//     log2(longest repeat in phrases) + 1 rounds (8 for 100 haplotypes at 0.1 % divergence).
 //   * BWT[i] = T[SA[i] - 1], bwlast[i] = last[SA[i] - 2], bwsai[i] = sai[SA[i] - 1] with the special
 //     cases of bwtparse.c:246-270: gathers;
 //   * ilist = positions i sorted stably by BWT[i] (bwtparse.c:294-298 is a counting sort with the
@@ -38,33 +40,56 @@ __global__ void __launch_bounds__(BP_T) bp_init_k(const u32 *__restrict__ parse,
     val[i] = (u32)i;
 }
 
-// flag[i] = 1 where a new group of equal keys starts (sorted order)
-__global__ void __launch_bounds__(BP_T) bp_flags_k(const u64 *__restrict__ key, u64 N, u8 *__restrict__ flag) {
-    const u64 i = (u64)blockIdx.x * BP_T + threadIdx.x;
-    if (i >= N) return;
-    flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+// flag[k] = 1 where a new group of equal keys starts (sorted order of the active suffixes)
+__global__ void __launch_bounds__(BP_T) bp_flags_k(const u64 *__restrict__ key, u64 M, u8 *__restrict__ flag) {
+    const u64 k = (u64)blockIdx.x * BP_T + threadIdx.x;
+    if (k >= M) return;
+    flag[k] = (k == 0 || key[k] != key[k - 1]) ? 1 : 0;
 }
 
-// dense rank of the group of sorted position i: (flags before i) + flag[i] - 1; stored by suffix
-__global__ void __launch_bounds__(BP_T) bp_ranks_k(const u32 *__restrict__ escan, const u8 *__restrict__ flag,
-                                                   const u32 *__restrict__ sa, u64 N, u32 *__restrict__ rank,
-                                                   u32 *__restrict__ rank_sorted) {
+__global__ void __launch_bounds__(BP_T) bp_iota_k(u32 *__restrict__ a, u64 n) {
     const u64 i = (u64)blockIdx.x * BP_T + threadIdx.x;
-    if (i >= N) return;
-    const u32 r = escan[i] + flag[i] - 1u;
-    rank_sorted[i] = r;
-    rank[sa[i]] = r;
+    if (i < n) a[i] = (u32)i;
 }
 
-// next round's key of the suffix at sorted position i: (its rank, the rank h symbols on) in 2b bits
-__global__ void __launch_bounds__(BP_T) bp_keys_k(const u32 *__restrict__ rank_sorted, const u32 *__restrict__ sa,
-                                                  const u32 *__restrict__ rank, u64 N, u64 h, int b,
-                                                  u64 *__restrict__ key) {
-    const u64 i = (u64)blockIdx.x * BP_T + threadIdx.x;
-    if (i >= N) return;
-    const u64 j = (u64)sa[i] + h;
-    const u64 lo = j < N ? rank[j] : 0u;
-    key[i] = ((u64)rank_sorted[i] << b) | lo;
+// head[g] = slot (position in the suffix array) where group g of the active list starts
+__global__ void __launch_bounds__(BP_T) bp_heads_k(const u8 *__restrict__ flag, const u32 *__restrict__ escan,
+                                                   const u32 *__restrict__ slot, u64 M, u32 *__restrict__ head) {
+    const u64 k = (u64)blockIdx.x * BP_T + threadIdx.x;
+    if (k < M && flag[k]) head[escan[k]] = slot[k];
+}
+
+// the sorted active suffixes go back to their slots; a suffix's rank is the slot where its group
+// starts (stable under refinement: only the groups that are split change); keep[k] = 0 for a group
+// of one -- that suffix is in its final place and leaves the active list
+__global__ void __launch_bounds__(BP_T) bp_update_k(const u8 *__restrict__ flag, const u32 *__restrict__ escan,
+                                                    const u32 *__restrict__ slot, const u32 *__restrict__ val,
+                                                    const u32 *__restrict__ head, u64 M, u32 *__restrict__ sa,
+                                                    u32 *__restrict__ rank, u32 *__restrict__ rs,
+                                                    u8 *__restrict__ keep) {
+    const u64 k = (u64)blockIdx.x * BP_T + threadIdx.x;
+    if (k >= M) return;
+    const u32 f = flag[k], s = val[k];
+    const u32 r = head[escan[k] + f - 1u];
+    sa[slot[k]] = s;
+    rank[s] = r;
+    rs[k] = r;
+    keep[k] = (f && (k + 1 == M || flag[k + 1])) ? 0 : 1;
+}
+
+// the suffixes that stay active, in order, with the next round's key: (rank, rank h symbols on)
+__global__ void __launch_bounds__(BP_T) bp_compact_k(const u8 *__restrict__ keep, const u32 *__restrict__ kscan,
+                                                     const u32 *__restrict__ slot, const u32 *__restrict__ val,
+                                                     const u32 *__restrict__ rs, const u32 *__restrict__ rank, u64 M,
+                                                     u64 N, u64 h, int b, u32 *__restrict__ slot2,
+                                                     u32 *__restrict__ val2, u64 *__restrict__ key2) {
+    const u64 k = (u64)blockIdx.x * BP_T + threadIdx.x;
+    if (k >= M || !keep[k]) return;
+    const u32 p = kscan[k], s = val[k];
+    const u64 j = (u64)s + h;
+    slot2[p] = slot[k];
+    val2[p] = s;
+    key2[p] = ((u64)rs[k] << b) | (j < N ? (u64)rank[j] + 1u : 0u);
 }
 
 // BWT of the parse and the permuted .last / .sai (bwtparse.c:243-272); SA[0] = n by construction
@@ -142,16 +167,22 @@ static int bwtparse_device_impl(pfpb200_ctx *ctx, const u32 *d_parse, u64 n, con
     const u32 launches0 = ctx->launches;
     PFP_CUDA(ctx, cudaEventRecord(evs[0], ctx->stream));
     u64 *k0 = nullptr, *k1 = nullptr;
-    u32 *v0 = nullptr, *v1 = nullptr, *rank = nullptr, *rsorted = nullptr, *escan = nullptr;
-    u8 *flag = nullptr;
+    u32 *v0 = nullptr, *v1 = nullptr, *rank = nullptr, *rs = nullptr, *escan = nullptr, *sa = nullptr;
+    u32 *slot = nullptr, *slot2 = nullptr, *head = nullptr;
+    u8 *flag = nullptr, *keep = nullptr;
     PFP_TRY(pfp_alloc_t(ctx, &k0, N));
     PFP_TRY(pfp_alloc_t(ctx, &k1, N));
     PFP_TRY(pfp_alloc_t(ctx, &v0, N));
     PFP_TRY(pfp_alloc_t(ctx, &v1, N));
+    PFP_TRY(pfp_alloc_t(ctx, &sa, N));
     PFP_TRY(pfp_alloc_t(ctx, &rank, N));
-    PFP_TRY(pfp_alloc_t(ctx, &rsorted, N));
+    PFP_TRY(pfp_alloc_t(ctx, &rs, N));
     PFP_TRY(pfp_alloc_t(ctx, &escan, N));
+    PFP_TRY(pfp_alloc_t(ctx, &slot, N));
+    PFP_TRY(pfp_alloc_t(ctx, &slot2, N));
+    PFP_TRY(pfp_alloc_t(ctx, &head, N));
     PFP_TRY(pfp_alloc_t(ctx, &flag, N));
+    PFP_TRY(pfp_alloc_t(ctx, &keep, N));
     // largest symbol: key bits of the first round and of the inverted list
     u32 *d_max = reinterpret_cast<u32 *>(&ctx->d_flags[2]);
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[1], 0, 2 * sizeof(u64), ctx->stream));
@@ -160,37 +191,47 @@ static int bwtparse_device_impl(pfpb200_ctx *ctx, const u32 *d_parse, u64 n, con
     PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[2], &ctx->d_flags[2], sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     bp_init_k<<<nb, BP_T, 0, ctx->stream>>>(d_parse, n, k0, v0);
     PFP_LAUNCHED(ctx);
+    bp_iota_k<<<nb, BP_T, 0, ctx->stream>>>(slot, N);
+    PFP_LAUNCHED(ctx);
     PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const u32 kmax = (u32)ctx->h_flags[2];
     const int sym_bits = bits_for(kmax);
-    const int b = bits_for(N - 1);                        // bits of a rank
+    const int b = bits_for(N);                            // bits of a rank + 1
     u64 *ks = nullptr;
-    u32 *sa = nullptr;
-    // round 1: the first two symbols.  The low half sorts over sym_bits, the high half starts at bit 32
-    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, N, 0, sym_bits, &ks, &sa));
+    u32 *vs = nullptr;
+    // round 1: all suffixes by their first two symbols.  The low half sorts over sym_bits, the high half starts at bit 32
+    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, N, 0, sym_bits, &ks, &vs));
     {
         u64 *ko = ks == k0 ? k1 : k0;
-        u32 *vo = sa == v0 ? v1 : v0;
-        PFP_TRY(pfp_radix_sort_pairs(ctx, ks, sa, ko, vo, N, 32, 32 + sym_bits, &ks, &sa));
+        u32 *vo = vs == v0 ? v1 : v0;
+        PFP_TRY(pfp_radix_sort_pairs(ctx, ks, vs, ko, vo, N, 32, 32 + sym_bits, &ks, &vs));
     }
     u32 rounds = 1;
-    u32 *d_groups = reinterpret_cast<u32 *>(&ctx->d_flags[1]);
+    u64 M = N;                                            // suffixes still in a group of two or more
+    u32 *d_cnt = reinterpret_cast<u32 *>(&ctx->d_flags[1]);
     for (u64 h = 2;; h *= 2, rounds++) {
-        bp_flags_k<<<nb, BP_T, 0, ctx->stream>>>(ks, N, flag);
+        // (ks, vs)[0..M): the active suffixes sorted by (rank, rank of the next h / 2 symbols); slot[k] = where the k-th goes
+        const u32 mb = pfp_blocks(M, BP_T);
+        bp_flags_k<<<mb, BP_T, 0, ctx->stream>>>(ks, M, flag);
         PFP_LAUNCHED(ctx);
-        PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, flag, escan, N, d_groups));
-        bp_ranks_k<<<nb, BP_T, 0, ctx->stream>>>(escan, flag, sa, N, rank, rsorted);
+        PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, flag, escan, M, nullptr));
+        bp_heads_k<<<mb, BP_T, 0, ctx->stream>>>(flag, escan, slot, M, head);
         PFP_LAUNCHED(ctx);
+        bp_update_k<<<mb, BP_T, 0, ctx->stream>>>(flag, escan, slot, vs, head, M, sa, rank, rs, keep);
+        PFP_LAUNCHED(ctx);
+        PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, keep, escan, M, d_cnt));
         PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[1], &ctx->d_flags[1], sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         PFP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        const u64 groups = (u32)ctx->h_flags[1];
-        if (groups == N) break;                           // every suffix has its own rank: sa[] is the suffix array
-        if (h >= N) return pfp_fail(ctx, PFPB200_E_INTERNAL, "bwtparse: prefix doubling did not converge");
+        const u64 M2 = (u32)ctx->h_flags[1];
+        if (M2 == 0) break;                               // every suffix has its own rank: sa[] is the suffix array
+        if (h >= 2 * N) return pfp_fail(ctx, PFPB200_E_INTERNAL, "bwtparse: prefix doubling did not converge");
         u64 *ko = ks == k0 ? k1 : k0;
-        u32 *vo = sa == v0 ? v1 : v0;
-        bp_keys_k<<<nb, BP_T, 0, ctx->stream>>>(rsorted, sa, rank, N, h, b, ks);
+        u32 *vo = vs == v0 ? v1 : v0;
+        bp_compact_k<<<mb, BP_T, 0, ctx->stream>>>(keep, escan, slot, vs, rs, rank, M, N, h, b, slot2, vo, ko);
         PFP_LAUNCHED(ctx);
-        PFP_TRY(pfp_radix_sort_pairs(ctx, ks, sa, ko, vo, N, 0, 2 * b, &ks, &sa));
+        { u32 *t = slot; slot = slot2; slot2 = t; }
+        M = M2;
+        PFP_TRY(pfp_radix_sort_pairs(ctx, ko, vo, ks, vs, M, 0, 2 * b, &ks, &vs));
     }
     PFP_CUDA(ctx, cudaEventRecord(evs[1], ctx->stream));
     // BWT, .bwlast, .bwsai, then the inverted list = positions sorted stably by BWT symbol
@@ -199,15 +240,14 @@ static int bwtparse_device_impl(pfpb200_ctx *ctx, const u32 *d_parse, u64 n, con
     PFP_TRY(pfp_alloc_t(ctx, &bwlast, N, true));
     if (d_sai) PFP_TRY(pfp_alloc_t(ctx, &bwsai, N * PFP_IBYTES, true));
     PFP_TRY(pfp_alloc_t(ctx, &ilist, N, true));
-    u64 *bk = ks == k0 ? k1 : k0;                          // the buffers the suffix array is not in
-    u32 *bv = sa == v0 ? v1 : v0;
+    u64 *bk = k0;                                          // the sort buffers are free: the suffix array has its own
+    u32 *bv = v0;
     bp_emit_k<<<nb, BP_T, 0, ctx->stream>>>(sa, d_parse, d_last, d_sai, n, bk, bv, bwlast, bwsai,
                                             reinterpret_cast<unsigned long long *>(&ctx->d_flags[0]));
     PFP_LAUNCHED(ctx);
     u64 *ik = nullptr;
     u32 *iv = nullptr;
-    // (the suffix array is dead now: its buffers are the sort's second pair)
-    PFP_TRY(pfp_radix_sort_pairs(ctx, bk, bv, ks, sa, N, 0, sym_bits, &ik, &iv));
+    PFP_TRY(pfp_radix_sort_pairs(ctx, bk, bv, k1, v1, N, 0, sym_bits, &ik, &iv));
     PFP_CUDA(ctx, cudaMemcpyAsync(ilist, iv, N * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
     PFP_CUDA(ctx, cudaEventRecord(evs[2], ctx->stream));
     PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[0], &ctx->d_flags[0], sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
