@@ -91,6 +91,7 @@ struct pfpb200_ctx {
     std::vector<void *> held;      // outputs: freed at the start of the next call / destroy
     void *bp_out[3] = {nullptr, nullptr, nullptr};   // held outputs of the last pfpb200_bwtparse_* call
     void *up_out = nullptr;        // held output of the last pfpb200_unparse_device call
+    void *pb_out[4] = {nullptr, nullptr, nullptr, nullptr};   // held outputs of the last pfpb200_pfbwt_* call
     void *pin_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // host outputs of parse_host,
     size_t pin_cap[5] = {0, 0, 0, 0, 0};                                 // kept and grown across calls
     // parse_host: .last/.sai are final after K2 and travel to the host on a second stream while

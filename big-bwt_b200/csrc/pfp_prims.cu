@@ -160,6 +160,7 @@ void pfp_release_held(pfpb200_ctx *ctx) {
     ctx->held.clear();
     ctx->bp_out[0] = ctx->bp_out[1] = ctx->bp_out[2] = nullptr;
     ctx->up_out = nullptr;
+    ctx->pb_out[0] = ctx->pb_out[1] = ctx->pb_out[2] = ctx->pb_out[3] = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------

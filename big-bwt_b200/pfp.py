@@ -18,6 +18,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libpfpb200.so")
 CLI_PATH = os.path.join(PKG_DIR, "gpuscan.x")
 BWTPARSE_CLI_PATH = os.path.join(PKG_DIR, "gpubwtparse.x")
 UNPARSE_CLI_PATH = os.path.join(PKG_DIR, "gpuunparse.x")
+PFBWT_CLI_PATH = os.path.join(PKG_DIR, "gpupfbwt.x")
+PFBWT_SA, PFBWT_SSA, PFBWT_ESA = 1, 2, 4
 
 F_SAI, F_FASTA, F_COMPRESS, F_VERBOSE, F_VERIFY = 1, 2, 4, 8, 16
 
@@ -65,6 +67,18 @@ class BwtParseResult(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ilist", "bwlast", "bwsai")}
 
 
+class PfbwtResult(C.Structure):
+    """include/pfpb200.h: pfpb200_pfbwt_result."""
+    _fields_ = [("bwt", C.c_void_p), ("n_bwt", C.c_uint64), ("sa", C.c_void_p), ("n_sa", C.c_uint64),
+                ("ssa", C.c_void_p), ("n_ssa", C.c_uint64), ("esa", C.c_void_p), ("n_esa", C.c_uint64),
+                ("dict_bytes", C.c_uint64), ("dict_words", C.c_uint64), ("parse_size", C.c_uint64),
+                ("easy", C.c_uint64), ("hard", C.c_uint64), ("rounds", C.c_uint32), ("launches", C.c_uint32),
+                ("ms_sa", C.c_float), ("ms_fill", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k not in ("bwt", "sa", "ssa", "esa")}
+
+
 @dataclass
 class BwtParseFiles:
     """.ilist / .bwlast / .bwsai as bytes (host copies)."""
@@ -110,6 +124,7 @@ SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_p
            "pfpb200_check_dict_order",
            "pfpb200_bwtparse_device", "pfpb200_bwtparse_host", "pfpb200_bwtparse_file",
            "pfpb200_unparse_device", "pfpb200_unparse_file",
+           "pfpb200_pfbwt_device", "pfpb200_pfbwt_file",
            "pfpb200_launch_count", "pfpb200_last_error", "pfpb200_abi_version"]
 
 
@@ -319,6 +334,36 @@ class Scanner:
         r = BwtParseResult()
         self._check(self.L.pfpb200_bwtparse_file(self.h, os.fsencode(basename), 1 if sai else 0, nseg, C.byref(r)))
         return r.as_dict()
+
+    # -- the last stage: pfbwt (pfbwt.cpp) ------------------------------------------------------------------
+    def pfbwt_device(self, dict_ptr, dict_bytes, occ_ptr, n_words, ilist_ptr, bwlast_ptr, bwsai_ptr, parse_size,
+                     w=10, flags=0) -> PfbwtResult:
+        """Device pointers in (outputs of parse_device and bwtparse_device on this scanner), device pointers out."""
+        self.L.pfpb200_pfbwt_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                C.POINTER(PfbwtResult)]
+        self.L.pfpb200_pfbwt_device.restype = C.c_int
+        r = PfbwtResult()
+        self._check(self.L.pfpb200_pfbwt_device(self.h, C.c_void_p(dict_ptr), dict_bytes, C.c_void_p(occ_ptr), n_words,
+                                                C.c_void_p(ilist_ptr), C.c_void_p(bwlast_ptr), C.c_void_p(bwsai_ptr or 0),
+                                                parse_size, w, flags, C.byref(r)))
+        return r
+
+    def pfbwt_file(self, basename, w=10, flags=0) -> dict:
+        self.L.pfpb200_pfbwt_file.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(PfbwtResult)]
+        self.L.pfpb200_pfbwt_file.restype = C.c_int
+        r = PfbwtResult()
+        self._check(self.L.pfpb200_pfbwt_file(self.h, os.fsencode(basename), w, flags, C.byref(r)))
+        return r.as_dict()
+
+    def bwt_of_text(self, text, w=10, p=100, flags=0):
+        """The whole pipeline on one context, nothing leaves HBM in between: parse -> bwtparse -> pfbwt.
+        `text`: CUDA uint8 tensor.  Returns (PfbwtResult, Outputs of the parse, BwtParseResult)."""
+        out = self.parse_device(text, w, p, sai=True)
+        bp = self.bwtparse_device(out.parse, out.n_phrases, out.last, out.sai)
+        r = self.pfbwt_device(out.dict, out.dict_bytes, out.occ, out.n_distinct, bp.ilist, bp.bwlast, bp.bwsai,
+                              bp.n_out, w, flags)
+        return r, out, bp
 
     # -- the inverse of the parse: unparse (unparse.c) ---------------------------------------------------
     def unparse_device(self, dict_ptr: int, dict_bytes: int, parse_ptr: int, n: int, strip_w: int = 0):

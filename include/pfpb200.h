@@ -350,6 +350,37 @@ int pfpb200_unparse_device(pfpb200_ctx *ctx, const uint8_t *d_dict, uint64_t dic
 int pfpb200_unparse_file(pfpb200_ctx *ctx, const char *basename, const char *outname, uint64_t *n_words,
                          uint64_t *n_text, float *ms);
 
+/* ---- the last stage: pfbwt --------------------------------------------------- *
+ * Replaces bwt() + main() of pfbwt.cpp (:109-242, :318-407): the BWT of the text -- n + 1 chars, the
+ * EOF char is 0 -- from the dictionary (.dict), the occurrences (.occ) and the outputs of bwtparse
+ * (.ilist, .bwlast, .bwsai); with PFPB200_PFBWT_SA the suffix array (`-S`: n values of 5 bytes,
+ * SABYTES, utils.h:12), with _SSA / _ESA the (position, value) pairs at the starts / ends of the
+ * BWT's runs (`-s` / `-e`, pfbwt.cpp:165-193).  Limits: dictionary < 4 GB (the reference's 32-bit
+ * build stops at 2 GB, pfbwt.cpp:333), parse < 2^32-2 words (:372).  Device pointers of the result
+ * are owned by the context until its next pfbwt or parse call; the outputs of earlier stages on the
+ * same context stay valid, so parse -> bwtparse -> pfbwt chains in HBM. */
+#define PFPB200_PFBWT_SA   1u   /* -S : full suffix array                                            */
+#define PFPB200_PFBWT_SSA  2u   /* -s : sampled suffix array at the starts of the runs (.ssa)        */
+#define PFPB200_PFBWT_ESA  4u   /* -e : ... at the ends of the runs (.esa)                           */
+typedef struct pfpb200_pfbwt_result {
+    const uint8_t *bwt;  uint64_t n_bwt;     /* n_bwt = text length + 1                              */
+    const uint8_t *sa;   uint64_t n_sa;      /* 5-byte values, n_bwt - 1 of them (NULL without _SA)  */
+    const uint8_t *ssa;  uint64_t n_ssa;     /* pairs of 5-byte values                               */
+    const uint8_t *esa;  uint64_t n_esa;
+    uint64_t dict_bytes, dict_words, parse_size;
+    uint64_t easy, hard;                     /* BWT chars written directly / through the merge       */
+    uint32_t rounds, launches;               /* prefix-doubling rounds of the dictionary suffix sort */
+    float ms_sa, ms_fill, ms_total;          /* CUDA-event times: suffix sort; BWT/SA emission; both */
+} pfpb200_pfbwt_result;
+
+int pfpb200_pfbwt_device(pfpb200_ctx *ctx, const uint8_t *d_dict, uint64_t dict_bytes, const uint32_t *d_occ,
+                         uint64_t n_words, const uint32_t *d_ilist, const uint8_t *d_bwlast,
+                         const uint8_t *d_bwsai /* NULL without SA flags */, uint64_t parse_size /* n_phrases + 1 */,
+                         uint32_t w, uint32_t flags, pfpb200_pfbwt_result *res);
+/* `pfbwt.x -w W [-S | -s -e] <basename>`: reads .dict .occ .ilist .bwlast [.bwsai], writes .bwt [.sa | .ssa .esa] */
+int pfpb200_pfbwt_file(pfpb200_ctx *ctx, const char *basename, uint32_t w, uint32_t flags,
+                       pfpb200_pfbwt_result *res);
+
 const char *pfpb200_strerror(int code);
 /* Message of the last failure on this context (CUDA error string, file name, ...). */
 const char *pfpb200_last_error(const pfpb200_ctx *ctx);

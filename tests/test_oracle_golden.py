@@ -99,3 +99,22 @@ def test_bwtparse_oracle_matches_live_reference(pkg):
     for nseg in (0, 3):
         want = bo.run_reference(f.parse, f.last, f.sai, f.occ, nseg=nseg)
         assert bo.bwtparse(f.parse, f.last, f.sai) == want, f"nseg={nseg}"
+
+
+# ---- the pfbwt stage: oracle/pfbwt_oracle.py against the reference binary ----
+def _pfbwt_golden():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_pfbwt.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    return {n: {f: (z[f"{n}/{f}"].tobytes() if z[f"{n}/{f}"].ndim else int(z[f"{n}/{f}"]))
+                for f in ("w", "p", "text", "dict", "occ", "ilist", "bwlast", "bwsai", "bwt", "sa", "ssa", "esa")}
+            for n in names}
+
+
+def test_pfbwt_oracle_matches_golden():
+    from oracle import pfbwt_oracle as po
+    cases = _pfbwt_golden()
+    assert len(cases) >= 6
+    for name, c in cases.items():
+        got = po.pfbwt(c["text"])
+        for ext in ("bwt", "sa", "ssa", "esa"):
+            assert got[ext] == c[ext], f"{name}: .{ext}"
