@@ -47,13 +47,22 @@ __global__ void __launch_bounds__(PB_T) pb_wend_k(const u8 *__restrict__ flag, c
     if (t < N && flag[t]) wend[wid[t]] = (u32)t;
 }
 
-// round 1: every position by its first two bytes; terminators get key 0 and sort in front
+// round 1: every position by its first PB_H0 = 8 bytes, big endian, cut behind the word's terminator
+// (zero padded); terminators get key 0 and sort in front
+constexpr u64 PB_H0 = 8;
 __global__ void __launch_bounds__(PB_T) pb_init_k(const u8 *__restrict__ d, u64 N, u64 *__restrict__ key,
                                                   u32 *__restrict__ val, u32 *__restrict__ slot) {
     const u64 t = (u64)blockIdx.x * PB_T + threadIdx.x;
     if (t >= N) return;
-    const u32 c0 = d[t];
-    key[t] = pb_term((u8)c0) ? 0u : ((u64)c0 << 8) | d[t + 1];
+    u64 k = 0;
+    bool live = true;
+#pragma unroll
+    for (u64 i = 0; i < PB_H0; i++) {
+        const u8 c = (live && t + i < N) ? d[t + i] : (u8)0;
+        if (pb_term(c)) live = false;                                // the terminator itself is part of the key
+        k = (k << 8) | ((i == 0 && !live) ? 0u : c);
+    }
+    key[t] = k;
     val[t] = (u32)t;
     slot[t] = (u32)t;
 }
@@ -349,10 +358,10 @@ static int pfbwt_device_impl(pfpb200_ctx *ctx, const u8 *d_dict, u64 N, const u3
     const int b = pb_bits(N);
     u64 *ks = nullptr;
     u32 *vs = nullptr;
-    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, N, 0, 16, &ks, &vs));
+    PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, N, 0, 64, &ks, &vs));
     u32 rounds = 1;
     u64 M = N;
-    for (u64 h = 2;; h *= 2, rounds++) {
+    for (u64 h = PB_H0;; h *= 2, rounds++) {
         const u32 mb = pfp_blocks(M, PB_T);
         pb_gflags_k<<<mb, PB_T, 0, ctx->stream>>>(ks, M, flag);
         PFP_LAUNCHED(ctx);
