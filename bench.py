@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the byte-exact output check after the timed region")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-t2", action="store_true", help="skip the file-to-files wall clock of gpuscan.x (N=1 only)")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the text -> BWT leg (parse + bwtparse + pfbwt, N=1 only)")
     ap.add_argument("--merge", default="partition", choices=["partition", "replicate"],
                     help="multi-GPU dictionary merge: range-partitioned all-to-all or replicated all-gather")
     return ap.parse_args()
@@ -321,6 +322,36 @@ def parity_check(job, pkg, synth, world, rank, local, dev, merge):
 # ------------------------------------------------------------------------------------------------
 # T2: page-cache-warm FASTA file -> five files closed, wall clock of the gpuscan.x process
 # ------------------------------------------------------------------------------------------------
+def pipeline_to_bwt(pkg, device, text, steps=3):
+    """The whole bigbwt pipeline on the GPU with the text resident in HBM: parse -> bwtparse -> pfbwt
+    (pfpb200_parse_device / _bwtparse_device / _pfbwt_device on one context, nothing leaves HBM in
+    between).  Wall clock of the three calls + each stage's CUDA-event time; reported beside the
+    metric, not part of it."""
+    import torch
+    try:
+        sc = pkg.pfp.Scanner(device)
+        runs = []
+        for _ in range(steps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r, out, bp = sc.bwt_of_text(text, W, P, flags=0)
+            wall = time.perf_counter() - t0
+            runs.append({"seconds": wall, "ms_parse": sc.stats.ms_total, "ms_bwtparse": bp.ms_total,
+                         "ms_pfbwt": r.ms_total, "ms_pfbwt_suffix_sort": r.ms_sa, "ms_pfbwt_emit": r.ms_fill,
+                         "doubling_rounds": {"bwtparse": bp.rounds, "pfbwt": r.rounds},
+                         "easy_chars": r.easy, "hard_chars": r.hard, "bwt_bytes": r.n_bwt})
+        sc.close()
+        torch.cuda.empty_cache()
+        med = sorted(runs[1:], key=lambda d: d["seconds"])[len(runs[1:]) // 2]
+        med["value"] = text.numel() / med["seconds"] / 1e9
+        med["unit"] = "GB/s of text, text in HBM -> BWT in HBM"
+        med["steps"] = steps
+        med["how"] = "Scanner.bwt_of_text: pfpb200_parse_device -> pfpb200_bwtparse_device -> pfpb200_pfbwt_device"
+        return med
+    except Exception as e:  # noqa: BLE001  (a failure here must not take the metric's line down)
+        return {"error": str(e)[:300]}
+
+
 def t2_file_to_files(a, pkg, synth, dev):
     """Writes the workload as a one-record-per-haplotype, 60-column FASTA (what `bigbwt -f` is
     given), runs `gpuscan.x <file> -w 10 -p 100 -s -f` twice as a subprocess -- process start, CUDA
@@ -444,6 +475,11 @@ def main():
         dist.all_gather_object(gathered, {k: round(v, 3) for k, v in stage_ms.items() if k.startswith("ms_phase_")})
         per_rank = {k: [g.get(k, 0.0) for g in gathered] for k in gathered[0]}
 
+    # ---- the stages after the parse, N = 1: text in HBM -> BWT in HBM ---------
+    pipeline = None
+    if world == 1 and not a.no_pipeline and a.workload == "pangenome" and n_local <= (6 << 30):
+        pipeline = pipeline_to_bwt(pkg, local, text)
+
     # ---- e2e: host buffers in, host buffers out ------------------------------------------------
     e2e = None
     host = None
@@ -540,6 +576,8 @@ def main():
         line["parity_check"] = parity
     if t2 is not None:
         line["t2_file_to_files"] = t2
+    if pipeline is not None:
+        line["pipeline_to_bwt"] = pipeline
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
