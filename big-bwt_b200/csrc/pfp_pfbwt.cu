@@ -32,6 +32,7 @@
 
 constexpr int PB_T = 256;
 constexpr u64 PB_BATCH = (u64)1 << 30;          // occurrences sorted at once in the hard groups
+constexpr u32 PB_BIG = 512;                     // easy members with more occurrences get a CTA instead of a thread
 
 __device__ __forceinline__ bool pb_term(u8 c) { return c <= PFP_END_OF_WORD; }   // EndOfWord, EndOfDict
 
@@ -185,11 +186,17 @@ __device__ __forceinline__ void pb_put5(u8 *__restrict__ a, u64 i, u64 x) {
 __global__ void __launch_bounds__(PB_T) pb_easy_k(PbView v, const u32 *__restrict__ cnt, const u32 *__restrict__ hcnt,
                                                   const u64 *__restrict__ off, const u32 *__restrict__ ilist,
                                                   const u8 *__restrict__ bwlast, const u8 *__restrict__ bwsai,
-                                                  u8 *__restrict__ bwt, u8 *__restrict__ sa5) {
+                                                  u8 *__restrict__ bwt, u8 *__restrict__ sa5, u32 *__restrict__ big,
+                                                  u32 *__restrict__ big_n, u32 big_cap) {
     const u64 k = (u64)blockIdx.x * PB_T + threadIdx.x;
     if (k >= v.N || cnt[k] == 0 || hcnt[k] != 0) return;
     u32 word, len; bool full; u8 c;
     const u32 n = pb_member(v, k, word, len, full, c);
+    if (n > PB_BIG) {                                                // a word with many occurrences: one CTA each, below
+        const u32 i = atomicAdd(big_n, 1u);
+        if (i < big_cap) big[i] = (u32)k;
+        return;
+    }
     const u64 o = off[k];
     const u32 is = v.istart[word] + 1u;                              // ilist[0] is the end symbol's entry (:376-383)
     for (u32 j = 0; j < n; j++) {
@@ -197,6 +204,27 @@ __global__ void __launch_bounds__(PB_T) pb_easy_k(PbView v, const u32 *__restric
         bwt[o + j] = full ? bwlast[ip] : c;
         if (sa5) pb_put5(sa5, o + j, (full && word == 0) ? pb_get5(bwsai, 0) - v.w   // the EOF suffix: the text length (:182)
                                                           : pb_get5(bwsai, ip) - len);
+    }
+}
+
+// the easy members with more than PB_BIG occurrences: the threads of a CTA share the loop
+__global__ void __launch_bounds__(PB_T) pb_easy_big_k(PbView v, const u32 *__restrict__ big, const u32 *__restrict__ big_n,
+                                                      u32 big_cap, const u64 *__restrict__ off,
+                                                      const u32 *__restrict__ ilist, const u8 *__restrict__ bwlast,
+                                                      const u8 *__restrict__ bwsai, u8 *__restrict__ bwt,
+                                                      u8 *__restrict__ sa5) {
+    const u32 nbig = min(*big_n, big_cap);
+    for (u32 b = blockIdx.x; b < nbig; b += gridDim.x) {
+        const u64 k = big[b];
+        u32 word, len; bool full; u8 c;
+        const u32 n = pb_member(v, k, word, len, full, c);
+        const u64 o = off[k];
+        const u32 is = v.istart[word] + 1u;
+        for (u32 j = threadIdx.x; j < n; j += PB_T) {
+            const u32 ip = (full || sa5) ? ilist[is + j] : 0u;
+            bwt[o + j] = full ? bwlast[ip] : c;
+            if (sa5) pb_put5(sa5, o + j, (full && word == 0) ? pb_get5(bwsai, 0) - v.w : pb_get5(bwsai, ip) - len);
+        }
     }
 }
 
@@ -425,7 +453,14 @@ static int pfbwt_device_impl(pfpb200_ctx *ctx, const u8 *d_dict, u64 N, const u3
         PFP_TRY(pfp_alloc_t(ctx, &sa5, n_bwt * PFP_IBYTES, true));
         ctx->pb_out[1] = sa5;
     }
-    pb_easy_k<<<nb, PB_T, 0, ctx->stream>>>(V, cnt, hcnt, off, d_ilist, d_bwlast, d_bwsai, bwt, sa5);
+    // (a member with more than PB_BIG occurrences contributes > PB_BIG chars: at most n_bwt / PB_BIG of them)
+    const u32 big_cap = (u32)(n_bwt / PB_BIG + 1);
+    u32 *big = nullptr, *big_n = reinterpret_cast<u32 *>(&ctx->d_flags[6]);
+    PFP_TRY(pfp_alloc_t(ctx, &big, big_cap));
+    PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[6], 0, sizeof(u64), ctx->stream));
+    pb_easy_k<<<nb, PB_T, 0, ctx->stream>>>(V, cnt, hcnt, off, d_ilist, d_bwlast, d_bwsai, bwt, sa5, big, big_n, big_cap);
+    PFP_LAUNCHED(ctx);
+    pb_easy_big_k<<<ctx->sm_count * 8, PB_T, 0, ctx->stream>>>(V, big, big_n, big_cap, off, d_ilist, d_bwlast, d_bwsai, bwt, sa5);
     PFP_LAUNCHED(ctx);
     // ---- 4. hard members: the merge of the ilist cursors as a sort, in batches ------------------------------------
     if (n_hard) {

@@ -81,6 +81,23 @@ def test_text_with_long_runs_and_all_byte_values(pkg, sc):
     assert got["bwt"] == want["bwt"] and got["sa"] == want["sa"]
 
 
+def test_tandem_repeats_words_with_thousands_of_occurrences(pkg, sc):
+    """A unit repeated 6000 times: a handful of words carry thousands of occurrences each (the CTA
+    path of the easy members, long per-member loops in the merge)."""
+    unit = pkg.synth.random_dna(211, 12).numpy().tobytes()
+    a = pkg.synth.random_dna(20_000, 13).numpy().tobytes() + unit * 6000 + pkg.synth.random_dna(20_000, 14).numpy().tobytes()
+    text = torch.from_numpy(np.frombuffer(a, np.uint8).copy()).cuda()
+    want = po.pfbwt(a)
+    for w, p in ((10, 100), (4, 10)):
+        r, out, _ = sc.bwt_of_text(text, w, p, flags=pkg.pfp.PFBWT_SA)
+        got = _fetch(sc, r)
+        assert got["bwt"] == want["bwt"] and got["sa"] == want["sa"], (w, p)
+        occ = np.frombuffer(sc.to_host(out.occ, 4 * out.n_distinct), np.uint32)
+        assert occ.max() > 1000
+        r, _, _ = sc.bwt_of_text(text, w, p, flags=0)
+        assert _fetch(sc, r)["bwt"] == want["bwt"]
+
+
 @pytest.mark.skipif(not (po.have_reference() and orc.have_ref("bwtparse")), reason="oracle/_ref not built")
 def test_cli_matches_reference(pkg):
     """gpupfbwt.x as the drop-in for pfbwtNT.x, and the whole GPU chain gpuscan.x -> gpubwtparse.x ->
