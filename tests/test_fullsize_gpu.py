@@ -37,7 +37,8 @@ def test_config2_pangenome_4gb_and_sweep_corners(pkg, sc):
     for (w, p, key) in [(10, 100, "config2 w10 p100"), (6, 50, "sweep w6 p50"), (16, 500, "sweep w16 p500"),
                         (32, 1000, "sweep w32 p1000"), (6, 1000, None), (32, 50, None)]:
         assert fc.check_case(sc, text, w, p, f"pangenome 4 GB w{w} p{p}", digest_key=key,
-                             text_key="pangenome" if key else None), f"w={w} p={p}"
+                             text_key="pangenome" if key else None,
+                             pipeline=(w, p) == (10, 100)), f"w={w} p={p}"     # config 2: also bwtparse + pfbwt -S
 
 
 def test_config4_random_8gb(pkg, sc):

@@ -62,7 +62,7 @@ def sha_dev(ptr, nbytes):
     return h.hexdigest()
 
 
-def check_case(sc, text, w, p, name, digest_key=None, text_key=None, prefix_phrases=200_000):
+def check_case(sc, text, w, p, name, digest_key=None, text_key=None, prefix_phrases=200_000, pipeline=False):
     n = text.numel()
     sc.parse_device(text, w, p, sai=True)               # warm-up: arena growth, table sizing hint
     torch.cuda.synchronize()
@@ -153,6 +153,30 @@ def check_case(sc, text, w, p, name, digest_key=None, text_key=None, prefix_phra
     except Exception as e:  # noqa: BLE001
         res["unparse_round_trip"] = {"error": str(e)[:200]}
         fails.append("unparse failed")
+    # the stages after the parse at full size, chained in HBM on the outputs above: bwtparse, pfbwt -S;
+    # digests of .ilist .bwlast .bwsai .bwt .sa against the unmodified reference chain's
+    # (tools/make_fullsize_digests_pipeline.py), where the build container has produced them
+    if pipeline:
+        try:
+            bp = sc.bwtparse_device(out.parse, out.n_phrases, out.last, out.sai)
+            r = sc.pfbwt_device(out.dict, out.dict_bytes, out.occ, out.n_distinct, bp.ilist, bp.bwlast, bp.bwsai,
+                                bp.n_out, w, 1)      # PFPB200_PFBWT_SA
+            res["pipeline"] = {"ms_bwtparse": round(bp.ms_total, 2), "ms_pfbwt": round(r.ms_total, 2),
+                               "bwt_bytes": r.n_bwt, "easy": r.easy, "hard": r.hard}
+            if r.n_bwt != n + 1: fails.append("pfbwt: |BWT| != n + 1")
+            ref = dg["cases"].get(digest_key or "", {}).get("pipeline")
+            if ref:
+                got = {"ilist": sha_dev(bp.ilist, 4 * bp.n_out), "bwlast": sha_dev(bp.bwlast, bp.n_out),
+                       "bwsai": sha_dev(bp.bwsai, 5 * bp.n_out), "bwt": sha_dev(r.bwt, r.n_bwt),
+                       "sa": sha_dev(r.sa, 5 * r.n_sa)}
+                res["pipeline"]["sha256_vs_reference"] = {e: got[e] == ref["sha256"][e] for e in got}
+                for e in got:
+                    if got[e] != ref["sha256"][e]: fails.append(f".{e} sha256 differs from the reference chain")
+            else:
+                res["pipeline"]["sha256_vs_reference"] = None
+        except Exception as e:  # noqa: BLE001
+            res["pipeline"] = {"error": str(e)[:300]}
+            fails.append("pipeline failed")
     res["ok"] = not fails
     res["fails"] = fails
     print(json.dumps(res), flush=True)
@@ -173,7 +197,8 @@ def main():
         text = pkg.synth.pangenome_text(40_000_000 // scale, 100, 2, device="cuda")
         if a.config in ("pangenome", "all"):
             ok &= check_case(sc, text, 10, 100, "config2 pangenome 100 x 40 Mbp",
-                             digest_key=None if a.small else "config2 w10 p100", text_key=None if a.small else "pangenome")
+                             digest_key=None if a.small else "config2 w10 p100", text_key=None if a.small else "pangenome",
+                             pipeline=True)
         if a.config in ("sweep", "all"):
             for w in (6, 10, 16, 32):
                 for p in (50, 100, 500, 1000):
