@@ -488,8 +488,60 @@ static int cut_and_parse_device(pfpb200_ctx *ctx, const u8 *d_text, u64 n_text, 
     return parse_device_impl(ctx, d_text, n, opts, dv, stats);
 }
 
+// file -> text in HBM -> the five streams in HBM; write_files: also into <path>.dict ... (parse_file)
+static int parse_file_impl(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts, pfpb200_stats *stats,
+                           bool write_files, pfpb200_outputs *dv_out);
+
 extern "C" int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts,
                                   pfpb200_stats *stats) {
+    const int rc = parse_file_impl(ctx, path, opts, stats, true, nullptr);
+    if (ctx && rc == PFPB200_OK) pfp_release_held(ctx);
+    return rc;
+}
+
+// `bigbwt <file> -w W -p P [-f] [-S | -s -e]` in one call (bigbwt:66-150 runs newscan, bwtparse and
+// pfbwt as three processes that hand each other files): the input streams into HBM, the three stages
+// run there, and only <path>.bwt (and .sa / .ssa / .esa) are written -- with keep_files != 0 also the
+// intermediate files the reference leaves behind with `bigbwt -k`.
+extern "C" int pfpb200_bigbwt_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts, uint32_t pfbwt_flags,
+                                   int keep_files, pfpb200_stats *stats, pfpb200_bwtparse_result *bp_out,
+                                   pfpb200_pfbwt_result *res) {
+    if (!ctx || !opts || !res) return PFPB200_E_ARG;
+    if (opts->flags & PFPB200_F_COMPRESS) return pfp_fail(ctx, PFPB200_E_ARG, "bigbwt: -c stops after the parse, use pfpb200_parse_file");
+    pfpb200_opts o = *opts;
+    o.flags |= PFPB200_F_SAI;                                  // the later stages take .sai whenever a suffix array is wanted
+    o.nseg = 0;
+    pfpb200_stats st;
+    pfpb200_outputs dv;
+    PFP_TRY(parse_file_impl(ctx, path, &o, &st, keep_files != 0, &dv));
+    if (stats) *stats = st;
+    const double t0 = wall_sec();
+    pfpb200_bwtparse_result bp;
+    PFP_TRY(pfpb200_bwtparse_device(ctx, dv.parse, dv.n_phrases, dv.last, dv.sai, &bp));
+    if (bp_out) *bp_out = bp;
+    PFP_TRY(pfpb200_pfbwt_device(ctx, dv.dict, dv.dict_bytes, dv.occ, dv.n_distinct, bp.ilist, bp.bwlast, bp.bwsai,
+                                 bp.n_out, o.w, pfbwt_flags, res));
+    char name[4096];
+    auto put = [&](const char *ext, const void *p, u64 bytes) -> int {
+        snprintf(name, sizeof(name), "%s.%s", path, ext);
+        return pfp_device_to_file(ctx, name, p, bytes);
+    };
+    if (keep_files) {
+        PFP_TRY(put("ilist", bp.ilist, bp.n_out * 4));
+        PFP_TRY(put("bwlast", bp.bwlast, bp.n_out));
+        PFP_TRY(put("bwsai", bp.bwsai, bp.n_out * PFP_IBYTES));
+    }
+    PFP_TRY(put("bwt", res->bwt, res->n_bwt));
+    if (pfbwt_flags & PFPB200_PFBWT_SA) PFP_TRY(put("sa", res->sa, res->n_sa * PFP_IBYTES));
+    if (pfbwt_flags & PFPB200_PFBWT_SSA) PFP_TRY(put("ssa", res->ssa, res->n_ssa * 2 * PFP_IBYTES));
+    if (pfbwt_flags & PFPB200_PFBWT_ESA) PFP_TRY(put("esa", res->esa, res->n_esa * 2 * PFP_IBYTES));
+    if (stats) stats->sec_write += (float)(wall_sec() - t0);     // (includes the two later stages: they are milliseconds to a second)
+    pfp_release_scratch(ctx);
+    return PFPB200_OK;
+}
+
+static int parse_file_impl(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts, pfpb200_stats *stats,
+                           bool write_files, pfpb200_outputs *dv_out) {
     PFP_TRY(check_opts(ctx, opts));
     if (!path) return pfp_fail(ctx, PFPB200_E_ARG, "null path");
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -555,12 +607,13 @@ extern "C" int pfpb200_parse_file(pfpb200_ctx *ctx, const char *path, const pfpb
     close(fd);
     if (rc != PFPB200_OK) { pfp_release_scratch(ctx); return rc; }
     const double t2 = wall_sec();
-    PFP_TRY(write_outputs_from_device(ctx, path, opts, dv));
+    if (write_files) PFP_TRY(write_outputs_from_device(ctx, path, opts, dv));
     if (stats) {
         stats->sec_read = (float)(t1 - t0);
         stats->sec_write = (float)(wall_sec() - t2);
     }
-    pfp_release_held(ctx);
+    pfp_release_scratch(ctx);
+    if (dv_out) *dv_out = dv;                                  // device pointers, held by the context
     return PFPB200_OK;
 }
 

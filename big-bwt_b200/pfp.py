@@ -19,6 +19,7 @@ CLI_PATH = os.path.join(PKG_DIR, "gpuscan.x")
 BWTPARSE_CLI_PATH = os.path.join(PKG_DIR, "gpubwtparse.x")
 UNPARSE_CLI_PATH = os.path.join(PKG_DIR, "gpuunparse.x")
 PFBWT_CLI_PATH = os.path.join(PKG_DIR, "gpupfbwt.x")
+BIGBWT_CLI_PATH = os.path.join(PKG_DIR, "gpubigbwt.x")
 PFBWT_SA, PFBWT_SSA, PFBWT_ESA = 1, 2, 4
 
 F_SAI, F_FASTA, F_COMPRESS, F_VERBOSE, F_VERIFY = 1, 2, 4, 8, 16
@@ -124,7 +125,7 @@ SYMBOLS = ["pfpb200_create", "pfpb200_destroy", "pfpb200_set_stream", "pfpb200_p
            "pfpb200_check_dict_order",
            "pfpb200_bwtparse_device", "pfpb200_bwtparse_host", "pfpb200_bwtparse_file",
            "pfpb200_unparse_device", "pfpb200_unparse_file",
-           "pfpb200_pfbwt_device", "pfpb200_pfbwt_file",
+           "pfpb200_pfbwt_device", "pfpb200_pfbwt_file", "pfpb200_bigbwt_file",
            "pfpb200_launch_count", "pfpb200_last_error", "pfpb200_abi_version"]
 
 
@@ -355,6 +356,17 @@ class Scanner:
         r = PfbwtResult()
         self._check(self.L.pfpb200_pfbwt_file(self.h, os.fsencode(basename), w, flags, C.byref(r)))
         return r.as_dict()
+
+    def bigbwt_file(self, path, w=10, p=100, fasta=False, flags=0, keep=False) -> dict:
+        """The whole pipeline for a file: <path>.bwt (+ .sa / .ssa / .esa) written, stages in HBM."""
+        self.L.pfpb200_bigbwt_file.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Opts), C.c_uint32, C.c_int,
+                                               C.POINTER(Stats), C.POINTER(BwtParseResult), C.POINTER(PfbwtResult)]
+        self.L.pfpb200_bigbwt_file.restype = C.c_int
+        o = Opts(w, p, _flags(True, fasta, False), 0)
+        bp, r = BwtParseResult(), PfbwtResult()
+        self._check(self.L.pfpb200_bigbwt_file(self.h, os.fsencode(path), C.byref(o), flags, 1 if keep else 0,
+                                               C.byref(self.stats), C.byref(bp), C.byref(r)))
+        return {"parse": self.stats.as_dict(), "bwtparse": bp.as_dict(), "pfbwt": r.as_dict()}
 
     def bwt_of_text(self, text, w=10, p=100, flags=0):
         """The whole pipeline on one context, nothing leaves HBM in between: parse -> bwtparse -> pfbwt.

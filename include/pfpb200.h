@@ -381,6 +381,15 @@ int pfpb200_pfbwt_device(pfpb200_ctx *ctx, const uint8_t *d_dict, uint64_t dict_
 int pfpb200_pfbwt_file(pfpb200_ctx *ctx, const char *basename, uint32_t w, uint32_t flags,
                        pfpb200_pfbwt_result *res);
 
+/* ---- the whole pipeline in one call --------------------------------------------------------------------- *
+ * What `bigbwt <file> -w W -p P [-f] [-S | -s -e] [-k]` does with three processes and the files between
+ * them (bigbwt:66-150): here the input streams into HBM, parse -> bwtparse -> pfbwt run there, and
+ * <path>.bwt (and .sa / .ssa / .esa per pfbwt_flags) are written; keep_files != 0 (`-k`) also writes
+ * the intermediate .dict .occ .parse .last .sai .ilist .bwlast .bwsai.  stats / bp may be NULL. */
+int pfpb200_bigbwt_file(pfpb200_ctx *ctx, const char *path, const pfpb200_opts *opts, uint32_t pfbwt_flags,
+                        int keep_files, pfpb200_stats *stats, pfpb200_bwtparse_result *bp,
+                        pfpb200_pfbwt_result *res);
+
 const char *pfpb200_strerror(int code);
 /* Message of the last failure on this context (CUDA error string, file name, ...). */
 const char *pfpb200_last_error(const pfpb200_ctx *ctx);

@@ -128,6 +128,35 @@ def test_cli_matches_reference(pkg):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+@pytest.mark.skipif(not (po.have_reference() and orc.have_ref("bwtparse")), reason="oracle/_ref not built")
+def test_gpubigbwt_one_process_matches_the_reference_chain(pkg):
+    """gpubigbwt.x: file in, .bwt / .sa out, the three stages in HBM in one process -- against
+    newscanNT.x + bwtparse + pfbwtNT.x; with -k the intermediate files are the reference's too."""
+    recs = [r.numpy() for r in pkg.synth.pangenome_records(50_000, 6, 37)]
+    fa = pkg.synth.to_fasta(recs)
+    tmp = tempfile.mkdtemp(prefix="bigbwtcli_")
+    try:
+        ours, ref = os.path.join(tmp, "ours.fa"), os.path.join(tmp, "ref.fa")
+        for pth in (ours, ref):
+            with open(pth, "wb") as f:
+                f.write(fa)
+        subprocess.run([orc.ref_exe("newscanNT.x"), ref, "-w", "10", "-p", "100", "-s", "-f"], check=True, stdout=subprocess.PIPE)
+        subprocess.run([orc.ref_exe("bwtparse"), ref, "-s"], check=True, stdout=subprocess.PIPE)
+        subprocess.run([orc.ref_exe("pfbwtNT.x"), "-w", "10", "-S", ref], check=True, stdout=subprocess.PIPE)
+        r = subprocess.run([pkg.pfp.BIGBWT_CLI_PATH, ours, "-w", "10", "-p", "100", "-f", "-S", "-k"], check=True,
+                           stdout=subprocess.PIPE, text=True)
+        assert "Hard bwt chars" in r.stdout
+        for ext in ("bwt", "sa", "dict", "occ", "parse", "last", "sai", "ilist", "bwlast", "bwsai"):
+            assert open(ours + "." + ext, "rb").read() == open(ref + "." + ext, "rb").read(), ext
+        plain = os.path.join(tmp, "plain.fa")
+        shutil.copy(ref, plain)
+        subprocess.run([pkg.pfp.BIGBWT_CLI_PATH, plain, "-f"], check=True, stdout=subprocess.PIPE)
+        assert open(plain + ".bwt", "rb").read() == open(ref + ".bwt", "rb").read()
+        assert not os.path.exists(plain + ".dict") and not os.path.exists(plain + ".sa")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def test_errors(pkg, sc):
     c = next(iter(_pfbwt_golden().values()))
     t = {k: _dev(c[k]) for k in ("dict", "occ", "ilist", "bwlast", "bwsai")}
