@@ -79,39 +79,60 @@ __global__ void __launch_bounds__(PB_T) pb_heads_k(const u8 *__restrict__ flag, 
     if (k < M && flag[k]) head[escan[k]] = slot[k];
 }
 
-// sorted active suffixes back to their slots; rank = slot where the group starts; a suffix leaves the
-// active list when it is alone in its group or compared to its end (length + terminator <= h)
+// lim[t] = position of the terminator of t's word (one gather per round instead of two)
+__global__ void __launch_bounds__(PB_T) pb_lim_k(const u32 *__restrict__ wid, const u32 *__restrict__ wend, u64 N,
+                                                 u32 *__restrict__ lim) {
+    const u64 t = (u64)blockIdx.x * PB_T + threadIdx.x;
+    if (t < N) lim[t] = wend[wid[t]];
+}
+
+// The sorted active suffixes: rank = slot where the group starts; a suffix leaves the active list
+// when it is alone in its group or compared to its end (length + terminator <= h) -- only then is it
+// written to the suffix array, and its rank only when it changed (both are random 4-byte stores).
+// KB > 0: the keys are (old rank << (KB + 1)) | (second rank << 1) | done, written by pb_compact_k;
+// KB = 0: the first round (raw bytes as keys) or 32-bit ranks: lengths and old ranks are not in the key.
 __global__ void __launch_bounds__(PB_T) pb_update_k(const u8 *__restrict__ flag, const u32 *__restrict__ escan,
                                                     const u32 *__restrict__ slot, const u32 *__restrict__ val,
-                                                    const u32 *__restrict__ head, const u32 *__restrict__ wid,
-                                                    const u32 *__restrict__ wend, u64 M, u64 h,
+                                                    const u64 *__restrict__ key, int kb, int first,
+                                                    const u32 *__restrict__ head, const u32 *__restrict__ lim, u64 M, u64 h,
                                                     u32 *__restrict__ sa, u32 *__restrict__ rank, u32 *__restrict__ rs,
                                                     u8 *__restrict__ keep) {
     const u64 k = (u64)blockIdx.x * PB_T + threadIdx.x;
     if (k >= M) return;
     const u32 f = flag[k], s = val[k];
     const u32 r = head[escan[k] + f - 1u];
-    sa[slot[k]] = s;
-    rank[s] = r;
-    rs[k] = r;
     const bool single = f && (k + 1 == M || flag[k + 1]);
-    const u64 len1 = (u64)wend[wid[s]] - s + 1;            // bytes of the suffix + its terminator
-    keep[k] = (single || len1 <= h) ? 0 : 1;
+    bool done, same = false;
+    if (kb > 0 && !first) {
+        const u64 kk = key[k];
+        done = (kk & 1u) != 0;
+        same = (u32)(kk >> (kb + 1)) == r;
+    } else {
+        done = (u64)lim[s] - s + 1 <= h;                      // bytes of the suffix + its terminator
+        if (!first) same = (u32)(key[k] >> 32) == r;
+    }
+    if (!same) rank[s] = r;
+    rs[k] = r;
+    const bool stay = !(single || done);
+    keep[k] = stay ? 1 : 0;
+    if (!stay) sa[slot[k]] = s;
 }
 
 __global__ void __launch_bounds__(PB_T) pb_compact_k(const u8 *__restrict__ keep, const u32 *__restrict__ kscan,
                                                      const u32 *__restrict__ slot, const u32 *__restrict__ val,
                                                      const u32 *__restrict__ rs, const u32 *__restrict__ rank,
-                                                     const u32 *__restrict__ wid, const u32 *__restrict__ wend, u64 M,
-                                                     u64 h, int b, u32 *__restrict__ slot2, u32 *__restrict__ val2,
+                                                     const u32 *__restrict__ lim, u64 M, u64 h, int kb,
+                                                     u32 *__restrict__ slot2, u32 *__restrict__ val2,
                                                      u64 *__restrict__ key2) {
     const u64 k = (u64)blockIdx.x * PB_T + threadIdx.x;
     if (k >= M || !keep[k]) return;
-    const u32 p = kscan[k], s = val[k];
+    const u32 p = kscan[k], s = val[k], l = lim[s];
     const u64 j = (u64)s + h;
+    const u64 r2 = j <= l ? (u64)rank[j] : 0u;                // the terminator's rank is 0
     slot2[p] = slot[k];
     val2[p] = s;
-    key2[p] = ((u64)rs[k] << b) | (j <= wend[wid[s]] ? (u64)rank[j] : 0u);   // the terminator's rank is 0
+    if (kb > 0) key2[p] = ((u64)rs[k] << (kb + 1)) | (r2 << 1) | (((u64)l - s + 1 <= 2 * h) ? 1u : 0u);
+    else key2[p] = ((u64)rs[k] << 32) | r2;
 }
 
 // ---- the walk over the sorted suffixes -----------------------------------------------------------
@@ -381,9 +402,15 @@ static int pfbwt_device_impl(pfpb200_ctx *ctx, const u8 *d_dict, u64 N, const u3
     PFP_TRY(pfp_alloc_t(ctx, &slot, N));
     PFP_TRY(pfp_alloc_t(ctx, &slot2, N));
     PFP_TRY(pfp_alloc_t(ctx, &head, N));
+    u32 *lim = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &lim, N));
+    pb_lim_k<<<nb, PB_T, 0, ctx->stream>>>(wid, wend, N, lim);
+    PFP_LAUNCHED(ctx);
     pb_init_k<<<nb, PB_T, 0, ctx->stream>>>(d_dict, N, k0, v0, slot);
     PFP_LAUNCHED(ctx);
     const int b = pb_bits(N);
+    const int kb = b <= 31 ? b : 0;                           // 2 b + 1 key bits fit into 64: old rank, second rank, done bit
+    const int sort_bits = kb ? 2 * b + 1 : 64;
     u64 *ks = nullptr;
     u32 *vs = nullptr;
     PFP_TRY(pfp_radix_sort_pairs(ctx, k0, v0, k1, v1, N, 0, 64, &ks, &vs));
@@ -396,7 +423,8 @@ static int pfbwt_device_impl(pfpb200_ctx *ctx, const u8 *d_dict, u64 N, const u3
         PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, flag, escan, M, nullptr));
         pb_heads_k<<<mb, PB_T, 0, ctx->stream>>>(flag, escan, slot, M, head);
         PFP_LAUNCHED(ctx);
-        pb_update_k<<<mb, PB_T, 0, ctx->stream>>>(flag, escan, slot, vs, head, wid, wend, M, h, sa, rank, rs, keep);
+        pb_update_k<<<mb, PB_T, 0, ctx->stream>>>(flag, escan, slot, vs, ks, kb, rounds == 1 ? 1 : 0, head, lim, M, h, sa,
+                                                  rank, rs, keep);
         PFP_LAUNCHED(ctx);
         PFP_TRY(pfp_exclusive_scan_u8_u32(ctx, keep, escan, M, d_cnt));
         PFP_CUDA(ctx, cudaMemcpyAsync(&ctx->h_flags[1], &ctx->d_flags[1], sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
@@ -406,12 +434,13 @@ static int pfbwt_device_impl(pfpb200_ctx *ctx, const u8 *d_dict, u64 N, const u3
         if (h >= 2 * N) return pfp_fail(ctx, PFPB200_E_INTERNAL, "pfbwt: prefix doubling did not converge");
         u64 *ko = ks == k0 ? k1 : k0;
         u32 *vo = vs == v0 ? v1 : v0;
-        pb_compact_k<<<mb, PB_T, 0, ctx->stream>>>(keep, escan, slot, vs, rs, rank, wid, wend, M, h, b, slot2, vo, ko);
+        pb_compact_k<<<mb, PB_T, 0, ctx->stream>>>(keep, escan, slot, vs, rs, rank, lim, M, h, kb, slot2, vo, ko);
         PFP_LAUNCHED(ctx);
         { u32 *t = slot; slot = slot2; slot2 = t; }
         M = M2;
-        PFP_TRY(pfp_radix_sort_pairs(ctx, ko, vo, ks, vs, M, 0, 2 * b, &ks, &vs));
+        PFP_TRY(pfp_radix_sort_pairs(ctx, ko, vo, ks, vs, M, 0, sort_bits, &ks, &vs));
     }
+    PFP_TRY(pfp_free_now(ctx, lim));
     PFP_TRY(pfp_free_now(ctx, k0)); PFP_TRY(pfp_free_now(ctx, k1)); PFP_TRY(pfp_free_now(ctx, v0));
     PFP_TRY(pfp_free_now(ctx, v1)); PFP_TRY(pfp_free_now(ctx, rs)); PFP_TRY(pfp_free_now(ctx, slot));
     PFP_TRY(pfp_free_now(ctx, slot2)); PFP_TRY(pfp_free_now(ctx, head)); PFP_TRY(pfp_free_now(ctx, keep));
