@@ -158,9 +158,12 @@ def check_case(sc, text, w, p, name, digest_key=None, text_key=None, prefix_phra
     # (tools/make_fullsize_digests_pipeline.py), where the build container has produced them
     if pipeline:
         try:
-            bp = sc.bwtparse_device(out.parse, out.n_phrases, out.last, out.sai)
-            r = sc.pfbwt_device(out.dict, out.dict_bytes, out.occ, out.n_distinct, bp.ilist, bp.bwlast, bp.bwsai,
-                                bp.n_out, w, 1)      # PFPB200_PFBWT_SA
+            # (a context of their own, closed afterwards: the scratch of the suffix sorts -- 58 B per dictionary
+            # byte -- goes back to the device instead of staying in the parse context's arena)
+            sc2 = type(sc)(sc.device)
+            bp = sc2.bwtparse_device(out.parse, out.n_phrases, out.last, out.sai)
+            r = sc2.pfbwt_device(out.dict, out.dict_bytes, out.occ, out.n_distinct, bp.ilist, bp.bwlast, bp.bwsai,
+                                 bp.n_out, w, 1)      # PFPB200_PFBWT_SA
             res["pipeline"] = {"ms_bwtparse": round(bp.ms_total, 2), "ms_pfbwt": round(r.ms_total, 2),
                                "bwt_bytes": r.n_bwt, "easy": r.easy, "hard": r.hard}
             if r.n_bwt != n + 1: fails.append("pfbwt: |BWT| != n + 1")
@@ -174,6 +177,7 @@ def check_case(sc, text, w, p, name, digest_key=None, text_key=None, prefix_phra
                     if got[e] != ref["sha256"][e]: fails.append(f".{e} sha256 differs from the reference chain")
             else:
                 res["pipeline"]["sha256_vs_reference"] = None
+            sc2.close()
         except Exception as e:  # noqa: BLE001
             res["pipeline"] = {"error": str(e)[:300]}
             fails.append("pipeline failed")
