@@ -57,6 +57,38 @@ def test_cli_rejects_bad_arguments(pkg):
     assert r.returncode == 1 and "Invalid number of arguments" in r.stdout
 
 
+def test_clis_of_the_later_stages_check_their_arguments(pkg):
+    """gpubwtparse.x / gpupfbwt.x / gpuunparse.x / gpubigbwt.x: the argument errors of the reference's
+    tools (bwtparse.c:131-160, pfbwt.cpp:257-315, unparse.c:33-64, bigbwt:59-61), before any GPU work."""
+    import subprocess
+    P = pkg.pfp
+    r = subprocess.run([P.BWTPARSE_CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage" in r.stdout and "permute also sa info" in r.stdout
+    r = subprocess.run([P.PFBWT_CLI_PATH, "-w", "10", "-S", "-s", "x"], capture_output=True, text=True)
+    assert r.returncode == 1 and "not both" in r.stdout
+    r = subprocess.run([P.PFBWT_CLI_PATH, "-w", "3", "x"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Windows size must be at least 4" in r.stdout
+    r = subprocess.run([P.PFBWT_CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 1 and "Invalid number of arguments" in r.stdout
+    r = subprocess.run([P.UNPARSE_CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage" in r.stdout
+    r = subprocess.run([P.BIGBWT_CLI_PATH, "x", "-S", "-e"], capture_output=True, text=True)
+    assert r.returncode == 1 and "not both" in r.stdout
+    r = subprocess.run([P.BIGBWT_CLI_PATH, "x", "-p", "5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Modulus must be at least 10" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_later_stage_clis_fail_loudly_without_a_gpu(pkg, tmp_path):
+    import subprocess
+    base = str(tmp_path / "x")
+    for exe in (pkg.pfp.BWTPARSE_CLI_PATH, pkg.pfp.UNPARSE_CLI_PATH, pkg.pfp.BIGBWT_CLI_PATH):
+        r = subprocess.run([exe, base], capture_output=True, text=True)
+        assert r.returncode == 1 and "cannot use CUDA device" in r.stderr, exe
+    r = subprocess.run([pkg.pfp.PFBWT_CLI_PATH, "-w", "10", base], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot use CUDA device" in r.stderr
+
+
 @pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith(("fasta", "fastq", "pangenome_fasta"))])
 def test_host_fasta_reader_matches_oracle(pkg, name):
     """The product's own kseq-equivalent reader (pfp_io.c) against the oracle's restatement,
