@@ -322,7 +322,7 @@ def parity_check(job, pkg, synth, world, rank, local, dev, merge):
 # ------------------------------------------------------------------------------------------------
 # T2: page-cache-warm FASTA file -> five files closed, wall clock of the gpuscan.x process
 # ------------------------------------------------------------------------------------------------
-def pipeline_to_bwt(pkg, device, text, steps=3):
+def pipeline_to_bwt(pkg, device, text, steps=3, cpu_sample_bytes=0):
     """The whole bigbwt pipeline on the GPU with the text resident in HBM: parse -> bwtparse -> pfbwt
     (pfpb200_parse_device / _bwtparse_device / _pfbwt_device on one context, nothing leaves HBM in
     between).  Wall clock of the three calls + each stage's CUDA-event time; reported beside the
@@ -340,9 +340,35 @@ def pipeline_to_bwt(pkg, device, text, steps=3):
                          "ms_pfbwt": r.ms_total, "ms_pfbwt_suffix_sort": r.ms_sa, "ms_pfbwt_emit": r.ms_fill,
                          "doubling_rounds": {"bwtparse": bp.rounds, "pfbwt": r.rounds},
                          "easy_chars": r.easy, "hard_chars": r.hard, "bwt_bytes": r.n_bwt})
+        # the reference's own later stages on a bounded sample (first haplotype), host cores, for the ratio
+        cpu = None
+        ref_dir = os.path.join(ROOT, "oracle", "_ref")
+        if cpu_sample_bytes and os.path.exists(os.path.join(ref_dir, "pfbwtNT.x")):
+            sub = text[:cpu_sample_bytes].clone()
+            o2 = sc.parse_device(sub, W, P, sai=True)
+            f = sc.fetch(o2)
+            tmp = tempfile.mkdtemp(prefix="pfppipe_")
+            try:
+                base = os.path.join(tmp, "x")
+                for ext in ("dict", "occ", "parse", "last", "sai"):
+                    with open(base + "." + ext, "wb") as fh:
+                        fh.write(getattr(f, ext))
+                t0 = time.perf_counter()
+                subprocess.run([os.path.join(ref_dir, "bwtparse"), base, "-s"], check=True, stdout=subprocess.DEVNULL)
+                t1 = time.perf_counter()
+                subprocess.run([os.path.join(ref_dir, "pfbwtNT.x"), "-w", str(W), base], check=True, stdout=subprocess.DEVNULL)
+                t2 = time.perf_counter()
+                r2, _, _ = sc.bwt_of_text(sub, W, P, flags=0)
+                same = open(base + ".bwt", "rb").read() == sc.to_host(r2.bwt, r2.n_bwt)
+                cpu = {"kind": "reference", "cores": 1, "value": sub.numel() / (t2 - t0) / 1e9, "unit": "GB/s of text",
+                       "bwtparse_s": t1 - t0, "pfbwt_s": t2 - t1, "bwt_identical": same,
+                       "sample": f"bwtparse -s + pfbwtNT.x (unmodified, oracle/_ref) on the GPU parse of the first {sub.numel()} bytes of the text"}
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
         sc.close()
         torch.cuda.empty_cache()
         med = sorted(runs[1:], key=lambda d: d["seconds"])[len(runs[1:]) // 2]
+        med["cpu_baseline"] = cpu
         med["value"] = text.numel() / med["seconds"] / 1e9
         med["unit"] = "GB/s of text, text in HBM -> BWT in HBM"
         med["steps"] = steps
@@ -493,7 +519,7 @@ def main():
     # ---- the stages after the parse, N = 1: text in HBM -> BWT in HBM ---------
     pipeline = None
     if world == 1 and not a.no_pipeline and a.workload == "pangenome" and n_local <= (6 << 30):
-        pipeline = pipeline_to_bwt(pkg, local, text)
+        pipeline = pipeline_to_bwt(pkg, local, text, cpu_sample_bytes=0 if a.no_cpu_baseline else min(n_local, a.base_len))
 
     # ---- e2e: host buffers in, host buffers out ------------------------------------------------
     e2e = None
