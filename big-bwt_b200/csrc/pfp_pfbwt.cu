@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(PB_T) pb_update_k(const u8 *__restrict__ flag,
                                                     const u32 *__restrict__ slot, const u32 *__restrict__ val,
                                                     const u64 *__restrict__ key, int kb, int first,
                                                     const u32 *__restrict__ head, const u32 *__restrict__ lim, u64 M, u64 h,
-                                                    u32 *__restrict__ sa, u32 *__restrict__ rank, u32 *__restrict__ rs,
+                                                    u64 *__restrict__ sa, u32 *__restrict__ rank, u32 *__restrict__ rs,
                                                     u8 *__restrict__ keep) {
     const u64 k = (u64)blockIdx.x * PB_T + threadIdx.x;
     if (k >= M) return;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(PB_T) pb_update_k(const u8 *__restrict__ flag,
     rs[k] = r;
     const bool stay = !(single || done);
     keep[k] = stay ? 1 : 0;
-    if (!stay) sa[slot[k]] = s;
+    if (!stay) sa[slot[k]] = ((u64)r << 32) | s;              // final place: (rank = start of its group, suffix) in one store
 }
 
 __global__ void __launch_bounds__(PB_T) pb_compact_k(const u8 *__restrict__ keep, const u32 *__restrict__ kscan,
@@ -162,28 +162,44 @@ __global__ void __launch_bounds__(PB_T) pb_compact_k(const u8 *__restrict__ keep
 // ---- the walk over the sorted suffixes -----------------------------------------------------------
 struct PbView {
     const u8 *d;
-    const u32 *sa, *rank, *wid, *wend, *occ, *istart;
+    const u64 *sa;              // per slot: (rank << 32) | suffix position
+    const u32 *wid, *wend, *occ, *istart;
+    uint2 *mrec;                // per slot, written by pb_count_k: {word, suffix length}
+    u16 *mc;                    // per slot: char in front | whole word << 8 | counts << 9
     u64 N;
     u32 w;
 };
-// occurrences this suffix contributes (0: terminator or length <= w), its word, length, char in front
-__device__ __forceinline__ u32 pb_member(const PbView &v, u64 k, u32 &word, u32 &len, bool &full, u8 &c) {
-    const u32 s = v.sa[k];
-    if (pb_term(v.d[s])) return 0;
-    word = v.wid[s];
-    len = v.wend[word] - s;
-    if (len <= v.w) return 0;                                        // pfbwt.cpp:152
-    full = s == 0 || v.d[s - 1] == PFP_END_OF_WORD;                  // :154
-    c = (s <= 1) ? (u8)0 : v.d[s - 1];                               // d[0] = 0 is the EOF char of the final BWT (:127)
-    return v.occ[word];
+// the member record of slot k (pb_count_k wrote it): word, length, char in front; false: terminator or length <= w
+__device__ __forceinline__ bool pb_member(const PbView &v, u64 k, u32 &word, u32 &len, bool &full, u8 &c) {
+    const u32 m = v.mc[k];
+    const uint2 r = v.mrec[k];
+    word = r.x; len = r.y;
+    full = (m & 0x100u) != 0;
+    c = (u8)m;
+    return (m & 0x200u) != 0;
 }
 
+// occurrences each sorted suffix contributes (0: terminator or length <= w), its member record, group starts
 __global__ void __launch_bounds__(PB_T) pb_count_k(PbView v, u32 *__restrict__ cnt, u8 *__restrict__ newgrp) {
     const u64 k = (u64)blockIdx.x * PB_T + threadIdx.x;
     if (k >= v.N) return;
-    u32 word, len; bool full; u8 c;
-    cnt[k] = pb_member(v, k, word, len, full, c);
-    newgrp[k] = (k == 0 || v.rank[v.sa[k]] != v.rank[v.sa[k - 1]]) ? 1 : 0;
+    const u64 e = v.sa[k];
+    const u32 s = (u32)e;
+    newgrp[k] = (k == 0 || (u32)(e >> 32) != (u32)(v.sa[k - 1] >> 32)) ? 1 : 0;
+    u32 word = 0, len = 0, n = 0, m = 0;
+    if (!pb_term(v.d[s])) {
+        word = v.wid[s];
+        len = v.wend[word] - s;
+        if (len > v.w) {                                             // pfbwt.cpp:152
+            const bool full = s == 0 || v.d[s - 1] == PFP_END_OF_WORD;   // :154
+            const u32 c = (s <= 1) ? 0u : v.d[s - 1];                // d[0] = 0 is the EOF char of the final BWT (:127)
+            m = c | (full ? 0x100u : 0u) | 0x200u;
+            n = v.occ[word];
+        }
+    }
+    v.mrec[k] = make_uint2(word, len);
+    v.mc[k] = (u16)m;
+    cnt[k] = n;
 }
 
 __global__ void __launch_bounds__(PB_T) pb_first_k(const u8 *__restrict__ newgrp, const u32 *__restrict__ gscan, u64 N,
@@ -236,7 +252,8 @@ __global__ void __launch_bounds__(PB_T) pb_easy_k(PbView v, const u32 *__restric
     const u64 k = (u64)blockIdx.x * PB_T + threadIdx.x;
     if (k >= v.N || cnt[k] == 0 || hcnt[k] != 0) return;
     u32 word, len; bool full; u8 c;
-    const u32 n = pb_member(v, k, word, len, full, c);
+    pb_member(v, k, word, len, full, c);
+    const u32 n = cnt[k];
     if (n > PB_BIG) {                                                // a word with many occurrences: one CTA each, below
         const u32 i = atomicAdd(big_n, 1u);
         if (i < big_cap) big[i] = (u32)k;
@@ -254,7 +271,7 @@ __global__ void __launch_bounds__(PB_T) pb_easy_k(PbView v, const u32 *__restric
 
 // the easy members with more than PB_BIG occurrences: the threads of a CTA share the loop
 __global__ void __launch_bounds__(PB_T) pb_easy_big_k(PbView v, const u32 *__restrict__ big, const u32 *__restrict__ big_n,
-                                                      u32 big_cap, const u64 *__restrict__ off,
+                                                      u32 big_cap, const u32 *__restrict__ cnt, const u64 *__restrict__ off,
                                                       const u32 *__restrict__ ilist, const u8 *__restrict__ bwlast,
                                                       const u8 *__restrict__ bwsai, u8 *__restrict__ bwt,
                                                       u8 *__restrict__ sa5) {
@@ -262,7 +279,8 @@ __global__ void __launch_bounds__(PB_T) pb_easy_big_k(PbView v, const u32 *__res
     for (u32 b = blockIdx.x; b < nbig; b += gridDim.x) {
         const u64 k = big[b];
         u32 word, len; bool full; u8 c;
-        const u32 n = pb_member(v, k, word, len, full, c);
+        pb_member(v, k, word, len, full, c);
+        const u32 n = cnt[k];
         const u64 o = off[k];
         const u32 is = v.istart[word] + 1u;
         for (u32 j = threadIdx.x; j < n; j += PB_T) {
@@ -280,7 +298,7 @@ __global__ void __launch_bounds__(PB_T) pb_gen_k(PbView v, const u32 *__restrict
                                                  u64 *__restrict__ key, u32 *__restrict__ val) {
     const u64 k = k0 + (u64)blockIdx.x * PB_T + threadIdx.x;
     if (k >= k1 || hcnt[k] == 0) return;
-    const u32 word = v.wid[v.sa[k]];
+    const u32 word = v.mrec[k].x;
     const u32 is = v.istart[word] + 1u, n = hcnt[k];
     const u64 g = (u64)(gscan[k] + newgrp[k] - 1u - g0) << 32;
     const u64 e = hoff[k] - e0;
@@ -413,7 +431,8 @@ static int pfbwt_device_impl(pfpb200_ctx *ctx, const u8 *d_dict, u64 N, const u3
     PFP_LAUNCHED(ctx);
     // ---- 2. suffix sort ----------------------------------------------------------------------------------
     u64 *k0 = nullptr, *k1 = nullptr;
-    u32 *v0 = nullptr, *v1 = nullptr, *sa = nullptr, *rank = nullptr, *rs = nullptr, *escan = nullptr;
+    u32 *v0 = nullptr, *v1 = nullptr, *rank = nullptr, *rs = nullptr, *escan = nullptr;
+    u64 *sa = nullptr;
     u32 *slot = nullptr, *slot2 = nullptr, *head = nullptr;
     PFP_TRY(pfp_alloc_t(ctx, &sa, N));
     PFP_TRY(pfp_alloc_t(ctx, &rank, N));
@@ -488,7 +507,12 @@ static int pfbwt_device_impl(pfpb200_ctx *ctx, const u8 *d_dict, u64 N, const u3
     PFP_TRY(pfp_free_now(ctx, slot2)); PFP_TRY(pfp_free_now(ctx, head)); PFP_TRY(pfp_free_now(ctx, keep));
     PFP_CUDA(ctx, cudaEventRecord(evs[1], ctx->stream));
     // ---- 3. ranges of the BWT, easy members ------------------------------------------------------------------
-    PbView V{d_dict, sa, rank, wid, wend, d_occ, istart, N, w};
+    PFP_TRY(pfp_free_now(ctx, rank));                        // the ranks travel with the suffix array from here on
+    uint2 *mrec = nullptr;
+    u16 *mc = nullptr;
+    PFP_TRY(pfp_alloc_t(ctx, &mrec, N));
+    PFP_TRY(pfp_alloc_t(ctx, &mc, N));
+    PbView V{d_dict, sa, wid, wend, d_occ, istart, mrec, mc, N, w};
     u32 *cnt = nullptr, *hcnt = nullptr, *gscan = escan, *first = nullptr;
     u8 *newgrp = flag, *mixed = nullptr;
     u64 *off = nullptr, *hoff = nullptr;
@@ -531,7 +555,7 @@ static int pfbwt_device_impl(pfpb200_ctx *ctx, const u8 *d_dict, u64 N, const u3
     PFP_CUDA(ctx, cudaMemsetAsync(&ctx->d_flags[6], 0, sizeof(u64), ctx->stream));
     pb_easy_k<<<nb, PB_T, 0, ctx->stream>>>(V, cnt, hcnt, off, d_ilist, d_bwlast, d_bwsai, bwt, sa5, big, big_n, big_cap);
     PFP_LAUNCHED(ctx);
-    pb_easy_big_k<<<ctx->sm_count * 8, PB_T, 0, ctx->stream>>>(V, big, big_n, big_cap, off, d_ilist, d_bwlast, d_bwsai, bwt, sa5);
+    pb_easy_big_k<<<ctx->sm_count * 8, PB_T, 0, ctx->stream>>>(V, big, big_n, big_cap, cnt, off, d_ilist, d_bwlast, d_bwsai, bwt, sa5);
     PFP_LAUNCHED(ctx);
     // ---- 4. hard members: the merge of the ilist cursors as a sort, in batches ------------------------------------
     if (n_hard) {
