@@ -21,6 +21,7 @@ static void usage(const char *exe) {
     printf("\t-e  \tcompute the end of run-length encoded BWT intervals of the sampled SA (.esa)\n");
     printf("\t-S  \tcompute the full suffix array (.sa)\n");
     printf("\t-k  \tkeep the intermediate files of the three stages\n");
+    printf("\t-t T\taccepted for compatibility (helper threads of the reference's stages)\n");
     printf("\t-g G\tCUDA device index, def. 0\n");
     exit(1);
 }
@@ -35,7 +36,7 @@ int main(int argc, char **argv) {
     puts("==== Command line:");
     for (int i = 0; i < argc; i++) printf(" %s", argv[i]);
     puts("");
-    while ((c = getopt(argc, argv, "w:p:fseSkhg:")) != -1) {
+    while ((c = getopt(argc, argv, "w:p:fseSkhg:t:v")) != -1) {
         switch (c) {
             case 'w': w = strtol(optarg, NULL, 10); break;
             case 'p': p = strtol(optarg, NULL, 10); break;
@@ -44,6 +45,8 @@ int main(int argc, char **argv) {
             case 'e': flags |= PFPB200_PFBWT_ESA; break;
             case 'S': flags |= PFPB200_PFBWT_SA; break;
             case 'k': keep = 1; break;
+            case 't': break;                       /* bigbwt -t T: helper threads of the CPU stages, nothing to do here */
+            case 'v': break;
             case 'g': device = atoi(optarg); break;
             case 'h': usage(argv[0]); break;
             default: puts("Unknown option. Use -h for help."); exit(1);
