@@ -280,7 +280,7 @@ int pfp_exclusive_scan_u8_u32(pfpb200_ctx *ctx, const u8 *in, u32 *out, u64 n, u
 // radix sort: per pass  histogram -> scan -> ranked scatter   (8-bit digits)
 // ------------------------------------------------------------------------------------------
 constexpr int RS_T = 256;
-constexpr int RS_I = 16;
+constexpr int RS_I = 8;
 constexpr int RS_TILE = RS_T * RS_I;   // 4096 pairs per CTA
 constexpr int RS_WARPS = RS_T / 32;
 constexpr int RS_SUB = RS_TILE / RS_WARPS;   // 512 consecutive items per warp
