@@ -64,3 +64,54 @@ def run_reference(files: dict, w: int, flags=("-S",)):
 
 def have_reference() -> bool:
     return os.path.exists(REF_PFBWT)
+
+
+def pfbwt_algorithm(dict_b: bytes, occ_b: bytes, ilist_b: bytes, bwlast_b: bytes, bwsai_b: bytes | None, w: int):
+    """The reference's ALGORITHM (pfbwt.cpp bwt(), :109-242) restated for small inputs, next to the
+    result definition above: sort the dictionary's suffixes (compute_dict_bwt_lcp, :483-515; here a
+    plain sort of the byte strings up to their word's EndOfWord), walk them in order, skip those of
+    length <= w (:152), emit for a whole word the .bwlast char of each of its occurrences (:154-203),
+    for a group of equal proper suffixes of several words the chars in front of them merged by the
+    words' positions in the BWT of the parse (fwrite_chars_same_suffix, :521-560 -- the heap merge
+    is a sort of the (ilist position, char) pairs).  Returns {'bwt', 'sa'} (sa = b'' without bwsai)."""
+    d = bytearray(dict_b)
+    occ = np.frombuffer(occ_b, dtype=np.uint32).astype(np.int64)
+    ilist = np.frombuffer(ilist_b, dtype=np.uint32).astype(np.int64)
+    sai = None
+    if bwsai_b:
+        a = np.frombuffer(bwsai_b, dtype=np.uint8).reshape(-1, SABYTES).astype(np.uint64)
+        sai = sum(a[:, j] << np.uint64(8 * j) for j in range(SABYTES)).astype(np.int64)
+    assert d[0] == 2 and d[-1] == 0                          # :126, :496
+    d[0] = 0                                                 # the EOF char of the final BWT (:127)
+    istart = np.concatenate([[1], 1 + np.cumsum(occ)])       # :376-383: ilist[0] belongs to the end symbol
+    assert istart[-1] == ilist.size
+    # (suffix bytes, word id, start) of every dictionary suffix longer than w
+    sufs, start, word = [], 0, 0
+    for e in range(len(d)):
+        if d[e] == 1:                                        # EndOfWord
+            for t in range(start, e):
+                if e - t > w:
+                    sufs.append((bytes(d[t:e]) if t else bytes([2]) + bytes(d[1:e]), word, t, t == start))
+            start, word = e + 1, word + 1
+    assert word == occ.size                                  # :360
+    sufs.sort(key=lambda s: (s[0], s[1]))                    # equal suffixes: the order inside a group is irrelevant
+    bwt, sa = bytearray(), []
+    i = 0
+    while i < len(sufs):
+        j = i
+        while j < len(sufs) and sufs[j][0] == sufs[i][0]:
+            j += 1
+        group = sufs[i:j]
+        length = len(group[0][0])
+        pairs = []
+        for _, wd, t, full in group:
+            for k in range(istart[wd], istart[wd + 1]):
+                pos = int(ilist[k])
+                pairs.append((pos, bwlast_b[pos] if full else d[t - 1], wd, full))
+        pairs.sort()                                         # the heap of ilist cursors (:536-558)
+        for pos, ch, wd, full in pairs:
+            bwt.append(ch)
+            if sai is not None and not (full and wd == 0):   # no SA entry for the first word of the parse (:157-163)
+                sa.append(int(sai[pos]) - length)
+        i = j
+    return {"bwt": bytes(bwt), "sa": _put5(np.array(sa, dtype=np.int64)) if sai is not None else b""}

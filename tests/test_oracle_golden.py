@@ -118,3 +118,15 @@ def test_pfbwt_oracle_matches_golden():
         got = po.pfbwt(c["text"])
         for ext in ("bwt", "sa", "ssa", "esa"):
             assert got[ext] == c[ext], f"{name}: .{ext}"
+
+
+def test_pfbwt_algorithm_restatement_matches_golden():
+    """The walk over the sorted dictionary suffixes with the ilist merge (pfbwt.cpp:109-242), restated,
+    gives the reference binary's .bwt and .sa from the reference's own intermediate files."""
+    from oracle import pfbwt_oracle as po
+    cases = _pfbwt_golden()
+    for name in ("short_w4_p10", "low_complexity_w4_p11", "identical_copies_w10_p50", "random_30k_w4_p10"):
+        c = cases[name]
+        got = po.pfbwt_algorithm(c["dict"], c["occ"], c["ilist"], c["bwlast"], c["bwsai"], c["w"])
+        assert got["bwt"] == c["bwt"], f"{name}: .bwt"
+        assert got["sa"] == c["sa"], f"{name}: .sa"
